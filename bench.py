@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: gausslegendre Gnodes/s at n = 1e9, device-resident, sharded
+over N B200s (BASELINE.json `metric`, config[1]).
+
+  python bench.py --gpus 1 --steps K --warmup W
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      # the CPU arm: the C oracle port on the host cores
+
+One step = one full generation of the n-point rule into HBM (no inputs: every node is a
+function of its index; 16 bytes written per node).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gausslegendre_gnodes_per_s"
+UNIT = "Gnodes/s"
+N_DEFAULT = 10 ** 9
+CPU_SAMPLE_N = 2 * 10 ** 8     # bounded CPU sample: a full gausslegendre(2e8), same branch as 1e9
+PUBLISHED_JULIA_GNODES = 0.0428  # docs/src/benchmark.md:21-22 (n = 1e9+1, hardware unstated)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json, torch copy_ read+write)"
+        except Exception:  # noqa: BLE001
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def cpu_oracle_rate(n_sample: int, threads: int, reps: int = 1):
+    """Gnodes/s of the C oracle (oracle/legendre_oracle.c) on a full gausslegendre(n_sample)."""
+    import numpy as np
+    import oracle
+    used = oracle.set_threads(threads)
+    x = np.zeros(n_sample)  # pre-faulted outputs
+    w = np.zeros(n_sample)
+    L = oracle.lib()
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rc = L.oracle_gausslegendre(n_sample, oracle._dp(x), oracle._dp(w))
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        best = dt if best is None else min(best, dt)
+    return n_sample / best / 1e9, used, best
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port (Julia is not installed on the box, so the reference itself cannot
+    run), all host threads, each step one full gausslegendre(CPU_SAMPLE_N)."""
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_oracle_rate(args.cpu_n, 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, used, _ = cpu_oracle_rate(args.cpu_n, 0)
+    dt = time.perf_counter() - t0
+    value = args.cpu_n * args.steps / dt / 1e9
+    rate1, _, _ = cpu_oracle_rate(args.cpu_n, 1)
+    sample = (f"each step = full oracle gausslegendre(n={args.cpu_n}) on the host "
+              f"(same branch as n=1e9: 1-term nodes, 0-term weights), OpenMP over {used} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (none read: nodes are generated from their index)",
+        "config": {"workload": f"gausslegendre(n={args.n}) Bogaert asymptotic path", "n": args.n,
+                   "cpu_sample_n": args.cpu_n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
+                         "single_thread_value": rate1, "host_cores": cores},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "published_reference": {"value": PUBLISHED_JULIA_GNODES, "unit": UNIT,
+                                "what": "Julia @btime gausslegendre(1000000001), docs/src/benchmark.md:21-22, hardware unstated"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--mode", default="pair", choices=["pair", "contiguous"])
+    ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import fgq_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.n
+    L = fgq_b200.lib()
+    shard = fgq_b200.gausslegendre_device(n, rank=rank, world=world, mode=args.mode)  # allocates
+    torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        fgq_b200.gausslegendre_device(n, rank=rank, world=world, mode=args.mode, out=shard)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0 = fgq_b200.launch_count()
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        fgq_b200.gausslegendre_device(n, rank=rank, world=world, mode=args.mode, out=shard)
+        ev[i + 1].record()
+    barrier()
+    launches = fgq_b200.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop()
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = n * args.steps / (total_ms_max * 1e-3) / 1e9
+
+    # invariant check of the last step's output: sum w = 2, sum w x^2 = 2/3 (all-reduced)
+    sums = fgq_b200.rule_moments_device(shard)
+    if world > 1:
+        dist.all_reduce(sums)
+    sums = sums.cpu().numpy()
+
+    # ---- end-to-end through the host-returning C-ABI call: device generation + D2H into pinned
+    # host buffers, every step (h2d = 0: the only input is the integer n).
+    e2e = None
+    if not args.no_e2e:
+        lo, hi = fgq_b200.index_partition(n, world)[rank]
+        hx = torch.empty(hi - lo, dtype=torch.float64, pin_memory=True)
+        hw = torch.empty(hi - lo, dtype=torch.float64, pin_memory=True)
+        out = (hx.numpy(), hw.numpy())
+        fgq_b200.gausslegendre(n, out=out, index_range=(lo, hi))  # warm-up (scratch allocation)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            fgq_b200.gausslegendre(n, out=out, index_range=(lo, hi))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": n * args.e2e_steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": 16 * n, "steps": args.e2e_steps,
+               "what": "fgq_gausslegendre_host_slice per rank into pinned host buffers (kernel + PCIe D2H, chunk-pipelined)",
+               "check_sum_w_minus_2": float(np.float64(hw.sum().item()) - 2.0) if world == 1 else None}
+        del hx, hw
+
+    if rank == 0:
+        peaks, peaks_src = measured_peaks()
+        # dominant kernel: legendre_asy_kernel<0,0,false> (the McMahon-tail launch); time it alone
+        k_lo, k_hi = fgq_b200.half_index_partition(n, world)[rank]
+        k_tail = max(k_lo, 13193)  # odd, like every shard boundary: keeps 16-byte alignment
+        tail_nodes = 2 * (k_hi - k_tail)
+        reps = 20
+        xl, wl = shard.segments[0][2], shard.segments[0][3]
+        if args.mode == "pair" and k_hi - k_tail > 0:
+            xr, wr = shard._right_full
+            off = k_tail - k_lo
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sp = torch.cuda.current_stream().cuda_stream
+            e0.record()
+            for _ in range(reps):
+                # right segment of [k_tail, k_hi) ends where the full one ends: same base pointers
+                fgq_b200._lib.check(L.fgq_gausslegendre_device_pair(
+                    n, k_tail, k_hi, xl.data_ptr() + 8 * off, wl.data_ptr() + 8 * off,
+                    xr.data_ptr(), wr.data_ptr(), sp))
+            e1.record()
+            torch.cuda.synchronize()
+            kern_ms = e0.elapsed_time(e1) / reps
+        else:
+            kern_ms = statistics.mean(step_ms)
+            tail_nodes = shard.count
+        achieved = 16.0 * tail_nodes / (kern_ms * 1e-3) / 1e9
+        dfma_tf, store_gbs = fgq_b200.measure_peaks()
+        roofline = {
+            "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+            "kernel": "legendre_asy_kernel<NT=0,WT=0,HEAD=false>", "kernel_ms": kern_ms,
+            "algorithmic_bytes_per_node": 16, "nodes_per_launch": tail_nodes,
+            "peak_source": peaks_src,
+            "store_only_peak_gbs": store_gbs, "frac_of_store_peak": achieved / store_gbs if store_gbs else None,
+            "fp64": {"algorithmic_flops_per_node": 22, "achieved_tflops": 22.0 * tail_nodes / (kern_ms * 1e-3) / 1e12,
+                     "dfma_peak_tflops": dfma_tf,
+                     "frac": (22.0 * tail_nodes / (kern_ms * 1e-3) / 1e12) / dfma_tf if dfma_tf else None},
+        }
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle
+            oracle.build()
+            r_all, used, t_all = cpu_oracle_rate(args.cpu_n, 0)
+            r_one, _, t_one = cpu_oracle_rate(args.cpu_n, 1)
+            cpu_baseline = {
+                "value": r_one, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"full oracle gausslegendre(n={args.cpu_n}) (same branch as n=1e9), one thread like the reference; {t_one:.2f} s",
+                "all_cores_value": r_all, "all_cores": used,
+                "published_julia": {"value": PUBLISHED_JULIA_GNODES, "what": "docs/src/benchmark.md:21-22, hardware unstated"},
+            }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (none read: nodes are generated from their index)",
+            "config": {"workload": f"gausslegendre(n={n}) Bogaert asymptotic path, device-resident, "
+                                   f"{args.mode}-sharded over {world} GPU(s)",
+                       "n": n, "shard_mode": args.mode,
+                       "l2": "each step writes 16*n/N bytes (>> 126 MB L2) and reads nothing; no flush needed"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "checks": {"sum_w_minus_2": float(sums[0] - 2.0), "sum_wx2_minus_2_3": float(sums[1] - 2.0 / 3.0)},
+            "step_ms_median": statistics.median(step_ms), "step_ms_min": min(step_ms),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,18 @@
+"""fgq_b200 — B200-native Gauss quadrature node/weight generation.
+
+Host-side mirror of FastGaussQuadrature.jl's public functions for the per-node generation
+path (reference src/FastGaussQuadrature.jl:7-19), over the C ABI of ``libfgq_cuda.so``
+(``include/fgq.h``).  Import it as ``import fgq_b200`` (see ``fgq_b200.py`` at the repo root).
+"""
+from ._lib import DomainError, FGQError, NotImplementedOnDevice, build, lib  # noqa: F401
+from .api import (  # noqa: F401
+    gausslegendre,
+    gausslegendre_batch,
+    gausslegendre_device,
+    half_index_partition,
+    index_partition,
+    LegendreShard,
+    rule_moments_device,
+    measure_peaks,
+    launch_count,
+)

@@ -1,0 +1,95 @@
+"""ctypes binding of libfgq_cuda.so (the C ABI declared in include/fgq.h).
+
+There is no CPU fallback: if the shared library is missing, cannot be loaded, or no CUDA
+device is visible, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfgq_cuda.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+FGQ_OK, FGQ_EDOMAIN, FGQ_ENOTIMPL, FGQ_EINVAL, FGQ_ECUDA = 0, 1, 2, 3, 100
+
+_i64 = ctypes.c_int64
+_dp = ctypes.POINTER(ctypes.c_double)
+_vp = ctypes.c_void_p
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+# name -> (restype, argtypes); must list every symbol include/fgq.h declares
+SIGNATURES = {
+    "fgq_version": (ctypes.c_int, []),
+    "fgq_last_error": (ctypes.c_char_p, []),
+    "fgq_warnings": (ctypes.c_int, []),
+    "fgq_device_count": (ctypes.c_int, []),
+    "fgq_launch_count": (_i64, []),
+    "fgq_gausslegendre_host": (ctypes.c_int, [_i64, _vp, _vp]),
+    "fgq_gausslegendre_host_slice": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp]),
+    "fgq_gausslegendre_device": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp, _vp]),
+    "fgq_gausslegendre_device_pair": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "fgq_gausslegendre_batch_device": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp]),
+    "fgq_gausslegendre_batch_host": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp]),
+    "fgq_rule_moments_device": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "fgq_measure_dfma_peak": (ctypes.c_int, [_dp]),
+    "fgq_measure_store_peak": (ctypes.c_int, [_i64, _dp]),
+    "fgq_debug_legendre_theta_device": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+class FGQError(RuntimeError):
+    """CUDA / internal failure inside libfgq_cuda.so."""
+
+
+class DomainError(ValueError):
+    """Mirror of Julia's DomainError at the reference's argument checks."""
+
+
+class NotImplementedOnDevice(NotImplementedError):
+    """Parameter region the reference serves off the hot path (eigen-solves, non-Float64)."""
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libfgq_cuda.so for sm_100a with nvcc (in-tree; cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode:
+        print(r.stdout)
+    if r.returncode:
+        raise FGQError("building libfgq_cuda.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FGQError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                " — this package has no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc == FGQ_OK:
+        return
+    msg = lib().fgq_last_error().decode("utf-8", "replace")
+    if rc == FGQ_EDOMAIN:
+        raise DomainError(msg)
+    if rc == FGQ_ENOTIMPL:
+        raise NotImplementedOnDevice(msg)
+    if rc == FGQ_EINVAL:
+        raise ValueError(msg)
+    raise FGQError(f"libfgq_cuda rc={rc}: {msg}")

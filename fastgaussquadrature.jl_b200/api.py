@@ -1,0 +1,210 @@
+"""Reference-facing functions.  Same names, argument meaning and error behaviour as the Julia
+package; each returns ``(x, w)`` as freshly allocated float64 arrays, nodes ascending.
+
+Host-returning calls (`gausslegendre(n)` ...) hand back numpy arrays, exactly like the
+reference hands back ``Vector{Float64}``.  The ``*_device`` calls are the device-resident
+variant: torch CUDA tensors that stay in HBM, sharded by rank (one process per GPU).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import DomainError, check, lib
+
+
+def _ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+def _as_int(n) -> int:
+    if isinstance(n, bool) or int(n) != n:
+        raise TypeError(f"n must be an integer, got {n!r}")  # Julia: MethodError for non-Integer n
+    return int(n)
+
+
+def _host_pair(n: int, pinned: bool):
+    """Two length-n float64 host arrays; pinned (page-locked) ones come from torch."""
+    if pinned:
+        import torch
+        tx = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        tw = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        return tx.numpy(), tw.numpy()
+    return np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
+
+
+def launch_count() -> int:
+    return int(lib().fgq_launch_count())
+
+
+# --------------------------------------------------------------------------------------------
+# Gauss-Legendre  (reference src/gausslegendre.jl:22-69)
+# --------------------------------------------------------------------------------------------
+
+def gausslegendre(n, *, pinned: bool = False, out: Optional[Tuple[np.ndarray, np.ndarray]] = None,
+                  index_range: Optional[Tuple[int, int]] = None):
+    """``gausslegendre(n) -> x, w`` (reference src/gausslegendre.jl:22,69).
+
+    n < 0 raises DomainError (gausslegendre.jl:26); n == 0 returns two empty arrays (:28).
+    ``out=(x, w)`` reuses caller buffers (e.g. pinned ones) instead of allocating.
+    ``index_range=(lo, hi)`` returns only nodes lo..hi-1 (0-based) — one process per GPU can
+    fetch its own part of a large rule.
+    """
+    n = _as_int(n)
+    if n < 0:
+        raise DomainError(f"DomainError({n}): Input n must be a non-negative integer")
+    lo, hi = (0, n) if index_range is None else (int(index_range[0]), int(index_range[1]))
+    if not (0 <= lo <= hi <= n):
+        raise ValueError(f"invalid index_range {index_range} for n={n}")
+    cnt = hi - lo
+    if out is not None:
+        x, w = out
+        if x.shape != (cnt,) or w.shape != (cnt,) or x.dtype != np.float64 or w.dtype != np.float64:
+            raise ValueError("out must be two float64 arrays of the requested length")
+    else:
+        x, w = _host_pair(cnt, pinned)
+    if cnt == 0:
+        return x, w
+    if index_range is None:
+        check(lib().fgq_gausslegendre_host(n, _ptr(x), _ptr(w)))
+    else:
+        check(lib().fgq_gausslegendre_host_slice(n, lo, hi, _ptr(x), _ptr(w)))
+    return x, w
+
+
+def gausslegendre_batch(n_i, offsets=None):
+    """Batch of small rules ``gausslegendre(n_i[r])``, 0 <= n_i <= 60, CSR layout.
+
+    Returns ``(offsets, x, w)``: rule r occupies ``x[offsets[r]:offsets[r+1]]``.  One warp per
+    rule on the device (closed forms / Newton on the recurrence, gausslegendre.jl:27-60,233-309).
+    """
+    n_i = np.ascontiguousarray(n_i, dtype=np.int32)
+    if n_i.ndim != 1:
+        raise ValueError("n_i must be one-dimensional")
+    if offsets is None:
+        offsets = np.zeros(len(n_i) + 1, dtype=np.int64)
+        np.cumsum(n_i, out=offsets[1:])
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    total = int(offsets[-1]) if len(offsets) else 0
+    x = np.empty(total, dtype=np.float64)
+    w = np.empty(total, dtype=np.float64)
+    if len(n_i):
+        check(lib().fgq_gausslegendre_batch_host(len(n_i), _ptr(n_i), _ptr(offsets), _ptr(x), _ptr(w)))
+    return offsets, x, w
+
+
+# ---- device-resident, sharded -----------------------------------------------------------------
+
+def index_partition(n: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous node-index ranges [lo, hi) per rank, boundaries on even indices so that every
+    shard's 16-byte vector stores stay aligned."""
+    b = [((r * n) // world) & ~1 for r in range(world)] + [n]
+    return [(b[r], b[r + 1]) for r in range(world)]
+
+
+def half_index_partition(n: int, world: int) -> List[Tuple[int, int]]:
+    """Mirror-pair sharding: rank r owns half-indices [k_lo, k_hi) (1-based), i.e. the contiguous
+    node-index range [k_lo-1, k_hi-1) AND its mirror image [n-k_hi+1, n-k_lo+1)."""
+    m = (n + 1) // 2
+    b = [((r * m) // world) & ~1 for r in range(world)] + [m]
+    return [(b[r] + 1, b[r + 1] + 1) for r in range(world)]
+
+
+@dataclass
+class LegendreShard:
+    """What one rank holds of an n-point rule: a list of (lo, hi, x, w) segments, x and w torch
+    CUDA tensors holding output indices [lo, hi)."""
+    n: int
+    rank: int
+    world: int
+    mode: str
+    segments: List[tuple] = field(default_factory=list)
+
+    @property
+    def count(self) -> int:
+        return sum(hi - lo for lo, hi, _, _ in self.segments)
+
+
+def _stream_ptr(stream) -> int:
+    import torch
+    s = torch.cuda.current_stream() if stream is None else stream
+    return int(s.cuda_stream)
+
+
+def gausslegendre_device(n, rank: int = 0, world: int = 1, mode: str = "pair", out: Optional[LegendreShard] = None,
+                         stream=None) -> LegendreShard:
+    """Device-resident ``gausslegendre(n)``: this rank's shard stays in HBM.
+
+    mode="pair": rank owns a half-index range; each half-index is evaluated once and stored
+    as +-x (two segments).  mode="contiguous": rank owns one node-index range [lo, hi).
+    Asynchronous on the current torch stream; pass ``out`` (a previous result) to reuse buffers.
+    No collective is involved: every node is a function of (n, index) alone.
+    """
+    import torch
+    n = _as_int(n)
+    if n < 0:
+        raise DomainError(f"DomainError({n}): Input n must be a non-negative integer")
+    if not torch.cuda.is_available():
+        raise _lib.FGQError("gausslegendre_device needs a CUDA device (no CPU fallback)")
+    L = lib()
+    sp = _stream_ptr(stream)
+    if mode == "pair" and n <= 60:
+        mode = "contiguous"  # tiny rules: the recurrence kernel writes plain index ranges
+    if mode == "contiguous":
+        lo, hi = index_partition(n, world)[rank]
+        if out is None:
+            x = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
+            w = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
+            out = LegendreShard(n, rank, world, mode, [(lo, hi, x, w)])
+        _, _, x, w = out.segments[0]
+        check(L.fgq_gausslegendre_device(n, lo, hi, x.data_ptr(), w.data_ptr(), sp))
+        return out
+    if mode != "pair":
+        raise ValueError("mode must be 'pair' or 'contiguous'")
+    k_lo, k_hi = half_index_partition(n, world)[rank]
+    cnt = k_hi - k_lo
+    m, mr = (n + 1) // 2, n // 2
+    has_centre = (n % 2 == 1) and (k_hi - 1 == m) and cnt > 0
+    if out is None:
+        pad = cnt + (cnt & 1)  # keep the right segment 16-byte aligned inside one allocation
+        xb = torch.empty(2 * pad, dtype=torch.float64, device="cuda")
+        wb = torch.empty(2 * pad, dtype=torch.float64, device="cuda")
+        xl, wl = xb[:cnt], wb[:cnt]
+        xr_full, wr_full = xb[pad:pad + cnt], wb[pad:pad + cnt]
+        skip = 1 if has_centre else 0
+        segs = [(k_lo - 1, k_hi - 1, xl, wl),
+                (n - k_hi + 1 + skip, n - k_lo + 1, xr_full[skip:], wr_full[skip:])]
+        out = LegendreShard(n, rank, world, mode, segs)
+        out._right_full = (xr_full, wr_full)
+    xl, wl = out.segments[0][2], out.segments[0][3]
+    xr_full, wr_full = out._right_full
+    if cnt > 0:
+        check(L.fgq_gausslegendre_device_pair(n, k_lo, k_hi, xl.data_ptr(), wl.data_ptr(),
+                                              xr_full.data_ptr(), wr_full.data_ptr(), sp))
+    return out
+
+
+def rule_moments_device(shard: LegendreShard, stream=None):
+    """(sum w, sum w x^2) of this rank's shard as a 2-element CUDA tensor (a fused-reduction
+    consumer; callers all-reduce it across ranks for the Σw = 2, ∫x² = 2/3 check)."""
+    import torch
+    sums = torch.zeros(2, dtype=torch.float64, device="cuda")
+    sp = _stream_ptr(stream)
+    for lo, hi, x, w in shard.segments:
+        if hi > lo:
+            check(lib().fgq_rule_moments_device(x.data_ptr(), w.data_ptr(), hi - lo, sums.data_ptr(), sp))
+    return sums
+
+
+def measure_peaks(store_bytes: int = 4 << 30):
+    """Roofline denominators on the current device: (FP64 TFLOP/s from the DFMA microbenchmark,
+    store-only HBM GB/s)."""
+    tf = ctypes.c_double(0.0)
+    gb = ctypes.c_double(0.0)
+    check(lib().fgq_measure_dfma_peak(ctypes.byref(tf)))
+    check(lib().fgq_measure_store_peak(int(store_bytes), ctypes.byref(gb)))
+    return tf.value, gb.value

@@ -1,0 +1,282 @@
+// capi.cu — status plumbing, library-owned scratch, host-returning entry points and the
+// rule-moments consumer of libfgq_cuda.so (see include/fgq.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace fgq {
+
+static thread_local char t_err[512] = "";
+static thread_local int t_warn = 0;
+static std::atomic<int64_t> g_launches{0};
+static std::mutex g_host_mutex;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+void clear_status() {
+    t_err[0] = 0;
+    t_warn = 0;
+}
+void add_warning(int bits) { t_warn |= bits; }
+void count_launch(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+HostPathLock::HostPathLock() { g_host_mutex.lock(); }
+HostPathLock::~HostPathLock() { g_host_mutex.unlock(); }
+
+constexpr int MAX_DEV = 16, MAX_SLOT = 8;
+static void* g_scratch[MAX_DEV][MAX_SLOT];
+static size_t g_scratch_bytes[MAX_DEV][MAX_SLOT];
+static cudaStream_t g_streams[MAX_DEV][2];
+static cudaEvent_t g_events[MAX_DEV][4];
+
+static int cur_dev(int* dev) {
+    FGQ_CUDA_TRY(cudaGetDevice(dev));
+    if (*dev < 0 || *dev >= MAX_DEV) {
+        set_error("device ordinal %d out of range", *dev);
+        return FGQ_EINVAL;
+    }
+    return FGQ_OK;
+}
+
+int scratch_device(size_t bytes, int slot, void** out) {
+    int dev;
+    FGQ_TRY(cur_dev(&dev));
+    if (g_scratch_bytes[dev][slot] < bytes) {
+        if (g_scratch[dev][slot]) {
+            FGQ_CUDA_TRY(cudaFree(g_scratch[dev][slot]));
+            g_scratch[dev][slot] = nullptr;
+            g_scratch_bytes[dev][slot] = 0;
+        }
+        FGQ_CUDA_TRY(cudaMalloc(&g_scratch[dev][slot], bytes));
+        g_scratch_bytes[dev][slot] = bytes;
+    }
+    *out = g_scratch[dev][slot];
+    return FGQ_OK;
+}
+
+int scratch_stream(int which, cudaStream_t* out) {
+    int dev;
+    FGQ_TRY(cur_dev(&dev));
+    if (!g_streams[dev][which])
+        FGQ_CUDA_TRY(cudaStreamCreateWithFlags(&g_streams[dev][which], cudaStreamNonBlocking));
+    *out = g_streams[dev][which];
+    return FGQ_OK;
+}
+
+int scratch_event(int which, cudaEvent_t* out) {
+    int dev;
+    FGQ_TRY(cur_dev(&dev));
+    if (!g_events[dev][which])
+        FGQ_CUDA_TRY(cudaEventCreateWithFlags(&g_events[dev][which], cudaEventDisableTiming));
+    *out = g_events[dev][which];
+    return FGQ_OK;
+}
+
+// sum w, sum w x^2: block-level tree + one atomicAdd pair per block
+__global__ void __launch_bounds__(256)
+rule_moments_kernel(const double* __restrict__ x, const double* __restrict__ w, int64_t count,
+                    double* __restrict__ sums) {
+    double s0 = 0.0, s2 = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const double xi = __ldcs(x + i), wi = __ldcs(w + i);
+        s0 += wi;
+        s2 = fma(wi * xi, xi, s2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_down_sync(0xffffffffu, s0, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    __shared__ double sh0[8], sh2[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        sh0[wid] = s0;
+        sh2[wid] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < 8; ++i) {
+            a += sh0[i];
+            b += sh2[i];
+        }
+        atomicAdd(sums, a);
+        atomicAdd(sums + 1, b);
+    }
+}
+
+}  // namespace fgq
+
+using namespace fgq;
+
+extern "C" int fgq_version(void) { return 100; }
+extern "C" const char* fgq_last_error(void) { return t_err; }
+extern "C" int fgq_warnings(void) { return t_warn; }
+extern "C" int64_t fgq_launch_count(void) { return g_launches.load(); }
+
+extern "C" int fgq_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int fgq_rule_moments_device(const double* x_dev, const double* w_dev, int64_t count,
+                                       double* sums_dev, void* stream) {
+    clear_status();
+    if (count < 0 || !sums_dev || (count > 0 && (!x_dev || !w_dev))) {
+        set_error("invalid moments request");
+        return FGQ_EINVAL;
+    }
+    if (count == 0) return FGQ_OK;
+    int64_t blocks = (count + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    rule_moments_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x_dev, w_dev, count,
+                                                                          sums_dev);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+// ---- host-returning drop-ins ----------------------------------------------------------------
+// Chunked: the kernel for chunk j+1 runs while chunk j drains over PCIe, so a 16 GB rule
+// needs only 2 x CHUNK nodes of device scratch.
+
+namespace fgq {
+
+int host_pipeline(int64_t lo_all, int64_t hi_all, double* x, double* w, SliceFn fn, void* ctx) {
+    const int64_t n = hi_all - lo_all;
+    if (n <= 0) return FGQ_OK;
+    if (!x || !w) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    HostPathLock lock;
+    const int64_t CHUNK = 1LL << 24;  // nodes per chunk: 128 MiB of x + 128 MiB of w
+    const int64_t chunk = n < CHUNK ? n : CHUNK;
+    const int nbuf = n > CHUNK ? 2 : 1;
+    double* buf[2] = {nullptr, nullptr};
+    for (int b = 0; b < nbuf; ++b) {
+        void* p;
+        FGQ_TRY(scratch_device((size_t)chunk * 16, b, &p));
+        buf[b] = (double*)p;
+    }
+    cudaStream_t s_compute, s_copy;
+    FGQ_TRY(scratch_stream(0, &s_compute));
+    FGQ_TRY(scratch_stream(1, &s_copy));
+    cudaEvent_t computed[2], drained[2];
+    for (int b = 0; b < 2; ++b) {
+        FGQ_TRY(scratch_event(b, &computed[b]));
+        FGQ_TRY(scratch_event(2 + b, &drained[b]));
+    }
+    int rc = FGQ_OK;
+    int64_t j = 0;
+    for (int64_t lo = 0; lo < n && rc == FGQ_OK; lo += chunk, ++j) {  // lo, hi relative to lo_all
+        const int64_t hi = lo + chunk < n ? lo + chunk : n;
+        const int b = (int)(j % nbuf);
+        double* xd = buf[b];
+        double* wd = buf[b] + chunk;
+        if (j >= nbuf) FGQ_CUDA_TRY(cudaStreamWaitEvent(s_compute, drained[b], 0));
+        rc = fn(ctx, lo_all + lo, lo_all + hi, xd, wd, s_compute);
+        if (rc != FGQ_OK) break;
+        FGQ_CUDA_TRY(cudaEventRecord(computed[b], s_compute));
+        FGQ_CUDA_TRY(cudaStreamWaitEvent(s_copy, computed[b], 0));
+        FGQ_CUDA_TRY(cudaMemcpyAsync(x + lo, xd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy));
+        FGQ_CUDA_TRY(cudaMemcpyAsync(w + lo, wd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy));
+        FGQ_CUDA_TRY(cudaEventRecord(drained[b], s_copy));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(s_compute);
+    cudaError_t e2 = cudaStreamSynchronize(s_copy);
+    if (rc != FGQ_OK) return rc;
+    FGQ_CUDA_TRY(e1);
+    FGQ_CUDA_TRY(e2);
+    return FGQ_OK;
+}
+
+}  // namespace fgq
+
+static int legendre_slice(void* ctx, int64_t lo, int64_t hi, double* xd, double* wd,
+                          cudaStream_t st) {
+    const int64_t n = *(const int64_t*)ctx;
+    return fgq_gausslegendre_device(n, lo, hi, xd, wd, (void*)st);
+}
+
+extern "C" int fgq_gausslegendre_host(int64_t n, double* x, double* w) {
+    clear_status();
+    if (n < 0) {
+        set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);
+        return FGQ_EDOMAIN;
+    }
+    return host_pipeline(0, n, x, w, legendre_slice, &n);
+}
+
+extern "C" int fgq_gausslegendre_host_slice(int64_t n, int64_t lo, int64_t hi, double* x, double* w) {
+    clear_status();
+    if (n < 0) {
+        set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);
+        return FGQ_EDOMAIN;
+    }
+    if (lo < 0 || hi < lo || hi > n) {
+        set_error("invalid slice [%lld, %lld) of n=%lld", (long long)lo, (long long)hi, (long long)n);
+        return FGQ_EINVAL;
+    }
+    return host_pipeline(lo, hi, x, w, legendre_slice, &n);
+}
+
+extern "C" int fgq_gausslegendre_batch_host(int64_t nrules, const int32_t* n_i,
+                                            const int64_t* offsets, double* x, double* w) {
+    clear_status();
+    if (nrules < 0 || (nrules > 0 && (!n_i || !offsets))) {
+        set_error("invalid batch description");
+        return FGQ_EINVAL;
+    }
+    if (nrules == 0) return FGQ_OK;
+    int64_t total = 0;
+    for (int64_t i = 0; i < nrules; ++i) {
+        if (n_i[i] < 0) {
+            set_error("DomainError(%d): Input n must be a non-negative integer", n_i[i]);
+            return FGQ_EDOMAIN;
+        }
+        if (n_i[i] > 60) {
+            set_error("batched rules are limited to n <= 60 (rule %lld has n=%d)", (long long)i, n_i[i]);
+            return FGQ_EINVAL;
+        }
+        if (offsets[i] < 0) {
+            set_error("negative offset");
+            return FGQ_EINVAL;
+        }
+        const int64_t end = offsets[i] + n_i[i];
+        if (end > total) total = end;
+    }
+    if (total == 0) return FGQ_OK;
+    if (!x || !w) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    HostPathLock lock;
+    void *p_out, *p_n, *p_off;
+    FGQ_TRY(scratch_device((size_t)total * 16, 0, &p_out));
+    FGQ_TRY(scratch_device((size_t)nrules * sizeof(int32_t), 2, &p_n));
+    FGQ_TRY(scratch_device((size_t)nrules * sizeof(int64_t), 3, &p_off));
+    cudaStream_t st;
+    FGQ_TRY(scratch_stream(0, &st));
+    double* xd = (double*)p_out;
+    double* wd = xd + total;
+    FGQ_CUDA_TRY(cudaMemcpyAsync(p_n, n_i, (size_t)nrules * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    FGQ_CUDA_TRY(cudaMemcpyAsync(p_off, offsets, (size_t)nrules * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    FGQ_TRY(fgq_gausslegendre_batch_device(nrules, (const int32_t*)p_n, (const int64_t*)p_off, xd, wd, (void*)st));
+    FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+    FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+    FGQ_CUDA_TRY(cudaStreamSynchronize(st));
+    return FGQ_OK;
+}

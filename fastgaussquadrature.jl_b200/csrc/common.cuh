@@ -1,0 +1,69 @@
+// common.cuh — shared plumbing of libfgq_cuda.so (error state, launch counter, scratch).
+#ifndef FGQ_COMMON_CUH_
+#define FGQ_COMMON_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/fgq.h"
+
+namespace fgq {
+
+// thread-local status (fgq_last_error / fgq_warnings)
+void set_error(const char* fmt, ...);
+void clear_status();
+void add_warning(int bits);
+void count_launch(int64_t n = 1);
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define FGQ_CUDA_TRY(expr)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            fgq::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                           __FILE__, __LINE__);                                         \
+            return FGQ_ECUDA + (int)_e;                                                 \
+        }                                                                               \
+    } while (0)
+
+#define FGQ_TRY(expr)              \
+    do {                           \
+        int _rc = (expr);          \
+        if (_rc != FGQ_OK) return _rc; \
+    } while (0)
+
+// Checks after a kernel launch (launch-configuration errors only; never synchronises).
+#define FGQ_LAUNCH_CHECK()                 \
+    do {                                   \
+        fgq::count_launch();               \
+        FGQ_CUDA_TRY(cudaGetLastError());  \
+    } while (0)
+
+// streaming (evict-first) stores: every output byte is written exactly once
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream2(double* p, double a, double b) {
+    __stcs(reinterpret_cast<double2*>(p), make_double2(a, b));
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Library-owned device scratch + pinned staging for the *_host entry points.
+// Guarded by a process-wide mutex (host entry points serialise).
+struct HostPathLock {
+    HostPathLock();
+    ~HostPathLock();
+};
+int scratch_device(size_t bytes, int slot, void** out);   // grow-only, per (device, slot)
+int scratch_stream(int which, cudaStream_t* out);          // two library streams
+int scratch_event(int which, cudaEvent_t* out);
+
+// Chunked compute -> D2H pipeline shared by every *_host entry point: fn fills device
+// buffers with output indices [lo, hi) of the rule; x/w receive hi-lo entries.
+typedef int (*SliceFn)(void* ctx, int64_t lo, int64_t hi, double* x_dev, double* w_dev,
+                       cudaStream_t st);
+int host_pipeline(int64_t lo, int64_t hi, double* x, double* w, SliceFn fn, void* ctx);
+
+}  // namespace fgq
+#endif

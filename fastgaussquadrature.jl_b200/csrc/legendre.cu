@@ -1,0 +1,574 @@
+// legendre.cu — Gauss-Legendre node/weight generation for sm_100a.
+//
+// Replaces, on the B200, the reference's array-pass implementation
+//   asy / legpts_nodes / legpts_weights      src/gausslegendre.jl:71-231
+//   besselZeroRoots / besselJ1               src/besselroots.jl:168-245
+//   rec / innerRec! / newt_step! / leg_initial_guess   src/gausslegendre.jl:233-309
+//   closed forms n <= 5                      src/gausslegendre.jl:27-60
+// with ONE fused kernel per (node-series, weight-series) branch: a thread derives
+// everything for two consecutive half-indices k from k itself, in registers, and only
+// ever WRITES 16 bytes per node (8 B node + 8 B weight); each half-index is evaluated
+// once and stored twice (+-x) with 16-byte streaming stores.  No global loads at all.
+//
+// Numerics: the reference's operation order is kept exactly (muladd/evalpoly -> fma,
+// everything else unfused; the file is compiled with --fmad=false), so the angle theta
+// is reproduced bit-for-bit and x, w differ from a libm-based evaluation only through
+// the final cos/sin (fgq_math.h).
+#include "common.cuh"
+#include "fgq_math.h"
+
+namespace fgq {
+
+// src/constants.jl:13-36 — first twenty zeros of J0
+__constant__ double c_j0_roots[20] = {
+    2.4048255576957728, 5.5200781102863106, 8.6537279129110122, 11.791534439014281,
+    14.930917708487785, 18.071063967910922, 21.211636629879258, 24.352471530749302,
+    27.493479132040254, 30.634606468431975, 33.775820213573568, 36.917098353664044,
+    40.058425764628239, 43.199791713176730, 46.341188371661814, 49.482609897397817,
+    52.624051841114996, 55.765510755019979, 58.906983926080942, 62.048469190227170};
+// src/constants.jl:93-106 — J1(j0k)^2, k = 1..10
+__constant__ double c_j1sq[10] = {
+    0.2695141239419169,  0.1157801385822037,  0.07368635113640822, 0.05403757319811628,
+    0.04266142901724309, 0.03524210349099610, 0.03002107010305467, 0.02614739149530809,
+    0.02315912182469139, 0.02078382912226786};
+
+struct LegConsts {
+    double vn, vn2, vn4, vn6, inv_vn2;
+};
+
+static LegConsts make_consts(int64_t n) {
+    LegConsts c;
+    c.vn = 1.0 / ((double)n + 0.5);
+    c.vn2 = c.vn * c.vn;
+    c.vn4 = c.vn2 * c.vn2;
+    c.vn6 = c.vn4 * c.vn2;
+    c.inv_vn2 = 1.0 / c.vn2;
+    return c;
+}
+
+// j0k and J1(j0k)^2 from the half-index k.  HEAD = the table / truncation bands of
+// besselroots.jl:177-194 and :212-239 (k <= 13191); !HEAD = the pure McMahon tail
+// (:195-198, :240-243), which is all a 5e8-index launch ever sees past its first warps.
+template <bool HEAD>
+__device__ __forceinline__ void bessel_pair(int64_t k, double& jk, double& j1sq) {
+    const double ak = FGQ_PI * fgq_k_minus_quarter(k);
+    const double rak = 1.0 / ak;
+    const double q = 0.125 * rak;  // == 0.125 / ak bit-for-bit (power-of-two scaling)
+    const double lead = 1.0 / (FGQ_PI * ak);
+    if (!HEAD) {
+        jk = ak + q;
+        j1sq = lead * 2.0;
+        return;
+    }
+    const double p3 = -401743168.0 / 105.0, p5 = 120928.0 / 15.0, p7 = -124.0 / 3.0;
+    if (k <= 20) {
+        jk = c_j0_roots[k - 1];
+    } else {
+        const double ak82 = q * q;
+        double e;
+        if (k <= 47)
+            e = fma(ak82, fma(ak82, fma(ak82, p3, p5), p7), 1.0);
+        else if (k <= 344)
+            e = fma(ak82, fma(ak82, p5, p7), 1.0);
+        else if (k <= 13191)
+            e = fma(ak82, p7, 1.0);
+        else
+            e = 1.0;
+        jk = ak + q * e;
+    }
+    const double c1 = -171497088497.0 / 15206400.0, c2 = 461797.0 / 1152.0,
+                 c3 = -172913.0 / 8064.0, c4 = 151.0 / 80.0, c5 = -7.0 / 24.0;
+    if (k <= 10) {
+        j1sq = c_j1sq[k - 1];
+    } else if (k <= 2279) {
+        const double ak2 = rak * rak;
+        double e;
+        if (k <= 15)
+            e = fma(ak2, fma(ak2, fma(ak2, fma(ak2, c1, c2), c3), c4), c5);
+        else if (k <= 21)
+            e = fma(ak2, fma(ak2, fma(ak2, c2, c3), c4), c5);
+        else if (k <= 55)
+            e = fma(ak2, fma(ak2, c3, c4), c5);
+        else if (k <= 279)
+            e = fma(ak2, c4, c5);
+        else
+            e = c5;
+        j1sq = lead * fma(e, ak2 * ak2, 2.0);
+    } else {
+        j1sq = lead * 2.0;
+    }
+}
+
+// theta-series, gausslegendre.jl:103-143.  NT = number of correction terms kept
+// (3: n<=255, 2: n<=3950, 1: otherwise).  NT = 0 is the n >= 2^25 shortcut: there the
+// single remaining correction (cot(a) - 1/a)/8 * vn^2 is below ulp(a)/2 for every k
+// (|corr|/a <= vn^2/24 < 2^-54), so a + corr rounds back to a and theta == a exactly.
+template <int NT>
+__device__ __forceinline__ double leg_theta(double ai, double u, const LegConsts& c) {
+    if (NT == 0) return ai;
+    double node = ai + (u - 1.0 / ai) / 8.0 * c.vn2;
+    if (NT >= 2) {
+        const double u2 = u * u;
+        const double ai2 = ai * ai;
+        const double ai3 = ai2 * ai;
+        const double v1 =
+            (6.0 * (1.0 + u2) / ai + 25.0 / ai3 - u * fma(31.0, u2, 33.0)) / 384.0;
+        if (NT >= 3) {
+            const double ai5 = ai2 * ai3;
+            const double v2 =
+                u * fma(u2, fma(u2, 3779.0 / 15360.0, 6350.0 / 15360.0), 2595.0 / 15360.0);
+            const double v3 = (1.0 + u2) * (-fma(31.0 / 1024.0, u2, 11.0 / 1024.0) / ai +
+                                            u / 512.0 / ai2 + -25.0 / 3072.0 / ai3);
+            const double v4 = (v2 - 1073.0 / 5120.0 / ai5 + v3);
+            node = fma(v1, c.vn4, node);
+            node = fma(v4, c.vn6, node);
+        } else {
+            node = fma(v1, c.vn4, node);
+        }
+    }
+    return node;
+}
+
+// W-series, gausslegendre.jl:162-224.  WT = number of terms (3: n<=170, 2: n<=1500,
+// 1: n<=850000, 0: otherwise).
+template <int WT>
+__device__ __forceinline__ double leg_wseries(double ai, double u, const LegConsts& c) {
+    if (WT == 0) return c.inv_vn2;
+    const double ai2 = ai * ai;
+    const double aim2 = 1.0 / ai2;
+    const double ua = u * ai;
+    const double W1 = fma(ua - 1.0, aim2, 1.0) / 8.0;
+    if (WT == 1) return c.inv_vn2 + W1;
+    const double u2 = u * u;
+    const double E1 = fma(u2, fma(u2, -56.0, -84.0), -27.0);
+    const double E2 = fma(-3.0, fma(u2, -2.0, 1.0), 6.0 * ua);
+    const double E3 = fma(ua, -31.0, 81.0);
+    const double W2 = fma(aim2, fma(aim2, E3, E2), E1) / 384.0;
+    if (WT == 2) return fma(c.vn2, W2, c.inv_vn2 + W1);
+    const double aim1 = 1.0 / ai;
+    const double F1 =
+        fma(u2, fma(u2, fma(u2, 151.0 / 160.0, 187.0 / 96.0), 295.0 / 256.0), 153.0 / 1024.0);
+    const double F2 = fma(u2, fma(u2, -35.0 / 384.0, -119.0 / 768.0), -65.0 / 1024.0) * u;
+    const double F3 = fma(u2, fma(u2, 7.0 / 384.0, 15.0 / 512.0), 5.0 / 512.0);
+    const double F4 = fma(u2, 1.0 / 512.0, -13.0 / 1536.0) * u;
+    const double F5 = fma(u2, -7.0 / 384.0, 53.0 / 3072.0);
+    const double F6 = 3749.0 / 15360.0 * u;
+    const double F7 = -1125.0 / 1024.0;
+    const double W3 = fma(
+        aim1, fma(aim1, fma(aim1, fma(aim1, fma(aim1, fma(aim1, F7, F6), F5), F4), F3), F2), F1);
+    return fma(c.vn2, fma(c.vn2, W3, W2), c.inv_vn2 + W1);
+}
+
+// One half-index: cx = cos(theta_k) > 0, w = weight.  (asy :76-80, legpts_weights :225-228)
+template <int NT, int WT, bool HEAD>
+__device__ __forceinline__ void leg_half_index(int64_t k, const LegConsts& c, double& cx,
+                                               double& w, double* theta_out = nullptr) {
+    double jk, j1sq;
+    bessel_pair<HEAD>(k, jk, j1sq);
+    const double a = jk * c.vn;
+    double s, ca;
+    fgq_sincos_q1(a, &s, &ca);
+    double u = 0.0;
+    if (NT > 0 || WT > 0) u = ca / s;  // cot(a)
+    if (NT == 0) {
+        cx = ca;
+        if (theta_out) *theta_out = a;
+    } else {
+        const double th = leg_theta<NT>(a, u, c);
+        if (theta_out) *theta_out = th;
+        cx = fgq_cos_q1(th);
+    }
+    const double W = leg_wseries<WT>(a, u, c);
+    w = 2.0 / (j1sq * (a / s) * W);
+}
+
+struct LegLaunch {
+    int64_t kbase;     // half-index of thread 0's first element
+    int64_t kmin, kmax;  // half-indices evaluated (inclusive)
+    int64_t kL0, kL1;  // left stores:  xl[k - kL0] = -cos(theta_k)      (empty if kL0 > kL1)
+    int64_t kR0, kR1;  // right stores: xr[kR1 - k] = +cos(theta_k)
+    int64_t kcentre;   // (n+1)/2 when n is odd (node forced to 0.0, gausslegendre.jl:91), else 0
+    double *xl, *wl, *xr, *wr;
+    int vecL, vecR;    // 16-byte stores legal on that side
+    LegConsts c;
+};
+
+constexpr int LEG_THREADS = 256;
+
+template <int NT, int WT, bool HEAD>
+__global__ void __launch_bounds__(LEG_THREADS)
+legendre_asy_kernel(const LegLaunch p) {
+    const int64_t t = (int64_t)blockIdx.x * LEG_THREADS + threadIdx.x;
+    const int64_t k0 = p.kbase + 2 * t;
+    if (k0 > p.kmax) return;
+    double cx[2], w[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        int64_t k = k0 + e;
+        k = k < p.kmin ? p.kmin : (k > p.kmax ? p.kmax : k);  // clamp: result unused if outside
+        leg_half_index<NT, WT, HEAD>(k, p.c, cx[e], w[e]);
+    }
+    const int64_t k1 = k0 + 1;
+    // left side: ascending addresses with k, nodes negated; odd-n centre forced to 0.0
+    {
+        const bool in0 = k0 >= p.kL0 && k0 <= p.kL1, in1 = k1 >= p.kL0 && k1 <= p.kL1;
+        const double x0 = (k0 == p.kcentre) ? 0.0 : -cx[0];
+        const double x1 = (k1 == p.kcentre) ? 0.0 : -cx[1];
+        if (p.vecL && in0 && in1) {
+            st_stream2(p.xl + (k0 - p.kL0), x0, x1);
+            st_stream2(p.wl + (k0 - p.kL0), w[0], w[1]);
+        } else {
+            if (in0) { st_stream(p.xl + (k0 - p.kL0), x0); st_stream(p.wl + (k0 - p.kL0), w[0]); }
+            if (in1) { st_stream(p.xl + (k1 - p.kL0), x1); st_stream(p.wl + (k1 - p.kL0), w[1]); }
+        }
+    }
+    // right side: descending addresses with k
+    {
+        const bool in0 = k0 >= p.kR0 && k0 <= p.kR1, in1 = k1 >= p.kR0 && k1 <= p.kR1;
+        if (p.vecR && in0 && in1) {
+            st_stream2(p.xr + (p.kR1 - k1), cx[1], cx[0]);
+            st_stream2(p.wr + (p.kR1 - k1), w[1], w[0]);
+        } else {
+            if (in0) { st_stream(p.xr + (p.kR1 - k0), cx[0]); st_stream(p.wr + (p.kR1 - k0), w[0]); }
+            if (in1) { st_stream(p.xr + (p.kR1 - k1), cx[1]); st_stream(p.wr + (p.kR1 - k1), w[1]); }
+        }
+    }
+}
+
+template <int NT>
+__global__ void legendre_theta_kernel(int64_t k_lo, int64_t k_hi, LegConsts c, double* theta) {
+    const int64_t k = k_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k_hi) return;
+    double cx, w, th;
+    if (NT == 0) leg_half_index<0, 0, true>(k, c, cx, w, &th);
+    if (NT == 1) leg_half_index<1, 0, true>(k, c, cx, w, &th);
+    if (NT == 2) leg_half_index<2, 1, true>(k, c, cx, w, &th);
+    if (NT == 3) leg_half_index<3, 2, true>(k, c, cx, w, &th);
+    theta[k - k_lo] = th;
+}
+
+static int node_terms(int64_t n) { return n <= 255 ? 3 : n <= 3950 ? 2 : n < (1LL << 25) ? 1 : 0; }
+static int weight_terms(int64_t n) { return n <= 170 ? 3 : n <= 1500 ? 2 : n <= 850000 ? 1 : 0; }
+
+typedef void (*LegKernel)(const LegLaunch);
+
+static LegKernel pick_kernel(int nt, int wt, bool head) {
+#define FGQ_PICK(NT, WT)                                                   \
+    if (nt == NT && wt == WT)                                              \
+        return head ? legendre_asy_kernel<NT, WT, true> : legendre_asy_kernel<NT, WT, false>;
+    FGQ_PICK(3, 3)
+    FGQ_PICK(3, 2)
+    FGQ_PICK(2, 2)
+    FGQ_PICK(2, 1)
+    FGQ_PICK(1, 1)
+    FGQ_PICK(1, 0)
+    FGQ_PICK(0, 0)
+#undef FGQ_PICK
+    return nullptr;
+}
+
+// Evaluate half-indices [kmin, kmax]; store left for k in [kL0,kL1], right for [kR0,kR1].
+static int launch_one(int64_t n, bool head, int64_t kmin, int64_t kmax, int64_t kL0, int64_t kL1,
+                      double* xl, double* wl, int64_t kR0, int64_t kR1, double* xr, double* wr,
+                      cudaStream_t st) {
+    if (kmin > kmax) return FGQ_OK;
+    LegLaunch p;
+    p.c = make_consts(n);
+    p.kmin = kmin;
+    p.kmax = kmax;
+    p.kL0 = kL0; p.kL1 = kL1; p.kR0 = kR0; p.kR1 = kR1;
+    p.xl = xl; p.wl = wl; p.xr = xr; p.wr = wr;
+    p.kcentre = (n & 1) ? (n + 1) / 2 : 0;
+    const bool hasL = kL0 <= kL1, hasR = kR0 <= kR1;
+    // pair parity: make the left pairs 16-byte aligned when there is a left side
+    p.kbase = kmin;
+    if (hasL) {
+        if (((p.kbase - kL0) & 1) != 0) p.kbase -= 1;
+    } else if (hasR) {
+        if (((kR1 - p.kbase - 1) & 1) != 0) p.kbase -= 1;
+    }
+    p.vecL = hasL && aligned16(xl) && aligned16(wl) && (((p.kbase - kL0) & 1) == 0);
+    p.vecR = hasR && aligned16(xr) && aligned16(wr) && (((kR1 - p.kbase - 1) & 1) == 0);
+    const int64_t npairs = (kmax - p.kbase) / 2 + 1;
+    const int64_t blocks = (npairs + LEG_THREADS - 1) / LEG_THREADS;
+    if (blocks > 0x7fffffffLL) {
+        set_error("legendre launch too large (%lld blocks)", (long long)blocks);
+        return FGQ_EINVAL;
+    }
+    LegKernel kern = pick_kernel(node_terms(n), weight_terms(n), head);
+    if (!kern) {
+        set_error("internal: no kernel for n=%lld", (long long)n);
+        return FGQ_EINVAL;
+    }
+    kern<<<(unsigned)blocks, LEG_THREADS, 0, st>>>(p);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+static inline int64_t imax(int64_t a, int64_t b) { return a > b ? a : b; }
+static inline int64_t imin(int64_t a, int64_t b) { return a < b ? a : b; }
+
+constexpr int64_t K_TAIL = 13192;  // first half-index served by the pure McMahon tail
+
+// Left stores xl[k-kL0] for k in [kL0,kL1]; right stores xr[kR1-k] for k in [kR0,kR1].
+int legendre_asy_launch(int64_t n, int64_t kL0, int64_t kL1, double* xl, double* wl, int64_t kR0,
+                        int64_t kR1, double* xr, double* wr, cudaStream_t st) {
+    for (int part = 0; part < 2; ++part) {
+        const bool head = part == 0;
+        const int64_t a = head ? 1 : K_TAIL;
+        const int64_t b = head ? K_TAIL - 1 : INT64_MAX / 4;
+        // clip both store ranges to this part
+        const int64_t L0 = imax(kL0, a), L1 = imin(kL1, b);
+        const int64_t R0 = imax(kR0, a), R1 = imin(kR1, b);
+        const bool hasL = L0 <= L1, hasR = R0 <= R1;
+        double* pxl = hasL ? xl + (L0 - kL0) : nullptr;
+        double* pwl = hasL ? wl + (L0 - kL0) : nullptr;
+        double* pxr = hasR ? xr + (kR1 - R1) : nullptr;
+        double* pwr = hasR ? wr + (kR1 - R1) : nullptr;
+        if (hasL && hasR && imax(L0, R0) <= imin(L1, R1) + 1) {
+            FGQ_TRY(launch_one(n, head, imin(L0, R0), imax(L1, R1), L0, L1, pxl, pwl, R0, R1, pxr,
+                               pwr, st));
+        } else {
+            if (hasL) FGQ_TRY(launch_one(n, head, L0, L1, L0, L1, pxl, pwl, 1, 0, nullptr, nullptr, st));
+            if (hasR) FGQ_TRY(launch_one(n, head, R0, R1, 1, 0, nullptr, nullptr, R0, R1, pxr, pwr, st));
+        }
+    }
+    return FGQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small rules: one warp per rule.  Lane j owns node j+1 of the m = n/2+1 Newton iterates
+// (rec, gausslegendre.jl:233-267); n <= 5 are the closed forms (:27-60).
+// ---------------------------------------------------------------------------------------------
+
+// gausslegendre.jl:269-290 for one abscissa
+__device__ __forceinline__ void leg_inner_rec(int n, double xj, double& P, double& PP) {
+    double Pm2 = 1.0, Pm1 = xj, PPm1 = 1.0, PPm2 = 0.0;
+    for (int k = 1; k <= n - 1; ++k) {
+        const double tk = (double)(2 * k + 1), dk = (double)k, dk1 = (double)(k + 1);
+        const double newP = fma(tk * Pm1, xj, -dk * Pm2) / dk1;
+        Pm2 = Pm1;
+        Pm1 = newP;
+        const double newPP = (tk * fma(xj, PPm1, Pm2) - dk * PPm2) / dk1;
+        PPm2 = PPm1;
+        PPm1 = newPP;
+    }
+    P = Pm1;
+    PP = PPm1;
+}
+
+__device__ __forceinline__ void leg_closed_form(int n, int i, double& x, double& w) {
+    x = 0.0;
+    w = 0.0;
+    if (n == 1) {
+        x = 0.0;
+        w = 2.0;
+    } else if (n == 2) {
+        const double s3 = sqrt(3.0);
+        x = (i == 0) ? -1.0 / s3 : 1.0 / s3;
+        w = 1.0;
+    } else if (n == 3) {
+        const double s = sqrt(3.0 / 5.0);
+        x = (i == 0) ? -s : (i == 1 ? 0.0 : s);
+        w = (i == 1) ? 8.0 / 9.0 : 5.0 / 9.0;
+    } else if (n == 4) {
+        const double a = 2.0 * sqrt(6.0 / 5.0) / 7.0, t = 3.0 / 7.0, s30 = sqrt(30.0);
+        const bool outer = (i == 0 || i == 3);
+        const double r = outer ? sqrt(t + a) : sqrt(t - a);
+        x = (i < 2) ? -r : r;
+        w = outer ? (18.0 - s30) / 36.0 : (18.0 + s30) / 36.0;
+    } else if (n == 5) {
+        const double b = 2.0 * sqrt(10.0 / 7.0), s70 = sqrt(70.0);
+        if (i == 2) {
+            x = 0.0;
+            w = 128.0 / 225.0;
+        } else {
+            const bool outer = (i == 0 || i == 4);
+            const double r = (outer ? sqrt(5.0 + b) : sqrt(5.0 - b)) / 3.0;
+            x = (i < 2) ? -r : r;
+            w = outer ? (322.0 - 13.0 * s70) / 900.0 : (322.0 + 13.0 * s70) / 900.0;
+        }
+    }
+}
+
+constexpr int REC_THREADS = 128;
+
+// n_i == nullptr: a single rule of n_single nodes, of which output indices [lo, hi) are
+// stored at x[i - lo]; otherwise CSR batch (lo = 0, hi = n).
+__global__ void __launch_bounds__(REC_THREADS)
+legendre_rec_batch_kernel(int64_t nrules, const int32_t* __restrict__ n_i,
+                          const int64_t* __restrict__ offsets, int n_single, int64_t lo, int64_t hi,
+                          double* __restrict__ x, double* __restrict__ w) {
+    const int64_t rule = ((int64_t)blockIdx.x * REC_THREADS + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (rule >= nrules) return;
+    int n;
+    double *xr, *wr;
+    if (n_i) {
+        n = n_i[rule];
+        const int64_t off = offsets[rule];
+        xr = x + off;
+        wr = w + off;
+        lo = 0;
+        hi = n;
+    } else {
+        n = n_single;
+        xr = x - lo;
+        wr = w - lo;
+    }
+    if (n <= 0 || n > 60) return;
+    if (n <= 5) {
+        if (lane < n && lane >= lo && lane < hi) {
+            double xv, wv;
+            leg_closed_form(n, lane, xv, wv);
+            xr[lane] = xv;
+            wr[lane] = wv;
+        }
+        return;
+    }
+    const int m = n / 2 + 1;
+    if (lane >= m) return;
+    // leg_initial_guess (:299-309): asymptotic nodes with the n <= 255 series, negated
+    LegConsts c;
+    c.vn = 1.0 / ((double)n + 0.5);
+    c.vn2 = c.vn * c.vn;
+    c.vn4 = c.vn2 * c.vn2;
+    c.vn6 = c.vn4 * c.vn2;
+    c.inv_vn2 = 0.0;
+    double jk, j1sq;
+    bessel_pair<true>(lane + 1, jk, j1sq);
+    const double a = jk * c.vn;
+    const double u = fgq_cot_q1(a);
+    double xj = fgq_cos_q1(leg_theta<3>(a, u, c)) * -1.0;
+    double P, PP;
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+        leg_inner_rec(n, xj, P, PP);
+        xj -= P / PP;
+    }
+    // weights use P' of the LAST evaluation, i.e. at the pre-update iterate (:262-264)
+    const double wv = 2.0 / ((1.0 - xj * xj) * (PP * PP));
+    const int i = lane;  // 0-based output index of the left copy
+    if (i < m - 1) {
+        if (i >= lo && i < hi) {
+            xr[i] = xj;
+            wr[i] = wv;
+        }
+        const int j = n - 1 - i;
+        if (j >= lo && j < hi) {
+            xr[j] = -xj;
+            wr[j] = wv;
+        }
+    } else if (n & 1) {  // i == m-1: the centre of an odd rule; for even n this lane's value is overwritten by the mirror (:258-261)
+        if (i >= lo && i < hi) {
+            xr[i] = xj;
+            wr[i] = wv;
+        }
+    }
+}
+
+int legendre_small_launch(int n, int64_t lo, int64_t hi, double* x, double* w, cudaStream_t st) {
+    legendre_rec_batch_kernel<<<1, REC_THREADS, 0, st>>>(1, nullptr, nullptr, n, lo, hi, x, w);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+}  // namespace fgq
+
+using namespace fgq;
+
+extern "C" int fgq_gausslegendre_device(int64_t n, int64_t lo, int64_t hi, double* x_dev,
+                                        double* w_dev, void* stream) {
+    clear_status();
+    if (n < 0) {
+        set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);
+        return FGQ_EDOMAIN;
+    }
+    if (lo < 0 || hi < lo || hi > n) {
+        set_error("invalid shard [%lld, %lld) of n=%lld", (long long)lo, (long long)hi, (long long)n);
+        return FGQ_EINVAL;
+    }
+    if (hi == lo) return FGQ_OK;
+    if (!x_dev || !w_dev) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (n <= 60) return legendre_small_launch((int)n, lo, hi, x_dev, w_dev, st);
+    const int64_t m = (n + 1) >> 1;  // left side incl. centre: indices [0, m) <-> k = i + 1
+    const int64_t mr = n >> 1;       // right side: indices [m, n) <-> k = n - i in [1, mr]
+    const int64_t kL0 = lo + 1, kL1 = imin(hi, m);
+    const int64_t rlo = imax(lo, m);  // first right-side output index of this shard
+    const int64_t kR0 = n - hi + 1, kR1 = imin(n - rlo, mr);
+    double* xr = x_dev + (rlo - lo);
+    double* wr = w_dev + (rlo - lo);
+    return legendre_asy_launch(n, kL0, kL1, x_dev, w_dev, kR0, kR1, xr, wr, st);
+}
+
+extern "C" int fgq_gausslegendre_device_pair(int64_t n, int64_t k_lo, int64_t k_hi, double* xl_dev,
+                                             double* wl_dev, double* xr_dev, double* wr_dev,
+                                             void* stream) {
+    clear_status();
+    if (n <= 60) {
+        set_error("mirror-pair shards need the asymptotic path (n > 60), got n=%lld", (long long)n);
+        return FGQ_EINVAL;
+    }
+    const int64_t m = (n + 1) >> 1, mr = n >> 1;
+    if (k_lo < 1 || k_hi < k_lo || k_hi > m + 1) {
+        set_error("invalid half-index shard [%lld, %lld) of n=%lld", (long long)k_lo,
+                  (long long)k_hi, (long long)n);
+        return FGQ_EINVAL;
+    }
+    if (k_hi == k_lo) return FGQ_OK;
+    if (!xl_dev || !wl_dev || !xr_dev || !wr_dev) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    const int64_t kL1 = imin(k_hi - 1, m), kR1 = imin(k_hi - 1, mr);
+    const int64_t skip = (k_hi - 1) - kR1;  // 1 iff this shard holds the centre of an odd rule
+    return legendre_asy_launch(n, k_lo, kL1, xl_dev, wl_dev, k_lo, kR1, xr_dev + skip,
+                               wr_dev + skip, as_stream(stream));
+}
+
+extern "C" int fgq_gausslegendre_batch_device(int64_t nrules, const int32_t* n_i_dev,
+                                              const int64_t* offsets_dev, double* x_dev,
+                                              double* w_dev, void* stream) {
+    clear_status();
+    if (nrules < 0 || (nrules > 0 && (!n_i_dev || !offsets_dev))) {
+        set_error("invalid batch description");
+        return FGQ_EINVAL;
+    }
+    if (nrules == 0) return FGQ_OK;
+    const int64_t warps_per_block = REC_THREADS / 32;
+    const int64_t blocks = (nrules + warps_per_block - 1) / warps_per_block;
+    if (blocks > 0x7fffffffLL) {
+        set_error("batch too large");
+        return FGQ_EINVAL;
+    }
+    legendre_rec_batch_kernel<<<(unsigned)blocks, REC_THREADS, 0, as_stream(stream)>>>(
+        nrules, n_i_dev, offsets_dev, 0, 0, 0, x_dev, w_dev);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+extern "C" int fgq_debug_legendre_theta_device(int64_t n, int64_t k_lo, int64_t k_hi,
+                                               double* theta_dev, void* stream) {
+    clear_status();
+    if (n <= 5 || k_lo < 1 || k_hi < k_lo) {
+        set_error("invalid theta request");
+        return FGQ_EINVAL;
+    }
+    if (k_hi == k_lo) return FGQ_OK;
+    const LegConsts c = make_consts(n);
+    const int64_t cnt = k_hi - k_lo;
+    const unsigned blocks = (unsigned)((cnt + 255) / 256);
+    cudaStream_t st = as_stream(stream);
+    switch (node_terms(n)) {
+        case 0: legendre_theta_kernel<0><<<blocks, 256, 0, st>>>(k_lo, k_hi, c, theta_dev); break;
+        case 1: legendre_theta_kernel<1><<<blocks, 256, 0, st>>>(k_lo, k_hi, c, theta_dev); break;
+        case 2: legendre_theta_kernel<2><<<blocks, 256, 0, st>>>(k_lo, k_hi, c, theta_dev); break;
+        default: legendre_theta_kernel<3><<<blocks, 256, 0, st>>>(k_lo, k_hi, c, theta_dev); break;
+    }
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}

@@ -1,0 +1,109 @@
+/* fgq.h — C ABI of libfgq_cuda.so: B200-native Gauss quadrature node/weight generation.
+ *
+ * This is the drop-in boundary for the per-node generation path of
+ * FastGaussQuadrature.jl v1.3.0.  The reference has no FFI layer of its own (it is pure
+ * Julia); its boundary is the exported Julia functions (src/FastGaussQuadrature.jl:7-19).
+ * Each entry point below states which reference function it replaces; the Julia
+ * `ccall` stubs a maintainer would add are in julia/FGQCuda.jl and INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; Float64 everywhere (the reference's generic-T
+ *     paths are out of scope: there is no CPU fallback in this library);
+ *   - return 0 = ok, FGQ_EDOMAIN = the reference would throw DomainError,
+ *     FGQ_ENOTIMPL = parameter region the reference serves with an eigen-solve or a
+ *     non-Float64 type (not on the hot path), >= FGQ_ECUDA = CUDA failure;
+ *     fgq_last_error() returns a thread-local message for the last non-zero return;
+ *   - *_host variants fill caller-allocated HOST buffers (a Julia Vector{Float64}, a
+ *     numpy array); the pointers are not retained after return;
+ *   - *_device variants fill caller-allocated DEVICE buffers on the current CUDA
+ *     device, asynchronously on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     default stream).  They never synchronise and never allocate, so they can be
+ *     captured in a CUDA graph.  One process per GPU; shard by passing each rank its
+ *     own index range;
+ *   - nodes are ascending, indices are 0-based in this header (Julia's are 1-based).
+ */
+#ifndef FGQ_H_
+#define FGQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGQ_OK 0
+#define FGQ_EDOMAIN 1
+#define FGQ_ENOTIMPL 2
+#define FGQ_EINVAL 3
+#define FGQ_ECUDA 100
+
+/* warning bits, cf. the reference's @warn sites (src/gausslaguerre.jl:118,257,424,570) */
+#define FGQ_WARN_LARGE_ALPHA 1
+#define FGQ_WARN_NEWTON_MAXITER 2
+#define FGQ_WARN_NONFINITE 4
+
+int fgq_version(void);
+const char* fgq_last_error(void);
+/* warning bits accumulated by this thread's last call */
+int fgq_warnings(void);
+/* number of visible CUDA devices (0 => every compute entry point fails with FGQ_ECUDA) */
+int fgq_device_count(void);
+
+/* ---- Gauss-Legendre: gausslegendre(n) — src/gausslegendre.jl:22-69 ---------------------- */
+
+/* x[0..n), w[0..n) on the host.  n < 0 -> FGQ_EDOMAIN (gausslegendre.jl:26). */
+int fgq_gausslegendre_host(int64_t n, double* x, double* w);
+/* Same, output indices [lo, hi) only -> x[0 .. hi-lo), w[0 .. hi-lo): lets each process of a
+ * multi-GPU job fetch its own part of a large rule over its own PCIe link. */
+int fgq_gausslegendre_host_slice(int64_t n, int64_t lo, int64_t hi, double* x, double* w);
+
+/* Contiguous node-index shard: writes nodes/weights with output index in [lo, hi) to
+ * x_dev[0 .. hi-lo), w_dev[0 .. hi-lo).  0 <= lo <= hi <= n. */
+int fgq_gausslegendre_device(int64_t n, int64_t lo, int64_t hi, double* x_dev, double* w_dev,
+                             void* stream);
+
+/* Mirror-pair shard (asymptotic path, n > 60): one evaluation per half-index k serves
+ * both +-x.  Half-indices k in [k_lo, k_hi) (1-based, 1 <= k_lo <= k_hi <= (n+1)/2 + 1):
+ *   left  slice = output indices [k_lo-1, k_hi-1)      -> xl_dev/wl_dev[0 .. k_hi-k_lo)
+ *   right slice = output indices [n-k_hi+1, n-k_lo+1)  -> xr_dev/wr_dev[0 .. k_hi-k_lo)
+ * For odd n the centre node (k = (n+1)/2) belongs to the left slice only; the right slice
+ * of a shard that contains it starts one element later (its element 0 is left untouched). */
+int fgq_gausslegendre_device_pair(int64_t n, int64_t k_lo, int64_t k_hi, double* xl_dev,
+                                  double* wl_dev, double* xr_dev, double* wr_dev, void* stream);
+
+/* Batch of small rules gausslegendre(n_i), CSR layout: rule i occupies
+ * [offsets[i], offsets[i]+n_i[i]) of x and w.  0 <= n_i <= 60 (closed forms for n <= 5,
+ * gausslegendre.jl:27-60; Newton on the three-term recurrence, :233-309).  One warp per rule. */
+int fgq_gausslegendre_batch_device(int64_t nrules, const int32_t* n_i_dev,
+                                   const int64_t* offsets_dev, double* x_dev, double* w_dev,
+                                   void* stream);
+int fgq_gausslegendre_batch_host(int64_t nrules, const int32_t* n_i, const int64_t* offsets,
+                                 double* x, double* w);
+
+/* ---- consumers / checks ------------------------------------------------------------------ */
+
+/* sums_dev[0] += sum w_i, sums_dev[1] += sum w_i x_i^2 over count entries (device buffers;
+ * zero sums_dev first).  The README's only use of a rule is dot(w, f.(x)) (README.md:27-30);
+ * this is that reduction for f = 1 and f = x^2, used as the sum-w / int x^2 check. */
+int fgq_rule_moments_device(const double* x_dev, const double* w_dev, int64_t count,
+                            double* sums_dev, void* stream);
+
+/* ---- roofline denominators (measured on the current device) ------------------------------ */
+
+/* DFMA issue-rate microbenchmark: independent FMA chains on every SM.  *tflops = 2*FMA/s/1e12. */
+int fgq_measure_dfma_peak(double* tflops);
+/* Store-only streaming bandwidth (16-byte st.global.cs over `bytes` of scratch), GB/s. */
+int fgq_measure_store_peak(int64_t bytes, double* gbs);
+
+/* ---- test hooks ---------------------------------------------------------------------------- */
+
+/* theta_k (the angle whose cosine is the node) for half-indices [k_lo, k_hi), asy path. */
+int fgq_debug_legendre_theta_device(int64_t n, int64_t k_lo, int64_t k_hi, double* theta_dev,
+                                    void* stream);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t fgq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGQ_H_ */

@@ -1,0 +1,123 @@
+"""CPU oracle package (TEST INFRASTRUCTURE — never imported by the product).
+
+ctypes front-end of ``oracle/_build/liboracle.so`` (built from ``oracle/*.c`` by
+``oracle/Makefile``; the C files cite the reference file:line they restate) plus
+the numpy/scipy restatements of the Jacobi/Hermite/Laguerre paths.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import this package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+_c_i64 = ctypes.c_int64
+_c_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def build(force: bool = False) -> str:
+    """Compile the C oracle (gcc, a few seconds)."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        for sfx in ("", "_twin"):
+            f = getattr(L, "oracle_gausslegendre" + sfx)
+            f.argtypes = [_c_i64, _c_dp, _c_dp]
+            f.restype = ctypes.c_int
+            f = getattr(L, "oracle_legendre_asy_half" + sfx)
+            f.argtypes = [_c_i64, _c_i64, _c_i64, _c_dp, _c_dp]
+            f.restype = ctypes.c_int
+            f = getattr(L, "oracle_legendre_theta" + sfx)
+            f.argtypes = [_c_i64, _c_i64, _c_i64, _c_dp]
+            f.restype = ctypes.c_int
+            f = getattr(L, "oracle_gausslegendre_batch" + sfx)
+            f.argtypes = [_c_i64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_c_i64), _c_dp, _c_dp]
+            f.restype = ctypes.c_int
+        L.oracle_set_threads.argtypes = [ctypes.c_int]
+        L.oracle_set_threads.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(_c_dp)
+
+
+def set_threads(n: int) -> int:
+    """1 = single thread (what the reference does); 0 = all cores."""
+    return lib().oracle_set_threads(int(n))
+
+
+def gausslegendre(n: int, twin: bool = False):
+    """Oracle of ``gausslegendre(n)`` (reference src/gausslegendre.jl:22-68)."""
+    if n < 0:
+        raise ValueError("DomainError: Input n must be a non-negative integer")
+    x = np.empty(n, dtype=np.float64)
+    w = np.empty(n, dtype=np.float64)
+    f = lib().oracle_gausslegendre_twin if twin else lib().oracle_gausslegendre
+    rc = f(n, _dp(x), _dp(w))
+    if rc:
+        raise RuntimeError(f"oracle_gausslegendre rc={rc}")
+    return x, w
+
+
+def legendre_asy_half(n: int, k0: int, k1: int, twin: bool = False):
+    """cos(theta_k), w_k for half-indices k0..k1 (1-based, inclusive) of the asy path."""
+    cnt = max(k1 - k0 + 1, 0)
+    x = np.empty(cnt, dtype=np.float64)
+    w = np.empty(cnt, dtype=np.float64)
+    f = lib().oracle_legendre_asy_half_twin if twin else lib().oracle_legendre_asy_half
+    rc = f(n, k0, k1, _dp(x), _dp(w))
+    if rc:
+        raise MemoryError("oracle_legendre_asy_half")
+    return x, w
+
+
+def legendre_theta(n: int, k0: int, k1: int, twin: bool = False):
+    cnt = max(k1 - k0 + 1, 0)
+    t = np.empty(cnt, dtype=np.float64)
+    f = lib().oracle_legendre_theta_twin if twin else lib().oracle_legendre_theta
+    if f(n, k0, k1, _dp(t)):
+        raise MemoryError("oracle_legendre_theta")
+    return t
+
+
+def gausslegendre_batch(n_i: np.ndarray, twin: bool = False):
+    """CSR batch of small rules: returns (offsets, x, w)."""
+    n_i = np.ascontiguousarray(n_i, dtype=np.int32)
+    offsets = np.zeros(len(n_i) + 1, dtype=np.int64)
+    np.cumsum(n_i, out=offsets[1:])
+    x = np.empty(int(offsets[-1]), dtype=np.float64)
+    w = np.empty(int(offsets[-1]), dtype=np.float64)
+    f = lib().oracle_gausslegendre_batch_twin if twin else lib().oracle_gausslegendre_batch
+    rc = f(len(n_i), n_i.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+           offsets.ctypes.data_as(ctypes.POINTER(_c_i64)), _dp(x), _dp(w))
+    if rc:
+        raise RuntimeError(f"oracle_gausslegendre_batch rc={rc}")
+    return offsets, x, w
+
+
+def ulp_diff(got: np.ndarray, ref: np.ndarray) -> np.ndarray:
+    """|got - ref| / spacing(|ref|) (SURVEY.md §8d parity metric); 0 where both are equal."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    d = np.abs(got - ref)
+    sp = np.spacing(np.abs(ref))
+    out = np.where(d == 0, 0.0, d / sp)
+    return out

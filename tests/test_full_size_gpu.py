@@ -1,0 +1,70 @@
+"""Full-size checks at the BASELINE.json configurations, using size-independent properties plus
+oracle comparisons on slices (the oracle cannot hold 1e9 nodes in a test)."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [10 ** 9, 10 ** 9 + 1])
+@pytest.mark.parametrize("mode", ["pair", "contiguous"])
+def test_legendre_1e9(fgq, oracle_mod, n, mode):
+    import torch
+    sh = fgq.gausslegendre_device(n, mode=mode)
+    sums = fgq.rule_moments_device(sh).cpu().numpy()
+    torch.cuda.synchronize()
+    # exact invariants: sum w = 2, sum w x^2 = 2/3
+    assert abs(sums[0] - 2.0) < 1e-11
+    assert abs(sums[1] - 2.0 / 3.0) < 1e-11
+    if mode == "contiguous":
+        (_, _, x, w), = sh.segments
+        left_x, left_w = x[: n // 2], w[: n // 2]
+        right_x, right_w = x[n - n // 2:], w[n - n // 2:]
+        if n % 2:
+            assert float(x[n // 2]) == 0.0
+    else:
+        (l0, l1, left_x, left_w), (r0, r1, right_x, right_w) = sh.segments
+        assert (l0, r1) == (0, n) and l1 - l0 == (n + 1) // 2 and r1 - r0 == n // 2
+        if n % 2:
+            assert float(left_x[-1]) == 0.0
+            left_x, left_w = left_x[:-1], left_w[:-1]
+    # symmetry: x[i] == -x[n-1-i], w[i] == w[n-1-i], bit for bit
+    assert bool(torch.equal(left_x, -right_x.flip(0)))
+    assert bool(torch.equal(left_w, right_w.flip(0)))
+    # ascending (non-strict: at n=1e9 neighbours near +-1 coalesce, docs/src/benchmark.md:25)
+    assert bool((left_x[1:] >= left_x[:-1]).all())
+    assert float(left_x[0]) > -1.0 and float(left_x[-1]) < 0.0
+    assert bool((left_w > 0).all())
+    # slices against the oracle: head (tables/bands), middle, centre
+    m = (n + 1) // 2
+    for k0 in (1, 13000, m // 2, m - 300000):
+        k1 = min(k0 + 300000 - 1, n // 2)
+        xs = -left_x[k0 - 1:k1].cpu().numpy()
+        ws = left_w[k0 - 1:k1].cpu().numpy()
+        xt, wt = oracle_mod.legendre_asy_half(n, k0, k1, twin=True)
+        assert np.array_equal(xs, xt) and np.array_equal(ws, wt)
+        xo, wo = oracle_mod.legendre_asy_half(n, k0, k1)
+        assert oracle_mod.ulp_diff(xs, xo).max() <= 2
+        assert oracle_mod.ulp_diff(ws, wo).max() <= 4
+
+
+def test_legendre_1e5_readme_example(fgq, oracle_mod):
+    """BASELINE config C1 = the README example (README.md:24-30): dot(w, x.^2) ~ 2/3."""
+    x, w = fgq.gausslegendre(100000)
+    assert abs(np.dot(w, x * x) - 2 / 3) < 5e-16
+    xo, wo = oracle_mod.gausslegendre(100000)
+    assert oracle_mod.ulp_diff(x, xo).max() <= 2 and oracle_mod.ulp_diff(w, wo).max() <= 4
+
+
+def test_batch_1e6_rules(fgq, oracle_mod):
+    """BASELINE config C5: 1e6 rules, n_i = default_rng(0).integers(2, 61)."""
+    n_i = np.random.default_rng(0).integers(2, 61, size=1_000_000)
+    off, x, w = fgq.gausslegendre_batch(n_i)
+    _, xt, wt = oracle_mod.gausslegendre_batch(n_i, twin=True)
+    assert np.array_equal(x, xt) and np.array_equal(w, wt)
+    # every rule integrates 1 and x^2 exactly: segment sums
+    sw = np.add.reduceat(w, off[:-1])
+    sx2 = np.add.reduceat(w * x * x, off[:-1])
+    assert np.abs(sw - 2).max() < 1e-14 and np.abs(sx2 - 2 / 3).max() < 1e-14

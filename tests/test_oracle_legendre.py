@@ -1,0 +1,93 @@
+"""CPU tests: the Legendre oracle against the reference's own golden vectors and invariants
+(reference test/test_gausslegendre.jl:1-53)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "legendre_reference_tests.json")))
+
+
+@pytest.mark.parametrize("twin", [False, True])
+@pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: f"n{c['n']}")
+def test_golden_values(oracle_mod, case, twin):
+    x, w = oracle_mod.gausslegendre(case["n"], twin=twin)
+    assert len(x) == case["n"] and len(w) == case["n"]
+    for i, v in case["x"].items():
+        assert abs(x[int(i) - 1] - v) < GOLD["tol"]
+    for i, v in case["w"].items():
+        assert abs(w[int(i) - 1] - v) < GOLD["tol"]
+    # test_gausslegendre.jl:23-24 (isapprox default rtol = sqrt(eps))
+    assert abs(np.dot(w, x * x) - 2 / 3) < 1.5e-8 * (2 / 3)
+    assert abs(np.dot(w, np.exp(x)) - (math.e - 1 / math.e)) < 1.5e-8 * 2.35
+
+
+def test_special_cases_and_moments(oracle_mod):
+    # test_gausslegendre.jl:4-14
+    with pytest.raises(ValueError):
+        oracle_mod.gausslegendre(-1)
+    x, w = oracle_mod.gausslegendre(0)
+    assert len(x) == 0 and len(w) == 0
+    for n in range(0, 11):
+        x, w = oracle_mod.gausslegendre(n)
+        for i in range(n):
+            r = 2 * i
+            assert abs(np.dot(w, x ** r) - 2 / (r + 1)) < 10 * np.finfo(float).eps
+
+
+@pytest.mark.parametrize("n", [6, 7, 33, 59, 60, 61, 100, 171, 256, 1501, 3951, 100001, 850001])
+def test_structure(oracle_mod, n):
+    x, w = oracle_mod.gausslegendre(n)
+    assert np.all(np.diff(x) > 0)
+    assert np.array_equal(x, -x[::-1]) and np.array_equal(w, w[::-1])
+    if n % 2:
+        assert x[n // 2] == 0.0  # gausslegendre.jl:91 (asy) / Newton fixed point (rec)
+    assert abs(math.fsum(w) - 2) < 1e-12  # 850001: first n without the W1 term, error ~vn^2/8
+
+
+def test_half_range_slices_agree_with_full_rule(oracle_mod):
+    n = 100001
+    x, w = oracle_mod.gausslegendre(n)
+    xh, wh = oracle_mod.legendre_asy_half(n, 1000, 20000)
+    assert np.array_equal(-xh, x[999:20000]) and np.array_equal(wh, w[999:20000])
+
+
+def test_twin_libm_gap(oracle_mod):
+    """The library's own sin/cos (fgq_math.h, 'twin' mode) against glibc: <= 1 ulp on nodes,
+    <= 4 ulp on weights — the gap the GPU parity tolerance has to absorb."""
+    for n in (251, 10013, 100000, 1000003):
+        x, w = oracle_mod.gausslegendre(n)
+        xt, wt = oracle_mod.gausslegendre(n, twin=True)
+        nz = x != 0
+        assert oracle_mod.ulp_diff(xt[nz], x[nz]).max() <= 1
+        assert oracle_mod.ulp_diff(wt, w).max() <= 4
+
+
+def test_theta_equals_a_beyond_2p25(oracle_mod):
+    """For n >= 2^25 the theta-correction is below half an ulp of a for every k, so the kernel's
+    NT=0 shortcut (theta == a) is exact: check the literal formula on sampled ranges."""
+    for n in (1 << 25, 10 ** 9):
+        m = (n + 1) // 2
+        for k0 in (1, 13000, m // 3, m - 200000):
+            k1 = k0 + 200000 - 1
+            th = oracle_mod.legendre_theta(n, k0, min(k1, m))
+            # a_k itself: theta of a hypothetical n with the series switched off is not exposed,
+            # so recompute a in numpy with the same operations (besselroots.jl:195-198)
+            k = np.arange(k0, min(k1, m) + 1, dtype=np.float64)
+            ak = np.pi * (k - 0.25)
+            jk = ak + 0.125 / ak
+            sel = k >= 13192
+            a = jk * (1.0 / (n + 0.5))
+            assert np.array_equal(th[sel], a[sel])
+
+
+def test_batch_matches_single_rules(oracle_mod):
+    rng = np.random.default_rng(0)
+    n_i = rng.integers(2, 61, size=2000)
+    off, x, w = oracle_mod.gausslegendre_batch(n_i)
+    for r in (0, 1, 17, 1999):
+        xs, ws = oracle_mod.gausslegendre(int(n_i[r]))
+        assert np.array_equal(x[off[r]:off[r + 1]], xs) and np.array_equal(w[off[r]:off[r + 1]], ws)
