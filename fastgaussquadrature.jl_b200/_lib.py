@@ -38,6 +38,7 @@ SIGNATURES = {
     "fgq_measure_dfma_peak": (ctypes.c_int, [_dp]),
     "fgq_measure_store_peak": (ctypes.c_int, [_i64, _dp]),
     "fgq_debug_legendre_theta_device": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp]),
+    "fgq_debug_fastdiv_check": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp]),
 }
 
 _lib = None

@@ -51,15 +51,17 @@ static LegConsts make_consts(int64_t n) {
 // (:195-198, :240-243), which is all a 5e8-index launch ever sees past its first warps.
 template <bool HEAD>
 __device__ __forceinline__ void bessel_pair(int64_t k, double& jk, double& j1sq) {
-    const double ak = FGQ_PI * fgq_k_minus_quarter(k);
+    const double ak = FGQ_PI_K * fgq_k_minus_quarter(k);
+    if (!HEAD) {
+        // k >= 13192 here: ak in [4e4, 2e9], no slow path needed
+        const double q = 0.125 * fgq_rcp_fast(ak);
+        jk = ak + q;
+        j1sq = fgq_rcp_fast(FGQ_PI_K * ak) * 2.0;
+        return;
+    }
     const double rak = 1.0 / ak;
     const double q = 0.125 * rak;  // == 0.125 / ak bit-for-bit (power-of-two scaling)
     const double lead = 1.0 / (FGQ_PI * ak);
-    if (!HEAD) {
-        jk = ak + q;
-        j1sq = lead * 2.0;
-        return;
-    }
     const double p3 = -401743168.0 / 105.0, p5 = 120928.0 / 15.0, p7 = -124.0 / 3.0;
     if (k <= 20) {
         jk = c_j0_roots[k - 1];
@@ -179,7 +181,50 @@ __device__ __forceinline__ void leg_half_index(int64_t k, const LegConsts& c, do
         cx = fgq_cos_q1(th);
     }
     const double W = leg_wseries<WT>(a, u, c);
-    w = 2.0 / (j1sq * (a / s) * W);
+    if (!HEAD && NT == 0 && WT == 0) {
+        // 2/t == 2*(1/t) bit-for-bit (power-of-two scaling); operands far inside the normal range
+        w = 2.0 * fgq_rcp_fast(j1sq * fgq_div_fast(a, s) * W);
+    } else {
+        w = 2.0 / (j1sq * (a / s) * W);
+    }
+}
+
+// -x through the integer pipe (the FP64 pipe is the scarce one here)
+__device__ __forceinline__ double neg_bits(double v) {
+    return __hiloint2double(__double2hiint(v) ^ 0x80000000, __double2loint(v));
+}
+
+// x * 2^e through the integer pipe (x normal, result normal)
+__device__ __forceinline__ double scale2(double x, int e) {
+    return __hiloint2double(__double2hiint(x) + (e << 20), __double2loint(x));
+}
+
+// The bulk of an n >= 2^25 launch: half-indices k >= K_JK_EXACT, where
+//   * 0.125/ak < ulp(ak)/2 (ak >= 2^25), so j0k = ak + 0.125/ak rounds to ak itself and the
+//     first reciprocal disappears (bit-identical; tests/test_full_size_gpu.py checks every k);
+//   * the whole block lies on one side of pi/4 (QUAD 0: theta <= pi/4, no reduction at all;
+//     QUAD 1: theta > pi/4, always reduce), so the quadrant selects disappear too.
+// Same bits as leg_half_index<0,0,false>, ~20% fewer FP64 instructions.
+constexpr int64_t K_JK_EXACT = 10680708;  // pi*(k - 1/4) >= 2^25
+
+template <int QUAD>
+__device__ __forceinline__ void leg_bulk(int64_t k, const LegConsts& c, double& cx, double& w) {
+    const double ak = FGQ_PI_K * fgq_k_minus_quarter(k);
+    const double j1sq = scale2(fgq_rcp_fast(FGQ_PI_K * ak), 1);
+    const double a = ak * c.vn;
+    double s;
+    if (QUAD == 0) {
+        s = fgq_ksin(a, 0.0);
+        cx = fgq_kcos(a, 0.0);
+    } else {
+        const double lo = FGQ_PIO2_LO_K;
+        const double z = a - FGQ_PIO2_HI_K;
+        const double r = z - lo;
+        const double rt = (z - r) - lo;
+        s = fgq_kcos(r, rt);
+        cx = neg_bits(fgq_ksin(r, rt));
+    }
+    w = scale2(fgq_rcp_fast(j1sq * fgq_div_fast(a, s) * c.inv_vn2), 1);
 }
 
 struct LegLaunch {
@@ -187,6 +232,8 @@ struct LegLaunch {
     int64_t kmin, kmax;  // half-indices evaluated (inclusive)
     int64_t kL0, kL1;  // left stores:  xl[k - kL0] = -cos(theta_k)      (empty if kL0 > kL1)
     int64_t kR0, kR1;  // right stores: xr[kR1 - k] = +cos(theta_k)
+    int64_t kin0, kin1;  // half-indices stored on BOTH sides with vector stores (interior fast path)
+    int64_t kq0_last;  // NT=0 only: last half-index with theta_k <= pi/4 (host bisection)
     int64_t kcentre;   // (n+1)/2 when n is odd (node forced to 0.0, gausslegendre.jl:91), else 0
     double *xl, *wl, *xr, *wr;
     int vecL, vecR;    // 16-byte stores legal on that side
@@ -195,11 +242,36 @@ struct LegLaunch {
 
 constexpr int LEG_THREADS = 256;
 
+
 template <int NT, int WT, bool HEAD>
 __global__ void __launch_bounds__(LEG_THREADS)
 legendre_asy_kernel(const LegLaunch p) {
     const int64_t t = (int64_t)blockIdx.x * LEG_THREADS + threadIdx.x;
     const int64_t k0 = p.kbase + 2 * t;
+    const int64_t k1 = k0 + 1;
+    // Interior blocks (every half-index of the block is stored on both sides with 16-byte
+    // stores, no centre node): no clamping, no per-element predicates.  All but the first and
+    // last block of a launch take this path.
+    const int64_t kb0 = p.kbase + 2 * (int64_t)blockIdx.x * LEG_THREADS;
+    const int64_t kb1 = kb0 + 2 * LEG_THREADS - 1;
+    if (kb0 >= p.kin0 && kb1 <= p.kin1) {
+        double cx0, w0, cx1, w1;
+        if (NT == 0 && WT == 0 && !HEAD && kb0 >= K_JK_EXACT && kb1 <= p.kq0_last) {
+            leg_bulk<0>(k0, p.c, cx0, w0);
+            leg_bulk<0>(k1, p.c, cx1, w1);
+        } else if (NT == 0 && WT == 0 && !HEAD && kb0 >= K_JK_EXACT && kb0 > p.kq0_last) {
+            leg_bulk<1>(k0, p.c, cx0, w0);
+            leg_bulk<1>(k1, p.c, cx1, w1);
+        } else {
+            leg_half_index<NT, WT, HEAD>(k0, p.c, cx0, w0);
+            leg_half_index<NT, WT, HEAD>(k1, p.c, cx1, w1);
+        }
+        st_stream2(p.xl + (k0 - p.kL0), neg_bits(cx0), neg_bits(cx1));
+        st_stream2(p.wl + (k0 - p.kL0), w0, w1);
+        st_stream2(p.xr + (p.kR1 - k1), cx1, cx0);
+        st_stream2(p.wr + (p.kR1 - k1), w1, w0);
+        return;
+    }
     if (k0 > p.kmax) return;
     double cx[2], w[2];
 #pragma unroll
@@ -208,12 +280,11 @@ legendre_asy_kernel(const LegLaunch p) {
         k = k < p.kmin ? p.kmin : (k > p.kmax ? p.kmax : k);  // clamp: result unused if outside
         leg_half_index<NT, WT, HEAD>(k, p.c, cx[e], w[e]);
     }
-    const int64_t k1 = k0 + 1;
     // left side: ascending addresses with k, nodes negated; odd-n centre forced to 0.0
     {
         const bool in0 = k0 >= p.kL0 && k0 <= p.kL1, in1 = k1 >= p.kL0 && k1 <= p.kL1;
-        const double x0 = (k0 == p.kcentre) ? 0.0 : -cx[0];
-        const double x1 = (k1 == p.kcentre) ? 0.0 : -cx[1];
+        const double x0 = (k0 == p.kcentre) ? 0.0 : neg_bits(cx[0]);
+        const double x1 = (k1 == p.kcentre) ? 0.0 : neg_bits(cx[1]);
         if (p.vecL && in0 && in1) {
             st_stream2(p.xl + (k0 - p.kL0), x0, x1);
             st_stream2(p.wl + (k0 - p.kL0), w[0], w[1]);
@@ -235,6 +306,30 @@ legendre_asy_kernel(const LegLaunch p) {
     }
 }
 
+// Counts half-indices in [k_lo, k_hi) for which the slow-path-free reciprocal/quotient of the
+// tail kernel gives a different node or weight than the IEEE operators (expected: 0).
+__global__ void __launch_bounds__(256)
+legendre_fastdiv_check_kernel(int64_t k_lo, int64_t k_hi, LegConsts c,
+                              unsigned long long* mismatches) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (int64_t k = k_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < k_hi; k += stride) {
+        double cf, wf, ci, wi;
+        leg_half_index<0, 0, false>(k, c, cf, wf);
+        leg_half_index<0, 0, true>(k, c, ci, wi);
+        bad += (__double_as_longlong(cf) != __double_as_longlong(ci)) ||
+               (__double_as_longlong(wf) != __double_as_longlong(wi));
+        if (k >= K_JK_EXACT) {  // the specialised bulk path must give the same bits as well
+            const double ak = FGQ_PI * fgq_k_minus_quarter(k);
+            const double a = ak * c.vn;
+            if (a <= FGQ_PIO4) leg_bulk<0>(k, c, cf, wf); else leg_bulk<1>(k, c, cf, wf);
+            bad += (__double_as_longlong(cf) != __double_as_longlong(ci)) ||
+                   (__double_as_longlong(wf) != __double_as_longlong(wi));
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 template <int NT>
 __global__ void legendre_theta_kernel(int64_t k_lo, int64_t k_hi, LegConsts c, double* theta) {
     const int64_t k = k_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -251,6 +346,17 @@ static int node_terms(int64_t n) { return n <= 255 ? 3 : n <= 3950 ? 2 : n < (1L
 static int weight_terms(int64_t n) { return n <= 170 ? 3 : n <= 1500 ? 2 : n <= 850000 ? 1 : 0; }
 
 typedef void (*LegKernel)(const LegLaunch);
+
+// a_k for k >= K_JK_EXACT exactly as leg_bulk computes it (host IEEE arithmetic, no contraction
+// possible: a product of a difference, then a product)
+static double tail_angle(int64_t k, double vn) {
+    volatile double ak = FGQ_PI * ((double)k - 0.25);
+    volatile double a = ak * vn;
+    return a;
+}
+
+static inline int64_t imax(int64_t a, int64_t b) { return a > b ? a : b; }
+static inline int64_t imin(int64_t a, int64_t b) { return a < b ? a : b; }
 
 static LegKernel pick_kernel(int nt, int wt, bool head) {
 #define FGQ_PICK(NT, WT)                                                   \
@@ -289,6 +395,27 @@ static int launch_one(int64_t n, bool head, int64_t kmin, int64_t kmax, int64_t 
     }
     p.vecL = hasL && aligned16(xl) && aligned16(wl) && (((p.kbase - kL0) & 1) == 0);
     p.vecR = hasR && aligned16(xr) && aligned16(wr) && (((kR1 - p.kbase - 1) & 1) == 0);
+    // interior = both sides present, both vectorisable, centre excluded
+    p.kin0 = 1;
+    p.kin1 = 0;
+    if (p.vecL && p.vecR) {
+        p.kin0 = imax(kL0, kR0);
+        p.kin1 = imin(kL1, kR1);
+        if (p.kcentre && p.kin1 >= p.kcentre) p.kin1 = p.kcentre - 1;
+    }
+    // last k with a_k <= pi/4, by bisection on the very arithmetic the kernel uses (a_k is
+    // monotone in k); only the n >= 2^25 kernel reads it
+    p.kq0_last = 0;
+    if (node_terms(n) == 0 && !head) {
+        int64_t lo_k = K_JK_EXACT, hi_k = (n + 1) / 2 + 1;  // invariant: a(lo_k) <= pi/4 < a(hi_k)
+        if (tail_angle(lo_k, p.c.vn) <= FGQ_PIO4 && tail_angle(hi_k, p.c.vn) > FGQ_PIO4) {
+            while (hi_k - lo_k > 1) {
+                const int64_t mid = lo_k + (hi_k - lo_k) / 2;
+                if (tail_angle(mid, p.c.vn) <= FGQ_PIO4) lo_k = mid; else hi_k = mid;
+            }
+            p.kq0_last = lo_k;
+        }
+    }
     const int64_t npairs = (kmax - p.kbase) / 2 + 1;
     const int64_t blocks = (npairs + LEG_THREADS - 1) / LEG_THREADS;
     if (blocks > 0x7fffffffLL) {
@@ -305,18 +432,20 @@ static int launch_one(int64_t n, bool head, int64_t kmin, int64_t kmax, int64_t 
     return FGQ_OK;
 }
 
-static inline int64_t imax(int64_t a, int64_t b) { return a > b ? a : b; }
-static inline int64_t imin(int64_t a, int64_t b) { return a < b ? a : b; }
-
-constexpr int64_t K_TAIL = 13192;  // first half-index served by the pure McMahon tail
+constexpr int64_t K_TAIL = 13192;  // first half-index the pure McMahon tail may serve
 
 // Left stores xl[k-kL0] for k in [kL0,kL1]; right stores xr[kR1-k] for k in [kR0,kR1].
 int legendre_asy_launch(int64_t n, int64_t kL0, int64_t kL1, double* xl, double* wl, int64_t kR0,
                         int64_t kR1, double* xr, double* wr, cudaStream_t st) {
+    // Head (tables / truncation bands, k < split) and tail (k >= split) launches.  The split is
+    // moved by one when that keeps the tail's left pointer 16-byte aligned (the head kernel is
+    // generic in k, so it may take k = 13192 as well).
+    int64_t split = K_TAIL;
+    if (kL0 <= kL1 && kL0 < split && ((split - kL0) & 1)) split += 1;
     for (int part = 0; part < 2; ++part) {
         const bool head = part == 0;
-        const int64_t a = head ? 1 : K_TAIL;
-        const int64_t b = head ? K_TAIL - 1 : INT64_MAX / 4;
+        const int64_t a = head ? 1 : split;
+        const int64_t b = head ? split - 1 : INT64_MAX / 4;
         // clip both store ranges to this part
         const int64_t L0 = imax(kL0, a), L1 = imin(kL1, b);
         const int64_t R0 = imax(kR0, a), R1 = imin(kR1, b);
@@ -569,6 +698,20 @@ extern "C" int fgq_debug_legendre_theta_device(int64_t n, int64_t k_lo, int64_t 
         case 2: legendre_theta_kernel<2><<<blocks, 256, 0, st>>>(k_lo, k_hi, c, theta_dev); break;
         default: legendre_theta_kernel<3><<<blocks, 256, 0, st>>>(k_lo, k_hi, c, theta_dev); break;
     }
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+extern "C" int fgq_debug_fastdiv_check(int64_t n, int64_t k_lo, int64_t k_hi,
+                                       unsigned long long* mismatches_dev, void* stream) {
+    clear_status();
+    if (n < (1LL << 25) || k_lo < 13192 || k_hi < k_lo || !mismatches_dev) {
+        set_error("invalid fastdiv check request");
+        return FGQ_EINVAL;
+    }
+    if (k_hi == k_lo) return FGQ_OK;
+    legendre_fastdiv_check_kernel<<<148 * 8, 256, 0, as_stream(stream)>>>(k_lo, k_hi, make_consts(n),
+                                                                          mismatches_dev);
     FGQ_LAUNCH_CHECK();
     return FGQ_OK;
 }

@@ -100,6 +100,11 @@ int fgq_measure_store_peak(int64_t bytes, double* gbs);
 /* theta_k (the angle whose cosine is the node) for half-indices [k_lo, k_hi), asy path. */
 int fgq_debug_legendre_theta_device(int64_t n, int64_t k_lo, int64_t k_hi, double* theta_dev,
                                     void* stream);
+/* *mismatches_dev += number of half-indices in [k_lo, k_hi) (k_lo >= 13192, n >= 2^25) whose
+ * node or weight differs between the tail kernel's slow-path-free reciprocal/quotient and the
+ * IEEE operators.  Expected 0. */
+int fgq_debug_fastdiv_check(int64_t n, int64_t k_lo, int64_t k_hi,
+                            unsigned long long* mismatches_dev, void* stream);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t fgq_launch_count(void);
 
