@@ -1,0 +1,106 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/fgq.h
+declares, the Python mirror binds all of them, argument checks that need no GPU behave like the
+reference, and there is no silent CPU fallback."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "fgq.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(fgq_[a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def fgq_cpu():
+    import fgq_b200
+    if not os.path.exists(fgq_b200._lib.LIB_PATH):
+        fgq_b200.build()
+    return fgq_b200
+
+
+def test_library_exports_every_declared_symbol(fgq_cpu):
+    names = _declared()
+    assert len(names) >= 10
+    out = subprocess.run(["nm", "-D", "--defined-only", fgq_cpu._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (fgq_[a-z0-9_]+)", out))
+    missing = [n for n in names if n not in exported]
+    assert not missing, f"declared in include/fgq.h but not exported: {missing}"
+
+
+def test_python_mirror_binds_every_declared_symbol(fgq_cpu):
+    L = fgq_cpu.lib()
+    for n in _declared():
+        assert n in fgq_cpu._lib.SIGNATURES, f"{n} has no ctypes signature"
+        assert hasattr(L, n)
+    assert L.fgq_version() >= 100
+
+
+def test_only_sm100a_code_in_the_library(fgq_cpu):
+    out = subprocess.run(["cuobjdump", "--list-elf", fgq_cpu._lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_domain_errors_need_no_gpu(fgq_cpu):
+    # gausslegendre.jl:26
+    with pytest.raises(fgq_cpu.DomainError):
+        fgq_cpu.gausslegendre(-1)
+    L = fgq_cpu.lib()
+    assert L.fgq_gausslegendre_host(-5, 0, 0) == 1
+    assert b"non-negative" in L.fgq_last_error()
+    x, w = fgq_cpu.gausslegendre(0)  # gausslegendre.jl:28
+    assert len(x) == 0 and len(w) == 0
+    with pytest.raises(TypeError):
+        fgq_cpu.gausslegendre(2.5)
+
+
+def test_no_cpu_fallback(fgq_cpu):
+    """Without a device every compute entry point fails loudly."""
+    if fgq_cpu.lib().fgq_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(fgq_cpu.FGQError):
+        fgq_cpu.gausslegendre(100)
+    with pytest.raises(fgq_cpu.FGQError):
+        fgq_cpu.gausslegendre_batch(np.array([5, 6, 7]))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fastgaussquadrature.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_partitions_cover_the_rule(fgq_cpu):
+    for n in (61, 100, 101, 1000003, 10 ** 9, 10 ** 9 + 1):
+        for world in (1, 2, 3, 4, 8):
+            parts = fgq_cpu.index_partition(n, world)
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            assert all(lo % 2 == 0 for lo, _ in parts)  # 16-byte aligned shard starts
+            hp = fgq_cpu.half_index_partition(n, world)
+            assert hp[0][0] == 1 and hp[-1][1] == (n + 1) // 2 + 1
+            assert all(hp[i][1] == hp[i + 1][0] for i in range(world - 1))
+            # the two segments of all ranks tile [0, n) exactly once
+            cover = np.zeros(min(n, 2000), dtype=int) if n <= 2000 else None
+            total = 0
+            for k_lo, k_hi in hp:
+                cnt = k_hi - k_lo
+                m = (n + 1) // 2
+                skip = 1 if (n % 2 and k_hi - 1 == m and cnt > 0) else 0
+                total += cnt + (cnt - skip)
+                if cover is not None:
+                    cover[k_lo - 1:k_hi - 1] += 1
+                    cover[n - k_hi + 1 + skip:n - k_lo + 1] += 1
+            assert total == n
+            if cover is not None:
+                assert np.all(cover == 1)
