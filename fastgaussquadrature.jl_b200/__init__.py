@@ -6,6 +6,8 @@ path (reference src/FastGaussQuadrature.jl:7-19), over the C ABI of ``libfgq_cud
 """
 from ._lib import DomainError, FGQError, NotImplementedOnDevice, build, lib  # noqa: F401
 from .api import (  # noqa: F401
+    gausshermite,
+    gausshermite_device,
     gausslegendre,
     gausslegendre_batch,
     gausslegendre_device,

@@ -34,6 +34,10 @@ SIGNATURES = {
     "fgq_gausslegendre_device_pair": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "fgq_gausslegendre_batch_device": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "fgq_gausslegendre_batch_host": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp]),
+    "fgq_gausshermite_host": (ctypes.c_int, [_i64, ctypes.c_int, _vp, _vp]),
+    "fgq_gausshermite_workspace_bytes": (_i64, [_i64]),
+    "fgq_gausshermite_device": (ctypes.c_int, [_i64, ctypes.c_int, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "fgq_gausshermite_sweeps": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int)]),
     "fgq_rule_moments_device": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "fgq_measure_dfma_peak": (ctypes.c_int, [_dp]),
     "fgq_measure_store_peak": (ctypes.c_int, [_i64, _dp]),

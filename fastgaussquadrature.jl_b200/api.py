@@ -188,6 +188,45 @@ def gausslegendre_device(n, rank: int = 0, world: int = 1, mode: str = "pair", o
     return out
 
 
+# --------------------------------------------------------------------------------------------
+# Gauss-Hermite  (reference src/gausshermite.jl:28-33)
+# --------------------------------------------------------------------------------------------
+
+def gausshermite(n, *, normalize: bool = False):
+    """``gausshermite(n; normalize=false) -> x, w`` (reference src/gausshermite.jl:28,33).
+
+    n < 0 raises DomainError (:38); n == 0 returns empty arrays (:40); n == 1 is the closed form
+    (:42).  2 <= n <= 200 raises NotImplementedOnDevice: the reference serves those with the
+    recurrence / Golub-Welsch branches, which are off the hot path."""
+    n = _as_int(n)
+    if n < 0:
+        raise DomainError(f"DomainError({n}): Input n must be a non-negative integer")
+    x, w = _host_pair(n, False)
+    if n == 0:
+        return x, w
+    if n == 1:  # gausshermite.jl:41-42, then :30-31
+        x[0] = 0.0
+        w[0] = np.sqrt(np.pi)
+        return (np.sqrt(2.0) * x, w / np.sqrt(np.pi)) if normalize else (x, w)
+    check(lib().fgq_gausshermite_host(n, int(bool(normalize)), _ptr(x), _ptr(w)))
+    return x, w
+
+
+def gausshermite_device(n, *, normalize: bool = False, stream=None):
+    """Device-resident ``gausshermite(n)``: returns (x, w, info) with x, w torch CUDA tensors."""
+    import torch
+    n = _as_int(n)
+    if n < 0:
+        raise DomainError(f"DomainError({n}): Input n must be a non-negative integer")
+    L = lib()
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    w = torch.empty(n, dtype=torch.float64, device="cuda")
+    ws = torch.empty(int(L.fgq_gausshermite_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+    check(L.fgq_gausshermite_device(n, int(bool(normalize)), 0, n, x.data_ptr(), w.data_ptr(),
+                                    ws.data_ptr(), _stream_ptr(stream)))
+    return x, w, ws
+
+
 def rule_moments_device(shard: LegendreShard, stream=None):
     """(sum w, sum w x^2) of this rank's shard as a 2-element CUDA tensor (a fused-reduction
     consumer; callers all-reduce it across ranks for the Σw = 2, ∫x² = 2/3 check)."""

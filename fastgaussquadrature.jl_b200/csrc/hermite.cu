@@ -1,0 +1,395 @@
+// hermite.cu — Gauss-Hermite nodes/weights, asymptotic (Airy) + Newton path, n > 200.
+//
+// Replaces, on the B200:
+//   gausshermite / unweightedgausshermite   src/gausshermite.jl:28-65
+//   hermite_asy                             src/gausshermite.jl:68-89
+//   hermpoly_asy_airy                       src/gausshermite.jl:171-250
+//   hermite_initialguess                    src/gausshermite.jl:252-323   (AIRY_ROOTS: constants.jl:121-135)
+//
+// The reference runs ~40 broadcast passes per Newton sweep over half-range vectors; here one thread
+// owns one half-range node: initial guess, every Newton sweep and the weight stay in registers, the
+// only state between sweeps is theta (8 B per node).  The reference's GLOBAL stopping rule
+// (||dtheta||_inf < sqrt(eps)/10 over all nodes, :79) is kept without a host round trip: each sweep
+// kernel reduces its max into the workspace, the last block to finish sets a `done` flag, and the
+// remaining (pre-enqueued) sweep launches exit immediately.  Then a reduction for the global
+// normalisation sum (:62) and a fold/scale kernel that also applies exp(-x^2) (:30).
+#include "airy.cuh"
+#include "common.cuh"
+
+namespace fgq {
+
+__constant__ double c_airy_roots[10] = {
+    -2.338107410459767, -4.08794944413097, -5.520559828095551, -6.786708090071759,
+    -7.944133587120853, -9.022650853340981, -10.04017434155809, -11.00852430373326,
+    -11.93601556323626, -12.828776752865757};
+
+struct HermiteState {   // lives at the start of the workspace
+    unsigned long long maxdt_bits[20];
+    unsigned int ticket[20];
+    int done;
+    int sweeps;
+    double norm_sum;
+    unsigned int sum_ticket;
+};
+
+struct HermiteParams {
+    int64_t n;
+    int64_t m;        // (n-1)>>1 (odd) or n>>1 (even): count of Tricomi/Airy guesses
+    int64_t nh;       // half-range length: m+1 (odd, leading 0) or m
+    int odd;
+    double a;         // +-0.5
+    double nu;        // 4m + 2a + 2
+    double musq;      // 2n+1
+    double sq_musq;   // sqrt(2n+1)
+    double musq16, musq13, musq23, musq43, musq2, musq103, musq83;  // powers of musq
+    double nu13, num13, num53, num73;
+    int64_t n_sin;    // floor(p n): guesses 1..n_sin are Tricomi's
+    int64_t airy_from;  // ceil(p n): guesses taken from the reversed Airy list start here (1-based)
+    double tol;
+};
+
+// gausshermite.jl:252-323 for one position i (1-based) of the m-vector
+__device__ double hermite_guess(const HermiteParams& p, int64_t i) {
+    const double PI = 3.141592653589793;
+    // the patched vector is [x_sin[1:n_sin]; x_airy[airy_from:m]]
+    int64_t src;
+    bool use_sin;
+    if (i <= p.n_sin) {
+        use_sin = true;
+        src = i;
+    } else {
+        use_sin = false;
+        src = p.airy_from + (i - p.n_sin - 1);
+    }
+    if (use_sin) {
+        const double rhs = (double)((4 * p.m + 3) - 4 * src) / p.nu * PI;
+        double T = PI / 2;
+        for (int k = 0; k < 7; ++k) {
+            const double val = T - sin(T) - rhs;
+            const double dval = 1.0 - cos(T);
+            T = T - val / dval;
+        }
+        const double ch = cos(T / 2);
+        const double tnk = ch * ch;
+        const double tm1 = tnk - 1.0;
+        return sqrt(p.nu * tnk - ((tnk + 0.25) / (tm1 * tm1) + (3.0 * p.a * p.a - 1.0)) / (3.0 * p.nu));
+    }
+    // x_init_airy = reverse(x_init): position src <- Airy root index j = m + 1 - src
+    const int64_t j = p.m + 1 - src;
+    double r;
+    if (j <= 10) {
+        r = c_airy_roots[j - 1];
+    } else {
+        const double t = 3.0 * PI / 8.0 * (double)(4 * j - 1);
+        const double it2 = 1.0 / (t * t);
+        const double it4 = it2 * it2, it6 = it4 * it2, it8 = it4 * it4, it10 = it8 * it2;
+        r = -(pow(t, 2.0 / 3.0) * (1.0 + 5.0 / 48.0 * it2 - 5.0 / 36.0 * it4 + (77125.0 / 82944.0) * it6 -
+                                   108056875.0 / 6967296.0 * it8 + 162375596875.0 / 334430208.0 * it10));
+    }
+    const double r2 = r * r, r3 = r2 * r, r4 = r2 * r2, r5 = r4 * r;
+    const double c223 = 1.5874010519681994;   // 2^(2/3)
+    const double c213 = 1.2599210498948732;   // 2^(1/3)
+    const double c243 = 2.5198420997897464;   // 2^(4/3)
+    const double v = p.nu + c223 * r * p.nu13 + (1.0 / 5.0 * c243) * r2 * p.num13 +
+                     (11.0 / 35.0 - p.a * p.a - 12.0 / 175.0) * r3 / p.nu +
+                     ((16.0 / 1575.0) * r + (92.0 / 7875.0) * r4) * c223 * p.num53 -
+                     ((15152.0 / 3031875.0) * r5 + (1088.0 / 121275.0) * r2) * c213 * p.num73;
+    return sqrt(fabs(v));
+}
+
+__global__ void hermite_init_kernel(HermiteParams p, HermiteState* st, double* theta) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        for (int i = 0; i < 20; ++i) {
+            st->maxdt_bits[i] = 0ull;
+            st->ticket[i] = 0u;
+        }
+        st->done = 0;
+        st->sweeps = 0;
+        st->norm_sum = 0.0;
+        st->sum_ticket = 0u;
+    }
+    if (t >= p.nh) return;
+    double x0;
+    if (p.odd) {
+        x0 = (t == 0) ? 0.0 : hermite_guess(p, t);  // [0; x_init][1:m+1]
+    } else {
+        x0 = hermite_guess(p, t + 1);
+    }
+    theta[t] = acos(x0 / p.sq_musq);
+}
+
+// gausshermite.jl:171-250 at one theta
+__device__ __forceinline__ void hermpoly_asy_airy(const HermiteParams& p, double th, double sinT,
+                                                  double cosT, double& val, double& dval) {
+    const double sin2T = 2.0 * cosT * sinT;
+    const double eta = 0.5 * th - 0.25 * sin2T;
+    const double chi = -pow(3.0 * eta / 2.0, 2.0 / 3.0);
+    const double phi = pow(-chi / (sinT * sinT), 0.25);
+    const double SQPI = 1.7724538509055159;  // sqrt(pi)
+    double C = 2.0 * SQPI * p.musq16 * phi;
+    double Airy0, Airy1;
+    airy_neg(p.musq23 * chi, Airy0, Airy1);
+
+    const double a1 = 15.0 / 144.0, b1 = -7.0 / 5.0 * a1;
+    const double a2 = 5.0 * 7.0 * 9.0 * 11.0 / 2.0 / (144.0 * 144.0), b2 = -13.0 / 11.0 * a2;
+    const double a3 = 7.0 * 9.0 * 11.0 * 13.0 * 15.0 * 17.0 / 6.0 / (144.0 * 144.0 * 144.0), b3 = -19.0 / 17.0 * a3;
+    const double c2 = cosT * cosT, c3 = c2 * cosT, c4 = c2 * c2, c5 = c4 * cosT, c7 = c5 * c2, c9 = c7 * c2;
+    const double u1 = (c3 - 6.0 * cosT) / 24.0;
+    const double u2 = (-9.0 * c4 + 249.0 * c2 + 145.0) / 1152.0;
+    const double u3 = (-4042.0 * c9 + 18189.0 * c7 - 28287.0 * c5 - 151995.0 * c3 - 259290.0 * cosT) / 414720.0;
+    const double phi2 = phi * phi, phi6 = phi2 * phi2 * phi2, phi12 = phi6 * phi6, phi18 = phi12 * phi6;
+    const double chi2 = chi * chi, chi3 = chi2 * chi, chi4 = chi2 * chi2, chi5 = chi4 * chi;
+
+    val = Airy0;
+    const double B0 = -(u1 * phi6 + a1) / chi2;
+    val = val + B0 * Airy1 / p.musq43;
+    const double A1 = (u2 * phi12 + b1 * u1 * phi6 + b2) / chi3;
+    val = val + A1 * Airy0 / p.musq2;
+    const double B1 = -(u3 * phi18 + a1 * u2 * phi12 + a2 * u1 * phi6 + a3) / chi5;
+    val = val + B1 * Airy1 / p.musq103;
+    val = C * val;
+
+    C = 2.5066282746310002 * p.musq13 / phi;  // sqrt(2 pi)
+    const double v1 = (c3 + 6.0 * cosT) / 24.0;
+    const double v2 = (15.0 * c4 - 327.0 * c2 - 143.0) / 1152.0;
+    const double v3 = (259290.0 * cosT + 238425.0 * c3 - 36387.0 * c5 + 18189.0 * c7 - 4042.0 * c9) / 414720.0;
+    const double C0 = -(phi6 * v1 + b1) / chi;
+    dval = C0 * Airy0 / p.musq23;
+    dval = dval + Airy1;
+    const double C1 = -(v3 * phi18 + b1 * v2 * phi12 + b2 * v1 * phi6 + b3) / chi4;
+    dval = dval + C1 * Airy0 / p.musq83;
+    const double D1 = (v2 * phi12 + a1 * v1 * phi6 + a2) / chi3;
+    dval = dval + D1 * Airy1 / p.musq2;
+    dval = C * dval;
+}
+
+constexpr int HERM_THREADS = 128;
+
+// One Newton sweep (gausshermite.jl:75-86) over the half range.
+__global__ void __launch_bounds__(HERM_THREADS)
+hermite_sweep_kernel(HermiteParams p, int sweep, HermiteState* st, double* theta, double* xh, double* wh) {
+    if (*((volatile int*)&st->done)) return;
+    const int64_t t = (int64_t)blockIdx.x * HERM_THREADS + threadIdx.x;
+    double adt = 0.0;
+    if (t < p.nh) {
+        double th = theta[t];
+        double s, c;
+        sincos(th, &s, &c);
+        double val, dval;
+        hermpoly_asy_airy(p, th, s, c, val, dval);
+        const double dth = -val / (1.4142135623730951 * p.sq_musq * dval * s);
+        th = th - dth;
+        theta[t] = th;
+        adt = fabs(dth);
+        if (dth != dth) adt = __longlong_as_double(0x7ff8000000000000LL);  // NaN poisons the norm, as norm() does
+        const double x = p.sq_musq * cos(th);
+        const double w = x * val + 1.4142135623730951 * dval;
+        xh[t] = x;
+        wh[t] = 1.0 / (w * w);
+    }
+    // block max of |dtheta| through the bit pattern (non-negative doubles order like integers; NaN sorts last)
+    unsigned long long bits = (unsigned long long)__double_as_longlong(adt);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, bits, o);
+        bits = other > bits ? other : bits;
+    }
+    __shared__ unsigned long long sh[HERM_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < HERM_THREADS / 32; ++i) bits = sh[i] > bits ? sh[i] : bits;
+        atomicMax(&st->maxdt_bits[sweep], bits);
+        __threadfence();
+        const unsigned int tk = atomicAdd(&st->ticket[sweep], 1u);
+        if (tk == gridDim.x - 1) {  // last block: apply the reference's stopping rule
+            const double mx = __longlong_as_double((long long)atomicMax(&st->maxdt_bits[sweep], 0ull));
+            st->sweeps = sweep + 1;
+            if (mx < p.tol) st->done = 1;
+            __threadfence();
+        }
+    }
+}
+
+// sum over the FOLDED rule of exp(-x^2) w (gausshermite.jl:62): twice the half-range sum, the centre
+// node of an odd rule counted once.
+__global__ void __launch_bounds__(256)
+hermite_normsum_kernel(HermiteParams p, HermiteState* st, const double* xh, const double* wh) {
+    double s = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < p.nh; t += stride) {
+        const double x = xh[t];
+        const double term = exp(-(x * x)) * wh[t];
+        s += (p.odd && t == 0) ? term : 2.0 * term;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __shared__ double sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int i = 0; i < 8; ++i) a += sh[i];
+        atomicAdd(&st->norm_sum, a);
+    }
+}
+
+// fold out (:55-61), global scale (:62), exp(-x^2) (:30), optional normalize (:31)
+__global__ void __launch_bounds__(256)
+hermite_fold_kernel(HermiteParams p, int normalize, const HermiteState* st, const double* xh,
+                    const double* wh, int64_t lo, int64_t hi, double* x, double* w) {
+    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // output index
+    if (i >= hi) return;
+    // half index: odd n: centre at nh-1 (output) <-> xh[0]; even: outputs nh-1 and nh <-> xh[0]
+    int64_t h;
+    bool neg;
+    if (i < p.nh) {
+        h = p.nh - 1 - i;
+        neg = true;
+    } else {
+        h = p.odd ? i - p.nh + 1 : i - p.nh;
+        neg = false;
+    }
+    const double xv = xh[h];
+    const double scale = 1.7724538509055159 / st->norm_sum;
+    double wv = wh[h] * scale;
+    wv = wv * exp(-(xv * xv));
+    double xo = neg ? -xv : xv;
+    if (normalize) {
+        xo = 1.4142135623730951 * xo;
+        wv = wv / 1.7724538509055159;
+    }
+    x[i - lo] = xo;
+    w[i - lo] = wv;
+}
+
+}  // namespace fgq
+
+using namespace fgq;
+
+static HermiteParams hermite_params(int64_t n) {
+    HermiteParams p;
+    p.n = n;
+    p.odd = (int)(n & 1);
+    if (p.odd) {
+        p.m = (n - 1) >> 1;
+        p.a = 0.5;
+        p.nh = p.m + 1;
+    } else {
+        p.m = n >> 1;
+        p.a = -0.5;
+        p.nh = p.m;
+    }
+    p.nu = (double)(4 * p.m) + 2.0 * p.a + 2.0;
+    p.musq = (double)(2 * n + 1);
+    p.sq_musq = sqrt(p.musq);
+    p.musq16 = pow(p.musq, 1.0 / 6.0);
+    p.musq13 = pow(p.musq, 1.0 / 3.0);
+    p.musq23 = pow(p.musq, 2.0 / 3.0);
+    p.musq43 = pow(p.musq, 4.0 / 3.0);
+    p.musq2 = p.musq * p.musq;
+    p.musq103 = pow(p.musq, 4.0 / 3.0 + 2.0);
+    p.musq83 = pow(p.musq, 2.0 / 3.0 + 2.0);
+    p.nu13 = pow(p.nu, 1.0 / 3.0);
+    p.num13 = pow(p.nu, -1.0 / 3.0);
+    p.num53 = pow(p.nu, -5.0 / 3.0);
+    p.num73 = pow(p.nu, -7.0 / 3.0);
+    const double pp = 0.4985 + 2.220446049250313e-16;
+    p.n_sin = (int64_t)floor(pp * (double)n);
+    p.airy_from = (int64_t)ceil(pp * (double)n);
+    if (p.n_sin > p.m) p.n_sin = p.m;
+    p.tol = sqrt(2.220446049250313e-16) / 10.0;
+    return p;
+}
+
+extern "C" int64_t fgq_gausshermite_workspace_bytes(int64_t n) {
+    if (n < 0) return 0;
+    const int64_t nh = (n >> 1) + 1;
+    return 1024 + 3 * 8 * nh;
+}
+
+extern "C" int fgq_gausshermite_device(int64_t n, int normalize, int64_t lo, int64_t hi, double* x_dev,
+                                       double* w_dev, void* workspace_dev, void* stream) {
+    clear_status();
+    if (n < 0) {
+        set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);
+        return FGQ_EDOMAIN;
+    }
+    if (n <= 200) {
+        set_error("gausshermite(%lld): n <= 200 uses the recurrence / Golub-Welsch branches "
+                  "(gausshermite.jl:43-48), which are not on the device path", (long long)n);
+        return FGQ_ENOTIMPL;
+    }
+    if (lo < 0 || hi < lo || hi > n) {
+        set_error("invalid shard [%lld, %lld) of n=%lld", (long long)lo, (long long)hi, (long long)n);
+        return FGQ_EINVAL;
+    }
+    if (!workspace_dev || (hi > lo && (!x_dev || !w_dev))) {
+        set_error("null pointer");
+        return FGQ_EINVAL;
+    }
+    cudaStream_t st = as_stream(stream);
+    const HermiteParams p = hermite_params(n);
+    HermiteState* state = (HermiteState*)workspace_dev;
+    double* theta = (double*)((char*)workspace_dev + 1024);
+    double* xh = theta + p.nh;
+    double* wh = xh + p.nh;
+    const unsigned b128 = (unsigned)((p.nh + HERM_THREADS - 1) / HERM_THREADS);
+    hermite_init_kernel<<<b128, HERM_THREADS, 0, st>>>(p, state, theta);
+    FGQ_LAUNCH_CHECK();
+    for (int s = 0; s < 20; ++s) {
+        hermite_sweep_kernel<<<b128, HERM_THREADS, 0, st>>>(p, s, state, theta, xh, wh);
+        FGQ_LAUNCH_CHECK();
+    }
+    int64_t rb = (p.nh + 255) / 256;
+    if (rb > 148 * 4) rb = 148 * 4;
+    hermite_normsum_kernel<<<(unsigned)rb, 256, 0, st>>>(p, state, xh, wh);
+    FGQ_LAUNCH_CHECK();
+    if (hi > lo) {
+        hermite_fold_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, st>>>(p, normalize, state, xh, wh,
+                                                                             lo, hi, x_dev, w_dev);
+        FGQ_LAUNCH_CHECK();
+    }
+    return FGQ_OK;
+}
+
+extern "C" int fgq_gausshermite_host(int64_t n, int normalize, double* x, double* w) {
+    clear_status();
+    if (n < 0) {
+        set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);
+        return FGQ_EDOMAIN;
+    }
+    if (n <= 200) {
+        set_error("gausshermite(%lld): n <= 200 uses the recurrence / Golub-Welsch branches "
+                  "(gausshermite.jl:43-48), which are not on the device path", (long long)n);
+        return FGQ_ENOTIMPL;
+    }
+    if (!x || !w) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    HostPathLock lock;
+    void *ws, *out;
+    FGQ_TRY(scratch_device((size_t)fgq_gausshermite_workspace_bytes(n), 6, &ws));
+    FGQ_TRY(scratch_device((size_t)n * 16, 0, &out));
+    cudaStream_t st;
+    FGQ_TRY(scratch_stream(0, &st));
+    double* xd = (double*)out;
+    double* wd = xd + n;
+    FGQ_TRY(fgq_gausshermite_device(n, normalize, 0, n, xd, wd, ws, (void*)st));
+    FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    FGQ_CUDA_TRY(cudaStreamSynchronize(st));
+    return FGQ_OK;
+}
+
+// number of Newton sweeps the last fgq_gausshermite_device call on this workspace needed
+extern "C" int fgq_gausshermite_sweeps(const void* workspace_dev, int* sweeps) {
+    clear_status();
+    if (!workspace_dev || !sweeps) return FGQ_EINVAL;
+    HermiteState h;
+    FGQ_CUDA_TRY(cudaMemcpy(&h, workspace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    *sweeps = h.sweeps;
+    return FGQ_OK;
+}

@@ -80,6 +80,23 @@ int fgq_gausslegendre_batch_device(int64_t nrules, const int32_t* n_i_dev,
 int fgq_gausslegendre_batch_host(int64_t nrules, const int32_t* n_i, const int64_t* offsets,
                                  double* x, double* w);
 
+/* ---- Gauss-Hermite: gausshermite(n; normalize) — src/gausshermite.jl:28-89,171-323 ---------- */
+
+/* Asymptotic (Airy) + Newton path, n > 200 (gausshermite.jl:49-50).  n < 0 -> FGQ_EDOMAIN (:38);
+ * 0 <= n <= 200 -> FGQ_ENOTIMPL (the reference's recurrence / Golub-Welsch branches are not on the
+ * device path).  normalize != 0 applies x*sqrt(2), w/sqrt(pi) (:31). */
+int fgq_gausshermite_host(int64_t n, int normalize, double* x, double* w);
+/* Device-resident.  The whole half-range is always solved on the current device (the Newton
+ * stopping rule and the normalisation sum are global); output indices [lo, hi) are written to
+ * x_dev/w_dev[0 .. hi-lo).  workspace_dev: fgq_gausshermite_workspace_bytes(n) bytes, 16-byte
+ * aligned.  Enqueues a fixed sequence of launches (no host synchronisation): the global
+ * stopping rule is evaluated on the device. */
+int64_t fgq_gausshermite_workspace_bytes(int64_t n);
+int fgq_gausshermite_device(int64_t n, int normalize, int64_t lo, int64_t hi, double* x_dev,
+                            double* w_dev, void* workspace_dev, void* stream);
+/* Newton sweeps the last call on this workspace used (synchronises; for tests/reporting). */
+int fgq_gausshermite_sweeps(const void* workspace_dev, int* sweeps);
+
 /* ---- consumers / checks ------------------------------------------------------------------ */
 
 /* sums_dev[0] += sum w_i, sums_dev[1] += sum w_i x_i^2 over count entries (device buffers;

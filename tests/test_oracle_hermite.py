@@ -1,0 +1,37 @@
+"""CPU tests: the Hermite oracle (numpy + AMOS Airy through scipy) against the reference's golden
+values for the asymptotic branch (test/test_gausshermite.jl:38-54)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import hermite_oracle as ho
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "hermite_reference_tests.json")))
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: f"n{c['n']}")
+def test_golden_values(case):
+    n = case["n"]
+    x, w = ho.gausshermite(n)
+    assert len(x) == n and len(w) == n
+    for i, (v, tol) in case["x"].items():
+        assert abs(x[int(i) - 1] - v) < tol
+    for i, (v, tol) in case["w"].items():
+        assert abs(w[int(i) - 1] - v) < tol
+    assert np.dot(w, x) < case["dot_wx_lt"]
+    assert abs(np.dot(w, x * x) - np.sqrt(np.pi) / 2) < case["dot_wx2_tol"]
+
+
+def test_structure_and_sweeps():
+    info = {}
+    x, w = ho.gausshermite(100000, info=info)
+    assert info["sweeps"] <= 4
+    assert np.all(np.diff(x) > 0)
+    assert abs(w.sum() - np.sqrt(np.pi)) < 1e-13
+    xn, wn = ho.gausshermite(1001, normalize=True)
+    assert abs(wn.sum() - 1) < 1e-13 and abs(np.dot(wn, xn * xn) - 1) < 1e-11
+    with pytest.raises(ValueError):
+        ho.gausshermite(-1)
