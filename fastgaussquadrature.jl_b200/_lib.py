@@ -34,6 +34,16 @@ SIGNATURES = {
     "fgq_gausslegendre_device_pair": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "fgq_gausslegendre_batch_device": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "fgq_gausslegendre_batch_host": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp]),
+    "fgq_gaussjacobi_host": (ctypes.c_int, [_i64, ctypes.c_double, ctypes.c_double, _vp, _vp]),
+    "fgq_gaussjacobi_workspace_bytes": (_i64, [_i64]),
+    "fgq_gaussjacobi_device": (ctypes.c_int, [_i64, ctypes.c_double, ctypes.c_double, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "fgq_gaussjacobi_stats": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "fgq_gaussradau_host": (ctypes.c_int, [_i64, _vp, _vp]),
+    "fgq_gausslobatto_host": (ctypes.c_int, [_i64, _vp, _vp]),
+    "fgq_gaussradau_device": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp]),
+    "fgq_gausslobatto_device": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp]),
+    "fgq_approx_besselroots": (ctypes.c_int, [ctypes.c_double, _i64, _vp]),
+    "fgq_besselj": (ctypes.c_double, [ctypes.c_double, ctypes.c_double]),
     "fgq_gausshermite_host": (ctypes.c_int, [_i64, ctypes.c_int, _vp, _vp]),
     "fgq_gausshermite_workspace_bytes": (_i64, [_i64]),
     "fgq_gausshermite_device": (ctypes.c_int, [_i64, ctypes.c_int, _i64, _i64, _vp, _vp, _vp, _vp]),

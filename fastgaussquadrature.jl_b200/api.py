@@ -189,6 +189,74 @@ def gausslegendre_device(n, rank: int = 0, world: int = 1, mode: str = "pair", o
 
 
 # --------------------------------------------------------------------------------------------
+# Gauss-Jacobi, Radau, Lobatto  (reference src/gaussjacobi.jl:23-55, gaussradau.jl, gausslobatto.jl)
+# --------------------------------------------------------------------------------------------
+
+def gaussjacobi(n, a, b):
+    """``gaussjacobi(n, α, β) -> x, w`` (reference src/gaussjacobi.jl:23).
+
+    Integer α, β are promoted to Float64 (regression #117).  Errors as in the reference: n < 0 or
+    min(α,β) <= -1 raise DomainError (:26-27, :44-45).  The device path covers the asymptotic
+    branch (n > 100, max(α,β) < 5) and (0,0) -> Legendre; the recurrence / Golub-Welsch /
+    Chebyshev regions raise NotImplementedOnDevice."""
+    n = _as_int(n)
+    a = float(a)
+    b = float(b)
+    if n < 0:
+        raise DomainError(f"DomainError({n}): gaussjacobi({n},{a},{b}) not defined: n must be non-negative.")
+    if a == 0.0 and b == 0.0:
+        return gausslegendre(n)
+    x, w = _host_pair(n, False)
+    if n == 0 and not (abs(a) == 0.5 and abs(b) == 0.5):
+        return x, w
+    check(lib().fgq_gaussjacobi_host(n, a, b, _ptr(x), _ptr(w)))
+    return x, w
+
+
+def gaussjacobi_device(n, a, b, stream=None):
+    """Device-resident ``gaussjacobi``: (x, w, workspace) as torch CUDA tensors."""
+    import torch
+    n = _as_int(n)
+    L = lib()
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    w = torch.empty(n, dtype=torch.float64, device="cuda")
+    ws = torch.empty(int(L.fgq_gaussjacobi_workspace_bytes(max(n, 0))) + 16, dtype=torch.uint8, device="cuda")
+    check(L.fgq_gaussjacobi_device(n, float(a), float(b), 0, n, x.data_ptr(), w.data_ptr(), ws.data_ptr(),
+                                   _stream_ptr(stream)))
+    return x, w, ws
+
+
+def gaussradau(n):
+    """``gaussradau(n) -> x, w`` (reference src/gaussradau.jl:31-49); x[0] == -1 exactly."""
+    n = _as_int(n)
+    if n <= 0:
+        raise DomainError(f"DomainError({n}): Input n must be a positive integer")
+    x, w = _host_pair(n, False)
+    check(lib().fgq_gaussradau_host(n, _ptr(x), _ptr(w)))
+    return x, w
+
+
+def gausslobatto(n):
+    """``gausslobatto(n) -> x, w`` (reference src/gausslobatto.jl:31-52); x[0] == -1, x[-1] == 1."""
+    n = _as_int(n)
+    if n <= 1:
+        raise DomainError(f"DomainError({n}): Lobatto undefined for n <= 1.")
+    x, w = _host_pair(n, False)
+    check(lib().fgq_gausslobatto_host(n, _ptr(x), _ptr(w)))
+    return x, w
+
+
+def approx_besselroots(nu, n):
+    """``approx_besselroots(ν, n)`` (reference src/besselroots.jl:23-67)."""
+    n = _as_int(n)
+    if n < 0:
+        raise DomainError(f"DomainError({n}): Input n must be a non-negative integer")
+    x = np.zeros(n, dtype=np.float64)
+    check(lib().fgq_approx_besselroots(float(nu), n, _ptr(x)))
+    return x
+
+
+# --------------------------------------------------------------------------------------------
 # Gauss-Hermite  (reference src/gausshermite.jl:28-33)
 # --------------------------------------------------------------------------------------------
 

@@ -1,0 +1,491 @@
+// jacobi.cu — Gauss-Jacobi nodes/weights for n > 100, max(alpha, beta) < 5, plus the
+// Gauss-Radau / Gauss-Lobatto epilogues built on it.
+//
+// Replaces, on the B200:
+//   gaussjacobi dispatch, jacobi_asy       src/gaussjacobi.jl:23-55, 170-194
+//   asy1, feval_asy1 (interior)            src/gaussjacobi.jl:196-361
+//   gaussradau(n), gausslobatto(n)         src/gaussradau.jl:31-49, src/gausslobatto.jl:31-52
+// (the 2 x 10 boundary nodes of asy2 and all parameter-only tables are planned on the host:
+//  jacobi_boundary.cu).
+//
+// The reference materialises ~10 dense 20 x N arrays per evaluation and runs a BLAS gemv per
+// series term; here one thread owns one node and keeps the whole 20-term expansion in registers:
+// per Newton sweep it reads and writes 8 B of state (theta) per node.  The two pieces of GLOBAL
+// data-dependent control are kept, evaluated on the device without host round trips:
+//   * the series is truncated where the inf-norm of a term over the interior set drops below
+//     eps/100 (:309): a norm pass (same device function, no stores) precedes each evaluation pass;
+//   * Newton stops on the inf-norm of the update over the interior set (:213,:235), then runs once
+//     more "for luck": the last block of each pass advances a per-half phase flag and the remaining
+//     pre-enqueued launches return immediately.
+#include <math.h>
+
+#include "common.cuh"
+#include "jacobi_plan.h"
+
+namespace fgq {
+
+struct JacobiState {
+    unsigned long long termnorm[2][11][9];  // [half][sweep][m-12]: max |dS1+dS2| over the interior set
+    unsigned long long dtnorm[2][11];
+    unsigned int ticket[2][11][2];
+    int phase[2];   // 0 iterate, 1 once more for luck, 2 done
+    int sweeps[2];  // Newton sweeps before the extra one
+    int terms[2][11];
+};
+
+struct JacobiLaunch {
+    JacobiHalfPlan hp;   // parameters of this half ((alpha,beta) swapped for the left one)
+    int half;            // 0: right (x > 0), 1: left
+    int sweep;
+    int64_t n;
+    int64_t first, count;  // global (0-based, ascending-x) index range of this half
+    int64_t idx_lo, idx_hi;  // interior index set [idx_lo, idx_hi) in global indices (:206, :228)
+    double wc;             // weightsConstant
+    int64_t lo, hi;        // output slice
+    double tol;
+};
+
+constexpr int JAC_THREADS = 128;
+
+// gaussjacobi.jl:254-361 for one node.  NORM: only the truncation norms of terms 12..20 are produced.
+template <bool NORM>
+__device__ __forceinline__ void feval_asy1_node(const JacobiHalfPlan& P, double nn, double t, int mbreak,
+                                                double& vals, double& ders, double* tnorm) {
+    const double PI = 3.141592653589793;
+    const double a = P.a, b = P.b;
+    double sinT_, cosT_;
+    sincos(t, &sinT_, &cosT_);
+    const double csc = (1.0 / sin(t / 2)) / 2;
+    const double sec = (1.0 / cos(t / 2)) / 2;
+    double pw[JAC_M];  // sinT[:, j] of the reference (:271), rescaled by secT after every term (:316)
+    pw[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j < JAC_M; ++j) pw[j] = pw[j - 1] * csc;
+    const double c0 = 2 * nn + a + b;
+    const double shift = (a + 0.5) * PI / 2;
+    double S = 0.0, S2 = 0.0;
+#pragma unroll
+    for (int m = 1; m <= JAC_M; ++m) {
+        if (!NORM || m >= 12) {
+            if (!NORM && m == mbreak) break;
+            const double A = (c0 + m) * t / 2 - shift;
+            double sA, cA;
+            sincos(A, &sA, &cA);
+            double d1 = 0.0, d2 = 0.0, d12 = 0.0, d22 = 0.0;
+#pragma unroll
+            for (int l = 0; l < m; l += 2) {
+                d1 = fma(pw[l], P.PHI[l][m - 1], d1);
+                if (!NORM) d12 = fma(pw[l], P.PHI2[l][m - 1], d12);
+            }
+#pragma unroll
+            for (int l = 1; l < m; l += 2) {
+                d2 = fma(pw[l], P.PHI[l][m - 1], d2);
+                if (!NORM) d22 = fma(pw[l], P.PHI2[l][m - 1], d22);
+            }
+            d1 *= cA;
+            d2 *= sA;
+            if (NORM) {
+                tnorm[m - 12] = fabs(d1 + d2);
+            } else {
+                const double cA2 = cA * cosT_ + sA * sinT_;
+                const double sA2 = sA * cosT_ - cA * sinT_;
+                S += d1;
+                S += d2;
+                S2 += d12 * cA2;
+                S2 += d22 * sA2;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < m; ++j) pw[j] *= sec;
+    }
+    if (NORM) return;
+    vals = P.C * S;
+    ders = (nn * ((a - b) - c0 * cosT_) * vals + (2 * (nn + a) * (nn + b) * P.C2) * S2) / c0 / sinT_;
+    const double denom = 1.0 / (pow(sin(fabs(t) / 2), a + 0.5) * pow(cos(t / 2), b + 0.5));
+    vals *= denom;
+    ders *= denom;
+}
+
+__device__ __forceinline__ unsigned long long block_max_bits(double v) {
+    unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, bits, o);
+        bits = other > bits ? other : bits;
+    }
+    __shared__ unsigned long long sh[JAC_THREADS / 32];
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int i = 1; i < JAC_THREADS / 32; ++i) bits = sh[i] > bits ? sh[i] : bits;
+    return bits;  // valid in thread 0
+}
+
+// Initial guesses (Gatteschi-Pittaluga, :200-201) for every node; theta-space of its own half.
+__global__ void jacobi_init_kernel(int64_t n, double a, double b, int64_t n_left, double* theta) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 0-based position in tt
+    if (i >= n) return;
+    const double PI = 3.141592653589793;
+    const double j = (double)(n - i);
+    const double d = 2 * (double)n + a + b + 1;
+    const double K = PI * (2 * j + a - 0.5) / d;
+    const double tt = K + (1 / (d * d)) * ((0.25 - a * a) * (1.0 / tan(K / 2)) - (0.25 - b * b) * tan(K / 2));
+    theta[i] = (i < n_left) ? PI - tt : tt;
+}
+
+template <bool NORM>
+__global__ void __launch_bounds__(JAC_THREADS)
+jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, double* theta, double* x, double* w) {
+    const int h = p.half;
+    const int phase = *((volatile int*)&st->phase[h]);
+    if (phase == 2) return;
+    const int64_t r = (int64_t)blockIdx.x * JAC_THREADS + threadIdx.x;
+    const int64_t ig = p.first + r;
+    const bool active = r < p.count;
+    const bool interior = active && ig >= p.idx_lo && ig < p.idx_hi;
+    const double nn = (double)p.n;
+    double t = active ? theta[ig] : 1.0;
+    if (NORM) {
+        double tn[9];
+        double dummy_v, dummy_d;
+        feval_asy1_node<true>(p.hp, nn, t, 0, dummy_v, dummy_d, tn);
+        for (int q = 0; q < 9; ++q) {
+            const unsigned long long bits = block_max_bits(interior ? tn[q] : 0.0);
+            if (threadIdx.x == 0) atomicMax(&st->termnorm[h][p.sweep][q], bits);
+        }
+        return;
+    }
+    // truncation index: first m >= 12 whose interior inf-norm is below eps/100 (:309)
+    int mbreak = 0;
+    for (int q = 0; q < 9; ++q) {
+        const double nm = __longlong_as_double((long long)st->termnorm[h][p.sweep][q]);
+        if (nm < 2.220446049250313e-16 / 100) {
+            mbreak = 12 + q;
+            break;
+        }
+    }
+    double adt = 0.0;
+    if (active) {
+        double vals, ders;
+        feval_asy1_node<false>(p.hp, nn, t, mbreak, vals, ders, nullptr);
+        const double dt = vals / ders;
+        t += dt;
+        theta[ig] = t;
+        if (interior) adt = (dt != dt) ? __longlong_as_double(0x7ff8000000000000LL) : fabs(dt);
+        if (ig >= p.lo && ig < p.hi) {
+            const double c = cos(t);
+            x[ig - p.lo] = h ? -c : c;                   // vcat(-x_left, x_right) (:246)
+            w[ig - p.lo] = (1.0 / (ders * ders)) * p.wc;  // 1 ./ ders.^2 (:222,:244), rmul! (:192)
+        }
+    }
+    const unsigned long long bits = block_max_bits(adt);
+    if (threadIdx.x == 0) {
+        atomicMax(&st->dtnorm[h][p.sweep], bits);
+        __threadfence();
+        const unsigned int tk = atomicAdd(&st->ticket[h][p.sweep][1], 1u);
+        if (tk == gridDim.x - 1) {
+            const double mx = __longlong_as_double((long long)atomicMax(&st->dtnorm[h][p.sweep], 0ull));
+            st->terms[h][p.sweep] = mbreak ? mbreak - 1 : JAC_M;
+            if (phase == 0) {
+                st->sweeps[h] += 1;
+                if (mx < p.tol || st->sweeps[h] == 10) st->phase[h] = 1;
+            } else {
+                st->phase[h] = 2;
+            }
+            __threadfence();
+        }
+    }
+}
+
+struct JacobiPatch {
+    double x[2 * JAC_NBDY], w[2 * JAC_NBDY];  // [0..10): left end (ascending), [10..20): right end
+    int64_t n, lo, hi;
+};
+
+// jacobi_asy :182-190: overwrite the 10 nodes next to each end with the boundary formula.
+__global__ void jacobi_patch_kernel(const JacobiPatch q, double* x, double* w) {
+    const int i = threadIdx.x;
+    if (i >= 2 * JAC_NBDY) return;
+    const int64_t ig = i < JAC_NBDY ? i : q.n - 2 * JAC_NBDY + i;
+    if (ig >= q.lo && ig < q.hi) {
+        x[ig - q.lo] = q.x[i];
+        w[ig - q.lo] = q.w[i];
+    }
+}
+
+// gaussradau.jl:41-48 / gausslobatto.jl:41-49: rescale the Jacobi weights and add fixed endpoints.
+// mode 1: Radau  (inner = gaussjacobi(n-1, 0, 1)): w /= (1 + x);   x[0] = -1, w[0] = 2/n^2
+// mode 2: Lobatto (inner = gaussjacobi(n-2, 1, 1)): w /= (1 - x^2); ends +-1, w = 2/(n(n-1))
+__global__ void endpoint_epilogue_kernel(int mode, int64_t n, int64_t lo, int64_t hi, double* x, double* w) {
+    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // output index of the n-point rule
+    if (i >= hi) return;
+    const double nn = (double)n;
+    if (i == 0) {
+        x[0] = -1.0;
+        w[0] = mode == 1 ? 2 / (nn * nn) : 2 / (nn * (nn - 1));
+    } else if (mode == 2 && i == n - 1) {
+        x[i - lo] = 1.0;
+        w[i - lo] = 2 / (nn * (nn - 1));
+    } else {
+        const double xi = x[i - lo];
+        w[i - lo] = mode == 1 ? w[i - lo] / (1 + xi) : w[i - lo] / (1 - xi * xi);
+    }
+}
+
+static double jacobi_tt_host(int64_t n, double a, double b, int64_t i) {
+    const double PI = 3.141592653589793;
+    const double j = (double)(n - i);
+    const double d = 2 * (double)n + a + b + 1;
+    const double K = PI * (2 * j + a - 0.5) / d;
+    return K + (1 / (d * d)) * ((0.25 - a * a) * (1.0 / tan(K / 2)) - (0.25 - b * b) * tan(K / 2));
+}
+
+}  // namespace fgq
+
+using namespace fgq;
+
+static int jacobi_check_args(int64_t n, double a, double b) {
+    if (n < 0) {
+        set_error("DomainError(%lld): gaussjacobi(%lld,%g,%g) not defined: n must be non-negative.",
+                  (long long)n, (long long)n, a, b);
+        return FGQ_EDOMAIN;
+    }
+    if (!(a > -1.0) || !(b > -1.0)) {
+        set_error("DomainError((%g, %g)): The Jacobi parameters correspond to a nonintegrable weight function", a, b);
+        return FGQ_EDOMAIN;
+    }
+    const double mx = a > b ? a : b;
+    if (n > 100 && mx < 5.0) return FGQ_OK;
+    if (n > 4000 && mx >= 5.0) {
+        set_error("gaussjacobi(%lld,%g,%g) is not implemented: n must be <= 4000 for max(a,b) >= 5.", (long long)n, a, b);
+        return FGQ_ENOTIMPL;
+    }
+    set_error("gaussjacobi(%lld,%g,%g): the reference serves this region with jacobi_rec (n <= 100) or "
+              "Golub-Welsch (max(a,b) >= 5), which are not on the device path", (long long)n, a, b);
+    return FGQ_ENOTIMPL;
+}
+
+extern "C" int64_t fgq_gaussjacobi_workspace_bytes(int64_t n) {
+    if (n < 0) return 0;
+    return 4096 + 8 * n;
+}
+
+// Core: the (alpha, beta) != (0,0), (+-1/2, +-1/2) asymptotic branch.
+static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t hi, double* x_dev, double* w_dev,
+                             void* workspace_dev, cudaStream_t st) {
+    JacobiState* state = (JacobiState*)workspace_dev;
+    static_assert(sizeof(JacobiState) <= 4096, "state must fit the workspace header");
+    double* theta = (double*)((char*)workspace_dev + 4096);
+    FGQ_CUDA_TRY(cudaMemsetAsync(state, 0, sizeof(JacobiState), st));
+    // split: tt is decreasing in the index; n_left = number of tt > pi/2 (:204)
+    const double PIO2 = 3.141592653589793 / 2;
+    int64_t n_left;
+    if (!(jacobi_tt_host(n, a, b, 0) > PIO2)) {
+        n_left = 0;
+    } else if (jacobi_tt_host(n, a, b, n - 1) > PIO2) {
+        n_left = n;
+    } else {
+        int64_t l = 0, r = n - 1;  // tt(l) > pi/2 >= tt(r)
+        while (r - l > 1) {
+            const int64_t mid = l + (r - l) / 2;
+            if (jacobi_tt_host(n, a, b, mid) > PIO2) l = mid; else r = mid;
+        }
+        n_left = r;
+    }
+    if (n_left < 2 * JAC_NBDY || n - n_left < 2 * JAC_NBDY) {
+        set_error("internal: degenerate interior split (%lld of %lld)", (long long)n_left, (long long)n);
+        return FGQ_EINVAL;
+    }
+    jacobi_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a, b, n_left, theta);
+    FGQ_LAUNCH_CHECK();
+
+    JacobiLaunch L[2];
+    jacobi_interior_plan(n, a, b, &L[0].hp);
+    jacobi_interior_plan(n, b, a, &L[1].hp);
+    const double wc = jacobi_weights_constant(n, a, b);
+    for (int h = 0; h < 2; ++h) {
+        L[h].half = h;
+        L[h].n = n;
+        L[h].wc = wc;
+        L[h].lo = lo;
+        L[h].hi = hi;
+        L[h].tol = sqrt(2.220446049250313e-16) / 100;
+    }
+    L[0].first = n_left;          L[0].count = n - n_left;
+    L[0].idx_lo = n_left;         L[0].idx_hi = n - (JAC_NBDY - 1);   // all but the last 9 (:206)
+    L[1].first = 0;               L[1].count = n_left;
+    L[1].idx_lo = JAC_NBDY;       L[1].idx_hi = n_left;              // all but the first 10 (:228)
+    for (int s = 0; s < 11; ++s) {
+        for (int h = 0; h < 2; ++h) {
+            L[h].sweep = s;
+            const unsigned blocks = (unsigned)((L[h].count + JAC_THREADS - 1) / JAC_THREADS);
+            jacobi_pass_kernel<true><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
+            FGQ_LAUNCH_CHECK();
+            jacobi_pass_kernel<false><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
+            FGQ_LAUNCH_CHECK();
+        }
+    }
+    // boundary nodes (host-planned, O(1)): right end with (a,b), left end with (b,a) mirrored (:182-190)
+    JacobiPatch q;
+    q.n = n;
+    q.lo = lo;
+    q.hi = hi;
+    double xb[JAC_NBDY], wb[JAC_NBDY];
+    jacobi_asy2(n, a, b, JAC_NBDY, xb, wb);
+    for (int i = 0; i < JAC_NBDY; ++i) {
+        q.x[JAC_NBDY + i] = xb[i];
+        q.w[JAC_NBDY + i] = wb[i] * wc;
+    }
+    if (a != b) jacobi_asy2(n, b, a, JAC_NBDY, xb, wb);
+    for (int i = 0; i < JAC_NBDY; ++i) {
+        q.x[i] = -xb[JAC_NBDY - 1 - i];
+        q.w[i] = wb[JAC_NBDY - 1 - i] * wc;
+    }
+    for (int i = 0; i < 2 * JAC_NBDY; ++i) {
+        if (!(q.x[i] == q.x[i]) || !(q.w[i] == q.w[i])) add_warning(FGQ_WARN_NONFINITE);
+    }
+    jacobi_patch_kernel<<<1, 32, 0, st>>>(q, x_dev, w_dev);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+extern "C" int fgq_gausslegendre_device(int64_t n, int64_t lo, int64_t hi, double* x_dev, double* w_dev,
+                                        void* stream);
+
+extern "C" int fgq_gaussjacobi_device(int64_t n, double a, double b, int64_t lo, int64_t hi, double* x_dev,
+                                      double* w_dev, void* workspace_dev, void* stream) {
+    clear_status();
+    if (n < 0) return jacobi_check_args(n, a, b);
+    if (lo < 0 || hi < lo || hi > n) {
+        set_error("invalid shard [%lld, %lld) of n=%lld", (long long)lo, (long long)hi, (long long)n);
+        return FGQ_EINVAL;
+    }
+    if (a == 0.0 && b == 0.0) return fgq_gausslegendre_device(n, lo, hi, x_dev, w_dev, stream);  // :29-30
+    if (fabs(a) == 0.5 && fabs(b) == 0.5) {
+        set_error("gaussjacobi(n, +-1/2, +-1/2) is Gauss-Chebyshev (gaussjacobi.jl:31-40): closed forms, "
+                  "not on the device path yet");
+        return FGQ_ENOTIMPL;
+    }
+    if (n == 0) return FGQ_OK;
+    FGQ_TRY(jacobi_check_args(n, a, b));
+    if (!workspace_dev || (hi > lo && (!x_dev || !w_dev))) {
+        set_error("null pointer");
+        return FGQ_EINVAL;
+    }
+    return jacobi_asy_device(n, a, b, lo, hi, x_dev, w_dev, workspace_dev, as_stream(stream));
+}
+
+// mode 1 = gaussradau(n), mode 2 = gausslobatto(n); the inner Jacobi rule has n - mode nodes and is
+// written one slot to the right so that the epilogue can fill the fixed endpoint(s) in place.
+static int endpoint_rule_device(int mode, int64_t n, double* x_dev, double* w_dev, void* workspace_dev,
+                                cudaStream_t st) {
+    const int64_t inner = n - mode;
+    const double a = mode == 1 ? 0.0 : 1.0, b = 1.0;
+    FGQ_TRY(jacobi_check_args(inner, a, b));
+    FGQ_TRY(jacobi_asy_device(inner, a, b, 0, inner, x_dev + 1, w_dev + 1, workspace_dev, st));
+    endpoint_epilogue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mode, n, 0, n, x_dev, w_dev);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+extern "C" int fgq_gaussradau_device(int64_t n, double* x_dev, double* w_dev, void* workspace_dev, void* stream) {
+    clear_status();
+    if (n <= 0) {
+        set_error("DomainError(%lld): Input n must be a positive integer", (long long)n);  // gaussradau.jl:34
+        return FGQ_EDOMAIN;
+    }
+    if (!x_dev || !w_dev || !workspace_dev) {
+        set_error("null pointer");
+        return FGQ_EINVAL;
+    }
+    return endpoint_rule_device(1, n, x_dev, w_dev, workspace_dev, as_stream(stream));
+}
+
+extern "C" int fgq_gausslobatto_device(int64_t n, double* x_dev, double* w_dev, void* workspace_dev, void* stream) {
+    clear_status();
+    if (n <= 1) {
+        set_error("DomainError(%lld): Lobatto undefined for n <= 1.", (long long)n);  // gausslobatto.jl:34
+        return FGQ_EDOMAIN;
+    }
+    if (!x_dev || !w_dev || !workspace_dev) {
+        set_error("null pointer");
+        return FGQ_EINVAL;
+    }
+    return endpoint_rule_device(2, n, x_dev, w_dev, workspace_dev, as_stream(stream));
+}
+
+// ---- host-returning drop-ins --------------------------------------------------------------------
+
+static int jacobi_family_host(int which, int64_t n, double a, double b, double* x, double* w) {
+    if (n == 0) return FGQ_OK;
+    if (!x || !w) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    HostPathLock lock;
+    void *ws, *out;
+    FGQ_TRY(scratch_device((size_t)fgq_gaussjacobi_workspace_bytes(n), 6, &ws));
+    FGQ_TRY(scratch_device((size_t)n * 16 + 64, 0, &out));
+    cudaStream_t st;
+    FGQ_TRY(scratch_stream(0, &st));
+    double* xd = (double*)out;
+    double* wd = xd + n + (n & 1);
+    int rc;
+    if (which == 0) rc = fgq_gaussjacobi_device(n, a, b, 0, n, xd, wd, ws, (void*)st);
+    else if (which == 1) rc = fgq_gaussradau_device(n, xd, wd, ws, (void*)st);
+    else rc = fgq_gausslobatto_device(n, xd, wd, ws, (void*)st);
+    if (rc != FGQ_OK) return rc;
+    FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    FGQ_CUDA_TRY(cudaStreamSynchronize(st));
+    return FGQ_OK;
+}
+
+extern "C" int fgq_gaussjacobi_host(int64_t n, double a, double b, double* x, double* w) {
+    clear_status();
+    if (n < 0) return jacobi_check_args(n, a, b);
+    return jacobi_family_host(0, n, a, b, x, w);
+}
+extern "C" int fgq_gaussradau_host(int64_t n, double* x, double* w) {
+    clear_status();
+    if (n <= 0) {
+        set_error("DomainError(%lld): Input n must be a positive integer", (long long)n);
+        return FGQ_EDOMAIN;
+    }
+    return jacobi_family_host(1, n, 0, 0, x, w);
+}
+extern "C" int fgq_gausslobatto_host(int64_t n, double* x, double* w) {
+    clear_status();
+    if (n <= 1) {
+        set_error("DomainError(%lld): Lobatto undefined for n <= 1.", (long long)n);
+        return FGQ_EDOMAIN;
+    }
+    return jacobi_family_host(2, n, 0, 0, x, w);
+}
+
+// sweeps[2] (right, left), terms[2] (series terms kept in the last evaluation): for tests/reporting
+extern "C" int fgq_gaussjacobi_stats(const void* workspace_dev, int* sweeps, int* terms) {
+    clear_status();
+    if (!workspace_dev || !sweeps || !terms) return FGQ_EINVAL;
+    JacobiState h;
+    FGQ_CUDA_TRY(cudaMemcpy(&h, workspace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 2; ++k) {
+        sweeps[k] = h.sweeps[k];
+        terms[k] = h.terms[k][h.sweeps[k] < 11 ? h.sweeps[k] : 10];
+    }
+    return FGQ_OK;
+}
+
+// host-planned Bessel pieces, exported for tests (test_besselroots.jl:7-12)
+extern "C" int fgq_approx_besselroots(double nu, int64_t n, double* x) {
+    clear_status();
+    if (n < 0) {
+        set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);  // besselroots.jl:41-43
+        return FGQ_EDOMAIN;
+    }
+    if (n > 0 && !x) return FGQ_EINVAL;
+    approx_besselroots(nu, (int)n, x);
+    return FGQ_OK;
+}
+extern "C" double fgq_besselj(double nu, double x) { return besselj_real(nu, x); }

@@ -80,6 +80,38 @@ int fgq_gausslegendre_batch_device(int64_t nrules, const int32_t* n_i_dev,
 int fgq_gausslegendre_batch_host(int64_t nrules, const int32_t* n_i, const int64_t* offsets,
                                  double* x, double* w);
 
+/* ---- Gauss-Jacobi: gaussjacobi(n, a, b) — src/gaussjacobi.jl:23-55,157-667 ------------------ */
+
+/* Asymptotic branch jacobi_asy (n > 100, max(a,b) < 5: gaussjacobi.jl:48-49): Hale-Townsend
+ * interior expansion + Newton on the device, 2 x 10 boundary nodes planned on the host.
+ *   n < 0, min(a,b) <= -1          -> FGQ_EDOMAIN  (:26-27, :44-45)
+ *   a == b == 0                    -> the Legendre path (:28-29)
+ *   |a| == |b| == 1/2              -> FGQ_ENOTIMPL (Chebyshev closed forms, :30-39; next row)
+ *   n <= 100, or max(a,b) >= 5     -> FGQ_ENOTIMPL (jacobi_rec / Golub-Welsch, :46-53) */
+int fgq_gaussjacobi_host(int64_t n, double a, double b, double* x, double* w);
+int64_t fgq_gaussjacobi_workspace_bytes(int64_t n);
+/* Device-resident: the whole rule is solved on the current device (Newton stopping rule and series
+ * truncation are global); output indices [lo, hi) go to x_dev/w_dev[0 .. hi-lo).  Enqueues a fixed
+ * sequence of launches; no host synchronisation. */
+int fgq_gaussjacobi_device(int64_t n, double a, double b, int64_t lo, int64_t hi, double* x_dev,
+                           double* w_dev, void* workspace_dev, void* stream);
+/* Newton sweeps (before the extra one) and series terms kept, for the right/left half. */
+int fgq_gaussjacobi_stats(const void* workspace_dev, int* sweeps2, int* terms2);
+
+/* gaussradau(n) — src/gaussradau.jl:31-49: gaussjacobi(n-1, 0, 1), w/(1+x), x[0] = -1, w[0] = 2/n^2.
+ * gausslobatto(n) — src/gausslobatto.jl:31-52: gaussjacobi(n-2, 1, 1), w/(1-x^2), ends +-1.
+ * n <= 0 (Radau) / n <= 1 (Lobatto) -> FGQ_EDOMAIN; inner rule with <= 100 nodes -> FGQ_ENOTIMPL.
+ * workspace: fgq_gaussjacobi_workspace_bytes(n). */
+int fgq_gaussradau_host(int64_t n, double* x, double* w);
+int fgq_gausslobatto_host(int64_t n, double* x, double* w);
+int fgq_gaussradau_device(int64_t n, double* x_dev, double* w_dev, void* workspace_dev, void* stream);
+int fgq_gausslobatto_device(int64_t n, double* x_dev, double* w_dev, void* workspace_dev, void* stream);
+
+/* approx_besselroots(nu, n) — src/besselroots.jl:23-67 (host-planned; 12-digit zeros of J_nu). */
+int fgq_approx_besselroots(double nu, int64_t n, double* x);
+/* J_nu(x), real order, moderate x: the host planner's stand-in for the reference's besselj. */
+double fgq_besselj(double nu, double x);
+
 /* ---- Gauss-Hermite: gausshermite(n; normalize) — src/gausshermite.jl:28-89,171-323 ---------- */
 
 /* Asymptotic (Airy) + Newton path, n > 200 (gausshermite.jl:49-50).  n < 0 -> FGQ_EDOMAIN (:38);

@@ -1,0 +1,55 @@
+"""CPU tests: the Jacobi/Radau/Lobatto oracle (numpy + AMOS besselj through scipy) against the
+reference's golden values for the asymptotic branch (test/test_gaussjacobi.jl, test_besselroots.jl)."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy.special import beta, jv
+
+from oracle import jacobi_oracle as jo
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "jacobi_reference_tests.json")))
+
+
+def _at(arr, i):
+    i = int(i)
+    return arr[i - 1] if i > 0 else arr[i]
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: f"n{c['n']}_{c['a']}_{c['b']}")
+def test_golden_values(case):
+    x, w = jo.gaussjacobi(case["n"], case["a"], case["b"])
+    assert len(x) == case["n"]
+    for i, v in case["x"].items():
+        assert abs(_at(x, i) - v) < GOLD["tol"]
+    for i, v in case["w"].items():
+        assert abs(_at(w, i) - v) < GOLD["tol"]
+    if "exp_integral" in case:
+        assert abs(np.dot(w, np.exp(x)) - case["exp_integral"]) < 1.5e-8 * case["exp_integral"]
+    if "sum_w" in case:
+        assert abs(w.sum() - 2 ** (case["a"] + 1) / (case["a"] + 1)) < GOLD["tol"]
+    assert np.all(np.diff(x) > 0)
+
+
+def test_besselroots():
+    # test/test_besselroots.jl:7-12
+    for nu in np.arange(0, 5.01, 0.1):
+        assert np.max(np.abs(jv(nu, jo.approx_besselroots(float(nu), 10)))) < 1e-11
+
+
+def test_radau_lobatto_structure():
+    x, w = jo.gaussradau(1001)
+    assert x[0] == -1.0 and abs(w.sum() - 2) < 1e-13 and abs(np.dot(w, x ** 3)) < 1e-13
+    x, w = jo.gausslobatto(1002)
+    assert x[0] == -1.0 and x[-1] == 1.0 and abs(w.sum() - 2) < 1e-13 and abs(np.dot(w, x * x) - 2 / 3) < 1e-13
+
+
+def test_large_n_continues_past_the_reference_bounds_error():
+    """For boundary angles below ~6e-6 (n > ~5.1e6) the reference's nck_mat(floor(1.25 kmax)) is
+    too small for kmax <= 3 and gaussjacobi raises BoundsError (gaussjacobi.jl:641,656-667); the
+    oracle (and the library) use the same binomials and simply continue.  Check the invariant."""
+    x, w = jo.gaussjacobi(6 * 10 ** 6, 0.3, -0.7)
+    assert abs(w.sum() - 2 ** 0.6 * beta(1.3, 0.3)) < 1e-13
+    assert np.all(np.diff(x) > 0)
