@@ -11,6 +11,8 @@ from .api import (  # noqa: F401
     gaussjacobi_device,
     gausslobatto,
     gaussradau,
+    gausslaguerre,
+    gausslaguerre_device,
     gausshermite,
     gausshermite_device,
     gausslegendre,

@@ -48,6 +48,10 @@ SIGNATURES = {
     "fgq_gausshermite_workspace_bytes": (_i64, [_i64]),
     "fgq_gausshermite_device": (ctypes.c_int, [_i64, ctypes.c_int, _i64, _i64, _vp, _vp, _vp, _vp]),
     "fgq_gausshermite_sweeps": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int)]),
+    "fgq_gausslaguerre_host": (ctypes.c_int, [_i64, ctypes.c_double, ctypes.c_int, _vp, _vp, _i64p]),
+    "fgq_gausslaguerre_workspace_bytes": (_i64, [_i64]),
+    "fgq_gausslaguerre_device": (ctypes.c_int, [_i64, ctypes.c_double, _vp, _vp, _vp, _vp]),
+    "fgq_gausslaguerre_stats": (ctypes.c_int, [_vp, _i64p, _i64p, _i64p, _i64p]),
     "fgq_rule_moments_device": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "fgq_measure_dfma_peak": (ctypes.c_int, [_dp]),
     "fgq_measure_store_peak": (ctypes.c_int, [_i64, _dp]),

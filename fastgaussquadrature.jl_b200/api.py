@@ -295,6 +295,44 @@ def gausshermite_device(n, *, normalize: bool = False, stream=None):
     return x, w, ws
 
 
+# --------------------------------------------------------------------------------------------
+# Gauss-Laguerre  (reference src/gausslaguerre.jl:1,23,59-96)
+# --------------------------------------------------------------------------------------------
+
+def gausslaguerre(n, alpha=0.0, *, reduced: bool = False):
+    """``gausslaguerre(n[, α]; reduced=false) -> x, w`` (reference src/gausslaguerre.jl:1,23,59).
+
+    α <= -1 or n < 0 raise DomainError (:60-65); n == 0 returns empty arrays (:69).  The device
+    path is the explicit-asymptotics branch (n >= 128, α < 5); smaller n / larger α raise
+    NotImplementedOnDevice.  ``reduced=True`` drops the tail of underflowed weights."""
+    n = _as_int(n)
+    alpha = float(alpha)
+    if alpha <= -1:
+        raise DomainError(f"DomainError({alpha}): The Laguerre parameter α ≤ -1 corresponds to a nonintegrable weight function")
+    if n < 0:
+        raise DomainError(f"DomainError({n}): gausslaguerre({n},{alpha}) not defined: n must be positive.")
+    x, w = _host_pair(n, False)
+    if n == 0:
+        return x, w
+    n_out = ctypes.c_int64(0)
+    check(lib().fgq_gausslaguerre_host(n, alpha, int(bool(reduced)), _ptr(x), _ptr(w), ctypes.byref(n_out)))
+    if reduced:
+        return x[:n_out.value].copy(), w[:n_out.value].copy()
+    return x, w
+
+
+def gausslaguerre_device(n, alpha=0.0, stream=None):
+    """Device-resident ``gausslaguerre``: (x, w, workspace) as torch CUDA tensors."""
+    import torch
+    n = _as_int(n)
+    L = lib()
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    w = torch.empty(n, dtype=torch.float64, device="cuda")
+    ws = torch.empty(int(L.fgq_gausslaguerre_workspace_bytes(max(n, 0))) + 16, dtype=torch.uint8, device="cuda")
+    check(L.fgq_gausslaguerre_device(n, float(alpha), x.data_ptr(), w.data_ptr(), ws.data_ptr(), _stream_ptr(stream)))
+    return x, w, ws
+
+
 def rule_moments_device(shard: LegendreShard, stream=None):
     """(sum w, sum w x^2) of this rank's shard as a 2-element CUDA tensor (a fused-reduction
     consumer; callers all-reduce it across ranks for the Σw = 2, ∫x² = 2/3 check)."""

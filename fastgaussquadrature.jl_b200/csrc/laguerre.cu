@@ -1,0 +1,555 @@
+// laguerre.cu — Gauss-Laguerre nodes/weights by explicit asymptotic expansions, n >= 128, alpha < 5.
+//
+// Replaces, on the B200:
+//   gausslaguerre dispatch              src/gausslaguerre.jl:59-96
+//   gausslaguerre_asy (T = -1)          src/gausslaguerre.jl:110-261
+//   gl_bulk / gl_bessel / gl_airy       src/gausslaguerre.jl:273-382
+//   sum_adaptive, gl_bulk_solve_t       src/gausslaguerre.jl:400-427
+//   region evaluators, compute_airy_root    src/gausslaguerre.jl:429-529
+//   gl_rec_newton, evalLaguerreRec (recompute hook only)   src/gausslaguerre.jl:547-579,625-641
+//
+// The reference walks k = 1..n in one scalar loop and hands over Bessel -> bulk -> Airy at the first
+// k where the next region's error estimate wins.  Every node's value depends only on (n, alpha, k)
+// and on the region it falls in, so here the two hand-over indices are found by "first index
+// where" reductions (atomicMin) over candidate ranges, then one thread per node evaluates the
+// region(s) it needs.  Nodes whose error estimate exceeds 1e-13 are appended to a list and redone
+// by Newton on the O(n) recurrence, one thread per flagged node (about 35 nodes at n = 1e6).
+#include <math.h>
+
+#include "airy.cuh"
+#include "bessel.cuh"
+#include "common.cuh"
+#include "jacobi_plan.h"
+
+namespace fgq {
+
+struct LaguerreParams {
+    int64_t n;
+    double alpha;
+    int alpha0;          // alpha == 0: the reference switches to its specialised formulas
+    double d;            // 1 / (4n + 2 alpha + 2)
+    int64_t k_airy;      // floor(0.9 n)
+    double jak_head[20]; // approx_besselroots(alpha, .) for k <= head_count (table / Piessens)
+    int head_count;
+    double mc[7];        // McMahon coefficients a1..a13 for this alpha (besselroots.jl:79-111)
+    double mu_m1;        // 4 alpha^2 - 1
+    BesselOrder jorder;  // order alpha - 1
+    double pn0;          // 1/sqrt(gamma(alpha+1))           (evalLaguerreRec :628)
+    double wnorm;        // (n^2 + alpha n)^(-1/2)           (gl_rec_newton :575)
+    double xmax;         // 4n + 2 alpha + 2
+};
+
+struct LaguerreState {
+    unsigned long long k_b;   // first k where the bulk expansion beats the Bessel one (sentinel n+1)
+    unsigned long long k_a;   // first k >= max(k_b+1, k_airy) where the Airy expansion beats the bulk one
+    unsigned long long n_out; // reduced rule: number of nodes before the first underflowed weight
+    unsigned int n_flagged;
+    unsigned int warn;
+};
+
+// Julia's max/min propagate NaN (CUDA's fmax/fmin drop it)
+__device__ __forceinline__ double jl_max(double a, double b) { return (a != a || b != b) ? a + b : fmax(a, b); }
+__device__ __forceinline__ double jl_min(double a, double b) { return (a != a || b != b) ? a + b : fmin(a, b); }
+
+__device__ __forceinline__ double evalpoly2(double x, double c0, double c1) { return fma(x, c1, c0); }
+
+template <int N>
+__device__ __forceinline__ double evalpoly(double x, const double (&c)[N]) {
+    double r = c[N - 1];
+#pragma unroll
+    for (int i = N - 2; i >= 0; --i) r = fma(x, r, c[i]);
+    return r;
+}
+
+// sum_adaptive (:400-409)
+template <int N>
+__device__ __forceinline__ void sum_adaptive(const double (&v)[N], double& z, double& delta) {
+    z = v[0];
+    int i = 0;
+    while (i < N - 1 && fabs(v[i + 1]) < fabs(v[i])) {
+        i += 1;
+        z += v[i];
+    }
+    delta = fabs(v[i + 1 < N ? i + 1 : N - 1]);
+}
+
+// besselroots.jl:74-116 with the alpha-only coefficients planned on the host
+__device__ __forceinline__ double mcmahon_dev(const LaguerreParams& p, int64_t k) {
+    const double b = 0.25 * (2 * p.alpha + 4 * (double)k - 1) * 3.141592653589793;
+    const double b2 = b * b;
+    return b - p.mu_m1 * (((((((p.mc[6] / b2 + p.mc[5]) / b2 + p.mc[4]) / b2 + p.mc[3]) / b2 + p.mc[2]) / b2 + p.mc[1]) / b2 + p.mc[0]) / b);
+}
+
+__device__ __forceinline__ double laguerre_jak(const LaguerreParams& p, int64_t k) {
+    return k <= p.head_count ? p.jak_head[k - 1] : mcmahon_dev(p, k);
+}
+
+// gl_bulk_solve_t (:411-427)
+__device__ __forceinline__ double gl_bulk_solve_t(const LaguerreParams& p, int64_t k, unsigned int* warn) {
+    const double PI = 3.141592653589793;
+    const double pt = (double)(4 * p.n - 4 * k + 3) * p.d;
+    double t = PI * PI / 16 * ((pt - 1) * (pt - 1));
+    double diff = 100;
+    int iter = 0;
+    while (fabs(diff) > 100 * 2.220446049250313e-16 && iter < 20) {
+        iter += 1;
+        diff = (pt * PI + 2 * sqrt(t - t * t) - acos(2 * t - 1)) * sqrt(t / (1 - t)) / 2;
+        t -= diff;
+    }
+    if (iter == 20 && warn) *warn |= FGQ_WARN_NEWTON_MAXITER;
+    return t;
+}
+
+// gausslaguerre_asy_bulk / asy0_bulk (:429-465) with gl_bulk (:273-322)
+__device__ void laguerre_bulk(const LaguerreParams& p, int64_t k, double& xk, double& wk, double& delta,
+                              unsigned int* warn) {
+    const double PI = 3.141592653589793;
+    const double d = p.d, al = p.alpha;
+    const double t = gl_bulk_solve_t(p, k, warn);
+    const double tinv = 1.0 / (1 - t);
+    const double _t = (1 - t) / t, _t2 = _t * _t, _t3 = _t2 * _t;
+    const double d2 = d * d, d4 = d2 * d2, d6 = d4 * d2;
+    double xs[4], ws[3];
+    const double tm1 = t - 1;
+    ws[0] = d2 / 6 * (2 * t + 3) / (tm1 * tm1 * tm1);
+    if (p.alpha0) {
+        { const double c[3] = {-4, -4, 5}; xs[0] = -d / 12 * evalpoly(tinv, c); }
+        { const double c[7] = {224, -336, -16, -576, 2814, -3815, 1600}; xs[1] = d2 * d * _t / 720 * evalpoly(tinv, c); }
+        { const double c[11] = {-285696, 714240, -516864, -13760, -17680, -1727136, 16131880, -48469876, 66424575, -43122800, 10797500};
+          xs[2] = -d4 * d / 181440 * _t2 * evalpoly(tinv, c); }
+        { const double c[15] = {210677760, -737372160, 916264704, -426423552, -10338048, 2863616, -26285280, -3062050944.0,
+                                43651480992.0, -212307298152.0, 518401904799.0, -714465642135.0, 566519158800.0, -241928673000.0, 43222750000.0};
+          xs[3] = d6 * d / 10886400 * _t3 * evalpoly(tinv, c); }
+        { const double c[9] = {0, 0, 112, 32, 1712, -12408, 27517, -24860, 8000}; ws[1] = d4 / 720 * _t2 * evalpoly(tinv, c); }
+        { const double c[13] = {0, 0, -71424, 159744, 20640, 28480, 4300160, -50986344, 201908326, -386872990, 393326325, -204917300, 43190000};
+          ws[2] = -d6 * _t3 / 90720 * evalpoly(tinv, c); }
+    } else {
+        const double a2 = al * al;
+        {
+            const double c1 = evalpoly2(a2, -4, 12);
+            const double c[3] = {c1, -4, 5};
+            xs[0] = -evalpoly(tinv, c) * d / 12;
+        }
+        {
+            const double q1[3] = {224, -960, 480}, q2[3] = {7, -30, 15};
+            const double c1 = evalpoly(a2, q1), c2 = evalpoly(a2, q2);
+            const double c[7] = {c1, -48 * c2, -16, -576, 2814, -3815, 1600};
+            xs[1] = d2 * d * _t / 720 * evalpoly(tinv, c);
+        }
+        {
+            const double q1[4] = {-285696, 1354752, -967680, 193536}, q2[4] = {-31, 147, -105, 21}, q3[4] = {-1346, 6405, -4620, 945};
+            const double q4[3] = {43, -126, 63}, q5[3] = {-221, -630, 315};
+            const double c1 = evalpoly(a2, q1), c2 = evalpoly(a2, q2), c3 = evalpoly(a2, q3), c4 = evalpoly(a2, q4), c5 = evalpoly(a2, q5);
+            const double c[11] = {c1, -23040 * c2, 384 * c3, -320 * c4, 80 * c5, -1727136, 16131880, -48469876, 66424575, -43122800, 10797500};
+            xs[2] = -d4 * d / 181440 * _t2 * evalpoly(tinv, c);
+        }
+        {
+            const double q1[5] = {210677760, -1028505600, 812851200, -232243200, 24883200}, q2[5] = {127, -620, 490, -140, 15};
+            const double q3[5] = {1193053, -5826660, 4613070, -1324260, 143325}, q4[5] = {555239, -2716980, 2163630, -631260, 70875};
+            const double q5[4] = {-641, 2960, -2155, 450}, q6[4] = {-1598, 17685, -13905, 3375};
+            const double q7[3] = {-7823, -9042, 4521}, q8[3] = {15948182, -206850, 103425}, q9[3] = {64957561, -24000, 12000};
+            const double c1 = evalpoly(a2, q1), c2 = evalpoly(a2, q2), c3 = evalpoly(a2, q3), c4 = evalpoly(a2, q4), c5 = evalpoly(a2, q5);
+            const double c6 = evalpoly(a2, q6), c7 = evalpoly(a2, q7), c8 = evalpoly(a2, q8), c9 = evalpoly(a2, q9);
+            const double c[15] = {c1, -5806080 * c2, 768 * c3, -768 * c4, 16128 * c5, -1792 * c6, 3360 * c7, -192 * c8, 672 * c9,
+                                  -212307298152.0, 518401904799.0, -714465642135.0, 566519158800.0, -241928673000.0, 43222750000.0};
+            xs[3] = d6 * d / 10886400 * _t3 * evalpoly(tinv, c);
+        }
+        {
+            const double q1[3] = {7, -30, 15};
+            const double c1 = evalpoly(a2, q1);
+            const double c[9] = {0, 0, 16 * c1, 32, 1712, -12408, 27517, -24860, 8000};
+            ws[1] = d4 * _t2 / 720 * evalpoly(tinv, c);
+        }
+        {
+            const double q1[4] = {-31, 147, -105, 21}, q2[4] = {-416, 1995, -1470, 315}, q3[3] = {43, -126, 63};
+            const double q4[3] = {-89, -378, 189}, q5[3] = {53752, -630, 315};
+            const double c1 = evalpoly(a2, q1), c2 = evalpoly(a2, q2), c3 = evalpoly(a2, q3), c4 = evalpoly(a2, q4), c5 = evalpoly(a2, q5);
+            const double c[13] = {0, 0, 2304 * c1, -384 * c2, 480 * c3, -320 * c4, 80 * c5, -50986344, 201908326, -386872990, 393326325, -204917300, 43190000};
+            ws[2] = -d6 * _t3 / 90720 * evalpoly(tinv, c);
+        }
+    }
+    double xdelta, wdelta;
+    sum_adaptive(xs, xk, xdelta);
+    sum_adaptive(ws, wk, wdelta);
+    xk += t / d;
+    double wfactor = exp(-xk) * 2 * PI * sqrt(t / (1 - t));
+    if (!p.alpha0) wfactor = pow(xk, al) * exp(-xk) * 2 * PI * sqrt(t / (1 - t));
+    wk = wfactor * (1 + wk);
+    wdelta *= wfactor;
+    delta = jl_max(xdelta, wdelta);
+}
+
+// gausslaguerre_asy_bessel / asy0_bessel (:468-506) with gl_bessel (:325-367)
+__device__ void laguerre_bessel(const LaguerreParams& p, double jak, double& xk, double& wk, double& delta) {
+    const double d = p.d, al = p.alpha;
+    const double j2 = jak * jak;
+    const double d2 = d * d, d4 = d2 * d2, d8 = d4 * d4;
+    double xdelta, wdelta;
+    if (p.alpha0) {
+        double xs[5], ws[5];
+        { const double c[2] = {-2, 1}; xs[0] = d2 * evalpoly(j2, c) / 3; }
+        { const double c[3] = {94, -57, 11}; xs[1] = d4 * evalpoly(j2, c) / 45; }
+        { const double c[4] = {-48308, 28102, -6516, 657}; xs[2] = d4 * d2 * evalpoly(j2, c) / 2835; }
+        { const double c[5] = {12059918, -6605817, 1456807, -172740, 10644}; xs[3] = d8 * evalpoly(j2, c) / 42525; }
+        { const double c[6] = {-11427291076.0, 6028914206.0, -1248722004, 138902061, -9908262, 410649}; xs[4] = d8 * d2 * evalpoly(j2, c) / 1403325; }
+        { const double c[2] = {-1, 1}; ws[0] = 2 * d2 * evalpoly(j2, c) / 3; }
+        { const double c[3] = {94, -114, 33}; ws[1] = d4 * evalpoly(j2, c) / 45; }
+        { const double c[4] = {-12077, 14051, -4887, 657}; ws[2] = 4 * d4 * d2 * evalpoly(j2, c) / 2835; }
+        { const double c[5] = {12059918, -13211634, 4370421, -690960, 53220}; ws[3] = d8 * evalpoly(j2, c) / 42525; }
+        { const double c[6] = {-5713645538.0, 6028914206.0, -1873083006, 277804122, -24770655, 1231947}; ws[4] = 2 * d8 * d2 * evalpoly(j2, c) / 1403325; }
+        sum_adaptive(xs, xk, xdelta);
+        sum_adaptive(ws, wk, wdelta);
+    } else {
+        const double a2 = al * al;
+        double xs[4], ws[4];
+        {
+            const double c1 = evalpoly2(a2, -2, 2);
+            const double cx[2] = {c1, 1}, cw[2] = {c1, 2};
+            xs[0] = d2 * evalpoly(j2, cx) / 3;
+            ws[0] = d2 * evalpoly(j2, cw) / 3;
+        }
+        {
+            const double q1[3] = {94, -140, 46};
+            const double c1 = evalpoly(a2, q1), c2 = evalpoly2(a2, -19, 11);
+            const double cx[3] = {c1, 3 * c2, 11}, cw[3] = {c1, 6 * c2, 33};
+            xs[1] = d4 * evalpoly(j2, cx) / 45;
+            ws[1] = d4 * evalpoly(j2, cw) / 45;
+        }
+        {
+            const double q1[4] = {-12077, 19887, -9303, 1493}, q2[3] = {14051, -10750, 2459};
+            const double c1 = evalpoly(a2, q1), c2 = evalpoly(a2, q2), c3 = evalpoly2(a2, -181, 73);
+            const double cx[4] = {4 * c1, 2 * c2, 36 * c3, 657}, cw[4] = {c1, c2, 27 * c3, 657};
+            xs[2] = d4 * d2 * evalpoly(j2, cx) / 2835;
+            ws[2] = 4 * d4 * d2 * evalpoly(j2, cw) / 2835;
+        }
+        {
+            const double q1[5] = {6029959, -10087180, 5095482, -1146220, 107959}, q2[4] = {-2201939, 1678761, -507801, 63299};
+            const double q3[3] = {1456807, -729422, 125671};
+            const double c1 = evalpoly(a2, q1), c2 = evalpoly(a2, q2), c3 = evalpoly(a2, q3), c4 = evalpoly2(a2, -2879, 887);
+            const double cx[5] = {2 * c1, 3 * c2, c3, 60 * c4, 10644}, cw[5] = {2 * c1, 6 * c2, 3 * c3, 240 * c4, 53220};
+            xs[3] = d8 * evalpoly(j2, cx) / 42525;
+            ws[3] = d8 * evalpoly(j2, cw) / 42525;
+        }
+        sum_adaptive(xs, xk, xdelta);
+        sum_adaptive(ws, wk, wdelta);
+    }
+    const double xfactor = jak * jak * d;
+    xk = xfactor * (1 + xk);
+    xdelta *= xfactor;
+    const double J = besselj_dev(p.jorder, jak);
+    double wfactor = 4 * d * exp(-xk) / (J * J);
+    if (!p.alpha0) wfactor = 4 * d * pow(xk, al) * exp(-xk) / (J * J);
+    wk = wfactor * (1 + wk);
+    wdelta *= wfactor;
+    delta = jl_max(xdelta, wdelta);
+}
+
+__constant__ double c_lag_airy_roots[11] = {
+    -2.338107410459767, -4.08794944413097, -5.520559828095551, -6.786708090071759,
+    -7.944133587120853, -9.022650853340981, -10.04017434155809, -11.00852430373326,
+    -11.93601556323626, -12.828776752865757, -13.69148903521072};
+
+// gausslaguerre_asy_airy (:519-529), compute_airy_root (:508-517), gl_airy (:370-382)
+__device__ void laguerre_airy(const LaguerreParams& p, int64_t k, double& xk, double& wk, double& delta) {
+    const double PI = 3.141592653589793;
+    const double d = p.d, al = p.alpha;
+    const int64_t index = p.n - k + 1;
+    double ak;
+    if (index <= 11) {
+        ak = c_lag_airy_roots[index - 1];
+    } else {
+        const double t = 3 * PI / 2 * ((double)index - 0.25);
+        const double c[5] = {6967296, 725760, -967680, 6478500, -10856875};
+        ak = -pow(t, 2.0 / 3.0) * evalpoly(1.0 / (t * t), c) / 6967296;
+    }
+    const double cbrt_d = cbrt(d), cbrt_d2 = cbrt_d * cbrt_d;
+    const double ak2 = ak * ak, ak3 = ak2 * ak, ak4 = ak2 * ak2;
+    double xs[3];
+    xs[0] = 1 / d + ak * cbrt(4.0) / cbrt_d;
+    xs[1] = ak2 * cbrt(16.0) / 5 * cbrt_d + (11.0 / 35 - al * al - 12.0 / 175 * ak3) * d +
+            (16.0 / 1575 * ak + 92.0 / 7875 * ak4) * cbrt(4.0) * d * cbrt_d2;
+    xs[2] = -(15152.0 / 3031875 * ak4 * ak + 1088.0 / 121275 * ak2) * cbrt(2.0) * d * d * cbrt_d;
+    double xdelta;
+    sum_adaptive(xs, xk, xdelta);
+    double ai, aip;
+    airy_neg(ak, ai, aip);
+    wk = 1.5874010519681994 * pow(xk, al + 1.0 / 3.0) * exp(-xk) / (aip * aip);  // 4^(1/3)
+    const double wdelta = fabs(wk);
+    delta = jl_max(xdelta, wdelta);
+}
+
+constexpr int LAG_THREADS = 128;
+
+// first k where delta_bulk < delta_bessel (:138-151)
+__global__ void __launch_bounds__(LAG_THREADS)
+laguerre_handover_bessel_kernel(const LaguerreParams p, LaguerreState* st) {
+    const int64_t k = 1 + (int64_t)blockIdx.x * LAG_THREADS + threadIdx.x;
+    if (k > p.n) return;
+    if ((unsigned long long)k >= *((volatile unsigned long long*)&st->k_b)) return;  // already beaten by a smaller k
+    double xb, wb, db, xu, wu, du;
+    laguerre_bessel(p, laguerre_jak(p, k), xb, wb, db);
+    laguerre_bulk(p, k, xu, wu, du, nullptr);
+    if (du < db) atomicMin(&st->k_b, (unsigned long long)k);
+}
+
+// first k >= max(k_b + 1, k_airy) where delta_airy < delta_bulk (:201-209)
+__global__ void __launch_bounds__(LAG_THREADS)
+laguerre_handover_airy_kernel(const LaguerreParams p, LaguerreState* st) {
+    const int64_t kb = (int64_t)st->k_b;
+    const int64_t start = kb + 1 > p.k_airy ? kb + 1 : p.k_airy;
+    const int64_t k = (start < 1 ? 1 : start) + (int64_t)blockIdx.x * LAG_THREADS + threadIdx.x;
+    if (k > p.n) return;
+    double xu, wu, du, xa, wa, da;
+    laguerre_bulk(p, k, xu, wu, du, nullptr);
+    laguerre_airy(p, k, xa, wa, da);
+    if (da < du) atomicMin(&st->k_a, (unsigned long long)k);
+}
+
+// One thread per node: the region walk of gausslaguerre_asy (:138-253) with the hand-over indices known.
+__global__ void __launch_bounds__(LAG_THREADS)
+laguerre_nodes_kernel(const LaguerreParams p, LaguerreState* st, double* x, double* w, double* delta_out,
+                      unsigned int* flagged) {
+    const int64_t k = 1 + (int64_t)blockIdx.x * LAG_THREADS + threadIdx.x;
+    if (k > p.n) return;
+    const int64_t kb = (int64_t)st->k_b;  // n + 1 when the Bessel expansion never loses
+    const int64_t ka = (int64_t)st->k_a;  // n + 1 when the bulk expansion never loses
+    unsigned int warn = 0;
+    double xk, wk, delta;
+    if (k <= kb) {
+        // loop A: both expansions are evaluated; Bessel is used except at k_b itself
+        double xb, wb, db, xu, wu, du;
+        laguerre_bessel(p, laguerre_jak(p, k), xb, wb, db);
+        laguerre_bulk(p, k, xu, wu, du, &warn);
+        const bool bulk = (k == kb);
+        xk = bulk ? xu : xb;
+        wk = bulk ? wu : wb;
+        delta = jl_min(db, du);
+    } else if (k < p.k_airy) {
+        laguerre_bulk(p, k, xk, wk, delta, &warn);  // loop B
+    } else if (k <= ka) {
+        // loop C: bulk against Airy; Airy is used at k_a itself
+        double xu, wu, du, xa, wa, da;
+        laguerre_bulk(p, k, xu, wu, du, &warn);
+        laguerre_airy(p, k, xa, wa, da);
+        const bool airy = (k == ka);
+        xk = airy ? xa : xu;
+        wk = airy ? wa : wu;
+        delta = jl_min(da, du);
+    } else {
+        laguerre_airy(p, k, xk, wk, delta);  // loop D
+    }
+    x[k - 1] = xk;
+    w[k - 1] = wk;
+    delta_out[k - 1] = delta;
+    if (delta > 1.0e-13) flagged[atomicAdd(&st->n_flagged, 1u)] = (unsigned int)(k - 1);
+    if (warn) atomicOr(&st->warn, warn);
+}
+
+// evalLaguerreRec (:625-641).  The loop stops early once everything is NaN (absorbing).
+__device__ void eval_laguerre_rec(int64_t n, double alpha, double pn0, double x, double& pn_out, double& pnd_out) {
+    double pnprev = 0.0, pn = pn0, pndprev = 0.0, pnd = 0.0;
+    for (int64_t k = 1; k <= n; ++k) {
+        const double dk = (double)k;
+        const double pnold = pn;
+        pn = (x - 2 * dk - alpha + 1) / sqrt(dk * (alpha + dk)) * pnold - sqrt((dk - 1 + alpha) * (dk - 1) / dk / (dk + alpha)) * pnprev;
+        pnprev = pnold;
+        const double pndold = pnd;
+        pnd = (pnold + (x - 2 * dk - alpha + 1) * pndold) / sqrt(dk * (alpha + dk)) - sqrt((dk - 1 + alpha) * (dk - 1) / dk / (alpha + dk)) * pndprev;
+        pndprev = pndold;
+        if (pn != pn && pnprev != pnprev && pnd != pnd && pndprev != pndprev) break;
+    }
+    pn_out = pn;
+    pnd_out = pnd;
+}
+
+// the recompute hook (:153-162 etc.): gl_rec_newton (:547-579) for every flagged node, accepted only
+// if it stays within 100 delta of the asymptotic value
+__global__ void laguerre_recompute_kernel(const LaguerreParams p, LaguerreState* st, double* x, double* w,
+                                          const double* delta_in, const unsigned int* flagged) {
+    const unsigned int cnt = st->n_flagged;
+    const double eps = 2.220446049250313e-16;
+    for (unsigned int f = blockIdx.x * blockDim.x + threadIdx.x; f < cnt; f += gridDim.x * blockDim.x) {
+        const unsigned int i = flagged[f];
+        const double x0 = x[i];
+        const double delta = delta_in[i];
+        double step = x0, xk = x0, xk_prev = x0, pn_prev = 1.7976931348623157e308, pn_deriv = 0.0;
+        int iter = 0;
+        while (fabs(step) > 40 * eps * xk && iter < 20) {
+            iter += 1;
+            double pn;
+            eval_laguerre_rec(p.n, p.alpha, p.pn0, xk, pn, pn_deriv);
+            if (fabs(pn) >= fabs(pn_prev) * (1 - 50 * eps)) {
+                xk = xk_prev;
+                break;
+            }
+            step = pn / pn_deriv;
+            xk_prev = xk;
+            xk -= step;
+            pn_prev = pn;
+        }
+        if (xk < 0 || xk > p.xmax || iter == 20) atomicOr(&st->warn, (unsigned int)FGQ_WARN_NEWTON_MAXITER);
+        double pn_min1, dummy;
+        eval_laguerre_rec(p.n - 1, p.alpha, p.pn0, xk, pn_min1, dummy);
+        const double wk = p.wnorm / pn_min1 / pn_deriv;
+        if (fabs(xk - x0) < 100 * delta) {
+            x[i] = xk;
+            w[i] = wk;
+        }
+    }
+}
+
+// reduced rule (:163-169 ...): the rule ends before the first weight below 10 floatmin
+__global__ void laguerre_reduced_kernel(int64_t n, const double* w, LaguerreState* st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (fabs(w[i]) < 10 * 2.2250738585072014e-308) atomicMin(&st->n_out, (unsigned long long)i);
+}
+
+}  // namespace fgq
+
+using namespace fgq;
+
+static int laguerre_check(int64_t n, double alpha) {
+    if (!(alpha > -1.0)) {
+        set_error("DomainError(%g): The Laguerre parameter alpha <= -1 corresponds to a nonintegrable weight function", alpha);
+        return FGQ_EDOMAIN;
+    }
+    if (n < 0) {
+        set_error("DomainError(%lld): gausslaguerre(%lld,%g) not defined: n must be positive.", (long long)n, (long long)n, alpha);
+        return FGQ_EDOMAIN;
+    }
+    if (n < 128 || alpha >= 5.0) {
+        set_error("gausslaguerre(%lld,%g): the reference serves n < 128 and alpha >= 5 with closed forms, Golub-Welsch or the "
+                  "recurrence rule (gausslaguerre.jl:70-95), which are not on the device path", (long long)n, alpha);
+        return FGQ_ENOTIMPL;
+    }
+    if (n > 4000000000LL) {
+        set_error("gausslaguerre: n too large");
+        return FGQ_EINVAL;
+    }
+    return FGQ_OK;
+}
+
+static LaguerreParams laguerre_params(int64_t n, double alpha) {
+    LaguerreParams p;
+    p.n = n;
+    p.alpha = alpha;
+    p.alpha0 = alpha == 0.0;
+    p.d = 1.0 / (4 * (double)n + 2 * alpha + 2);
+    p.k_airy = (int64_t)floor(0.9 * (double)n);
+    p.xmax = 4 * (double)n + 2 * alpha + 2;
+    // approx_besselroots(alpha, k_bessel): only the first 20 (alpha = 0) / 6 entries are not McMahon
+    p.head_count = alpha == 0.0 ? 20 : ((-1 <= alpha && alpha <= 5) ? 6 : 0);
+    if (p.head_count) approx_besselroots(alpha, p.head_count, p.jak_head);
+    const double mu = 4 * alpha * alpha;
+    p.mu_m1 = mu - 1;
+    p.mc[0] = 1.0 / 8;
+    p.mc[1] = (7 * mu - 31) / 384;
+    p.mc[2] = 4 * (3779 + mu * (-982 + 83 * mu)) / 61440;
+    p.mc[3] = 6 * (-6277237 + mu * (1585743 + mu * (-153855 + 6949 * mu))) / 20643840;
+    p.mc[4] = 144 * (2092163573.0 + mu * (-512062548 + mu * (48010494 + mu * (-2479316 + 70197 * mu)))) / 11890851840.0;
+    p.mc[5] = 720 * (-8249725736393.0 + mu * (1982611456181.0 + mu * (-179289628602.0 + mu * (8903961290.0 + mu * (-287149133 + mu * 5592657))))) / 10463949619200.0;
+    p.mc[6] = 576 * (423748443625564327.0 + mu * (-100847472093088506.0 + mu * (8929489333108377.0 + mu * (-426353946885548.0 + mu * (13172003634537.0 + mu * (-291245357370.0 + mu * 4148944183.0)))))) / 13059009124761600.0;
+    // order alpha - 1 of besselj(alpha - 1, jak) (:484); alpha = 0 -> J_{-1} = -J_1 (:501)
+    double nu = alpha - 1;
+    p.jorder.sign = 1.0;
+    if (nu < 0 && nu == floor(nu)) {
+        const double m = -nu;
+        p.jorder.sign = fmod(m, 2.0) == 0.0 ? 1.0 : -1.0;
+        nu = m;
+    }
+    p.jorder.nu = nu;
+    p.jorder.rgamma = 1.0 / tgamma(nu + 1);
+    const double c = (nu / 2 + 0.25) * 3.141592653589793;
+    p.jorder.cosc = cos(c);
+    p.jorder.sinc = sin(c);
+    p.pn0 = 1 / sqrt(tgamma(alpha + 1));
+    p.wnorm = pow((double)n * (double)n + alpha * (double)n, -0.5);
+    return p;
+}
+
+extern "C" int64_t fgq_gausslaguerre_workspace_bytes(int64_t n) {
+    if (n < 0) return 0;
+    return 256 + 8 * n + 4 * n + 64;
+}
+
+extern "C" int fgq_gausslaguerre_device(int64_t n, double alpha, double* x_dev, double* w_dev,
+                                        void* workspace_dev, void* stream) {
+    clear_status();
+    FGQ_TRY(laguerre_check(n, alpha));
+    if (!x_dev || !w_dev || !workspace_dev) {
+        set_error("null pointer");
+        return FGQ_EINVAL;
+    }
+    if (alpha * alpha / (double)n > 1) add_warning(FGQ_WARN_LARGE_ALPHA);  // :117-119
+    cudaStream_t st = as_stream(stream);
+    const LaguerreParams p = laguerre_params(n, alpha);
+    LaguerreState* state = (LaguerreState*)workspace_dev;
+    double* delta = (double*)((char*)workspace_dev + 256);
+    unsigned int* flagged = (unsigned int*)(delta + n);
+    LaguerreState init;
+    init.k_b = (unsigned long long)(n + 1);
+    init.k_a = (unsigned long long)(n + 1);
+    init.n_out = (unsigned long long)n;
+    init.n_flagged = 0;
+    init.warn = 0;
+    FGQ_CUDA_TRY(cudaMemcpyAsync(state, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)((n + LAG_THREADS - 1) / LAG_THREADS);
+    laguerre_handover_bessel_kernel<<<blocks, LAG_THREADS, 0, st>>>(p, state);
+    FGQ_LAUNCH_CHECK();
+    // candidates k >= k_airy (the kernel skips those <= k_b)
+    const int64_t cand = n - (p.k_airy < 1 ? 1 : p.k_airy) + 1;
+    laguerre_handover_airy_kernel<<<(unsigned)((cand + LAG_THREADS - 1) / LAG_THREADS), LAG_THREADS, 0, st>>>(p, state);
+    FGQ_LAUNCH_CHECK();
+    laguerre_nodes_kernel<<<blocks, LAG_THREADS, 0, st>>>(p, state, x_dev, w_dev, delta, flagged);
+    FGQ_LAUNCH_CHECK();
+    laguerre_recompute_kernel<<<64, 64, 0, st>>>(p, state, x_dev, w_dev, delta, flagged);
+    FGQ_LAUNCH_CHECK();
+    laguerre_reduced_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, w_dev, state);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+// k_b, k_a (n+1 = never), number of recomputed candidates, reduced length; synchronises.
+extern "C" int fgq_gausslaguerre_stats(const void* workspace_dev, int64_t* k_b, int64_t* k_a, int64_t* n_flagged,
+                                       int64_t* n_reduced) {
+    clear_status();
+    if (!workspace_dev) return FGQ_EINVAL;
+    LaguerreState h;
+    FGQ_CUDA_TRY(cudaMemcpy(&h, workspace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    if (k_b) *k_b = (int64_t)h.k_b;
+    if (k_a) *k_a = (int64_t)h.k_a;
+    if (n_flagged) *n_flagged = (int64_t)h.n_flagged;
+    if (n_reduced) *n_reduced = (int64_t)h.n_out;
+    if (h.warn) add_warning((int)h.warn);
+    return FGQ_OK;
+}
+
+extern "C" int fgq_gausslaguerre_host(int64_t n, double alpha, int reduced, double* x, double* w, int64_t* n_out) {
+    clear_status();
+    FGQ_TRY(laguerre_check(n, alpha));
+    if (!x || !w) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    HostPathLock lock;
+    void *ws, *out;
+    FGQ_TRY(scratch_device((size_t)fgq_gausslaguerre_workspace_bytes(n), 6, &ws));
+    FGQ_TRY(scratch_device((size_t)n * 16, 0, &out));
+    cudaStream_t st;
+    FGQ_TRY(scratch_stream(0, &st));
+    double* xd = (double*)out;
+    double* wd = xd + n;
+    FGQ_TRY(fgq_gausslaguerre_device(n, alpha, xd, wd, ws, (void*)st));
+    const int warn0 = fgq_warnings();
+    LaguerreState h;
+    FGQ_CUDA_TRY(cudaMemcpyAsync(&h, ws, sizeof(h), cudaMemcpyDeviceToHost, st));
+    FGQ_CUDA_TRY(cudaStreamSynchronize(st));
+    const int64_t cnt = reduced ? (int64_t)h.n_out : n;
+    FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+    FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+    FGQ_CUDA_TRY(cudaStreamSynchronize(st));
+    if (n_out) *n_out = cnt;
+    add_warning(warn0 | (int)h.warn);
+    return FGQ_OK;
+}

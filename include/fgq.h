@@ -129,6 +129,24 @@ int fgq_gausshermite_device(int64_t n, int normalize, int64_t lo, int64_t hi, do
 /* Newton sweeps the last call on this workspace used (synchronises; for tests/reporting). */
 int fgq_gausshermite_sweeps(const void* workspace_dev, int* sweeps);
 
+/* ---- Gauss-Laguerre: gausslaguerre(n, alpha; reduced) — src/gausslaguerre.jl:59-261,273-529 --- */
+
+/* Explicit asymptotic expansions (gausslaguerre_asy with T = -1, recompute = true: the call at
+ * gausslaguerre.jl:91), n >= 128 and alpha < 5.  alpha <= -1 or n < 0 -> FGQ_EDOMAIN (:60-65);
+ * n < 128 or alpha >= 5 -> FGQ_ENOTIMPL (closed forms / Golub-Welsch / recurrence rule, :70-95).
+ * reduced != 0: only the nodes before the first weight below 10*floatmin are returned (:163-169);
+ * *n_out receives the number of entries written (n when reduced == 0).  Warning bits mirror the
+ * reference's @warn sites (fgq_warnings()). */
+int fgq_gausslaguerre_host(int64_t n, double alpha, int reduced, double* x, double* w, int64_t* n_out);
+int64_t fgq_gausslaguerre_workspace_bytes(int64_t n);
+/* Device-resident: x_dev/w_dev hold all n entries; the reduced length is available through
+ * fgq_gausslaguerre_stats.  Enqueues a fixed sequence of launches; no host synchronisation. */
+int fgq_gausslaguerre_device(int64_t n, double alpha, double* x_dev, double* w_dev, void* workspace_dev,
+                             void* stream);
+/* hand-over indices (1-based; n+1 = never), number of recompute candidates, reduced length. */
+int fgq_gausslaguerre_stats(const void* workspace_dev, int64_t* k_b, int64_t* k_a, int64_t* n_flagged,
+                            int64_t* n_reduced);
+
 /* ---- consumers / checks ------------------------------------------------------------------ */
 
 /* sums_dev[0] += sum w_i, sums_dev[1] += sum w_i x_i^2 over count entries (device buffers;

@@ -25,7 +25,9 @@ _c_dp = ctypes.POINTER(ctypes.c_double)
 
 def build(force: bool = False) -> str:
     """Compile the C oracle (gcc, a few seconds)."""
-    if force or not os.path.exists(_LIB_PATH):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".c")]
+    stale = os.path.exists(_LIB_PATH) and any(os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in srcs)
+    if force or stale or not os.path.exists(_LIB_PATH):
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     return _LIB_PATH
@@ -49,6 +51,10 @@ def lib():
             f = getattr(L, "oracle_gausslegendre_batch" + sfx)
             f.argtypes = [_c_i64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_c_i64), _c_dp, _c_dp]
             f.restype = ctypes.c_int
+        L.oracle_gl_rec_newton.argtypes = [ctypes.c_double, _c_i64, ctypes.c_double, _c_dp, _c_dp]
+        L.oracle_gl_rec_newton.restype = None
+        L.oracle_eval_laguerre_rec.argtypes = [_c_i64, ctypes.c_double, ctypes.c_double, _c_dp, _c_dp]
+        L.oracle_eval_laguerre_rec.restype = None
         L.oracle_set_threads.argtypes = [ctypes.c_int]
         L.oracle_set_threads.restype = ctypes.c_int
         _lib = L
@@ -111,6 +117,14 @@ def gausslegendre_batch(n_i: np.ndarray, twin: bool = False):
     if rc:
         raise RuntimeError(f"oracle_gausslegendre_batch rc={rc}")
     return offsets, x, w
+
+
+def gl_rec_newton(x0: float, n: int, alpha: float):
+    """gl_rec_newton(x0, n, alpha) of src/gausslaguerre.jl:547-579 -> (xk, wk)."""
+    xk = ctypes.c_double(0.0)
+    wk = ctypes.c_double(0.0)
+    lib().oracle_gl_rec_newton(float(x0), int(n), float(alpha), ctypes.byref(xk), ctypes.byref(wk))
+    return xk.value, wk.value
 
 
 def ulp_diff(got: np.ndarray, ref: np.ndarray) -> np.ndarray:
