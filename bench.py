@@ -145,6 +145,95 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def time_other_configs(fgq_b200, cpu: bool):
+    """The other BASELINE.json configs (parity-test cases, not the bench line): device-resident time
+    per call with CUDA events (best of 3 after a warm-up), Mnodes/s, and the CPU oracle on a bounded
+    sample beside it.  Reported under "other_configs"; the headline metric is untouched."""
+    import numpy as np
+    import torch
+    out = {}
+
+    def dev_time(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best
+
+    def cpu_time(fn):
+        t0 = time.perf_counter()
+        fn()
+        return time.perf_counter() - t0
+
+    L = fgq_b200.lib()
+    chk = fgq_b200._lib.check
+    # C1: gausslegendre(1e5), the README example
+    n = 100_000
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    w = torch.empty(n, dtype=torch.float64, device="cuda")
+    sp = torch.cuda.current_stream().cuda_stream
+    ms = dev_time(lambda: chk(L.fgq_gausslegendre_device(n, 0, n, x.data_ptr(), w.data_ptr(), sp)), reps=10)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        fgq_b200.gausslegendre(n)
+    host_ms = (time.perf_counter() - t0) / 20 * 1e3
+    out["C1_gausslegendre_1e5"] = {"device_ms": ms, "mnodes_per_s": n / ms / 1e3, "host_call_ms": host_ms,
+                                   "published_julia_ms": 2.192}
+    # C3: gaussjacobi(1e7, 0.3, -0.7)
+    n = 10_000_000
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    w = torch.empty(n, dtype=torch.float64, device="cuda")
+    ws = torch.empty(int(L.fgq_gaussjacobi_workspace_bytes(n)) + 16, dtype=torch.uint8, device="cuda")
+    ms = dev_time(lambda: chk(L.fgq_gaussjacobi_device(n, 0.3, -0.7, 0, n, x.data_ptr(), w.data_ptr(), ws.data_ptr(), sp)))
+    out["C3_gaussjacobi_1e7"] = {"device_ms": ms, "mnodes_per_s": n / ms / 1e3,
+                                 "sum_w_err": float(w.sum().item() - 4.554443087962173)}
+    # C4: gausshermite(1e6), gausslaguerre(1e6)
+    n = 1_000_000
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    w = torch.empty(n, dtype=torch.float64, device="cuda")
+    ws = torch.empty(int(L.fgq_gausshermite_workspace_bytes(n)) + 16, dtype=torch.uint8, device="cuda")
+    ms = dev_time(lambda: chk(L.fgq_gausshermite_device(n, 0, 0, n, x.data_ptr(), w.data_ptr(), ws.data_ptr(), sp)))
+    out["C4_gausshermite_1e6"] = {"device_ms": ms, "mnodes_per_s": n / ms / 1e3,
+                                  "sum_w_err": float(w.sum().item() - np.sqrt(np.pi))}
+    ws = torch.empty(int(L.fgq_gausslaguerre_workspace_bytes(n)) + 16, dtype=torch.uint8, device="cuda")
+    ms = dev_time(lambda: chk(L.fgq_gausslaguerre_device(n, 0.0, x.data_ptr(), w.data_ptr(), ws.data_ptr(), sp)))
+    out["C4_gausslaguerre_1e6"] = {"device_ms": ms, "mnodes_per_s": n / ms / 1e3, "sum_w_err": float(w.sum().item() - 1.0)}
+    # C5: 1e6 small rules, n in [2, 60]
+    n_i = np.random.default_rng(0).integers(2, 61, size=1_000_000).astype(np.int32)
+    off = np.zeros(len(n_i) + 1, dtype=np.int64)
+    np.cumsum(n_i, out=off[1:])
+    tot = int(off[-1])
+    dn = torch.from_numpy(n_i).cuda()
+    do = torch.from_numpy(off).cuda()
+    x = torch.empty(tot, dtype=torch.float64, device="cuda")
+    w = torch.empty(tot, dtype=torch.float64, device="cuda")
+    ms = dev_time(lambda: chk(L.fgq_gausslegendre_batch_device(len(n_i), dn.data_ptr(), do.data_ptr(), x.data_ptr(), w.data_ptr(), sp)))
+    out["C5_batch_1e6_rules"] = {"device_ms": ms, "mrules_per_s": len(n_i) / ms / 1e3, "mnodes_per_s": tot / ms / 1e3, "nodes": tot}
+    if cpu:
+        import oracle
+        from oracle import hermite_oracle, jacobi_oracle, laguerre_oracle
+        oracle.set_threads(1)
+        t = cpu_time(lambda: oracle.gausslegendre(100_000))
+        out["C1_gausslegendre_1e5"]["cpu_oracle_ms_1thread"] = t * 1e3
+        t = cpu_time(lambda: jacobi_oracle.gaussjacobi(200_000, 0.3, -0.7))
+        out["C3_gaussjacobi_1e7"]["cpu_oracle"] = {"sample_n": 200_000, "seconds": t, "mnodes_per_s": 0.2 / t, "kind": "port (numpy)"}
+        t = cpu_time(lambda: hermite_oracle.gausshermite(1_000_000))
+        out["C4_gausshermite_1e6"]["cpu_oracle"] = {"sample_n": 1_000_000, "seconds": t, "mnodes_per_s": 1.0 / t, "kind": "port (numpy)"}
+        t = cpu_time(lambda: laguerre_oracle.gausslaguerre(1_000_000, 0.0))
+        out["C4_gausslaguerre_1e6"]["cpu_oracle"] = {"sample_n": 1_000_000, "seconds": t, "mnodes_per_s": 1.0 / t, "kind": "port (numpy)"}
+        t = cpu_time(lambda: oracle.gausslegendre_batch(n_i))
+        out["C5_batch_1e6_rules"]["cpu_oracle_1thread"] = {"seconds": t, "mrules_per_s": 1.0 / t, "kind": "port (C)"}
+        oracle.set_threads(0)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,6 +246,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -296,6 +386,11 @@ def main():
                 "all_cores_value": r_all, "all_cores": used,
                 "published_julia": {"value": PUBLISHED_JULIA_GNODES, "what": "docs/src/benchmark.md:21-22, hardware unstated"},
             }
+        other = None
+        if world == 1 and not args.no_other_configs:
+            del shard
+            torch.cuda.empty_cache()
+            other = time_other_configs(fgq_b200, cpu=not args.no_cpu_baseline)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
@@ -309,6 +404,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "checks": {"sum_w_minus_2": float(sums[0] - 2.0), "sum_wx2_minus_2_3": float(sums[1] - 2.0 / 3.0)},
             "step_ms_median": statistics.median(step_ms), "step_ms_min": min(step_ms),
+            "other_configs": other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
