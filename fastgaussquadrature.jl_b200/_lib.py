@@ -44,6 +44,8 @@ SIGNATURES = {
     "fgq_gausslobatto_device": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp]),
     "fgq_approx_besselroots": (ctypes.c_int, [ctypes.c_double, _i64, _vp]),
     "fgq_besselj": (ctypes.c_double, [ctypes.c_double, ctypes.c_double]),
+    "fgq_gausschebyshev_host": (ctypes.c_int, [ctypes.c_int, _i64, _vp, _vp]),
+    "fgq_gausschebyshev_device": (ctypes.c_int, [ctypes.c_int, _i64, _i64, _i64, _vp, _vp, _vp]),
     "fgq_gausshermite_host": (ctypes.c_int, [_i64, ctypes.c_int, _vp, _vp]),
     "fgq_gausshermite_workspace_bytes": (_i64, [_i64]),
     "fgq_gausshermite_device": (ctypes.c_int, [_i64, ctypes.c_int, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -206,8 +206,11 @@ def gaussjacobi(n, a, b):
         raise DomainError(f"DomainError({n}): gaussjacobi({n},{a},{b}) not defined: n must be non-negative.")
     if a == 0.0 and b == 0.0:
         return gausslegendre(n)
+    if abs(a) == 0.5 and abs(b) == 0.5:      # gaussjacobi.jl:30-39
+        kind = 1 if (a < 0 and b < 0) else 2 if (a > 0 and b > 0) else 3 if a < 0 else 4
+        return _chebyshev(kind, n)
     x, w = _host_pair(n, False)
-    if n == 0 and not (abs(a) == 0.5 and abs(b) == 0.5):
+    if n == 0:
         return x, w
     check(lib().fgq_gaussjacobi_host(n, a, b, _ptr(x), _ptr(w)))
     return x, w
@@ -244,6 +247,36 @@ def gausslobatto(n):
     x, w = _host_pair(n, False)
     check(lib().fgq_gausslobatto_host(n, _ptr(x), _ptr(w)))
     return x, w
+
+
+def _chebyshev(kind: int, n):
+    n = _as_int(n)
+    if n < 0:
+        raise DomainError(f"DomainError({n}): Input n must be a non-negative integer")
+    x, w = _host_pair(n, False)
+    if n:
+        check(lib().fgq_gausschebyshev_host(kind, n, _ptr(x), _ptr(w)))
+    return x, w
+
+
+def gausschebyshevt(n):
+    """``gausschebyshevt(n)`` (reference src/gausschebyshev.jl:22-26)."""
+    return _chebyshev(1, n)
+
+
+def gausschebyshevu(n):
+    """``gausschebyshevu(n)`` (reference src/gausschebyshev.jl:51-55)."""
+    return _chebyshev(2, n)
+
+
+def gausschebyshevv(n):
+    """``gausschebyshevv(n)`` (reference src/gausschebyshev.jl:80-84)."""
+    return _chebyshev(3, n)
+
+
+def gausschebyshevw(n):
+    """``gausschebyshevw(n)`` (reference src/gausschebyshev.jl:109-113)."""
+    return _chebyshev(4, n)
 
 
 def approx_besselroots(nu, n):

@@ -352,6 +352,8 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
 
 extern "C" int fgq_gausslegendre_device(int64_t n, int64_t lo, int64_t hi, double* x_dev, double* w_dev,
                                         void* stream);
+extern "C" int fgq_gausschebyshev_device(int kind, int64_t n, int64_t lo, int64_t hi, double* x_dev,
+                                         double* w_dev, void* stream);
 
 extern "C" int fgq_gaussjacobi_device(int64_t n, double a, double b, int64_t lo, int64_t hi, double* x_dev,
                                       double* w_dev, void* workspace_dev, void* stream) {
@@ -362,10 +364,9 @@ extern "C" int fgq_gaussjacobi_device(int64_t n, double a, double b, int64_t lo,
         return FGQ_EINVAL;
     }
     if (a == 0.0 && b == 0.0) return fgq_gausslegendre_device(n, lo, hi, x_dev, w_dev, stream);  // :29-30
-    if (fabs(a) == 0.5 && fabs(b) == 0.5) {
-        set_error("gaussjacobi(n, +-1/2, +-1/2) is Gauss-Chebyshev (gaussjacobi.jl:31-40): closed forms, "
-                  "not on the device path yet");
-        return FGQ_ENOTIMPL;
+    if (fabs(a) == 0.5 && fabs(b) == 0.5) {  // :30-39
+        const int kind = (a < 0 && b < 0) ? 1 : (a > 0 && b > 0) ? 2 : (a < 0 ? 3 : 4);
+        return fgq_gausschebyshev_device(kind, n, lo, hi, x_dev, w_dev, stream);
     }
     if (n == 0) return FGQ_OK;
     FGQ_TRY(jacobi_check_args(n, a, b));

@@ -86,7 +86,7 @@ int fgq_gausslegendre_batch_host(int64_t nrules, const int32_t* n_i, const int64
  * interior expansion + Newton on the device, 2 x 10 boundary nodes planned on the host.
  *   n < 0, min(a,b) <= -1          -> FGQ_EDOMAIN  (:26-27, :44-45)
  *   a == b == 0                    -> the Legendre path (:28-29)
- *   |a| == |b| == 1/2              -> FGQ_ENOTIMPL (Chebyshev closed forms, :30-39; next row)
+ *   |a| == |b| == 1/2              -> the Chebyshev closed forms (:30-39)
  *   n <= 100, or max(a,b) >= 5     -> FGQ_ENOTIMPL (jacobi_rec / Golub-Welsch, :46-53) */
 int fgq_gaussjacobi_host(int64_t n, double a, double b, double* x, double* w);
 int64_t fgq_gaussjacobi_workspace_bytes(int64_t n);
@@ -111,6 +111,14 @@ int fgq_gausslobatto_device(int64_t n, double* x_dev, double* w_dev, void* works
 int fgq_approx_besselroots(double nu, int64_t n, double* x);
 /* J_nu(x), real order, moderate x: the host planner's stand-in for the reference's besselj. */
 double fgq_besselj(double nu, double x);
+
+/* ---- Gauss-Chebyshev: gausschebyshevt/u/v/w(n) — src/gausschebyshev.jl:22-113 ------------------ */
+
+/* kind 1..4 = t, u, v, w (weights (1-x^2)^-1/2, (1-x^2)^1/2, sqrt((1+x)/(1-x)), sqrt((1-x)/(1+x)));
+ * also what gaussjacobi(n, -+1/2, -+1/2) routes to (gaussjacobi.jl:30-39).  n < 0 -> FGQ_EDOMAIN. */
+int fgq_gausschebyshev_host(int kind, int64_t n, double* x, double* w);
+int fgq_gausschebyshev_device(int kind, int64_t n, int64_t lo, int64_t hi, double* x_dev, double* w_dev,
+                              void* stream);
 
 /* ---- Gauss-Hermite: gausshermite(n; normalize) — src/gausshermite.jl:28-89,171-323 ---------- */
 
