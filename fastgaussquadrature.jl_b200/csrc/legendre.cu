@@ -268,8 +268,28 @@ legendre_asy_kernel(const LegLaunch p) {
         }
         st_stream2(p.xl + (k0 - p.kL0), neg_bits(cx0), neg_bits(cx1));
         st_stream2(p.wl + (k0 - p.kL0), w0, w1);
-        st_stream2(p.xr + (p.kR1 - k1), cx1, cx0);
-        st_stream2(p.wr + (p.kR1 - k1), w1, w0);
+        if (p.vecR) {
+            st_stream2(p.xr + (p.kR1 - k1), cx1, cx0);
+            st_stream2(p.wr + (p.kR1 - k1), w1, w0);
+        } else {
+            // odd n: the mirrored pair of this thread straddles a 16-byte boundary; the aligned pair is
+            // (k0, k0-1), whose second element is the previous lane's k1 -> one shuffle, and only the
+            // two ends of each warp fall back to 8-byte stores
+            const double pc1 = __shfl_up_sync(0xffffffffu, cx1, 1);
+            const double pw1 = __shfl_up_sync(0xffffffffu, w1, 1);
+            const int lane = threadIdx.x & 31;
+            if (lane > 0) {
+                st_stream2(p.xr + (p.kR1 - k0), cx0, pc1);
+                st_stream2(p.wr + (p.kR1 - k0), w0, pw1);
+            } else {
+                st_stream(p.xr + (p.kR1 - k0), cx0);
+                st_stream(p.wr + (p.kR1 - k0), w0);
+            }
+            if (lane == 31) {
+                st_stream(p.xr + (p.kR1 - k1), cx1);
+                st_stream(p.wr + (p.kR1 - k1), w1);
+            }
+        }
         return;
     }
     if (k0 > p.kmax) return;
@@ -386,19 +406,27 @@ static int launch_one(int64_t n, bool head, int64_t kmin, int64_t kmax, int64_t 
     p.xl = xl; p.wl = wl; p.xr = xr; p.wr = wr;
     p.kcentre = (n & 1) ? (n + 1) / 2 : 0;
     const bool hasL = kL0 <= kL1, hasR = kR0 <= kR1;
-    // pair parity: make the left pairs 16-byte aligned when there is a left side
+    // Pair parity.  Element k of the left side lives at xl + (k - kL0), of the right side at
+    // xr + (kR1 - k); a 16-byte store needs an even offset from a 16-byte boundary, so the parity of
+    // the pointer itself (in units of 8 bytes) counts too (e.g. the right segment of an odd rule
+    // starts one element into its allocation).  Prefer aligned left pairs; the right side then
+    // either has its own pair aligned (vecR) or the pair shifted by one element (vecR_shifted).
+    auto par8 = [](const double* q) { return (int64_t)((reinterpret_cast<uintptr_t>(q) >> 3) & 1); };
+    const bool okL = hasL && par8(xl) == par8(wl);
+    const bool okR = hasR && par8(xr) == par8(wr);
     p.kbase = kmin;
-    if (hasL) {
-        if (((p.kbase - kL0) & 1) != 0) p.kbase -= 1;
-    } else if (hasR) {
-        if (((kR1 - p.kbase - 1) & 1) != 0) p.kbase -= 1;
+    if (okL) {
+        if (((par8(xl) + p.kbase - kL0) & 1) != 0) p.kbase -= 1;
+    } else if (okR) {
+        if (((par8(xr) + kR1 - p.kbase - 1) & 1) != 0) p.kbase -= 1;
     }
-    p.vecL = hasL && aligned16(xl) && aligned16(wl) && (((p.kbase - kL0) & 1) == 0);
-    p.vecR = hasR && aligned16(xr) && aligned16(wr) && (((kR1 - p.kbase - 1) & 1) == 0);
+    p.vecL = okL && (((par8(xl) + p.kbase - kL0) & 1) == 0);
+    p.vecR = okR && (((par8(xr) + kR1 - p.kbase - 1) & 1) == 0);
     // interior = both sides present, both vectorisable, centre excluded
     p.kin0 = 1;
     p.kin1 = 0;
-    if (p.vecL && p.vecR) {
+    const bool vecR_shifted = okR && !p.vecR;
+    if (p.vecL && (p.vecR || vecR_shifted)) {
         p.kin0 = imax(kL0, kR0);
         p.kin1 = imin(kL1, kR1);
         if (p.kcentre && p.kin1 >= p.kcentre) p.kin1 = p.kcentre - 1;
@@ -441,7 +469,9 @@ int legendre_asy_launch(int64_t n, int64_t kL0, int64_t kL1, double* xl, double*
     // moved by one when that keeps the tail's left pointer 16-byte aligned (the head kernel is
     // generic in k, so it may take k = 13192 as well).
     int64_t split = K_TAIL;
-    if (kL0 <= kL1 && kL0 < split && ((split - kL0) & 1)) split += 1;
+    if (kL0 <= kL1 && kL0 < split &&
+        ((((reinterpret_cast<uintptr_t>(xl) >> 3) & 1) + (uintptr_t)(split - kL0)) & 1))
+        split += 1;
     for (int part = 0; part < 2; ++part) {
         const bool head = part == 0;
         const int64_t a = head ? 1 : split;
