@@ -401,8 +401,16 @@ __global__ void laguerre_recompute_kernel(const LaguerreParams p, LaguerreState*
 // reduced rule (:163-169 ...): the rule ends before the first weight below 10 floatmin
 __global__ void laguerre_reduced_kernel(int64_t n, const double* w, LaguerreState* st) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (fabs(w[i]) < 10 * 2.2250738585072014e-308) atomicMin(&st->n_out, (unsigned long long)i);
+    // ~98 % of the weights underflow at n = 1e6: aggregate per warp and skip indices that cannot
+    // lower the minimum any more, instead of a million atomics on one address
+    unsigned long long cand = ~0ull;
+    if (i < n && fabs(w[i]) < 10 * 2.2250738585072014e-308) cand = (unsigned long long)i;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, cand, o);
+        cand = other < cand ? other : cand;
+    }
+    if ((threadIdx.x & 31) == 0 && cand < *((volatile unsigned long long*)&st->n_out)) atomicMin(&st->n_out, cand);
 }
 
 }  // namespace fgq

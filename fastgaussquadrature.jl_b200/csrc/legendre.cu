@@ -500,17 +500,29 @@ int legendre_asy_launch(int64_t n, int64_t kL0, int64_t kL1, double* xl, double*
 // (rec, gausslegendre.jl:233-267); n <= 5 are the closed forms (:27-60).
 // ---------------------------------------------------------------------------------------------
 
-// gausslegendre.jl:269-290 for one abscissa
+// a / b for b = k + 1 (an exact small integer) without nvcc's slow-path scaffolding: same bits as
+// the IEEE quotient for every normal a (|P_k|, |P'_k| stay within [1e-300, 1e6] here; a signed zero
+// numerator is passed through, which is what IEEE gives for b > 0).
+__device__ __forceinline__ double div_by_count(double a, double b) {
+    const double q = fgq_div_fast(a, b);
+    return a == 0.0 ? a : q;
+}
+
+// gausslegendre.jl:269-290 for one abscissa.  The loop counters are kept as doubles (exact), so the
+// quarter-rate I2F.F64 conversions of 2k+1, k, k+1 leave the inner loop.
 __device__ __forceinline__ void leg_inner_rec(int n, double xj, double& P, double& PP) {
     double Pm2 = 1.0, Pm1 = xj, PPm1 = 1.0, PPm2 = 0.0;
+    double tk = 3.0, dk = 1.0, dk1 = 2.0;
     for (int k = 1; k <= n - 1; ++k) {
-        const double tk = (double)(2 * k + 1), dk = (double)k, dk1 = (double)(k + 1);
-        const double newP = fma(tk * Pm1, xj, -dk * Pm2) / dk1;
+        const double newP = div_by_count(fma(tk * Pm1, xj, -dk * Pm2), dk1);
         Pm2 = Pm1;
         Pm1 = newP;
-        const double newPP = (tk * fma(xj, PPm1, Pm2) - dk * PPm2) / dk1;
+        const double newPP = div_by_count(tk * fma(xj, PPm1, Pm2) - dk * PPm2, dk1);
         PPm2 = PPm1;
         PPm1 = newPP;
+        tk += 2.0;
+        dk = dk1;
+        dk1 += 1.0;
     }
     P = Pm1;
     PP = PPm1;
