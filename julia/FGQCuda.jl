@@ -44,6 +44,62 @@ function gausslegendre_batch(ns::Vector{Int32})
     return offsets, x, w
 end
 
+# gaussjacobi(n, α, β) — src/gaussjacobi.jl:23-55 (asymptotic branch n > 100, max(α,β) < 5; (0,0) and
+# (±1/2, ±1/2) are routed to the Legendre / Chebyshev kernels by the library, as the reference does)
+function gaussjacobi(n::Integer, α::Real, β::Real)
+    n < 0 && throw(DomainError(n, "gaussjacobi($n,$α,$β) not defined: n must be non-negative."))
+    x = Vector{Float64}(undef, n); w = Vector{Float64}(undef, n)
+    n == 0 && return x, w
+    GC.@preserve x w check(ccall((:fgq_gaussjacobi_host, libfgq), Cint,
+        (Int64, Float64, Float64, Ptr{Float64}, Ptr{Float64}), n, Float64(α), Float64(β), x, w), (α, β))
+    return x, w
+end
+
+# gaussradau(n) — src/gaussradau.jl:31-49;  gausslobatto(n) — src/gausslobatto.jl:31-52
+for (f, sym) in ((:gaussradau, :fgq_gaussradau_host), (:gausslobatto, :fgq_gausslobatto_host))
+    @eval function $f(n::Integer)
+        x = Vector{Float64}(undef, max(n, 0)); w = similar(x)
+        GC.@preserve x w check(ccall(($(QuoteNode(sym)), libfgq), Cint,
+            (Int64, Ptr{Float64}, Ptr{Float64}), n, x, w), n)
+        return x, w
+    end
+end
+
+# gausschebyshevt/u/v/w(n) — src/gausschebyshev.jl:22-113
+for (f, kind) in ((:gausschebyshevt, 1), (:gausschebyshevu, 2), (:gausschebyshevv, 3), (:gausschebyshevw, 4))
+    @eval function $f(n::Integer)
+        n < 0 && throw(DomainError(n, "Input n must be a non-negative integer"))
+        x = Vector{Float64}(undef, n); w = similar(x)
+        n == 0 && return x, w
+        GC.@preserve x w check(ccall((:fgq_gausschebyshev_host, libfgq), Cint,
+            (Cint, Int64, Ptr{Float64}, Ptr{Float64}), $kind, n, x, w), n)
+        return x, w
+    end
+end
+
+# gausshermite(n; normalize) — src/gausshermite.jl:28-33 (asymptotic branch n > 200)
+function gausshermite(n::Integer; normalize = false)
+    n < 0 && throw(DomainError(n, "Input n must be a non-negative integer"))
+    x = Vector{Float64}(undef, n); w = similar(x)
+    n == 0 && return x, w
+    GC.@preserve x w check(ccall((:fgq_gausshermite_host, libfgq), Cint,
+        (Int64, Cint, Ptr{Float64}, Ptr{Float64}), n, normalize ? 1 : 0, x, w), n)
+    return x, w
+end
+
+# gausslaguerre(n, α; reduced) — src/gausslaguerre.jl:59-96 (explicit asymptotics, n >= 128, α < 5)
+function gausslaguerre(n::Integer, α::Real = 0.0; reduced = false)
+    α ≤ -1 && throw(DomainError(α, "The Laguerre parameter α ≤ -1 corresponds to a nonintegrable weight function"))
+    n < 0 && throw(DomainError(n, "gausslaguerre($n,$α) not defined: n must be positive."))
+    x = Vector{Float64}(undef, n); w = similar(x)
+    n == 0 && return x, w
+    nout = Ref{Int64}(0)
+    GC.@preserve x w check(ccall((:fgq_gausslaguerre_host, libfgq), Cint,
+        (Int64, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Ref{Int64}), n, Float64(α), reduced ? 1 : 0, x, w, nout), n)
+    reduced && (resize!(x, nout[]); resize!(w, nout[]))
+    return x, w
+end
+
 # Device-resident shard (with CUDA.jl): x_dev, w_dev are CuVector{Float64} of length hi-lo;
 # asynchronous on `stream`; output indices are 0-based here, [lo, hi).
 function gausslegendre_device!(x_dev, w_dev, n::Integer, lo::Integer, hi::Integer, stream::Ptr{Cvoid} = C_NULL)
