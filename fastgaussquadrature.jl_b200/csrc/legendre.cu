@@ -101,14 +101,21 @@ __device__ __forceinline__ void bessel_pair(int64_t k, double& jk, double& j1sq)
     }
 }
 
+// a/b and 1/b: IEEE operators on the head (tables, tiny launch), slow-path-free versions on the
+// tail, where every operand is far inside the normal range (same bits: fgq_math.h).
+template <bool FAST>
+__device__ __forceinline__ double dv(double a, double b) { return FAST ? fgq_div_fast(a, b) : a / b; }
+template <bool FAST>
+__device__ __forceinline__ double rc(double b) { return FAST ? fgq_rcp_fast(b) : 1.0 / b; }
+
 // theta-series, gausslegendre.jl:103-143.  NT = number of correction terms kept
 // (3: n<=255, 2: n<=3950, 1: otherwise).  NT = 0 is the n >= 2^25 shortcut: there the
 // single remaining correction (cot(a) - 1/a)/8 * vn^2 is below ulp(a)/2 for every k
 // (|corr|/a <= vn^2/24 < 2^-54), so a + corr rounds back to a and theta == a exactly.
-template <int NT>
+template <int NT, bool FAST = false>
 __device__ __forceinline__ double leg_theta(double ai, double u, const LegConsts& c) {
     if (NT == 0) return ai;
-    double node = ai + (u - 1.0 / ai) / 8.0 * c.vn2;
+    double node = ai + (u - rc<FAST>(ai)) / 8.0 * c.vn2;
     if (NT >= 2) {
         const double u2 = u * u;
         const double ai2 = ai * ai;
@@ -133,11 +140,11 @@ __device__ __forceinline__ double leg_theta(double ai, double u, const LegConsts
 
 // W-series, gausslegendre.jl:162-224.  WT = number of terms (3: n<=170, 2: n<=1500,
 // 1: n<=850000, 0: otherwise).
-template <int WT>
+template <int WT, bool FAST = false>
 __device__ __forceinline__ double leg_wseries(double ai, double u, const LegConsts& c) {
     if (WT == 0) return c.inv_vn2;
     const double ai2 = ai * ai;
-    const double aim2 = 1.0 / ai2;
+    const double aim2 = rc<FAST>(ai2);
     const double ua = u * ai;
     const double W1 = fma(ua - 1.0, aim2, 1.0) / 8.0;
     if (WT == 1) return c.inv_vn2 + W1;
@@ -170,18 +177,19 @@ __device__ __forceinline__ void leg_half_index(int64_t k, const LegConsts& c, do
     const double a = jk * c.vn;
     double s, ca;
     fgq_sincos_q1(a, &s, &ca);
+    constexpr bool FAST = !HEAD && NT <= 1 && WT <= 1;  // tail launches of the large-n branches
     double u = 0.0;
-    if (NT > 0 || WT > 0) u = ca / s;  // cot(a)
+    if (NT > 0 || WT > 0) u = dv<FAST>(ca, s);  // cot(a)
     if (NT == 0) {
         cx = ca;
         if (theta_out) *theta_out = a;
     } else {
-        const double th = leg_theta<NT>(a, u, c);
+        const double th = leg_theta<NT, FAST>(a, u, c);
         if (theta_out) *theta_out = th;
         cx = fgq_cos_q1(th);
     }
-    const double W = leg_wseries<WT>(a, u, c);
-    if (!HEAD && NT == 0 && WT == 0) {
+    const double W = leg_wseries<WT, FAST>(a, u, c);
+    if (FAST) {
         // 2/t == 2*(1/t) bit-for-bit (power-of-two scaling); operands far inside the normal range
         w = 2.0 * fgq_rcp_fast(j1sq * fgq_div_fast(a, s) * W);
     } else {
