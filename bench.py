@@ -186,6 +186,12 @@ def time_other_configs(fgq_b200, cpu: bool):
     host_ms = (time.perf_counter() - t0) / 20 * 1e3
     out["C1_gausslegendre_1e5"] = {"device_ms": ms, "mnodes_per_s": n / ms / 1e3, "host_call_ms": host_ms,
                                    "published_julia_ms": 2.192}
+    # consumer fusion on the headline config: generate-and-reduce, nothing stored (FP64-bound)
+    nf = 10 ** 9
+    ms = dev_time(lambda: fgq_b200.gausslegendre_moments_fused(nf))
+    sf = fgq_b200.gausslegendre_moments_fused(nf).cpu().numpy()
+    out["fused_moments_gausslegendre_1e9"] = {"device_ms": ms, "gnodes_per_s": nf / ms / 1e6,
+                                              "sum_w_minus_2": float(sf[0] - 2), "sum_wx2_minus_2_3": float(sf[1] - 2 / 3)}
     # C3: gaussjacobi(1e7, 0.3, -0.7)
     n = 10_000_000
     x = torch.empty(n, dtype=torch.float64, device="cuda")

@@ -55,6 +55,7 @@ SIGNATURES = {
     "fgq_gausslaguerre_device": (ctypes.c_int, [_i64, ctypes.c_double, _vp, _vp, _vp, _vp]),
     "fgq_gausslaguerre_stats": (ctypes.c_int, [_vp, _i64p, _i64p, _i64p, _i64p]),
     "fgq_rule_moments_device": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "fgq_gausslegendre_moments_fused_device": (ctypes.c_int, [_i64, _i64, _i64, ctypes.c_int, _vp, _vp]),
     "fgq_measure_dfma_peak": (ctypes.c_int, [_dp]),
     "fgq_measure_store_peak": (ctypes.c_int, [_i64, _dp]),
     "fgq_debug_legendre_theta_device": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp]),

@@ -378,6 +378,19 @@ def rule_moments_device(shard: LegendreShard, stream=None):
     return sums
 
 
+def gausslegendre_moments_fused(n, rank: int = 0, world: int = 1, with_exp: bool = False, stream=None):
+    """(sum w, sum w x^2[, sum w exp(x)]) of ``gausslegendre(n)`` for this rank's half-index shard,
+    generated and reduced in one kernel — nothing is stored (consumer fusion).
+    Returns a 3-element CUDA tensor; all-reduce it across ranks."""
+    import torch
+    n = _as_int(n)
+    sums = torch.zeros(3, dtype=torch.float64, device="cuda")
+    k_lo, k_hi = half_index_partition(n, world)[rank]
+    check(lib().fgq_gausslegendre_moments_fused_device(n, k_lo, k_hi, int(bool(with_exp)), sums.data_ptr(),
+                                                       _stream_ptr(stream)))
+    return sums
+
+
 def measure_peaks(store_bytes: int = 4 << 30):
     """Roofline denominators on the current device: (FP64 TFLOP/s from the DFMA microbenchmark,
     store-only HBM GB/s)."""

@@ -358,6 +358,85 @@ legendre_fastdiv_check_kernel(int64_t k_lo, int64_t k_hi, LegConsts c,
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Consumer fusion: the README's only use of a rule is dot(w, f.(x))
+// (README.md:27-30).  This kernel generates the nodes in registers and reduces on the fly —
+// sum w, sum w x^2 and optionally sum w exp(x) — so the 16 B/node store disappears and the path
+// is purely FP64-bound.  Each half-index contributes both +-x.
+// ---------------------------------------------------------------------------------------------
+struct FusedLaunch {
+    int64_t kmin, kmax;   // half-indices evaluated (inclusive)
+    int64_t kq0_last;     // as in LegLaunch
+    int64_t kcentre;      // (n+1)/2 for odd n: that half-index is the single node x = 0
+    int with_exp;
+    LegConsts c;
+};
+
+__device__ __forceinline__ void kahan_add(double& s, double& comp, double v) {
+    const double y = v - comp;
+    const double t = s + y;
+    comp = (t - s) - y;
+    s = t;
+}
+
+template <int NT, int WT, bool HEAD>
+__global__ void __launch_bounds__(LEG_THREADS)
+legendre_fused_moments_kernel(const FusedLaunch p, double* sums) {
+    double s0 = 0, c0 = 0, s2 = 0, c2 = 0, se = 0, ce = 0;
+    const int64_t ntiles = (p.kmax - p.kmin) / (2 * LEG_THREADS) + 1;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t kb0 = p.kmin + tile * 2 * LEG_THREADS;
+        const int64_t kb1 = kb0 + 2 * LEG_THREADS - 1;
+        const int64_t k0 = kb0 + 2 * threadIdx.x;
+        double cx[2], w[2];
+        const bool full = kb1 <= p.kmax;
+        if (NT == 0 && WT == 0 && !HEAD && full && kb0 >= K_JK_EXACT && kb1 <= p.kq0_last) {
+            leg_bulk<0>(k0, p.c, cx[0], w[0]);
+            leg_bulk<0>(k0 + 1, p.c, cx[1], w[1]);
+        } else if (NT == 0 && WT == 0 && !HEAD && full && kb0 >= K_JK_EXACT && kb0 > p.kq0_last) {
+            leg_bulk<1>(k0, p.c, cx[0], w[0]);
+            leg_bulk<1>(k0 + 1, p.c, cx[1], w[1]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t k = k0 + e > p.kmax ? p.kmax : k0 + e;
+                leg_half_index<NT, WT, HEAD>(k, p.c, cx[e], w[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int64_t k = k0 + e;
+            if (k > p.kmax) continue;
+            const bool centre = (k == p.kcentre);
+            const double x = centre ? 0.0 : cx[e];
+            const double mult = centre ? 1.0 : 2.0;
+            kahan_add(s0, c0, mult * w[e]);
+            kahan_add(s2, c2, mult * (w[e] * x) * x);
+            if (p.with_exp) {
+                const double ex = exp(x);
+                kahan_add(se, ce, centre ? w[e] : w[e] * (ex + 1.0 / ex));
+            }
+        }
+    }
+    double v[3] = {s0, s2, se};
+    __shared__ double sh[3][LEG_THREADS / 32];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+        if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double a = 0.0;
+        for (int i = 0; i < LEG_THREADS / 32; ++i) a += sh[threadIdx.x][i];
+        atomicAdd(sums + threadIdx.x, a);
+    }
+}
+
+typedef void (*FusedKernel)(const FusedLaunch, double*);
+static FusedKernel pick_fused(int nt, int wt, bool head);
+
 template <int NT>
 __global__ void legendre_theta_kernel(int64_t k_lo, int64_t k_hi, LegConsts c, double* theta) {
     const int64_t k = k_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,6 +453,18 @@ static int node_terms(int64_t n) { return n <= 255 ? 3 : n <= 3950 ? 2 : n < (1L
 static int weight_terms(int64_t n) { return n <= 170 ? 3 : n <= 1500 ? 2 : n <= 850000 ? 1 : 0; }
 
 typedef void (*LegKernel)(const LegLaunch);
+static double tail_angle(int64_t k, double vn);
+
+// last k with a_k <= pi/4, by bisection on the very arithmetic the kernel uses (a_k is monotone in k)
+static int64_t quarter_split(int64_t n, double vn) {
+    int64_t lo_k = 10680708, hi_k = (n + 1) / 2 + 1;  // K_JK_EXACT; invariant: a(lo_k) <= pi/4 < a(hi_k)
+    if (!(tail_angle(lo_k, vn) <= FGQ_PIO4 && tail_angle(hi_k, vn) > FGQ_PIO4)) return 0;
+    while (hi_k - lo_k > 1) {
+        const int64_t mid = lo_k + (hi_k - lo_k) / 2;
+        if (tail_angle(mid, vn) <= FGQ_PIO4) lo_k = mid; else hi_k = mid;
+    }
+    return lo_k;
+}
 
 // a_k for k >= K_JK_EXACT exactly as leg_bulk computes it (host IEEE arithmetic, no contraction
 // possible: a product of a difference, then a product)
@@ -398,6 +489,21 @@ static LegKernel pick_kernel(int nt, int wt, bool head) {
     FGQ_PICK(1, 0)
     FGQ_PICK(0, 0)
 #undef FGQ_PICK
+    return nullptr;
+}
+
+static FusedKernel pick_fused(int nt, int wt, bool head) {
+#define FGQ_PICKF(NT, WT)                                                  \
+    if (nt == NT && wt == WT)                                              \
+        return head ? legendre_fused_moments_kernel<NT, WT, true> : legendre_fused_moments_kernel<NT, WT, false>;
+    FGQ_PICKF(3, 3)
+    FGQ_PICKF(3, 2)
+    FGQ_PICKF(2, 2)
+    FGQ_PICKF(2, 1)
+    FGQ_PICKF(1, 1)
+    FGQ_PICKF(1, 0)
+    FGQ_PICKF(0, 0)
+#undef FGQ_PICKF
     return nullptr;
 }
 
@@ -439,19 +545,8 @@ static int launch_one(int64_t n, bool head, int64_t kmin, int64_t kmax, int64_t 
         p.kin1 = imin(kL1, kR1);
         if (p.kcentre && p.kin1 >= p.kcentre) p.kin1 = p.kcentre - 1;
     }
-    // last k with a_k <= pi/4, by bisection on the very arithmetic the kernel uses (a_k is
-    // monotone in k); only the n >= 2^25 kernel reads it
-    p.kq0_last = 0;
-    if (node_terms(n) == 0 && !head) {
-        int64_t lo_k = K_JK_EXACT, hi_k = (n + 1) / 2 + 1;  // invariant: a(lo_k) <= pi/4 < a(hi_k)
-        if (tail_angle(lo_k, p.c.vn) <= FGQ_PIO4 && tail_angle(hi_k, p.c.vn) > FGQ_PIO4) {
-            while (hi_k - lo_k > 1) {
-                const int64_t mid = lo_k + (hi_k - lo_k) / 2;
-                if (tail_angle(mid, p.c.vn) <= FGQ_PIO4) lo_k = mid; else hi_k = mid;
-            }
-            p.kq0_last = lo_k;
-        }
-    }
+    // only the n >= 2^25 kernel reads the pi/4 split
+    p.kq0_last = (node_terms(n) == 0 && !head) ? quarter_split(n, p.c.vn) : 0;
     const int64_t npairs = (kmax - p.kbase) / 2 + 1;
     const int64_t blocks = (npairs + LEG_THREADS - 1) / LEG_THREADS;
     if (blocks > 0x7fffffffLL) {
@@ -763,5 +858,38 @@ extern "C" int fgq_debug_fastdiv_check(int64_t n, int64_t k_lo, int64_t k_hi,
     legendre_fastdiv_check_kernel<<<148 * 8, 256, 0, as_stream(stream)>>>(k_lo, k_hi, make_consts(n),
                                                                           mismatches_dev);
     FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+extern "C" int fgq_gausslegendre_moments_fused_device(int64_t n, int64_t k_lo, int64_t k_hi, int with_exp,
+                                                      double* sums_dev, void* stream) {
+    clear_status();
+    if (n <= 60) {
+        set_error("fused moments need the asymptotic path (n > 60), got n=%lld", (long long)n);
+        return FGQ_EINVAL;
+    }
+    const int64_t m = (n + 1) >> 1;
+    if (k_lo < 1 || k_hi < k_lo || k_hi > m + 1 || !sums_dev) {
+        set_error("invalid half-index shard [%lld, %lld) of n=%lld", (long long)k_lo, (long long)k_hi, (long long)n);
+        return FGQ_EINVAL;
+    }
+    if (k_hi == k_lo) return FGQ_OK;
+    cudaStream_t st = as_stream(stream);
+    for (int part = 0; part < 2; ++part) {
+        const bool head = part == 0;
+        FusedLaunch p;
+        p.kmin = head ? k_lo : imax(k_lo, K_TAIL);
+        p.kmax = head ? imin(k_hi - 1, K_TAIL - 1) : k_hi - 1;
+        if (p.kmin > p.kmax) continue;
+        p.c = make_consts(n);
+        p.kcentre = (n & 1) ? m : 0;
+        p.with_exp = with_exp;
+        p.kq0_last = (node_terms(n) == 0 && !head) ? quarter_split(n, p.c.vn) : 0;
+        FusedKernel kern = pick_fused(node_terms(n), weight_terms(n), head);
+        const int64_t ntiles = (p.kmax - p.kmin) / (2 * LEG_THREADS) + 1;
+        const int64_t blocks = imin(ntiles, 148 * 8);
+        kern<<<(unsigned)blocks, LEG_THREADS, 0, st>>>(p, sums_dev);
+        FGQ_LAUNCH_CHECK();
+    }
     return FGQ_OK;
 }

@@ -163,6 +163,14 @@ int fgq_gausslaguerre_stats(const void* workspace_dev, int64_t* k_b, int64_t* k_
 int fgq_rule_moments_device(const double* x_dev, const double* w_dev, int64_t count,
                             double* sums_dev, void* stream);
 
+/* Fused generate-and-reduce (no stores): sums_dev[0] += sum w, sums_dev[1] += sum w x^2 and, when
+ * with_exp != 0, sums_dev[2] += sum w exp(x), over the nodes of half-indices [k_lo, k_hi) of the
+ * n-point Gauss-Legendre rule AND their mirror images (n > 60).  sums_dev: 3 doubles, zeroed by
+ * the caller; all-reduce across ranks for a sharded rule.  This is dot(w, f.(x)) of README.md:27-30
+ * without ever materialising x and w. */
+int fgq_gausslegendre_moments_fused_device(int64_t n, int64_t k_lo, int64_t k_hi, int with_exp,
+                                           double* sums_dev, void* stream);
+
 /* ---- roofline denominators (measured on the current device) ------------------------------ */
 
 /* DFMA issue-rate microbenchmark: independent FMA chains on every SM.  *tflops = 2*FMA/s/1e12. */

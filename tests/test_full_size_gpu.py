@@ -80,3 +80,15 @@ def test_fast_division_is_ieee_over_the_full_range(fgq, n):
     fgq._lib.check(fgq.lib().fgq_debug_fastdiv_check(n, 13192, m + 1, bad.data_ptr(), 0))
     torch.cuda.synchronize()
     assert int(bad.item()) == 0
+
+
+@pytest.mark.parametrize("n", [61, 1013, 100001, 3000000, 1 << 25, 10 ** 9, 10 ** 9 + 1])
+def test_fused_moments(fgq, n):
+    """Consumer fusion: generate-and-reduce without stores gives the exact invariants
+    (sum w = 2, int x^2 = 2/3, int exp = e - 1/e: test_gausslegendre.jl:23-24) and the same sums over
+    any rank split."""
+    import torch
+    s = fgq.gausslegendre_moments_fused(n, with_exp=True).cpu().numpy()
+    assert abs(s[0] - 2) < 2e-13 and abs(s[1] - 2 / 3) < 1e-13 and abs(s[2] - (math.e - 1 / math.e)) < 3e-13
+    parts = sum(fgq.gausslegendre_moments_fused(n, rank=r, world=4, with_exp=True) for r in range(4)).cpu().numpy()
+    assert np.abs(parts - s).max() < 1e-13
