@@ -92,3 +92,31 @@ def test_fused_moments(fgq, n):
     assert abs(s[0] - 2) < 2e-13 and abs(s[1] - 2 / 3) < 1e-13 and abs(s[2] - (math.e - 1 / math.e)) < 3e-13
     parts = sum(fgq.gausslegendre_moments_fused(n, rank=r, world=4, with_exp=True) for r in range(4)).cpu().numpy()
     assert np.abs(parts - s).max() < 1e-13
+
+
+def test_legendre_1e9_every_index_against_the_oracle(fgq, oracle_mod):
+    """at n = 1e9 compare EVERY index, not a sample.  The GPU rule is pulled back in
+    chunks of 2.5e7 half-indices and compared with the C oracle: bit-for-bit against the twin mode;
+    against the libm mode nodes <= 1-2 ulp, weights <= 4 ulp except a ~1e-6 fraction at 5
+    (profiles/r01_parity_legendre_1e9.md holds the full histogram)."""
+    import torch
+    n = 10 ** 9
+    oracle_mod.set_threads(0)
+    sh = fgq.gausslegendre_device(n, mode="pair")
+    torch.cuda.synchronize()
+    (_, _, xl, wl), _ = sh.segments
+    m = n // 2
+    CH = 25_000_000
+    over4 = 0
+    for k0 in range(1, m + 1, CH):
+        k1 = min(k0 + CH - 1, m)
+        gx = (-xl[k0 - 1:k1]).cpu().numpy()
+        gw = wl[k0 - 1:k1].cpu().numpy()
+        xt, wt = oracle_mod.legendre_asy_half(n, k0, k1, twin=True)
+        assert np.array_equal(gx, xt) and np.array_equal(gw, wt), f"twin mismatch in half-indices {k0}..{k1}"
+        xo, wo = oracle_mod.legendre_asy_half(n, k0, k1)
+        assert oracle_mod.ulp_diff(gx, xo).max() <= 2
+        uw = oracle_mod.ulp_diff(gw, wo)
+        assert uw.max() <= 5
+        over4 += int(np.count_nonzero(uw > 4))
+    assert over4 <= 4e-6 * m
