@@ -233,6 +233,124 @@ __global__ void endpoint_epilogue_kernel(int mode, int64_t n, int64_t lo, int64_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// n <= 100: jacobi_rec / HalfRec / innerjacobi_rec! (gaussjacobi.jl:61-155).  One block per rule:
+// threads 0..63 own the x > 0 half with (alpha, beta), threads 64..127 the mirrored half with
+// (beta, alpha); each thread is one Newton iterate on the three-term recurrence.  The reference's
+// per-half stopping rule (max dx^2 <= eps/1e6, :117-125) is a two-warp reduction through shared memory.
+// ---------------------------------------------------------------------------------------------
+struct JacobiRecParams {
+    int n;
+    double alpha, beta;
+    double c;        // 2^(a+b+1) G(2+a) G(2+b) / (G(2+a+b)(a+1)(b+1))  (:89)
+    int64_t lo, hi;  // output slice
+};
+
+// innerjacobi_rec! for one abscissa (:129-155)
+__device__ __forceinline__ void jacobi_inner_rec(int n, double xj, double a, double b, double& P, double& PP) {
+    double Pj = (a - b + (a + b + 2) * xj) / 2;
+    double Pm1 = 1.0;
+    double PPj = (a + b + 2) / 2;
+    double PPm1 = 0.0;
+    for (int k = 1; k <= n - 1; ++k) {
+        const double dk = (double)k;
+        const double k0 = fma(2.0, dk, a + b);
+        const double k1 = k0 + 1;
+        const double k2 = k0 + 2;
+        const double A = 2 * (dk + 1) * (dk + (a + b + 1)) * k0;
+        const double B = k1 * (a * a - b * b);
+        const double C = k0 * k1 * k2;
+        const double D = 2 * (dk + a) * (dk + b) * k2;
+        const double c1 = fma(C, xj, B);
+        const double newP = fma(-D, Pm1, c1 * Pj) / A;
+        const double oldP = Pj;
+        Pm1 = oldP;   // (Pm1, Pj) = (Pj, ...): the right-hand side uses the OLD Pm1
+        Pj = newP;
+        const double newPP = fma(c1, PPj, fma(-D, PPm1, C * Pm1)) / A;  // C * Pm1 uses the NEW Pm1 (= old Pj), as in :148-149
+        PPm1 = PPj;
+        PPj = newPP;
+    }
+    P = Pj;
+    PP = PPj;
+}
+
+__global__ void __launch_bounds__(128) jacobi_rec_kernel(const JacobiRecParams p, double* x, double* w) {
+    const double PI = 3.141592653589793;
+    const int tid = threadIdx.x;
+    const int h = tid >> 6;          // 0: HalfRec(n, alpha, beta, 1); 1: HalfRec(n, beta, alpha, 0)
+    const int i0 = tid & 63;
+    const int n = p.n;
+    const int m1 = (n + 1) / 2, m2 = n / 2;
+    const int m = h == 0 ? m1 : m2;
+    const bool active = i0 < m;
+    const double a = h == 0 ? p.alpha : p.beta;
+    const double b = h == 0 ? p.beta : p.alpha;
+    __shared__ double s_dx2[4];
+    __shared__ int s_done[2];
+    __shared__ double xs[128], wsum[128];
+    if (tid < 2) s_done[tid] = 0;
+    // initial guess (:97-109)
+    const double c1 = 1 / (2 * (double)n + a + b + 1);
+    const double a1 = 0.25 - a * a, b1 = 0.25 - b * b, c12 = c1 * c1;
+    double xj = 0.0, P1 = 0.0, P2 = 1.0;
+    if (active) {
+        const double r = (double)(m - i0);  // r[i] = m, m-1, ..., 1
+        const double C = fma(2.0, r, a - 0.5) * (PI * c1);
+        const double C_2 = C / 2;
+        xj = cos(fma(c12, fma(-b1, tan(C_2), a1 * (1.0 / tan(C_2))), C));
+    }
+    __syncthreads();
+    for (int it = 0; it < 10; ++it) {
+        const bool run = !s_done[h];
+        double dx2 = 0.0;
+        if (run && active) {
+            jacobi_inner_rec(n, xj, a, b, P1, P2);
+            const double dx = P1 / P2;
+            dx2 = dx * dx;
+            xj = xj - dx;
+        }
+        // max over the half (ifelse(_dx2 > dx2, ...) never picks up a NaN, :119-122)
+        double mx = dx2 > 0.0 ? dx2 : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_down_sync(0xffffffffu, mx, o);
+            mx = other > mx ? other : mx;
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) s_dx2[tid >> 5] = mx;
+        __syncthreads();
+        if (tid < 2 && !s_done[tid]) {
+            const double m0 = s_dx2[2 * tid], m1v = s_dx2[2 * tid + 1];
+            const double mm = m1v > m0 ? m1v : m0;
+            if (!(mm > 2.220446049250313e-16 / 1.0e6)) s_done[tid] = 1;
+        }
+        __syncthreads();
+        if (s_done[0] && s_done[1]) break;
+    }
+    // once more for derivatives (:127)
+    if (active) jacobi_inner_rec(n, xj, a, b, P1, P2);
+    // assemble (:69-88): left half mirrored, sum in the reference's order
+    if (active) {
+        const double xi = h == 0 ? xj : -xj;
+        const int idx = h == 0 ? m2 + i0 : m2 - 1 - i0;
+        xs[idx] = xi;
+        wsum[idx] = 1 / ((1 - xi * xi) * (P2 * P2));
+    }
+    __syncthreads();
+    __shared__ double s_scale;
+    if (tid == 0) {
+        double sum_w = 0.0;
+        for (int i = 0; i < m2; ++i) sum_w += wsum[m2 - 1 - i];
+        for (int i = 0; i < m1; ++i) sum_w += wsum[m2 + i];
+        s_scale = p.c / sum_w;
+    }
+    __syncthreads();
+    if (tid < n && tid >= p.lo && tid < p.hi) {
+        x[tid - p.lo] = xs[tid];
+        w[tid - p.lo] = wsum[tid] * s_scale;
+    }
+}
+
 static double jacobi_tt_host(int64_t n, double a, double b, int64_t i) {
     const double PI = 3.141592653589793;
     const double j = (double)(n - i);
@@ -245,25 +363,55 @@ static double jacobi_tt_host(int64_t n, double a, double b, int64_t i) {
 
 using namespace fgq;
 
+// Dispatch of gaussjacobi.jl:23-55 for the general (alpha, beta): 0 ok (asy), -1 ok (rec / closed form).
 static int jacobi_check_args(int64_t n, double a, double b) {
     if (n < 0) {
         set_error("DomainError(%lld): gaussjacobi(%lld,%g,%g) not defined: n must be non-negative.",
                   (long long)n, (long long)n, a, b);
         return FGQ_EDOMAIN;
     }
+    if (n <= 1) return FGQ_OK;  // :40-43 come before the integrability check in the reference
     if (!(a > -1.0) || !(b > -1.0)) {
         set_error("DomainError((%g, %g)): The Jacobi parameters correspond to a nonintegrable weight function", a, b);
         return FGQ_EDOMAIN;
     }
     const double mx = a > b ? a : b;
-    if (n > 100 && mx < 5.0) return FGQ_OK;
-    if (n > 4000 && mx >= 5.0) {
+    if (mx < 5.0) return FGQ_OK;
+    if (n > 4000) {
         set_error("gaussjacobi(%lld,%g,%g) is not implemented: n must be <= 4000 for max(a,b) >= 5.", (long long)n, a, b);
         return FGQ_ENOTIMPL;
     }
-    set_error("gaussjacobi(%lld,%g,%g): the reference serves this region with jacobi_rec (n <= 100) or "
-              "Golub-Welsch (max(a,b) >= 5), which are not on the device path", (long long)n, a, b);
+    set_error("gaussjacobi(%lld,%g,%g): max(a,b) >= 5 is served by a Golub-Welsch eigen-solve in the reference "
+              "(gaussjacobi.jl:50-51), which is not on the device path", (long long)n, a, b);
     return FGQ_ENOTIMPL;
+}
+
+static int jacobi_rec_device(int64_t n, double a, double b, int64_t lo, int64_t hi, double* x_dev, double* w_dev,
+                             cudaStream_t st) {
+    JacobiRecParams p;
+    p.n = (int)n;
+    p.alpha = a;
+    p.beta = b;
+    p.lo = lo;
+    p.hi = hi;
+    if (n == 1) {
+        // :42-43: x = (b-a)/(a+b+2), w = 2^(a+b+1) beta(a+1, b+1); reuse the patch kernel for the single node
+        JacobiPatch q;
+        q.n = 2 * JAC_NBDY;  // maps patch slot 0 to output index 0
+        q.lo = lo;
+        q.hi = hi;
+        for (int i = 0; i < 2 * JAC_NBDY; ++i) q.x[i] = q.w[i] = 0.0;
+        q.x[0] = (b - a) / (a + b + 2);
+        q.w[0] = pow(2.0, a + b + 1) * (tgamma(a + 1) * tgamma(b + 1) / tgamma(a + b + 2));
+        if (hi > 1) q.hi = 1;
+        jacobi_patch_kernel<<<1, 32, 0, st>>>(q, x_dev, w_dev);
+        FGQ_LAUNCH_CHECK();
+        return FGQ_OK;
+    }
+    p.c = pow(2.0, a + b + 1) * tgamma(2 + a) * tgamma(2 + b) / (tgamma(2 + a + b) * (a + 1) * (b + 1));
+    jacobi_rec_kernel<<<1, 128, 0, st>>>(p, x_dev, w_dev);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
 }
 
 extern "C" int64_t fgq_gaussjacobi_workspace_bytes(int64_t n) {
@@ -370,8 +518,13 @@ extern "C" int fgq_gaussjacobi_device(int64_t n, double a, double b, int64_t lo,
     }
     if (n == 0) return FGQ_OK;
     FGQ_TRY(jacobi_check_args(n, a, b));
-    if (!workspace_dev || (hi > lo && (!x_dev || !w_dev))) {
+    if (hi > lo && (!x_dev || !w_dev)) {
         set_error("null pointer");
+        return FGQ_EINVAL;
+    }
+    if (n <= 100) return jacobi_rec_device(n, a, b, lo, hi, x_dev, w_dev, as_stream(stream));  // :46-47
+    if (!workspace_dev) {
+        set_error("null workspace pointer");
         return FGQ_EINVAL;
     }
     return jacobi_asy_device(n, a, b, lo, hi, x_dev, w_dev, workspace_dev, as_stream(stream));
@@ -381,10 +534,26 @@ extern "C" int fgq_gaussjacobi_device(int64_t n, double a, double b, int64_t lo,
 // written one slot to the right so that the epilogue can fill the fixed endpoint(s) in place.
 static int endpoint_rule_device(int mode, int64_t n, double* x_dev, double* w_dev, void* workspace_dev,
                                 cudaStream_t st) {
+    // closed forms: gaussradau.jl:34-37, gausslobatto.jl:36-39
+    if ((mode == 1 && n <= 2) || (mode == 2 && n <= 3)) {
+        JacobiPatch q;
+        q.n = 2 * JAC_NBDY;
+        q.lo = 0;
+        q.hi = n;
+        for (int i = 0; i < 2 * JAC_NBDY; ++i) q.x[i] = q.w[i] = 0.0;
+        if (mode == 1 && n == 1) { q.x[0] = -1; q.w[0] = 2; }
+        if (mode == 1 && n == 2) { q.x[0] = -1; q.x[1] = 1.0 / 3; q.w[0] = 0.5; q.w[1] = 1.5; }
+        if (mode == 2 && n == 2) { q.x[0] = -1; q.x[1] = 1; q.w[0] = 1; q.w[1] = 1; }
+        if (mode == 2 && n == 3) { q.x[0] = -1; q.x[1] = 0; q.x[2] = 1; q.w[0] = 1.0 / 3; q.w[1] = 4.0 / 3; q.w[2] = 1.0 / 3; }
+        jacobi_patch_kernel<<<1, 32, 0, st>>>(q, x_dev, w_dev);
+        FGQ_LAUNCH_CHECK();
+        return FGQ_OK;
+    }
     const int64_t inner = n - mode;
     const double a = mode == 1 ? 0.0 : 1.0, b = 1.0;
     FGQ_TRY(jacobi_check_args(inner, a, b));
-    FGQ_TRY(jacobi_asy_device(inner, a, b, 0, inner, x_dev + 1, w_dev + 1, workspace_dev, st));
+    if (inner <= 100) FGQ_TRY(jacobi_rec_device(inner, a, b, 0, inner, x_dev + 1, w_dev + 1, st));
+    else FGQ_TRY(jacobi_asy_device(inner, a, b, 0, inner, x_dev + 1, w_dev + 1, workspace_dev, st));
     endpoint_epilogue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mode, n, 0, n, x_dev, w_dev);
     FGQ_LAUNCH_CHECK();
     return FGQ_OK;

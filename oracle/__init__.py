@@ -55,6 +55,8 @@ def lib():
         L.oracle_gl_rec_newton.restype = None
         L.oracle_eval_laguerre_rec.argtypes = [_c_i64, ctypes.c_double, ctypes.c_double, _c_dp, _c_dp]
         L.oracle_eval_laguerre_rec.restype = None
+        L.oracle_innerjacobi_rec.argtypes = [_c_i64, _c_i64, _c_dp, ctypes.c_double, ctypes.c_double, _c_dp, _c_dp]
+        L.oracle_innerjacobi_rec.restype = None
         L.oracle_set_threads.argtypes = [ctypes.c_int]
         L.oracle_set_threads.restype = ctypes.c_int
         _lib = L
@@ -125,6 +127,15 @@ def gl_rec_newton(x0: float, n: int, alpha: float):
     wk = ctypes.c_double(0.0)
     lib().oracle_gl_rec_newton(float(x0), int(n), float(alpha), ctypes.byref(xk), ctypes.byref(wk))
     return xk.value, wk.value
+
+
+def innerjacobi_rec(n: int, x: np.ndarray, a: float, b: float):
+    """innerjacobi_rec! of src/gaussjacobi.jl:129-155 (C, muladd -> fma) -> (P, PP)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    P = np.empty_like(x)
+    PP = np.empty_like(x)
+    lib().oracle_innerjacobi_rec(int(n), len(x), _dp(x), float(a), float(b), _dp(P), _dp(PP))
+    return P, PP
 
 
 def ulp_diff(got: np.ndarray, ref: np.ndarray) -> np.ndarray:

@@ -10,8 +10,8 @@ Radau / Lobatto epilogues built on it:
   bary, bessel_taylor, nck_mat  src/gaussjacobi.jl:601-667
   approx_besselroots, McMahon, piessens   src/besselroots.jl:23-165
   gaussradau(n), gausslobatto(n)          src/gaussradau.jl:31-49, src/gausslobatto.jl:31-52
-Only the branch n > 100, max(a,b) < 5 (jacobi_asy) is restated; jacobi_rec (n <= 100) and the
-Golub-Welsch eigen-solve are out of scope.
+jacobi_rec / HalfRec / innerjacobi_rec! (n <= 100)   src/gaussjacobi.jl:61-155
+The Golub-Welsch eigen-solve (max(a,b) >= 5) is out of scope.
 
 Arithmetic outside /root/reference: `besselj(nu, x)` is SpecialFunctions.jl -> AMOS zbesj;
 scipy.special.jv is the same AMOS routine.  The dense products in feval_asy1 are BLAS gemv in the
@@ -441,28 +441,106 @@ def jacobi_asy(n, a, b, info=None):
     return x, w
 
 
+# ---- n <= 100: gaussjacobi.jl:61-155 --------------------------------------------------------------
+
+def innerjacobi_rec(n, x, a, b):
+    """:129-155 — in C (oracle/jacobi_rec_oracle.c) so that muladd is a true fma."""
+    from . import innerjacobi_rec as _c
+    return _c(n, x, a, b)
+
+
+def half_rec(n, a, b, flag):
+    """:94-127"""
+    m = int(np.ceil(n / 2)) if flag == 1 else int(np.floor(n / 2))
+    r = np.arange(m, 0, -1, dtype=np.float64)
+    c1 = 1 / (2 * n + a + b + 1)
+    a1 = 0.25 - a ** 2
+    b1 = 0.25 - b ** 2
+    c12 = c1 ** 2
+    C = (2.0 * r + (a - 0.5)) * (PI * c1)
+    C_2 = C / 2
+    x = np.cos(c12 * (-b1 * np.tan(C_2) + a1 * (1 / np.tan(C_2))) + C)
+    for _ in range(10):
+        P1, P2 = innerjacobi_rec(n, x, a, b)
+        dx = P1 / P2
+        dx2 = 0.0
+        for v in dx * dx:            # ifelse(_dx2 > dx2, _dx2, dx2): NaN never wins
+            if v > dx2:
+                dx2 = v
+        x = x - dx
+        if not (dx2 > EPS / 1.0e6):
+            break
+    P1, P2 = innerjacobi_rec(n, x, a, b)
+    return x, P2
+
+
+def jacobi_rec(n, a, b):
+    """:61-92"""
+    from math import gamma
+    x11, x12 = half_rec(n, a, b, 1)
+    x21, x22 = half_rec(n, b, a, 0)
+    x = np.zeros(n)
+    w = np.zeros(n)
+    m1, m2 = len(x11), len(x21)
+    sum_w = 0.0
+    for i in range(1, m2 + 1):
+        idx = m2 + 1 - i
+        xi = -x21[i - 1]
+        wi = 1 / ((1 - xi ** 2) * x22[i - 1] ** 2)
+        w[idx - 1] = wi
+        x[idx - 1] = xi
+        sum_w += wi
+    for i in range(1, m1 + 1):
+        idx = m2 + i
+        xi = x11[i - 1]
+        wi = 1 / ((1 - xi ** 2) * x12[i - 1] ** 2)
+        w[idx - 1] = wi
+        x[idx - 1] = xi
+        sum_w += wi
+    c = (2 ** (a + b + 1) * gamma(2 + a) * gamma(2 + b) / (gamma(2 + a + b) * (a + 1) * (b + 1)))
+    return x, w * (c / sum_w)
+
+
 def gaussjacobi(n, a, b, info=None):
-    """:23-55 (asymptotic branch only)."""
+    """:23-55 for general (a, b): closed form n = 1, recurrence n <= 100, asymptotics n > 100 (max(a,b) < 5).
+    (0,0) -> Legendre and (+-1/2, +-1/2) -> Chebyshev live in their own oracles."""
+    from math import gamma
     a = float(a)
     b = float(b)
     if n < 0:
         raise ValueError("DomainError: n must be non-negative")
+    if n == 0:
+        return np.zeros(0), np.zeros(0)
+    if n == 1:
+        return np.array([(b - a) / (a + b + 2)]), np.array([2 ** (a + b + 1) * gamma(a + 1) * gamma(b + 1) / gamma(a + b + 2)])
     if min(a, b) <= -1.0:
         raise ValueError("DomainError: nonintegrable weight function")
-    if not (n > 100 and max(a, b) < 5.0):
-        raise NotImplementedError("oracle restates the jacobi_asy branch only (n > 100, max(a,b) < 5)")
+    if max(a, b) >= 5.0:
+        raise NotImplementedError("Golub-Welsch branch (max(a,b) >= 5) is out of scope")
+    if n <= 100:
+        return jacobi_rec(n, a, b)
     return jacobi_asy(n, a, b, info)
 
 
 def gaussradau(n):
-    """gaussradau.jl:31-49 for n - 1 > 100."""
+    """gaussradau.jl:31-49"""
+    if n == 1:
+        return np.array([-1.0]), np.array([2.0])
+    if n == 2:
+        return np.array([-1.0, 1 / 3]), np.array([0.5, 1.5])
     x, w = gaussjacobi(n - 1, 0.0, 1.0)
     w = w / (1 + x)
     return np.concatenate([[-1.0], x]), np.concatenate([[2 / n ** 2], w])
 
 
 def gausslobatto(n):
-    """gausslobatto.jl:31-52 for n - 2 > 100."""
+    """gausslobatto.jl:31-52"""
+    if n <= 1:
+        raise ValueError("DomainError: Lobatto undefined for n <= 1.")
+    if n == 2:
+        return np.array([-1.0, 1.0]), np.array([1.0, 1.0])
+    if n == 3:
+        return np.array([-1.0, 0.0, 1.0]), np.array([1 / 3, 4 / 3, 1 / 3])
     x, w = gaussjacobi(n - 2, 1.0, 1.0)
     w = w / (1 - x ** 2)
     e = 2 / (n * (n - 1))

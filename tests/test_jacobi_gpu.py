@@ -46,8 +46,10 @@ def test_dispatch_and_errors(fgq):
         fgq.gaussjacobi(200, -1.0, 0.2)
     with pytest.raises(fgq.DomainError):
         fgq.gaussjacobi(200, 0.3, -1.5)
-    with pytest.raises(fgq.NotImplementedOnDevice):  # jacobi_rec region
-        fgq.gaussjacobi(42, -0.1, 0.3)
+    with pytest.raises(fgq.NotImplementedOnDevice):  # Golub-Welsch region (gaussjacobi.jl:50-51)
+        fgq.gaussjacobi(42, 6.0, 0.3)
+    x, w = fgq.gaussjacobi(1, 1.0, 2.0)            # test_gaussjacobi.jl:171-179
+    assert abs(x[0] - 0.2) < 1e-14 and abs(w[0] - 4 / 3) < 1e-14
     with pytest.raises(fgq.NotImplementedOnDevice):  # gaussjacobi.jl:53
         fgq.gaussjacobi(5000, 6.0, 0.0)
     x, w = fgq.gaussjacobi(0, 0.3, 0.1)
@@ -109,6 +111,60 @@ def test_parity_with_oracle(fgq, n, a, b):
     assert rw.max() <= 2e-13, f"weights differ by {rw.max()} relatively"
     assert np.all(np.diff(x) > 0)
     assert abs(w.sum() - 2 ** (a + b + 1) * beta(a + 1, b + 1)) < 2e-13 * max(1.0, w.sum())
+
+
+def test_radau_lobatto_reference_goldens(fgq):
+    # test/test_gaussradau.jl:6-29, test/test_gausslobatto.jl:13-36
+    for rule, key in ((fgq.gaussradau, "radau"), (fgq.gausslobatto, "lobatto")):
+        g = GOLD[key]
+        x, w = rule(g["n"])
+        assert len(x) == g["n"]
+        for i, v in g["x"].items():
+            assert abs(x[int(i) - 1] - v) < GOLD["tol"]
+        for i, v in g["w"].items():
+            assert abs(w[int(i) - 1] - v) < GOLD["tol"]
+        assert x[0] == -1.0 and abs(np.dot(w, np.exp(x)) - (np.e - 1 / np.e)) < 1e-14
+    x, w = fgq.gaussradau(1)
+    assert x[0] == -1.0 and w[0] == 2.0
+    x, w = fgq.gaussradau(2)
+    assert np.allclose(x, [-1, 1 / 3], rtol=1e-15) and np.allclose(w, [0.5, 1.5], rtol=1e-15)
+    x, w = fgq.gausslobatto(2)
+    assert np.array_equal(x, [-1, 1]) and np.array_equal(w, [1, 1])
+    x, w = fgq.gausslobatto(3)
+    assert np.array_equal(x, [-1, 0, 1]) and np.allclose(w, [1 / 3, 4 / 3, 1 / 3], rtol=1e-15)
+    x, w = fgq.gausslobatto(42)
+    assert x[-1] == 1.0 and abs(np.dot(w, x * x) - 2 / 3) < 1e-14
+
+
+@pytest.mark.parametrize("n", list(range(2, 12)) + [20, 41, 42, 57, 99, 100])
+@pytest.mark.parametrize("a,b", [(-0.1, 0.3), (0.9, -0.1), (1.0, 1.0), (0.0, 1.0), (4.5, -0.9), (0.3, -0.7)])
+def test_recurrence_branch_parity(fgq, n, a, b):
+    """n <= 100: jacobi_rec (gaussjacobi.jl:61-155), one block per rule."""
+    x, w = fgq.gaussjacobi(n, a, b)
+    xo, wo = jo.gaussjacobi(n, a, b)
+    assert np.abs(x - xo).max() <= 4 * EPS
+    # w = c / ((1 - x^2) P'(x)^2 sum): one ulp of x moves the weight by ~2|x|/(1 - x^2) ulps
+    # (more precisely by ~(2 + |a| + |b|)/(1 - |x|): P'' / P' = (a - b + (a + b + 2) x)/(1 - x^2) at a root)
+    bound = 64 * EPS + 2 * (2 + abs(a) + abs(b)) / (1 - np.abs(xo)) * (np.abs(x - xo) + 2 * EPS)
+    rel = np.abs(w - wo) / wo
+    assert np.all(rel <= bound), f"worst {np.max(rel / bound)} x bound"
+    assert abs(w.sum() - 2 ** (a + b + 1) * beta(a + 1, b + 1)) < 2e-13 * max(1.0, w.sum())
+
+
+def test_compatible_with_legendre_and_chebyshev(fgq):
+    """test_gaussjacobi.jl:8-147: gaussjacobi at (0,0), (+-1/2,+-1/2) and their floating-point
+    neighbours agrees with Gauss-Legendre / Gauss-Chebyshev: ||dx||_2 < 4e-15, ||dw||_2 < 1e-13."""
+    cheb = {(-0.5, -0.5): fgq.gausschebyshevt, (0.5, 0.5): fgq.gausschebyshevu,
+            (-0.5, 0.5): fgq.gausschebyshevv, (0.5, -0.5): fgq.gausschebyshevw}
+    n_range = list(range(0, 11)) + list(range(20, 101, 10)) + [120, 300]
+    for (a0, b0), ref in [((0.0, 0.0), fgq.gausslegendre)] + list(cheb.items()):
+        for n in n_range:
+            x, w = ref(n)
+            for a in (a0, np.nextafter(a0, 1), np.nextafter(a0, -1)):
+                for b in (b0, np.nextafter(b0, 1), np.nextafter(b0, -1)):
+                    xj, wj = fgq.gaussjacobi(n, a, b)
+                    assert np.linalg.norm(x - xj) < 4e-15, (n, a, b)
+                    assert np.linalg.norm(w - wj) < 1e-13, (n, a, b)
 
 
 @pytest.mark.parametrize("n", [1001, 2002, 100003])

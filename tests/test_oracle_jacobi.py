@@ -39,6 +39,22 @@ def test_besselroots():
         assert np.max(np.abs(jv(nu, jo.approx_besselroots(float(nu), 10)))) < 1e-11
 
 
+def test_radau_lobatto_goldens():
+    # test/test_gaussradau.jl:21-29, test/test_gausslobatto.jl:27-36 (n = 42: recurrence branch)
+    for rule, key in ((jo.gaussradau, "radau"), (jo.gausslobatto, "lobatto")):
+        g = GOLD[key]
+        x, w = rule(g["n"])
+        for i, v in g["x"].items():
+            assert abs(x[int(i) - 1] - v) < GOLD["tol"]
+        for i, v in g["w"].items():
+            assert abs(w[int(i) - 1] - v) < GOLD["tol"]
+        assert x[0] == -1.0 and abs(np.dot(w, np.exp(x)) - (np.e - 1 / np.e)) < 1e-14
+    x, w = jo.gaussradau(2)
+    assert np.allclose(x, [-1, 1 / 3]) and np.allclose(w, [0.5, 1.5])
+    x, w = jo.gausslobatto(3)
+    assert np.allclose(x, [-1, 0, 1]) and np.allclose(w, [1 / 3, 4 / 3, 1 / 3])
+
+
 def test_radau_lobatto_structure():
     x, w = jo.gaussradau(1001)
     assert x[0] == -1.0 and abs(w.sum() - 2) < 1e-13 and abs(np.dot(w, x ** 3)) < 1e-13
