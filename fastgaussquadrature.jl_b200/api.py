@@ -296,19 +296,15 @@ def approx_besselroots(nu, n):
 def gausshermite(n, *, normalize: bool = False):
     """``gausshermite(n; normalize=false) -> x, w`` (reference src/gausshermite.jl:28,33).
 
-    n < 0 raises DomainError (:38); n == 0 returns empty arrays (:40); n == 1 is the closed form
-    (:42).  2 <= n <= 200 raises NotImplementedOnDevice: the reference serves those with the
-    recurrence / Golub-Welsch branches, which are off the hot path."""
+    n < 0 raises DomainError (:38); n == 0 returns empty arrays (:40).  All n are served on the
+    device: n <= 20 by a tiny eigen-solve (the reference's Golub-Welsch, :43-45), n <= 200 by Newton
+    on the recurrence (:46-48), larger n by the Airy-type asymptotics (:49-50)."""
     n = _as_int(n)
     if n < 0:
         raise DomainError(f"DomainError({n}): Input n must be a non-negative integer")
     x, w = _host_pair(n, False)
     if n == 0:
         return x, w
-    if n == 1:  # gausshermite.jl:41-42, then :30-31
-        x[0] = 0.0
-        w[0] = np.sqrt(np.pi)
-        return (np.sqrt(2.0) * x, w / np.sqrt(np.pi)) if normalize else (x, w)
     check(lib().fgq_gausshermite_host(n, int(bool(normalize)), _ptr(x), _ptr(w)))
     return x, w
 

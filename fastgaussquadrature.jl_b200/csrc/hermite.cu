@@ -15,6 +15,7 @@
 // normalisation sum (:62) and a fold/scale kernel that also applies exp(-x^2) (:30).
 #include "airy.cuh"
 #include "common.cuh"
+#include "gw.cuh"
 
 namespace fgq {
 
@@ -212,6 +213,83 @@ hermite_sweep_kernel(HermiteParams p, int sweep, HermiteState* st, double* theta
     }
 }
 
+// hermpoly_rec(n, x0) (gausshermite.jl:113-137): scaled Hermite polynomial and derivative by the
+// recurrence, regularised by powers of exp(-x0^2/(4n)) whenever |H| >= 100.
+__device__ void hermpoly_rec(int n, double x0, double& val, double& dval) {
+    const double w = exp(-(x0 * x0) / (4 * (double)n));
+    int wc = 0;
+    double Hold = 1.0, H = x0;
+    for (int k = 1; k <= n - 1; ++k) {
+        const double k1 = (double)(k + 1);
+        const double Hnew = x0 * H / sqrt(k1) - Hold / sqrt(k1 / (double)k);
+        Hold = H;
+        H = Hnew;
+        while (fabs(H) >= 100 && wc < n) {
+            H *= w;
+            Hold *= w;
+            wc += 1;
+        }
+    }
+    for (int q = wc + 1; q <= n; ++q) {
+        H *= w;
+        Hold *= w;
+    }
+    val = H;
+    dval = -x0 * H + sqrt((double)n) * Hold;
+}
+
+// hermite_rec (gausshermite.jl:91-111), 21 <= n <= 200: one block, one thread per half-range node,
+// at most 10 Newton steps with the global stopping rule ||dx||_inf < sqrt(eps).
+__global__ void __launch_bounds__(128) hermite_rec_kernel(HermiteParams p, double* xh, double* wh) {
+    const int t = threadIdx.x;
+    const bool active = t < p.nh;
+    const double SQ2 = 1.4142135623730951;
+    double x0 = 0.0, val = 0.0, dval = 1.0;
+    if (active) {
+        x0 = p.odd ? (t == 0 ? 0.0 : hermite_guess(p, t)) : hermite_guess(p, t + 1);
+        x0 *= SQ2;
+    }
+    __shared__ double s_mx[4];
+    for (int it = 0; it < 10; ++it) {
+        double adx = 0.0;
+        if (active) {
+            hermpoly_rec((int)p.n, x0, val, dval);
+            double dx = val / dval;
+            if (dx != dx) dx = 0.0;
+            x0 = x0 - dx;
+            adx = fabs(dx);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) adx = fmax(adx, __shfl_down_sync(0xffffffffu, adx, o));
+        __syncthreads();
+        if ((t & 31) == 0) s_mx[t >> 5] = adx;
+        __syncthreads();
+        const double mx = fmax(fmax(s_mx[0], s_mx[1]), fmax(s_mx[2], s_mx[3]));
+        if (mx < 1.4901161193847656e-08) break;  // sqrt(eps)
+    }
+    if (active) {
+        xh[t] = x0 / SQ2;
+        wh[t] = 1.0 / (dval * dval);
+    }
+}
+
+// hermite_gw (gausshermite.jl:325-341), 2 <= n <= 20: eigenvalues of the Jacobi matrix, upper half.
+__global__ void hermite_gw_kernel(HermiteParams p, double* xh, double* wh) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = (int)p.n;
+    double d[GW_MAX], e[GW_MAX], z[GW_MAX];
+    for (int i = 0; i < n; ++i) d[i] = 0.0;
+    for (int k = 1; k <= n - 1; ++k) e[k - 1] = sqrt((double)k / 2);
+    tridiag_ql_first_row(n, d, e, z);
+    const int first = n / 2;  // i = floor(n/2)+1 : n (1-based)
+    for (int i = first; i < n; ++i) {
+        const double x = d[i];
+        const double w = 1.7724538509055159 * (z[i] * z[i]);
+        xh[i - first] = x;
+        wh[i - first] = exp(x * x) * w;
+    }
+}
+
 // sum over the FOLDED rule of exp(-x^2) w (gausshermite.jl:62): twice the half-range sum, the centre
 // node of an odd rule counted once.
 __global__ void __launch_bounds__(256)
@@ -316,31 +394,40 @@ extern "C" int fgq_gausshermite_device(int64_t n, int normalize, int64_t lo, int
         set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);
         return FGQ_EDOMAIN;
     }
-    if (n <= 200) {
-        set_error("gausshermite(%lld): n <= 200 uses the recurrence / Golub-Welsch branches "
-                  "(gausshermite.jl:43-48), which are not on the device path", (long long)n);
-        return FGQ_ENOTIMPL;
-    }
     if (lo < 0 || hi < lo || hi > n) {
         set_error("invalid shard [%lld, %lld) of n=%lld", (long long)lo, (long long)hi, (long long)n);
         return FGQ_EINVAL;
     }
+    if (n == 0) return FGQ_OK;
     if (!workspace_dev || (hi > lo && (!x_dev || !w_dev))) {
         set_error("null pointer");
         return FGQ_EINVAL;
     }
     cudaStream_t st = as_stream(stream);
-    const HermiteParams p = hermite_params(n);
+    HermiteParams p = hermite_params(n);
     HermiteState* state = (HermiteState*)workspace_dev;
     double* theta = (double*)((char*)workspace_dev + 1024);
     double* xh = theta + p.nh;
     double* wh = xh + p.nh;
     const unsigned b128 = (unsigned)((p.nh + HERM_THREADS - 1) / HERM_THREADS);
-    hermite_init_kernel<<<b128, HERM_THREADS, 0, st>>>(p, state, theta);
+    hermite_init_kernel<<<b128, HERM_THREADS, 0, st>>>(p, state, theta);  // also resets the state
     FGQ_LAUNCH_CHECK();
-    for (int s = 0; s < 20; ++s) {
-        hermite_sweep_kernel<<<b128, HERM_THREADS, 0, st>>>(p, s, state, theta, xh, wh);
+    if (n == 1) {
+        // gausshermite.jl:41-42: x = [0], w = [sqrt(pi)] before the common normalisation
+        const double one_x = 0.0, one_w = 1.7724538509055159;
+        FGQ_CUDA_TRY(cudaMemcpyAsync(xh, &one_x, 8, cudaMemcpyHostToDevice, st));
+        FGQ_CUDA_TRY(cudaMemcpyAsync(wh, &one_w, 8, cudaMemcpyHostToDevice, st));
+    } else if (n <= 20) {
+        hermite_gw_kernel<<<1, 32, 0, st>>>(p, xh, wh);  // :43-45
         FGQ_LAUNCH_CHECK();
+    } else if (n <= 200) {
+        hermite_rec_kernel<<<1, 128, 0, st>>>(p, xh, wh);  // :46-48
+        FGQ_LAUNCH_CHECK();
+    } else {
+        for (int s = 0; s < 20; ++s) {
+            hermite_sweep_kernel<<<b128, HERM_THREADS, 0, st>>>(p, s, state, theta, xh, wh);
+            FGQ_LAUNCH_CHECK();
+        }
     }
     int64_t rb = (p.nh + 255) / 256;
     if (rb > 148 * 4) rb = 148 * 4;
@@ -360,11 +447,7 @@ extern "C" int fgq_gausshermite_host(int64_t n, int normalize, double* x, double
         set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);
         return FGQ_EDOMAIN;
     }
-    if (n <= 200) {
-        set_error("gausshermite(%lld): n <= 200 uses the recurrence / Golub-Welsch branches "
-                  "(gausshermite.jl:43-48), which are not on the device path", (long long)n);
-        return FGQ_ENOTIMPL;
-    }
+    if (n == 0) return FGQ_OK;
     if (!x || !w) {
         set_error("null output pointer");
         return FGQ_EINVAL;

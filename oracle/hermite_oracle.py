@@ -6,8 +6,8 @@ numpy restatement of the asymptotic Gauss-Hermite path of FastGaussQuadrature.jl
   hermpoly_asy_airy                       src/gausshermite.jl:171-250
   hermite_initialguess                    src/gausshermite.jl:252-323
   AIRY_ROOTS                              src/constants.jl:121-135
-Only n > 200 (the asymptotic branch, :48-50) is restated: the n <= 200 recurrence and the n <= 20
-Golub-Welsch eigen-solve are out of scope.
+  hermite_rec, hermpoly_rec               src/gausshermite.jl:91-137   (21 <= n <= 200)
+  hermite_gw                              src/gausshermite.jl:325-341  (n <= 20; LAPACK through scipy)
 
 Arithmetic outside /root/reference: `airyai`/`airyaiprime` are SpecialFunctions.jl -> AMOS `zairy`
 (version unpinned in the reference).  scipy.special.airy on a COMPLEX argument calls the same AMOS
@@ -152,13 +152,69 @@ def hermite_asy(n: int, info: dict | None = None):
     return x, w
 
 
+def hermpoly_rec(n: int, x0: float):
+    """gausshermite.jl:113-137 (scalar)."""
+    import math
+    w = math.exp(-x0 ** 2 / (4 * n))
+    wc = 0
+    Hold = 1.0
+    H = x0
+    for k in range(1, n):
+        Hold, H = H, (x0 * H / math.sqrt(k + 1.0) - Hold / math.sqrt((k + 1.0) / k))
+        while abs(H) >= 100 and wc < n:
+            H *= w
+            Hold *= w
+            wc += 1
+    for _ in range(wc + 1, n + 1):
+        H *= w
+        Hold *= w
+    return H, -x0 * H + math.sqrt(float(n)) * Hold
+
+
+def hermite_rec(n: int):
+    """gausshermite.jl:91-111 (Float64: at most 10 Newton steps)."""
+    x0 = hermite_initialguess(n) * np.sqrt(2.0)
+    val = None
+    for _ in range(10):
+        val = np.array([hermpoly_rec(n, float(v)) for v in x0])
+        with np.errstate(all="ignore"):
+            dx = val[:, 0] / val[:, 1]
+        dx[np.isnan(dx)] = 0
+        x0 = x0 - dx
+        if np.max(np.abs(dx)) < np.sqrt(EPS):
+            break
+    x0 = x0 / np.sqrt(2.0)
+    return x0, 1 / val[:, 1] ** 2
+
+
+def hermite_gw(n: int):
+    """gausshermite.jl:325-341 (LAPACK symmetric-tridiagonal eigen-solve, as in the reference)."""
+    from scipy.linalg import eigh_tridiagonal
+    beta = np.sqrt(np.arange(1, n, dtype=np.float64) / 2)
+    D, V = eigh_tridiagonal(np.zeros(n), beta)
+    ind = np.argsort(D)
+    x = D[ind]
+    w = np.sqrt(PI) * V[0, ind] ** 2
+    i0 = n // 2
+    x = x[i0:]
+    w = w[i0:]
+    return x, np.exp(x ** 2) * w
+
+
 def unweightedgausshermite(n: int, info: dict | None = None):
-    """gausshermite.jl:35-65 (asymptotic branch only)."""
+    """gausshermite.jl:35-65."""
     if n < 0:
         raise ValueError("DomainError: Input n must be a non-negative integer")
-    if n <= 200:
-        raise NotImplementedError("oracle restates the asymptotic branch only (n > 200)")
-    xh, wh = hermite_asy(n, info)
+    if n == 0:
+        return np.zeros(0), np.zeros(0)
+    if n == 1:
+        xh, wh = np.array([0.0]), np.array([np.sqrt(PI)])
+    elif n <= 20:
+        xh, wh = hermite_gw(n)
+    elif n <= 200:
+        xh, wh = hermite_rec(n)
+    else:
+        xh, wh = hermite_asy(n, info)
     if n % 2:
         w = np.concatenate([wh[::-1], wh[1:]])
         x = np.concatenate([-xh[::-1], xh[1:]])

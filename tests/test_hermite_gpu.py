@@ -29,6 +29,34 @@ def test_reference_golden_values(fgq, case):
         assert abs(w[int(i) - 1] - v) < tol
     assert np.dot(w, x) < case["dot_wx_lt"]
     assert abs(np.dot(w, x * x) - np.sqrt(np.pi) / 2) < case["dot_wx2_tol"]
+    if "poly_integral" in case:   # test_gausshermite.jl:35-36
+        assert abs(np.dot(w, 1 + x + x ** 2 + x ** 3) - case["poly_integral"]) < 1.5e-8 * case["poly_integral"]  # Julia isapprox, rtol = sqrt(eps)
+
+
+def test_all_small_n(fgq):
+    """test_gausshermite.jl:97-106 ("All"): n = 2..220 spans Golub-Welsch (<= 20), recurrence (<= 200)
+    and asymptotics; plus parity with the oracle (LAPACK eigen-solve / recurrence / AMOS)."""
+    tol = 1e-14
+    for n in range(2, 221):
+        x, w = fgq.gausshermite(n)
+        assert len(x) == n and len(w) == n
+        assert np.dot(w, x) < tol and abs(np.dot(w, x ** 2) - np.sqrt(np.pi) / 2) < 1000 * tol
+        xo, wo = ho.gausshermite(n)
+        assert np.abs(x - xo).max() <= 8 * np.spacing(np.sqrt(2 * n + 1)), n
+        nz = wo > 1e-290
+        assert np.all(np.abs(w[nz] - wo[nz]) / wo[nz] <= 1e-13 + 4 * np.abs(xo[nz]) * 8 * np.spacing(np.sqrt(2 * n + 1))), n
+
+
+def test_normalize_small_n(fgq):
+    # test_gausshermite.jl:80-95
+    for t in range(1, 7):
+        x, w = fgq.gausshermite(t, normalize=True)
+        v = 1.0
+        for k in range(2, 2 * t, 2):
+            v *= (k - 1)
+            assert abs(v - np.dot(x ** k, w)) < 1e-13 * v
+        for k in range(1, 2 * t, 2):
+            assert abs(np.dot(x ** k, w)) < 1e-13
 
 
 def test_api_edges(fgq):
@@ -38,8 +66,8 @@ def test_api_edges(fgq):
     assert len(x) == 0 and len(w) == 0
     x, w = fgq.gausshermite(1)                 # :8-10
     assert x[0] == 0.0 and abs(w[0] - np.sqrt(np.pi)) < 1e-15
-    with pytest.raises(fgq.NotImplementedOnDevice):
-        fgq.gausshermite(42)                   # recurrence branch: off the device path
+    x, w = fgq.gausshermite(2)
+    assert np.allclose(x, [-np.sqrt(0.5), np.sqrt(0.5)], rtol=4e-16) and np.allclose(w, [np.sqrt(np.pi) / 2] * 2, rtol=4e-16)
 
 
 @pytest.mark.parametrize("n", [201, 251, 500, 1000, 1001, 4001, 100000, 100001, 1000000, 1000001])

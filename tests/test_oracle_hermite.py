@@ -23,6 +23,8 @@ def test_golden_values(case):
         assert abs(w[int(i) - 1] - v) < tol
     assert np.dot(w, x) < case["dot_wx_lt"]
     assert abs(np.dot(w, x * x) - np.sqrt(np.pi) / 2) < case["dot_wx2_tol"]
+    if "poly_integral" in case:
+        assert abs(np.dot(w, 1 + x + x ** 2 + x ** 3) - case["poly_integral"]) < 1.5e-8 * case["poly_integral"]  # Julia isapprox, rtol = sqrt(eps)
 
 
 def test_structure_and_sweeps():
