@@ -331,9 +331,10 @@ def gausshermite_device(n, *, normalize: bool = False, stream=None):
 def gausslaguerre(n, alpha=0.0, *, reduced: bool = False):
     """``gausslaguerre(n[, α]; reduced=false) -> x, w`` (reference src/gausslaguerre.jl:1,23,59).
 
-    α <= -1 or n < 0 raise DomainError (:60-65); n == 0 returns empty arrays (:69).  The device
-    path is the explicit-asymptotics branch (n >= 128, α < 5); smaller n / larger α raise
-    NotImplementedOnDevice.  ``reduced=True`` drops the tail of underflowed weights."""
+    α <= -1 or n < 0 raise DomainError (:60-65); n == 0 returns empty arrays (:69).  n >= 128 with
+    α < 5 is the explicit-asymptotics branch; n < 128 (closed forms, Golub-Welsch, recurrence rule)
+    and α >= 5 (recurrence rule, up to n = 4096) are served by a single-thread kernel, as the work is
+    sequential there.  ``reduced=True`` drops the tail of underflowed weights."""
     n = _as_int(n)
     alpha = float(alpha)
     if alpha <= -1:

@@ -19,6 +19,7 @@
 #include "airy.cuh"
 #include "bessel.cuh"
 #include "common.cuh"
+#include "gw.cuh"
 #include "jacobi_plan.h"
 
 namespace fgq {
@@ -362,40 +363,112 @@ __device__ void eval_laguerre_rec(int64_t n, double alpha, double pn0, double x,
     pnd_out = pnd;
 }
 
-// the recompute hook (:153-162 etc.): gl_rec_newton (:547-579) for every flagged node, accepted only
-// if it stays within 100 delta of the asymptotic value
+// gl_rec_newton (:547-579)
+__device__ void gl_rec_newton_dev(const LaguerreParams& p, double x0, bool computeweight, double& xk_out,
+                                  double& wk_out, unsigned int* warn) {
+    const double eps = 2.220446049250313e-16;
+    double step = x0, xk = x0, xk_prev = x0, pn_prev = 1.7976931348623157e308, pn_deriv = 0.0;
+    int iter = 0;
+    while (fabs(step) > 40 * eps * xk && iter < 20) {
+        iter += 1;
+        double pn;
+        eval_laguerre_rec(p.n, p.alpha, p.pn0, xk, pn, pn_deriv);
+        if (fabs(pn) >= fabs(pn_prev) * (1 - 50 * eps)) {
+            xk = xk_prev;
+            break;
+        }
+        step = pn / pn_deriv;
+        xk_prev = xk;
+        xk -= step;
+        pn_prev = pn;
+    }
+    if (xk < 0 || xk > p.xmax || iter == 20) *warn |= (unsigned int)FGQ_WARN_NEWTON_MAXITER;
+    xk_out = xk;
+    wk_out = 0.0;
+    if (computeweight) {
+        double pn_min1, dummy;
+        eval_laguerre_rec(p.n - 1, p.alpha, p.pn0, xk, pn_min1, dummy);
+        wk_out = p.wnorm / pn_min1 / pn_deriv;
+    }
+}
+
+// the recompute hook (:153-162 etc.): gl_rec_newton for every flagged node, accepted only if it stays
+// within 100 delta of the asymptotic value
 __global__ void laguerre_recompute_kernel(const LaguerreParams p, LaguerreState* st, double* x, double* w,
                                           const double* delta_in, const unsigned int* flagged) {
     const unsigned int cnt = st->n_flagged;
-    const double eps = 2.220446049250313e-16;
     for (unsigned int f = blockIdx.x * blockDim.x + threadIdx.x; f < cnt; f += gridDim.x * blockDim.x) {
         const unsigned int i = flagged[f];
         const double x0 = x[i];
         const double delta = delta_in[i];
-        double step = x0, xk = x0, xk_prev = x0, pn_prev = 1.7976931348623157e308, pn_deriv = 0.0;
-        int iter = 0;
-        while (fabs(step) > 40 * eps * xk && iter < 20) {
-            iter += 1;
-            double pn;
-            eval_laguerre_rec(p.n, p.alpha, p.pn0, xk, pn, pn_deriv);
-            if (fabs(pn) >= fabs(pn_prev) * (1 - 50 * eps)) {
-                xk = xk_prev;
-                break;
-            }
-            step = pn / pn_deriv;
-            xk_prev = xk;
-            xk -= step;
-            pn_prev = pn;
-        }
-        if (xk < 0 || xk > p.xmax || iter == 20) atomicOr(&st->warn, (unsigned int)FGQ_WARN_NEWTON_MAXITER);
-        double pn_min1, dummy;
-        eval_laguerre_rec(p.n - 1, p.alpha, p.pn0, xk, pn_min1, dummy);
-        const double wk = p.wnorm / pn_min1 / pn_deriv;
+        unsigned int warn = 0;
+        double xk, wk;
+        gl_rec_newton_dev(p, x0, true, xk, wk, &warn);
+        if (warn) atomicOr(&st->warn, warn);
         if (fabs(xk - x0) < 100 * delta) {
             x[i] = xk;
             w[i] = wk;
         }
     }
+}
+
+// Small rules, one thread (the work is inherently sequential and tiny):
+//   n = 1, 2      closed forms                                   (:70-78)
+//   n < 15        Golub-Welsch on the Jacobi matrix              (gausslaguerre_GW :535-542)
+//   otherwise     gausslaguerre_rec (:582-618): Newton on the recurrence, node after node, each
+//                 initial guess extrapolated from the seven previous nodes
+struct LaguerreSmall {
+    double g1;          // gamma(1 + alpha)
+    double g2;          // gamma(alpha + 2)
+    double jak_pre[7];  // approx_besselroots(alpha, min(n, 7))
+};
+
+__global__ void laguerre_small_kernel(const LaguerreParams p, const LaguerreSmall q, LaguerreState* st, double* x, double* w) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = (int)p.n;
+    const double al = p.alpha;
+    if (n == 1) {
+        x[0] = 1 + al;
+        w[0] = q.g1;
+        return;
+    }
+    if (n == 2) {
+        const double s = sqrt(al + 2);
+        x[0] = al + 2 - s;
+        x[1] = al + 2 + s;
+        w[0] = ((al - s + 2) * q.g2) / (2 * (al + 2) * ((s - 1) * (s - 1)));
+        w[1] = ((al + s + 2) * q.g2) / (2 * (al + 2) * ((s + 1) * (s + 1)));
+        return;
+    }
+    if (n < 15) {
+        double d[GW_MAX], e[GW_MAX], z[GW_MAX];
+        for (int k = 1; k <= n; ++k) d[k - 1] = 2 * (double)k + (al - 1);
+        for (int k = 1; k <= n - 1; ++k) e[k - 1] = sqrt((double)k * (al + (double)k));
+        tridiag_ql_first_row(n, d, e, z);
+        for (int i = 0; i < n; ++i) {
+            x[i] = d[i];
+            w[i] = q.g1 * (z[i] * z[i]);
+        }
+        return;
+    }
+    const int n_pre = n < 7 ? n : 7;
+    const double nu = 4 * (double)n + 2 * al + 2;
+    bool no_underflow = true;
+    unsigned int warn = 0;
+    for (int k = 1; k <= n; ++k) {
+        double xk;
+        if (k <= n_pre) {
+            xk = q.jak_pre[k - 1] * q.jak_pre[k - 1] / nu;
+        } else {
+            xk = 7 * x[k - 2] - 21 * x[k - 3] + 35 * x[k - 4] - 35 * x[k - 5] + 21 * x[k - 6] - 7 * x[k - 7] + x[k - 8];
+        }
+        double wk;
+        gl_rec_newton_dev(p, xk, no_underflow, xk, wk, &warn);
+        if (no_underflow && fabs(wk) < 10 * 2.2250738585072014e-308) no_underflow = false;
+        x[k - 1] = xk;
+        w[k - 1] = wk;
+    }
+    if (warn) atomicOr(&st->warn, warn);
 }
 
 // reduced rule (:163-169 ...): the rule ends before the first weight below 10 floatmin
@@ -417,6 +490,8 @@ __global__ void laguerre_reduced_kernel(int64_t n, const double* w, LaguerreStat
 
 using namespace fgq;
 
+constexpr int64_t LAG_REC_MAX = 4096;  // sequential recurrence rule: one thread, O(n^2) dependent steps
+
 static int laguerre_check(int64_t n, double alpha) {
     if (!(alpha > -1.0)) {
         set_error("DomainError(%g): The Laguerre parameter alpha <= -1 corresponds to a nonintegrable weight function", alpha);
@@ -426,9 +501,9 @@ static int laguerre_check(int64_t n, double alpha) {
         set_error("DomainError(%lld): gausslaguerre(%lld,%g) not defined: n must be positive.", (long long)n, (long long)n, alpha);
         return FGQ_EDOMAIN;
     }
-    if (n < 128 || alpha >= 5.0) {
-        set_error("gausslaguerre(%lld,%g): the reference serves n < 128 and alpha >= 5 with closed forms, Golub-Welsch or the "
-                  "recurrence rule (gausslaguerre.jl:70-95), which are not on the device path", (long long)n, alpha);
+    if (alpha >= 5.0 && n > LAG_REC_MAX) {
+        set_error("gausslaguerre(%lld,%g): alpha >= 5 is served by the O(n^2) recurrence rule in the reference "
+                  "(gausslaguerre.jl:93-94); the device path takes it up to n = %lld", (long long)n, alpha, (long long)LAG_REC_MAX);
         return FGQ_ENOTIMPL;
     }
     if (n > 4000000000LL) {
@@ -485,6 +560,7 @@ extern "C" int fgq_gausslaguerre_device(int64_t n, double alpha, double* x_dev, 
                                         void* workspace_dev, void* stream) {
     clear_status();
     FGQ_TRY(laguerre_check(n, alpha));
+    if (n == 0) return FGQ_OK;
     if (!x_dev || !w_dev || !workspace_dev) {
         set_error("null pointer");
         return FGQ_EINVAL;
@@ -502,6 +578,19 @@ extern "C" int fgq_gausslaguerre_device(int64_t n, double alpha, double* x_dev, 
     init.n_flagged = 0;
     init.warn = 0;
     FGQ_CUDA_TRY(cudaMemcpyAsync(state, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    if (n == 0) return FGQ_OK;
+    if (n < 128 || alpha >= 5.0) {  // gausslaguerre.jl:70-95: closed forms, Golub-Welsch, recurrence rule
+        LaguerreSmall q;
+        q.g1 = tgamma(1 + alpha);
+        q.g2 = tgamma(alpha + 2);
+        for (int i = 0; i < 7; ++i) q.jak_pre[i] = 0.0;
+        approx_besselroots(alpha, (int)(n < 7 ? n : 7), q.jak_pre);
+        laguerre_small_kernel<<<1, 32, 0, st>>>(p, q, state, x_dev, w_dev);
+        FGQ_LAUNCH_CHECK();
+        laguerre_reduced_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, w_dev, state);
+        FGQ_LAUNCH_CHECK();
+        return FGQ_OK;
+    }
     const unsigned blocks = (unsigned)((n + LAG_THREADS - 1) / LAG_THREADS);
     laguerre_handover_bessel_kernel<<<blocks, LAG_THREADS, 0, st>>>(p, state);
     FGQ_LAUNCH_CHECK();
@@ -536,6 +625,10 @@ extern "C" int fgq_gausslaguerre_stats(const void* workspace_dev, int64_t* k_b, 
 extern "C" int fgq_gausslaguerre_host(int64_t n, double alpha, int reduced, double* x, double* w, int64_t* n_out) {
     clear_status();
     FGQ_TRY(laguerre_check(n, alpha));
+    if (n == 0) {
+        if (n_out) *n_out = 0;
+        return FGQ_OK;
+    }
     if (!x || !w) {
         set_error("null output pointer");
         return FGQ_EINVAL;

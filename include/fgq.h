@@ -122,9 +122,9 @@ int fgq_gausschebyshev_device(int kind, int64_t n, int64_t lo, int64_t hi, doubl
 
 /* ---- Gauss-Hermite: gausshermite(n; normalize) — src/gausshermite.jl:28-89,171-323 ---------- */
 
-/* Asymptotic (Airy) + Newton path, n > 200 (gausshermite.jl:49-50).  n < 0 -> FGQ_EDOMAIN (:38);
- * 0 <= n <= 200 -> FGQ_ENOTIMPL (the reference's recurrence / Golub-Welsch branches are not on the
- * device path).  normalize != 0 applies x*sqrt(2), w/sqrt(pi) (:31). */
+/* n > 200: asymptotic (Airy) + Newton path (gausshermite.jl:49-50); 21..200: Newton on the regularised
+ * recurrence (:46-48); 2..20: eigen-solve of the Jacobi matrix (:43-45); n = 1 closed form.
+ * n < 0 -> FGQ_EDOMAIN (:38).  normalize != 0 applies x*sqrt(2), w/sqrt(pi) (:31). */
 int fgq_gausshermite_host(int64_t n, int normalize, double* x, double* w);
 /* Device-resident.  The whole half-range is always solved on the current device (the Newton
  * stopping rule and the normalisation sum are global); output indices [lo, hi) are written to
@@ -140,8 +140,9 @@ int fgq_gausshermite_sweeps(const void* workspace_dev, int* sweeps);
 /* ---- Gauss-Laguerre: gausslaguerre(n, alpha; reduced) — src/gausslaguerre.jl:59-261,273-529 --- */
 
 /* Explicit asymptotic expansions (gausslaguerre_asy with T = -1, recompute = true: the call at
- * gausslaguerre.jl:91), n >= 128 and alpha < 5.  alpha <= -1 or n < 0 -> FGQ_EDOMAIN (:60-65);
- * n < 128 or alpha >= 5 -> FGQ_ENOTIMPL (closed forms / Golub-Welsch / recurrence rule, :70-95).
+ * gausslaguerre.jl:91) for n >= 128 and alpha < 5; closed forms (n <= 2), Golub-Welsch (n < 15) and
+ * the recurrence rule (n < 128, or alpha >= 5 up to n = 4096) on a single thread (:70-95).
+ * alpha <= -1 or n < 0 -> FGQ_EDOMAIN (:60-65); alpha >= 5 with n > 4096 -> FGQ_ENOTIMPL.
  * reduced != 0: only the nodes before the first weight below 10*floatmin are returned (:163-169);
  * *n_out receives the number of entries written (n when reduced == 0).  Warning bits mirror the
  * reference's @warn sites (fgq_warnings()). */

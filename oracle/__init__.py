@@ -53,6 +53,8 @@ def lib():
             f.restype = ctypes.c_int
         L.oracle_gl_rec_newton.argtypes = [ctypes.c_double, _c_i64, ctypes.c_double, _c_dp, _c_dp]
         L.oracle_gl_rec_newton.restype = None
+        L.oracle_gl_rec_newton2.argtypes = [ctypes.c_double, _c_i64, ctypes.c_double, ctypes.c_int, _c_dp, _c_dp]
+        L.oracle_gl_rec_newton2.restype = None
         L.oracle_eval_laguerre_rec.argtypes = [_c_i64, ctypes.c_double, ctypes.c_double, _c_dp, _c_dp]
         L.oracle_eval_laguerre_rec.restype = None
         L.oracle_innerjacobi_rec.argtypes = [_c_i64, _c_i64, _c_dp, ctypes.c_double, ctypes.c_double, _c_dp, _c_dp]
@@ -121,11 +123,11 @@ def gausslegendre_batch(n_i: np.ndarray, twin: bool = False):
     return offsets, x, w
 
 
-def gl_rec_newton(x0: float, n: int, alpha: float):
-    """gl_rec_newton(x0, n, alpha) of src/gausslaguerre.jl:547-579 -> (xk, wk)."""
+def gl_rec_newton(x0: float, n: int, alpha: float, computeweight: bool = True):
+    """gl_rec_newton(x0, n, alpha; computeweight) of src/gausslaguerre.jl:547-579 -> (xk, wk)."""
     xk = ctypes.c_double(0.0)
     wk = ctypes.c_double(0.0)
-    lib().oracle_gl_rec_newton(float(x0), int(n), float(alpha), ctypes.byref(xk), ctypes.byref(wk))
+    lib().oracle_gl_rec_newton2(float(x0), int(n), float(alpha), int(bool(computeweight)), ctypes.byref(xk), ctypes.byref(wk))
     return xk.value, wk.value
 
 

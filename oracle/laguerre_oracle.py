@@ -9,8 +9,8 @@ numpy restatement of the explicit-asymptotics Gauss-Laguerre path of FastGaussQu
   region evaluators                src/gausslaguerre.jl:429-529
   compute_airy_root                src/gausslaguerre.jl:508-517
   gl_rec_newton, evalLaguerreRec   src/gausslaguerre.jl:547-579,625-641 (C: laguerre_rec_oracle.c)
-Only the branch n >= 128, alpha < 5 (Float64) is restated; Golub-Welsch (n < 15) and the plain
-recurrence rule (n < 128 or alpha >= 5) are out of scope.
+  gausslaguerre_rec                src/gausslaguerre.jl:582-618   (15 <= n < 128, or alpha >= 5)
+  gausslaguerre_GW                 src/gausslaguerre.jl:535-542   (n < 15; LAPACK through scipy)
 
 The reference walks k = 1..n sequentially and hands over Bessel -> bulk -> Airy at the first k where
 the next region's error estimate wins.  Here the three expansions are evaluated for whole index
@@ -302,13 +302,59 @@ def gausslaguerre_asy(n, al, reduced=False, recompute=True, info=None):
     return x, w
 
 
+def gausslaguerre_rec(n, al, reduced=False):
+    """:582-618"""
+    x = np.zeros(n)
+    w = np.zeros(n)
+    n_pre = min(n, 7)
+    nu = 4 * n + 2 * al + 2
+    x_pre = approx_besselroots(al, n_pre) ** 2 / nu
+    no_underflow = True
+    for k in range(1, n + 1):
+        if k <= n_pre:
+            xk = x_pre[k - 1]
+        else:
+            xk = (7 * x[k - 2] - 21 * x[k - 3] + 35 * x[k - 4] - 35 * x[k - 5] + 21 * x[k - 6] - 7 * x[k - 7] + x[k - 8])
+        xk, wk = gl_rec_newton(xk, n, al, computeweight=no_underflow)
+        if no_underflow and abs(wk) < UNDERFLOW:
+            no_underflow = False
+        if reduced and not no_underflow:
+            return x[:k - 1], w[:k - 1]
+        x[k - 1] = xk
+        w[k - 1] = wk
+    return x, w
+
+
+def gausslaguerre_gw(n, al):
+    """:535-542 (LAPACK symmetric-tridiagonal eigen-solve, as in the reference)."""
+    from math import gamma
+    from scipy.linalg import eigh_tridiagonal
+    k = np.arange(1, n + 1, dtype=np.float64)
+    diag = 2 * k + (al - 1)
+    off = np.sqrt(k[:-1] * (al + k[:-1]))
+    x, V = eigh_tridiagonal(diag, off)
+    return x, gamma(al + 1) * V[0, :] ** 2
+
+
 def gausslaguerre(n, al=0.0, reduced=False, info=None):
-    """:59-96 (asymptotic branch only)."""
+    """:59-96"""
+    from math import gamma, sqrt
     al = float(al)
     if al <= -1:
         raise ValueError("DomainError: alpha <= -1")
     if n < 0:
         raise ValueError("DomainError: n must be positive")
+    if n == 0:
+        return np.zeros(0), np.zeros(0)
+    if n == 1:
+        return np.array([1 + al]), np.array([gamma(1 + al)])
+    if n == 2:
+        s = sqrt(al + 2)
+        return (np.array([al + 2 - s, al + 2 + s]),
+                np.array([((al - s + 2) * gamma(al + 2)) / (2 * (al + 2) * (s - 1) ** 2),
+                          ((al + s + 2) * gamma(al + 2)) / (2 * (al + 2) * (s + 1) ** 2)]))
+    if n < 15:
+        return gausslaguerre_gw(n, al)
     if n < 128 or al >= 5:
-        raise NotImplementedError("oracle restates gausslaguerre_asy only (n >= 128, alpha < 5)")
+        return gausslaguerre_rec(n, al, reduced=reduced)
     return gausslaguerre_asy(n, al, reduced=reduced, recompute=True, info=info)

@@ -35,8 +35,12 @@ void oracle_eval_laguerre_rec(int64_t n, double alpha, double x, double* pn, dou
     eval_laguerre_rec(n, alpha, x, pn, pnd);
 }
 
-/* gl_rec_newton(x0, n, alpha; maxiter = 20, computeweight = true) -> (xk, wk) */
+/* gl_rec_newton(x0, n, alpha; maxiter = 20, computeweight) -> (xk, wk) */
+void oracle_gl_rec_newton2(double x0, int64_t n, double alpha, int computeweight, double* xk_out, double* wk_out);
 void oracle_gl_rec_newton(double x0, int64_t n, double alpha, double* xk_out, double* wk_out) {
+    oracle_gl_rec_newton2(x0, n, alpha, 1, xk_out, wk_out);
+}
+void oracle_gl_rec_newton2(double x0, int64_t n, double alpha, int computeweight, double* xk_out, double* wk_out) {
     const double eps = DBL_EPSILON;
     double step = x0;
     int iter = 0;
@@ -55,9 +59,12 @@ void oracle_gl_rec_newton(double x0, int64_t n, double alpha, double* xk_out, do
         xk -= step;
         pn_prev = pn;
     }
-    double pn_min1, dummy;
-    eval_laguerre_rec(n - 1, alpha, xk, &pn_min1, &dummy);
-    const double nn = (double)n;
     *xk_out = xk;
-    *wk_out = pow(nn * nn + alpha * nn, -0.5) / pn_min1 / pn_deriv;
+    *wk_out = 0.0;
+    if (computeweight) {
+        double pn_min1, dummy;
+        eval_laguerre_rec(n - 1, alpha, xk, &pn_min1, &dummy);
+        const double nn = (double)n;
+        *wk_out = pow(nn * nn + alpha * nn, -0.5) / pn_min1 / pn_deriv;
+    }
 }

@@ -37,9 +37,10 @@ def test_api_edges(fgq):
     x, w = fgq.gausslaguerre(0)
     assert len(x) == 0
     with pytest.raises(fgq.NotImplementedOnDevice):
-        fgq.gausslaguerre(42)                   # recurrence branch
-    with pytest.raises(fgq.NotImplementedOnDevice):
-        fgq.gausslaguerre(500, 6.0)             # alpha >= 5 -> recurrence rule
+        fgq.gausslaguerre(5000, 6.0)            # alpha >= 5 -> O(n^2) recurrence rule, device path stops at n = 4096
+    for c in GOLD["closed_forms"]:              # test_gausslaguerre.jl:66-72
+        x, w = fgq.gausslaguerre(c["n"], c["alpha"])
+        assert np.allclose(x, c["x"], rtol=1e-15, atol=0) and np.allclose(w, c["w"], rtol=1e-14, atol=0)
     xr, wr = fgq.gausslaguerre(350000, 0.44, reduced=True)   # test_gausslaguerre.jl:142-144
     assert wr[-1] < 100 * np.finfo(float).tiny and len(xr) < 350000
     xo, wo = lo.gausslaguerre(350000, 0.44, reduced=True)
@@ -85,3 +86,31 @@ def test_parity_with_oracle(fgq, n, alpha):
     assert np.all(np.diff(x) > 0)
     if alpha == 0.0:
         assert abs(w.sum() - 1) < 1e-13 and abs(np.dot(w, x) - 1) < 1e-13
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.5, -0.7, 2.5, 6.0])
+def test_small_rules_parity(fgq, alpha):
+    """n < 128 (and alpha >= 5): closed forms, Golub-Welsch (on-device QL vs the oracle's LAPACK) and the
+    sequential recurrence rule (gausslaguerre.jl:70-95, 535-542, 582-618)."""
+    from math import gamma
+    for n in [1, 2, 3, 5, 10, 14, 15, 16, 31, 42, 64, 100, 127] + ([128, 300] if alpha >= 5 else []):
+        x, w = fgq.gausslaguerre(n, alpha)
+        xo, wo = lo.gausslaguerre(n, alpha)
+        eps = np.finfo(float).eps
+        if 3 <= n < 15:   # eigenvalues of the Jacobi matrix: absolute accuracy eps*||J|| in LAPACK and in the QL kernel
+            assert np.abs(x - xo).max() <= 8 * eps * xo.max(), (n, alpha)
+        else:
+            # the rule stops Newton at |step| <= 40 eps x (gausslaguerre.jl:556): two libms stop up to ~2 x 40 eps apart
+            assert (np.abs(x - xo) / xo).max() <= 256 * eps, (n, alpha)
+        nz = wo > 1e-290
+        # recurrence rule: w = c / (p_{n-1}(x) p_n'(x~)) with p_n' taken at the PREVIOUS Newton iterate
+        # (gausslaguerre.jl:556-575); one Newton step more or less moves it at the 1e-12 level
+        assert np.all(np.abs(w[nz] - wo[nz]) / wo[nz] <= 1e-11 + 2 * np.abs(x - xo)[nz]), (n, alpha)
+        assert np.count_nonzero((w == 0) != (wo == 0)) == 0
+        # sum w = Gamma(alpha + 1) wherever the reference algorithm itself delivers it (at n = 15, alpha = 6 its
+        # extrapolated initial guesses make Newton find one root twice: sum w = 820 instead of 720, reproduced)
+        if abs(wo.sum() - gamma(alpha + 1)) < 1e-12 * gamma(alpha + 1):
+            assert abs(w.sum() - gamma(alpha + 1)) < 2e-12 * gamma(alpha + 1)
+    xr, wr = fgq.gausslaguerre(100, alpha, reduced=True)
+    xo, wo = lo.gausslaguerre(100, alpha, reduced=True)
+    assert len(xr) == len(xo)

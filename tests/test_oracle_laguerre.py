@@ -27,6 +27,21 @@ def test_golden_values(case):
     assert np.all(np.diff(x) > 0)
 
 
+def test_closed_forms_and_small_rules():
+    from math import gamma
+    for c in GOLD["closed_forms"]:   # test_gausslaguerre.jl:66-72
+        x, w = lo.gausslaguerre(c["n"], c["alpha"])
+        assert np.allclose(x, c["x"], rtol=1e-15, atol=0) and np.allclose(w, c["w"], rtol=1e-14, atol=0)
+    # GW vs rec vs default (test_gausslaguerre.jl:91-99)
+    xg, wg = lo.gausslaguerre_gw(42, 0.0)
+    xr, wr = lo.gausslaguerre_rec(42, 0.0)
+    assert abs(xg[36] - 98.388267163326702) < 1e-13 and abs(xr[36] - 98.388267163326702) < 1e-13
+    assert abs(wg[6] - 0.055372813167092) < 1e-13 and abs(wr[6] - 0.055372813167092) < 1e-13
+    for n, al in ((10, 0.5), (64, 2.5), (100, 6.0)):
+        x, w = lo.gausslaguerre(n, al)
+        assert abs(w.sum() - gamma(al + 1)) < 1e-12 * gamma(al + 1)
+
+
 def test_reduced_rule():
     # test_gausslaguerre.jl:142-144
     x, w = lo.gausslaguerre(350000, 0.44, reduced=True)
