@@ -412,13 +412,8 @@ extern "C" int fgq_gausshermite_device(int64_t n, int normalize, int64_t lo, int
     const unsigned b128 = (unsigned)((p.nh + HERM_THREADS - 1) / HERM_THREADS);
     hermite_init_kernel<<<b128, HERM_THREADS, 0, st>>>(p, state, theta);  // also resets the state
     FGQ_LAUNCH_CHECK();
-    if (n == 1) {
-        // gausshermite.jl:41-42: x = [0], w = [sqrt(pi)] before the common normalisation
-        const double one_x = 0.0, one_w = 1.7724538509055159;
-        FGQ_CUDA_TRY(cudaMemcpyAsync(xh, &one_x, 8, cudaMemcpyHostToDevice, st));
-        FGQ_CUDA_TRY(cudaMemcpyAsync(wh, &one_w, 8, cudaMemcpyHostToDevice, st));
-    } else if (n <= 20) {
-        hermite_gw_kernel<<<1, 32, 0, st>>>(p, xh, wh);  // :43-45
+    if (n <= 20) {  // :41-45; n = 1 (x = 0, w = sqrt(pi), :41-42) is the 1 x 1 case of the same kernel
+        hermite_gw_kernel<<<1, 32, 0, st>>>(p, xh, wh);
         FGQ_LAUNCH_CHECK();
     } else if (n <= 200) {
         hermite_rec_kernel<<<1, 128, 0, st>>>(p, xh, wh);  // :46-48

@@ -20,6 +20,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "fgq_math.h"
 #include "jacobi_plan.h"
 
 namespace fgq {
@@ -70,7 +71,7 @@ __device__ __forceinline__ void feval_asy1_node(const JacobiHalfPlan& P, double 
             if (!NORM && m == mbreak) break;
             const double A = (c0 + m) * t / 2 - shift;
             double sA, cA;
-            sincos(A, &sA, &cA);
+            fgq_sincos_medium(A, &sA, &cA);
             double d1 = 0.0, d2 = 0.0, d12 = 0.0, d22 = 0.0;
 #pragma unroll
             for (int l = 0; l < m; l += 2) {

@@ -281,6 +281,14 @@ __device__ void laguerre_airy(const LaguerreParams& p, int64_t k, double& xk, do
 
 constexpr int LAG_THREADS = 128;
 
+__global__ void laguerre_state_init_kernel(LaguerreState* st, int64_t n) {
+    st->k_b = (unsigned long long)(n + 1);
+    st->k_a = (unsigned long long)(n + 1);
+    st->n_out = (unsigned long long)n;
+    st->n_flagged = 0;
+    st->warn = 0;
+}
+
 // first k where delta_bulk < delta_bessel (:138-151)
 __global__ void __launch_bounds__(LAG_THREADS)
 laguerre_handover_bessel_kernel(const LaguerreParams p, LaguerreState* st) {
@@ -571,13 +579,8 @@ extern "C" int fgq_gausslaguerre_device(int64_t n, double alpha, double* x_dev, 
     LaguerreState* state = (LaguerreState*)workspace_dev;
     double* delta = (double*)((char*)workspace_dev + 256);
     unsigned int* flagged = (unsigned int*)(delta + n);
-    LaguerreState init;
-    init.k_b = (unsigned long long)(n + 1);
-    init.k_a = (unsigned long long)(n + 1);
-    init.n_out = (unsigned long long)n;
-    init.n_flagged = 0;
-    init.warn = 0;
-    FGQ_CUDA_TRY(cudaMemcpyAsync(state, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    laguerre_state_init_kernel<<<1, 1, 0, st>>>(state, n);  // a kernel, not a memcpy: stays graph-capturable
+    FGQ_LAUNCH_CHECK();
     if (n == 0) return FGQ_OK;
     if (n < 128 || alpha >= 5.0) {  // gausslaguerre.jl:70-95: closed forms, Golub-Welsch, recurrence rule
         LaguerreSmall q;

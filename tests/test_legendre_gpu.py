@@ -197,3 +197,44 @@ def test_batch_small_rules(fgq, oracle_mod):
     # weights of the recurrence path are ill-conditioned in the Newton iterate (SURVEY.md §7
     # hard part 2): against a different libm they are pinned in absolute terms only
     assert np.abs(w - wo).max() < 1e-14
+
+
+def test_device_entry_points_are_graph_capturable(fgq):
+    """include/fgq.h promises that the *_device entry points only enqueue work (no allocation, no
+    synchronisation): capture them in a CUDA graph and replay."""
+    import torch
+    L = fgq.lib()
+    n = 200001
+    x = torch.zeros(n, dtype=torch.float64, device="cuda")
+    w = torch.zeros(n, dtype=torch.float64, device="cuda")
+    wsj = torch.empty(int(L.fgq_gaussjacobi_workspace_bytes(n)) + 16, dtype=torch.uint8, device="cuda")
+    xj = torch.zeros(n, dtype=torch.float64, device="cuda")
+    wj = torch.zeros(n, dtype=torch.float64, device="cuda")
+    wsl = torch.empty(int(L.fgq_gausslaguerre_workspace_bytes(n)) + 16, dtype=torch.uint8, device="cuda")
+    xl = torch.zeros(n, dtype=torch.float64, device="cuda")
+    wl = torch.zeros(n, dtype=torch.float64, device="cuda")
+    wsh = torch.empty(int(L.fgq_gausshermite_workspace_bytes(n)) + 16, dtype=torch.uint8, device="cuda")
+    xh = torch.zeros(n, dtype=torch.float64, device="cuda")
+    wh = torch.zeros(n, dtype=torch.float64, device="cuda")
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            sp = torch.cuda.current_stream().cuda_stream
+            fgq._lib.check(L.fgq_gausslegendre_device(n, 0, n, x.data_ptr(), w.data_ptr(), sp))
+            fgq._lib.check(L.fgq_gaussjacobi_device(n, 0.3, -0.7, 0, n, xj.data_ptr(), wj.data_ptr(), wsj.data_ptr(), sp))
+            fgq._lib.check(L.fgq_gausslaguerre_device(n, 0.5, xl.data_ptr(), wl.data_ptr(), wsl.data_ptr(), sp))
+            fgq._lib.check(L.fgq_gausshermite_device(n, 0, 0, n, xh.data_ptr(), wh.data_ptr(), wsh.data_ptr(), sp))
+    for t in (x, w, xj, wj, xl, wl, xh, wh):
+        t.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    x1, w1 = fgq.gausslegendre(n)
+    assert np.array_equal(x.cpu().numpy(), x1) and np.array_equal(w.cpu().numpy(), w1)
+    x2, w2 = fgq.gaussjacobi(n, 0.3, -0.7)
+    assert np.array_equal(xj.cpu().numpy(), x2) and np.array_equal(wj.cpu().numpy(), w2)
+    x3, w3 = fgq.gausslaguerre(n, 0.5)
+    assert np.array_equal(xl.cpu().numpy(), x3) and np.array_equal(wl.cpu().numpy(), w3)
+    x4, w4 = fgq.gausshermite(n)
+    assert np.array_equal(xh.cpu().numpy(), x4) and np.array_equal(wh.cpu().numpy(), w4)
