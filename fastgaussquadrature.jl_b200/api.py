@@ -197,8 +197,8 @@ def gaussjacobi(n, a, b):
 
     Integer α, β are promoted to Float64 (regression #117).  Errors as in the reference: n < 0 or
     min(α,β) <= -1 raise DomainError (:26-27, :44-45).  The device path covers the asymptotic
-    branch (n > 100, max(α,β) < 5) and (0,0) -> Legendre; the recurrence / Golub-Welsch /
-    Chebyshev regions raise NotImplementedOnDevice."""
+    branch (n > 100), the recurrence (n <= 100), the Golub-Welsch region (max(α,β) >= 5, n <= 4000),
+    (0,0) -> Legendre and (±1/2, ±1/2) -> Chebyshev; max(α,β) >= 5 with n > 4000 raises, as in the reference."""
     n = _as_int(n)
     a = float(a)
     b = float(b)
@@ -229,13 +229,17 @@ def gaussjacobi_device(n, a, b, stream=None):
     return x, w, ws
 
 
-def gaussradau(n):
-    """``gaussradau(n) -> x, w`` (reference src/gaussradau.jl:31-49); x[0] == -1 exactly."""
+def gaussradau(n, a=None, b=None):
+    """``gaussradau(n) -> x, w`` (reference src/gaussradau.jl:31-49) and ``gaussradau(n, α, β)``
+    (:52-69, general Jacobi weight); x[0] == -1 exactly."""
     n = _as_int(n)
     if n <= 0:
         raise DomainError(f"DomainError({n}): Input n must be a positive integer")
     x, w = _host_pair(n, False)
-    check(lib().fgq_gaussradau_host(n, _ptr(x), _ptr(w)))
+    if a is None and b is None:
+        check(lib().fgq_gaussradau_host(n, _ptr(x), _ptr(w)))
+    else:
+        check(lib().fgq_gaussradau_jacobi_host(n, float(a), float(b), _ptr(x), _ptr(w)))
     return x, w
 
 

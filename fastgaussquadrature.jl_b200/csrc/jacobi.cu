@@ -352,6 +352,98 @@ __global__ void __launch_bounds__(128) jacobi_rec_kernel(const JacobiRecParams p
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// max(alpha, beta) >= 5, n <= 4000: the reference's jacobi_gw (gaussjacobi.jl:570-599) is a dense
+// LAPACK eigen-solve of the n x n Jacobi matrix.  The per-node-parallel equivalent used here:
+//   * thread k finds the k-th eigenvalue of the symmetric tridiagonal matrix by bisection on
+//     Sturm counts (every eigenvalue independently, O(n) per count, ~60 counts);
+//   * the weight is mu0 / sum_j p_j(x_k)^2 with the orthonormal polynomials p_j from the three-term
+//     recurrence — the squared first component of the normalised eigenvector, without eigenvectors.
+// The same kernel serves the general Gauss-Radau rule gaussradau(n, a, b) (gaussradau.jl:52-69), whose
+// Jacobi matrix differs in its last diagonal entry.
+// ---------------------------------------------------------------------------------------------
+// jacobi_jacobimatrix (:570-584); radau != 0 replaces the last diagonal entry (gaussradau.jl:63-64)
+__global__ void jacobi_matrix_kernel(int n, double a, double b, int radau, double* diag, double* off) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0-based row
+    if (i >= n) return;
+    const double s = a + b;
+    const double nn = (double)n;
+    const double ii = (double)(i + 1);  // 1-based index
+    double d;
+    if (i == 0) {
+        d = (b - a) / (2 + s);
+    } else if (i < n - 1) {
+        const double si = 2 * ii + s;
+        d = (b * b - a * a) / ((si - 2) * si);
+    } else {
+        d = (b * b - a * a) / ((2 * nn - 2 + s) * (2 * nn + s));
+    }
+    if (radau && i == n - 1) {
+        const double m = nn - 1;
+        d = -1 + 2 * m * (m + a) / ((2 * m + s) * (2 * m + s + 1));
+    }
+    diag[i] = d;
+    if (i < n - 1) {
+        double e;
+        if (i == 0) {
+            e = 2 * sqrt((1 + a) * (1 + b) / (s + 3)) / (s + 2);
+        } else {
+            const double si = 2 * ii + s;
+            e = 2 * sqrt(ii * (ii + a) * (ii + b) * (ii + s) / (si * si - 1)) / si;
+        }
+        off[i] = e;
+    }
+}
+
+__device__ __forceinline__ int sturm_count(int n, const double* __restrict__ d, const double* __restrict__ e,
+                                           double x, double pivmin) {
+    // LAPACK dlaebz convention: a pivot inside (-pivmin, pivmin) is replaced by -pivmin BEFORE it is counted
+    double q = d[0] - x;
+    if (fabs(q) < pivmin) q = -pivmin;
+    int cnt = q <= 0.0;
+    for (int i = 1; i < n; ++i) {
+        q = (d[i] - x) - e[i - 1] * e[i - 1] / q;
+        if (fabs(q) < pivmin) q = -pivmin;
+        cnt += q <= 0.0;
+    }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(128)
+tridiag_gw_kernel(int n, const double* __restrict__ d, const double* __restrict__ e, double mu0, int fix_first,
+                  double* x, double* w) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    // Gershgorin interval and pivmin
+    double lo = 1e300, hi = -1e300, emax2 = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < n - 1 ? fabs(e[i]) : 0.0);
+        lo = fmin(lo, d[i] - r);
+        hi = fmax(hi, d[i] + r);
+        if (i < n - 1) emax2 = fmax(emax2, e[i] * e[i]);
+    }
+    const double pivmin = 2.2250738585072014e-308 * fmax(1.0, emax2) * 4;
+    const double span = hi - lo;
+    lo -= 2.220446049250313e-16 * span * n + pivmin;
+    hi += 2.220446049250313e-16 * span * n + pivmin;
+    for (int it = 0; it < 200; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (mid <= lo || mid >= hi) break;  // interval exhausted to the last ulp
+        if (sturm_count(n, d, e, mid, pivmin) >= k + 1) hi = mid; else lo = mid;
+    }
+    const double xk = 0.5 * (lo + hi);
+    // orthonormal recurrence: e_j p_{j+1} = (x - d_j) p_j - e_{j-1} p_{j-1}, p_0 = 1
+    double pm1 = 0.0, p = 1.0, ssum = 1.0;
+    for (int j = 0; j < n - 1; ++j) {
+        const double pn = ((xk - d[j]) * p - (j > 0 ? e[j - 1] : 0.0) * pm1) / e[j];
+        pm1 = p;
+        p = pn;
+        ssum += p * p;
+    }
+    x[k] = (fix_first && k == 0) ? -1.0 : xk;  // gaussradau.jl:67
+    w[k] = mu0 / ssum;
+}
+
 static double jacobi_tt_host(int64_t n, double a, double b, int64_t i) {
     const double PI = 3.141592653589793;
     const double j = (double)(n - i);
@@ -378,13 +470,35 @@ static int jacobi_check_args(int64_t n, double a, double b) {
     }
     const double mx = a > b ? a : b;
     if (mx < 5.0) return FGQ_OK;
-    if (n > 4000) {
+    if (n > 4000) {  // :52-53: ErrorException in the reference
         set_error("gaussjacobi(%lld,%g,%g) is not implemented: n must be <= 4000 for max(a,b) >= 5.", (long long)n, a, b);
         return FGQ_ENOTIMPL;
     }
-    set_error("gaussjacobi(%lld,%g,%g): max(a,b) >= 5 is served by a Golub-Welsch eigen-solve in the reference "
-              "(gaussjacobi.jl:50-51), which is not on the device path", (long long)n, a, b);
-    return FGQ_ENOTIMPL;
+    return FGQ_OK;
+}
+
+// jacobimoment (:586-591)
+static double jacobi_moment(double a, double b) {
+    const double s = a + b;
+    return exp((s + 1) * log(2.0) + lgamma(a + 1) + lgamma(b + 1) - lgamma(2 + s));
+}
+
+// jacobi_gw (:593-599) / gaussradau(n, a, b) (gaussradau.jl:52-69) through bisection + recurrence
+static int jacobi_gw_device(int64_t n, double a, double b, int radau, int64_t lo, int64_t hi, double* x_dev,
+                            double* w_dev, void* workspace_dev, cudaStream_t st) {
+    double* diag = (double*)((char*)workspace_dev + 4096);
+    double* off = diag + n;
+    double* xfull = x_dev;
+    double* wfull = w_dev;
+    if (lo != 0 || hi != n) {
+        set_error("the Golub-Welsch branch writes whole rules only (lo = 0, hi = n)");
+        return FGQ_EINVAL;
+    }
+    jacobi_matrix_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((int)n, a, b, radau, diag, off);
+    FGQ_LAUNCH_CHECK();
+    tridiag_gw_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((int)n, diag, off, jacobi_moment(a, b), radau, xfull, wfull);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
 }
 
 static int jacobi_rec_device(int64_t n, double a, double b, int64_t lo, int64_t hi, double* x_dev, double* w_dev,
@@ -417,7 +531,7 @@ static int jacobi_rec_device(int64_t n, double a, double b, int64_t lo, int64_t 
 
 extern "C" int64_t fgq_gaussjacobi_workspace_bytes(int64_t n) {
     if (n < 0) return 0;
-    return 4096 + 8 * n;
+    return 4096 + 16 * n;
 }
 
 // Core: the (alpha, beta) != (0,0), (+-1/2, +-1/2) asymptotic branch.
@@ -523,6 +637,14 @@ extern "C" int fgq_gaussjacobi_device(int64_t n, double a, double b, int64_t lo,
         set_error("null pointer");
         return FGQ_EINVAL;
     }
+    if (n == 1) return jacobi_rec_device(n, a, b, lo, hi, x_dev, w_dev, as_stream(stream));   // :42-43
+    if ((a > b ? a : b) >= 5.0) {                                                              // :50-51
+        if (!workspace_dev) {
+            set_error("null workspace pointer");
+            return FGQ_EINVAL;
+        }
+        return jacobi_gw_device(n, a, b, 0, lo, hi, x_dev, w_dev, workspace_dev, as_stream(stream));
+    }
     if (n <= 100) return jacobi_rec_device(n, a, b, lo, hi, x_dev, w_dev, as_stream(stream));  // :46-47
     if (!workspace_dev) {
         set_error("null workspace pointer");
@@ -588,6 +710,9 @@ extern "C" int fgq_gausslobatto_device(int64_t n, double* x_dev, double* w_dev, 
 
 // ---- host-returning drop-ins --------------------------------------------------------------------
 
+extern "C" int fgq_gaussradau_jacobi_device(int64_t n, double a, double b, double* x_dev, double* w_dev,
+                                            void* workspace_dev, void* stream);
+
 static int jacobi_family_host(int which, int64_t n, double a, double b, double* x, double* w) {
     if (n == 0) return FGQ_OK;
     if (!x || !w) {
@@ -605,6 +730,7 @@ static int jacobi_family_host(int which, int64_t n, double a, double b, double* 
     int rc;
     if (which == 0) rc = fgq_gaussjacobi_device(n, a, b, 0, n, xd, wd, ws, (void*)st);
     else if (which == 1) rc = fgq_gaussradau_device(n, xd, wd, ws, (void*)st);
+    else if (which == 3) rc = fgq_gaussradau_jacobi_device(n, a, b, xd, wd, ws, (void*)st);
     else rc = fgq_gausslobatto_device(n, xd, wd, ws, (void*)st);
     if (rc != FGQ_OK) return rc;
     FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
@@ -633,6 +759,46 @@ extern "C" int fgq_gausslobatto_host(int64_t n, double* x, double* w) {
         return FGQ_EDOMAIN;
     }
     return jacobi_family_host(2, n, 0, 0, x, w);
+}
+
+// gaussradau(n, a, b) — gaussradau.jl:52-69
+extern "C" int fgq_gaussradau_jacobi_device(int64_t n, double a, double b, double* x_dev, double* w_dev,
+                                            void* workspace_dev, void* stream) {
+    clear_status();
+    if (n <= 0) {
+        set_error("DomainError(%lld): Input N must be a positive integer", (long long)n);  // :53-55
+        return FGQ_EDOMAIN;
+    }
+    if (n > 4000) {
+        set_error("gaussradau(%lld,%g,%g): the eigenvalue kernel is sized for n <= 4000", (long long)n, a, b);
+        return FGQ_ENOTIMPL;
+    }
+    if (!x_dev || !w_dev || !workspace_dev) {
+        set_error("null pointer");
+        return FGQ_EINVAL;
+    }
+    if (n == 1) {  // :61
+        JacobiPatch q;
+        q.n = 2 * JAC_NBDY;
+        q.lo = 0;
+        q.hi = 1;
+        for (int i = 0; i < 2 * JAC_NBDY; ++i) q.x[i] = q.w[i] = 0.0;
+        q.x[0] = -1.0;
+        q.w[0] = jacobi_moment(a, b);
+        jacobi_patch_kernel<<<1, 32, 0, as_stream(stream)>>>(q, x_dev, w_dev);
+        FGQ_LAUNCH_CHECK();
+        return FGQ_OK;
+    }
+    return jacobi_gw_device(n, a, b, 1, 0, n, x_dev, w_dev, workspace_dev, as_stream(stream));
+}
+
+extern "C" int fgq_gaussradau_jacobi_host(int64_t n, double a, double b, double* x, double* w) {
+    clear_status();
+    if (n <= 0) {
+        set_error("DomainError(%lld): Input N must be a positive integer", (long long)n);
+        return FGQ_EDOMAIN;
+    }
+    return jacobi_family_host(3, n, a, b, x, w);
 }
 
 // sweeps[2] (right, left), terms[2] (series terms kept in the last evaluation): for tests/reporting

@@ -87,7 +87,10 @@ int fgq_gausslegendre_batch_host(int64_t nrules, const int32_t* n_i, const int64
  *   n < 0, min(a,b) <= -1          -> FGQ_EDOMAIN  (:26-27, :44-45)
  *   a == b == 0                    -> the Legendre path (:28-29)
  *   |a| == |b| == 1/2              -> the Chebyshev closed forms (:30-39)
- *   n <= 100, or max(a,b) >= 5     -> FGQ_ENOTIMPL (jacobi_rec / Golub-Welsch, :46-53) */
+ *   n <= 100                       -> jacobi_rec (:46-47), one block per rule; n = 1 closed form (:42-43)
+ *   max(a,b) >= 5, n <= 4000       -> the Golub-Welsch rule (:50-51) computed per node: eigenvalue of the
+ *                                     Jacobi matrix by Sturm bisection, weight from the orthonormal recurrence
+ *   max(a,b) >= 5, n > 4000        -> FGQ_ENOTIMPL (the reference raises an ErrorException, :52-53) */
 int fgq_gaussjacobi_host(int64_t n, double a, double b, double* x, double* w);
 int64_t fgq_gaussjacobi_workspace_bytes(int64_t n);
 /* Device-resident: the whole rule is solved on the current device (Newton stopping rule and series
@@ -106,6 +109,13 @@ int fgq_gaussradau_host(int64_t n, double* x, double* w);
 int fgq_gausslobatto_host(int64_t n, double* x, double* w);
 int fgq_gaussradau_device(int64_t n, double* x_dev, double* w_dev, void* workspace_dev, void* stream);
 int fgq_gausslobatto_device(int64_t n, double* x_dev, double* w_dev, void* workspace_dev, void* stream);
+
+/* gaussradau(n, a, b) — src/gaussradau.jl:52-69 (general Jacobi weight): eigenvalues of the modified
+ * Jacobi matrix, computed per node as above; x[0] = -1 exactly (:67).  n <= 0 -> FGQ_EDOMAIN;
+ * n > 4000 -> FGQ_ENOTIMPL.  workspace: fgq_gaussjacobi_workspace_bytes(n). */
+int fgq_gaussradau_jacobi_host(int64_t n, double a, double b, double* x, double* w);
+int fgq_gaussradau_jacobi_device(int64_t n, double a, double b, double* x_dev, double* w_dev,
+                                 void* workspace_dev, void* stream);
 
 /* approx_besselroots(nu, n) — src/besselroots.jl:23-67 (host-planned; 12-digit zeros of J_nu). */
 int fgq_approx_besselroots(double nu, int64_t n, double* x);

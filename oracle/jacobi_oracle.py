@@ -501,6 +501,51 @@ def jacobi_rec(n, a, b):
     return x, w * (c / sum_w)
 
 
+def jacobi_jacobimatrix(n, a, b):
+    """:570-584 -> (diag, offdiag)"""
+    s_ = a + b
+    ii = np.arange(2, n, dtype=np.float64)
+    si = 2 * ii + s_
+    aa = np.concatenate([[(b - a) / (2 + s_)], (b ** 2 - a ** 2) / ((si - 2) * si),
+                         [(b ** 2 - a ** 2) / ((2 * n - 2 + s_) * (2 * n + s_))]])
+    bb = np.concatenate([[2 * np.sqrt((1 + a) * (1 + b) / (s_ + 3)) / (s_ + 2)],
+                         2 * np.sqrt(ii * (ii + a) * (ii + b) * (ii + s_) / (si ** 2 - 1)) / si])
+    return aa, bb
+
+
+def jacobimoment(a, b):
+    """:586-591"""
+    from math import exp, lgamma, log
+    s_ = a + b
+    return exp((s_ + 1) * log(2.0) + lgamma(a + 1) + lgamma(b + 1) - lgamma(2 + s_))
+
+
+def jacobi_gw(n, a, b):
+    """:593-599 (LAPACK symmetric-tridiagonal eigen-solve, as in the reference)."""
+    from scipy.linalg import eigh_tridiagonal
+    aa, bb = jacobi_jacobimatrix(n, a, b)
+    x, V = eigh_tridiagonal(aa, bb)
+    return x, V[0, :] ** 2 * jacobimoment(a, b)
+
+
+def gaussradau_jacobi(n, a, b):
+    """gaussradau.jl:52-69"""
+    from scipy.linalg import eigh_tridiagonal
+    if n <= 0:
+        raise ValueError("DomainError: Input N must be a positive integer")
+    m = n - 1
+    s_ = a + b
+    mu = jacobimoment(a, b)
+    if n == 1:
+        return np.array([-1.0]), np.array([mu])
+    aa, bb = jacobi_jacobimatrix(n, a, b)
+    aa[-1] = -1 + 2 * m * float(m + a) / ((2 * m + s_) * (2 * m + s_ + 1))
+    x, V = eigh_tridiagonal(aa, bb)
+    w = V[0, :] ** 2 * mu
+    x[0] = -1
+    return x, w
+
+
 def gaussjacobi(n, a, b, info=None):
     """:23-55 for general (a, b): closed form n = 1, recurrence n <= 100, asymptotics n > 100 (max(a,b) < 5).
     (0,0) -> Legendre and (+-1/2, +-1/2) -> Chebyshev live in their own oracles."""
@@ -515,8 +560,12 @@ def gaussjacobi(n, a, b, info=None):
         return np.array([(b - a) / (a + b + 2)]), np.array([2 ** (a + b + 1) * gamma(a + 1) * gamma(b + 1) / gamma(a + b + 2)])
     if min(a, b) <= -1.0:
         raise ValueError("DomainError: nonintegrable weight function")
+    if n <= 100 and max(a, b) < 5.0:
+        return jacobi_rec(n, a, b)
     if max(a, b) >= 5.0:
-        raise NotImplementedError("Golub-Welsch branch (max(a,b) >= 5) is out of scope")
+        if n > 4000:
+            raise NotImplementedError("ErrorException: n must be <= 4000 for max(a,b) >= 5")
+        return jacobi_gw(n, a, b)
     if n <= 100:
         return jacobi_rec(n, a, b)
     return jacobi_asy(n, a, b, info)

@@ -46,11 +46,11 @@ def test_dispatch_and_errors(fgq):
         fgq.gaussjacobi(200, -1.0, 0.2)
     with pytest.raises(fgq.DomainError):
         fgq.gaussjacobi(200, 0.3, -1.5)
-    with pytest.raises(fgq.NotImplementedOnDevice):  # Golub-Welsch region (gaussjacobi.jl:50-51)
-        fgq.gaussjacobi(42, 6.0, 0.3)
+    x, w = fgq.gaussjacobi(20, 11.0, 0.0)          # test_gaussjacobi.jl:212-216 (Golub-Welsch region)
+    assert x.shape == (20,) and x.dtype == np.float64
     x, w = fgq.gaussjacobi(1, 1.0, 2.0)            # test_gaussjacobi.jl:171-179
     assert abs(x[0] - 0.2) < 1e-14 and abs(w[0] - 4 / 3) < 1e-14
-    with pytest.raises(fgq.NotImplementedOnDevice):  # gaussjacobi.jl:53
+    with pytest.raises(fgq.NotImplementedOnDevice):  # gaussjacobi.jl:53 (ErrorException in the reference)
         fgq.gaussjacobi(5000, 6.0, 0.0)
     x, w = fgq.gaussjacobi(0, 0.3, 0.1)
     assert len(x) == 0
@@ -194,3 +194,44 @@ def test_config_c3_full_size(fgq):
     # first moment of the Jacobi weight: (b - a)/(a + b + 2) * mu0
     assert abs(float((w * x).sum()) - (b - a) / (a + b + 2) * 4.554443087962173) < 1e-12
     assert float(x[0]) > -1 and float(x[-1]) < 1
+
+
+@pytest.mark.parametrize("n,a,b", [(2, 6.0, 0.3), (6, 5.0, 5.0), (7, 6.5, 6.5), (20, 11.0, 0.0), (100, 19.0, 21.0), (257, 5.0, -0.5), (1000, 7.5, 12.0), (4000, 5.5, 0.0)])
+def test_golub_welsch_region(fgq, n, a, b):
+    """max(a,b) >= 5 (gaussjacobi.jl:50-51, 570-599): the reference's dense eigen-solve against the
+    per-node bisection + recurrence kernel.  LAPACK delivers eigenvalues to eps*||J|| absolutely."""
+    x, w = fgq.gaussjacobi(n, a, b)
+    xo, wo = jo.gaussjacobi(n, a, b)
+    assert np.abs(x - xo).max() <= 16 * EPS
+    # LAPACK returns the eigenvector matrix to eps ABSOLUTELY, so the oracle's weight mu0*V[1,k]^2 is only good
+    # to ~n*eps*sqrt(w*mu0); the recurrence formula of the kernel keeps relative accuracy on tiny weights.
+    mu0 = jo.jacobimoment(a, b)
+    bound = 64 * n * EPS * np.sqrt(wo * mu0) + 1e-12 * wo
+    print(f"GW n={n} a={a} b={b}: node err {np.abs(x - xo).max() / EPS:.1f} eps, weight err / bound {np.max(np.abs(w - wo) / bound):.3f}")
+    assert np.all(np.abs(w - wo) <= bound)
+    assert abs(w.sum() - jo.jacobimoment(a, b)) < 1e-13 * w.sum()
+    assert np.all(np.diff(x) > 0)
+
+
+def test_general_radau(fgq):
+    """gaussradau(n, a, b) (gaussradau.jl:52-69; test_gaussradau.jl:31-50)."""
+    for a, b in ((0.1, 0.2), (0.0, -0.5)):
+        for n in list(range(1, 12)) + [40, 257, 1000]:
+            x, w = fgq.gaussradau(n, a, b)
+            xo, wo = jo.gaussradau_jacobi(n, a, b)
+            assert x[0] == -1.0 and len(x) == n
+            print(n, a, b, np.abs(x - xo).max() / EPS, np.abs(w - wo).max())
+            assert np.abs(x - xo).max() <= 16 * EPS and np.abs(w - wo).max() <= 1e-13
+            if n > 5:
+                continue
+            xj, wj = jo.gaussjacobi(n, a, b)
+            assert abs(w.sum() - wj.sum()) < 1e-14
+            for j in range(1, 2 * n - 1):
+                assert abs(np.dot(w, x ** j) - np.dot(wj, xj ** j)) < 1e-14
+    for n in (2, 3, 40):   # compare with Gauss-Radau-Legendre
+        x, w = fgq.gaussradau(n, 0, 0)
+        xr, wr = fgq.gaussradau(n)
+        print(n, np.abs(x - xr).max(), np.abs(w - wr).max())
+        assert np.allclose(x, xr, rtol=0, atol=1e-13) and np.allclose(w, wr, rtol=0, atol=1e-13)
+    with pytest.raises(fgq.DomainError):
+        fgq.gaussradau(0, 0, 0)
