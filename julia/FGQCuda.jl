@@ -65,6 +65,15 @@ for (f, sym) in ((:gaussradau, :fgq_gaussradau_host), (:gausslobatto, :fgq_gauss
     end
 end
 
+# gaussradau(n, α, β) — src/gaussradau.jl:52-69
+function gaussradau(n::Integer, α::Real, β::Real)
+    n ≤ 0 && throw(DomainError(n, "Input N must be a positive integer"))
+    x = Vector{Float64}(undef, n); w = similar(x)
+    GC.@preserve x w check(ccall((:fgq_gaussradau_jacobi_host, libfgq), Cint,
+        (Int64, Float64, Float64, Ptr{Float64}, Ptr{Float64}), n, Float64(α), Float64(β), x, w), n)
+    return x, w
+end
+
 # gausschebyshevt/u/v/w(n) — src/gausschebyshev.jl:22-113
 for (f, kind) in ((:gausschebyshevt, 1), (:gausschebyshevu, 2), (:gausschebyshevv, 3), (:gausschebyshevw, 4))
     @eval function $f(n::Integer)
