@@ -373,8 +373,8 @@ def main():
             "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"],
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the committed ncu --set full
-            # capture (profiles/r01_legendre_1e9_ncu.md): 15.941633 GB + 51 kB for the n = 1e9, 1-GPU launch
-            "traffic": 15.941684e9 if (n == 10 ** 9 and world == 1 and args.mode == "pair") else None,
+            # capture (profiles/r01_legendre_1e9_ncu.md): 15.943408 GB + 0.5 MB for the n = 1e9, 1-GPU launch
+            "traffic": 15.943935e9 if (n == 10 ** 9 and world == 1 and args.mode == "pair") else None,
             "kernel": "legendre_asy_kernel<NT=0,WT=0,HEAD=false>", "kernel_ms": kern_ms,
             "algorithmic_bytes_per_node": 16, "nodes_per_launch": tail_nodes,
             "peak_source": peaks_src,
