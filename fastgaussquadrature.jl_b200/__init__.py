@@ -22,6 +22,7 @@ from .api import (  # noqa: F401
     gausslegendre,
     gausslegendre_batch,
     gausslegendre_device,
+    gausslegendre_host_pair,
     gausslegendre_moments_fused,
     half_index_partition,
     index_partition,

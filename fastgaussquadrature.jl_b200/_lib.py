@@ -30,6 +30,7 @@ SIGNATURES = {
     "fgq_launch_count": (_i64, []),
     "fgq_gausslegendre_host": (ctypes.c_int, [_i64, _vp, _vp]),
     "fgq_gausslegendre_host_slice": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp]),
+    "fgq_gausslegendre_host_pair": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "fgq_gausslegendre_device": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp, _vp]),
     "fgq_gausslegendre_device_pair": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "fgq_gausslegendre_batch_device": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp]),

@@ -76,6 +76,25 @@ def gausslegendre(n, *, pinned: bool = False, out: Optional[Tuple[np.ndarray, np
     return x, w
 
 
+def gausslegendre_host_pair(n, rank: int = 0, world: int = 1, out=None, pinned: bool = True):
+    """This rank's mirror-pair shard of ``gausslegendre(n)`` in HOST memory: returns
+    ``[(lo, hi, x, w), (lo, hi, x, w)]`` (left segment, mirrored right segment) like
+    ``gausslegendre_device(mode="pair")``.  Only the left segment crosses PCIe."""
+    n = _as_int(n)
+    k_lo, k_hi = half_index_partition(n, world)[rank]
+    cnt = k_hi - k_lo
+    m = (n + 1) // 2
+    skip = 1 if (n % 2 == 1 and k_hi - 1 == m and cnt > 0) else 0
+    if out is None:
+        xl, wl = _host_pair(cnt, pinned)
+        xr, wr = _host_pair(cnt, pinned)
+    else:
+        xl, wl, xr, wr = out
+    if cnt:
+        check(lib().fgq_gausslegendre_host_pair(n, k_lo, k_hi, _ptr(xl), _ptr(wl), _ptr(xr), _ptr(wr)))
+    return [(k_lo - 1, k_hi - 1, xl, wl), (n - k_hi + 1 + skip, n - k_lo + 1, xr[skip:], wr[skip:])], (xl, wl, xr, wr)
+
+
 def gausslegendre_batch(n_i, offsets=None):
     """Batch of small rules ``gausslegendre(n_i[r])``, 0 <= n_i <= 60, CSR layout.
 

@@ -5,6 +5,8 @@
 
 #include <atomic>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -211,11 +213,123 @@ static int legendre_slice(void* ctx, int64_t lo, int64_t hi, double* xd, double*
     return fgq_gausslegendre_device(n, lo, hi, xd, wd, (void*)st);
 }
 
+// Host-returning mirror-pair shard: only the LEFT slice (half-indices [k_lo, k_hi)) crosses PCIe; the
+// mirrored slice x[n-1-i] = -x[i], w[n-1-i] = w[i] is a data movement, done by host threads chunk by
+// chunk while the next chunk is still in flight.  Halves the D2H bytes of a rule, which is what bounds
+// the host-returning call (16 B/node at ~57 GB/s against 7 TB/s of generation).
+extern "C" int fgq_gausslegendre_host_pair(int64_t n, int64_t k_lo, int64_t k_hi, double* xl, double* wl,
+                                           double* xr, double* wr) {
+    clear_status();
+    if (n <= 60) {
+        set_error("mirror-pair shards need the asymptotic path (n > 60), got n=%lld", (long long)n);
+        return FGQ_EINVAL;
+    }
+    const int64_t m = (n + 1) >> 1, mr = n >> 1;
+    if (k_lo < 1 || k_hi < k_lo || k_hi > m + 1) {
+        set_error("invalid half-index shard [%lld, %lld) of n=%lld", (long long)k_lo, (long long)k_hi, (long long)n);
+        return FGQ_EINVAL;
+    }
+    const int64_t cnt = k_hi - k_lo;
+    if (cnt == 0) return FGQ_OK;
+    if (!xl || !wl || !xr || !wr) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    HostPathLock lock;
+    int dev;
+    FGQ_CUDA_TRY(cudaGetDevice(&dev));
+    const int64_t CHUNK = 1LL << 24;
+    const int64_t chunk = cnt < CHUNK ? cnt : CHUNK;
+    const int64_t nchunks = (cnt + chunk - 1) / chunk;
+    const int nbuf = nchunks > 1 ? 2 : 1;
+    double* buf[2] = {nullptr, nullptr};
+    for (int b = 0; b < nbuf; ++b) {
+        void* p;
+        FGQ_TRY(scratch_device((size_t)chunk * 16, b, &p));
+        buf[b] = (double*)p;
+    }
+    cudaStream_t s_compute, s_copy;
+    FGQ_TRY(scratch_stream(0, &s_compute));
+    FGQ_TRY(scratch_stream(1, &s_copy));
+    std::vector<cudaEvent_t> computed(nchunks), landed(nchunks);
+    for (int64_t j = 0; j < nchunks; ++j) {
+        FGQ_CUDA_TRY(cudaEventCreateWithFlags(&computed[j], cudaEventDisableTiming));
+        FGQ_CUDA_TRY(cudaEventCreateWithFlags(&landed[j], cudaEventDisableTiming));
+    }
+    int rc = FGQ_OK;
+    for (int64_t j = 0; j < nchunks && rc == FGQ_OK; ++j) {
+        const int64_t lo = j * chunk, hi = lo + chunk < cnt ? lo + chunk : cnt;  // relative to k_lo
+        const int b = (int)(j % nbuf);
+        double* xd = buf[b];
+        double* wd = buf[b] + chunk;
+        if (j >= nbuf) cudaStreamWaitEvent(s_compute, landed[j - nbuf], 0);
+        // left slice = output indices [k_lo-1+lo, k_lo-1+hi)
+        rc = fgq_gausslegendre_device(n, k_lo - 1 + lo, k_lo - 1 + hi, xd, wd, (void*)s_compute);
+        if (rc != FGQ_OK) break;
+        cudaEventRecord(computed[j], s_compute);
+        cudaStreamWaitEvent(s_copy, computed[j], 0);
+        cudaMemcpyAsync(xl + lo, xd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy);
+        cudaMemcpyAsync(wl + lo, wd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy);
+        cudaEventRecord(landed[j], s_copy);
+    }
+    if (rc == FGQ_OK) {
+        // element e of the left slice (half-index k = k_lo + e) mirrors to right-slice position cnt-1-e;
+        // the centre of an odd rule (k = m) has no mirror image
+        const int64_t mirror_cnt = (k_hi - 1 > mr) ? cnt - 1 : cnt;
+        unsigned hw = std::thread::hardware_concurrency();
+        const int T = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+        std::vector<std::thread> workers;
+        std::atomic<int> failed{0};
+        for (int t = 0; t < T; ++t) {
+            workers.emplace_back([&, t]() {
+                cudaSetDevice(dev);
+                for (int64_t j = 0; j < nchunks; ++j) {
+                    if (cudaEventSynchronize(landed[j]) != cudaSuccess) {
+                        failed = 1;
+                        return;
+                    }
+                    const int64_t lo = j * chunk, hi0 = lo + chunk < cnt ? lo + chunk : cnt;
+                    const int64_t hi = hi0 < mirror_cnt ? hi0 : mirror_cnt;
+                    const int64_t len = hi - lo;
+                    if (len <= 0) continue;
+                    const int64_t a = lo + len * t / T, bnd = lo + len * (t + 1) / T;
+                    for (int64_t e = a; e < bnd; ++e) {
+                        xr[cnt - 1 - e] = -xl[e];
+                        wr[cnt - 1 - e] = wl[e];
+                    }
+                }
+            });
+        }
+        for (auto& th : workers) th.join();
+        if (failed) {
+            set_error("device-to-host copy failed");
+            rc = FGQ_ECUDA;
+        }
+    }
+    cudaError_t e1 = cudaStreamSynchronize(s_compute);
+    cudaError_t e2 = cudaStreamSynchronize(s_copy);
+    for (int64_t j = 0; j < nchunks; ++j) {
+        cudaEventDestroy(computed[j]);
+        cudaEventDestroy(landed[j]);
+    }
+    if (rc != FGQ_OK) return rc;
+    FGQ_CUDA_TRY(e1);
+    FGQ_CUDA_TRY(e2);
+    return FGQ_OK;
+}
+
 extern "C" int fgq_gausslegendre_host(int64_t n, double* x, double* w) {
     clear_status();
     if (n < 0) {
         set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);
         return FGQ_EDOMAIN;
+    }
+    if (n >= (1LL << 21) && x && w) {
+        // large rules: ship the left half only and mirror it on the host (see fgq_gausslegendre_host_pair)
+        const int64_t m = (n + 1) >> 1, mr = n >> 1;
+        // right slice = output indices [n - m, n): its element 0 is the centre itself for odd n (untouched)
+        return fgq_gausslegendre_host_pair(n, 1, m + 1, x, w, x + (n - m), w + (n - m));
+        (void)mr;
     }
     return host_pipeline(0, n, x, w, legendre_slice, &n);
 }

@@ -57,6 +57,14 @@ int fgq_gausslegendre_host(int64_t n, double* x, double* w);
  * multi-GPU job fetch its own part of a large rule over its own PCIe link. */
 int fgq_gausslegendre_host_slice(int64_t n, int64_t lo, int64_t hi, double* x, double* w);
 
+/* Host-returning mirror-pair shard (n > 60): half-indices [k_lo, k_hi) as in
+ * fgq_gausslegendre_device_pair; only the left slice crosses PCIe, the mirrored slice
+ * (x[n-1-i] = -x[i], w[n-1-i] = w[i]) is written by host threads while the next chunk is in flight.
+ * xl/wl and xr/wr receive k_hi-k_lo entries each (element 0 of xr/wr is left untouched when the shard
+ * holds the centre of an odd rule).  fgq_gausslegendre_host uses it for n >= 2^21. */
+int fgq_gausslegendre_host_pair(int64_t n, int64_t k_lo, int64_t k_hi, double* xl, double* wl,
+                                double* xr, double* wr);
+
 /* Contiguous node-index shard: writes nodes/weights with output index in [lo, hi) to
  * x_dev[0 .. hi-lo), w_dev[0 .. hi-lo).  0 <= lo <= hi <= n. */
 int fgq_gausslegendre_device(int64_t n, int64_t lo, int64_t hi, double* x_dev, double* w_dev,

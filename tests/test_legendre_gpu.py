@@ -238,3 +238,22 @@ def test_device_entry_points_are_graph_capturable(fgq):
     assert np.array_equal(xl.cpu().numpy(), x3) and np.array_equal(wl.cpu().numpy(), w3)
     x4, w4 = fgq.gausshermite(n)
     assert np.array_equal(xh.cpu().numpy(), x4) and np.array_equal(wh.cpu().numpy(), w4)
+
+
+@pytest.mark.parametrize("n", [(1 << 21) + 4, (1 << 21) + 5, 3 * (1 << 24) + 7, 2 * (1 << 25) + 10])
+def test_host_symmetric_path(fgq, oracle_mod, n):
+    """n >= 2^21: the host-returning call ships only the left half over PCIe and mirrors it on the host;
+    the result must still be the twin oracle's rule bit for bit (incl. the centre of odd rules)."""
+    x, w = fgq.gausslegendre(n)
+    xt, wt = oracle_mod.gausslegendre(n, twin=True)
+    assert np.array_equal(x, xt) and np.array_equal(w, wt)
+    for world in (1, 3):
+        xa = np.full(n, np.nan)
+        wa = np.full(n, np.nan)
+        for r in range(world):
+            segs, _ = fgq.gausslegendre_host_pair(n, r, world, pinned=False)
+            for lo, hi, xs, ws in segs:
+                assert np.all(np.isnan(xa[lo:hi]))
+                xa[lo:hi] = xs
+                wa[lo:hi] = ws
+        assert np.array_equal(xa, xt) and np.array_equal(wa, wt)
