@@ -2,7 +2,8 @@
 
 numpy restatement of src/gausschebyshev.jl:22-26, 51-55, 80-84, 109-113 (closed forms).  Julia's
 cospi/sinpi reduce the argument exactly; the same reduction is done here before calling libm.
-The reference pins these rules only through integral identities (test/test_gausschebyshev.jl)."""
+The reference pins these rules only through integral identities (test/test_gausschebyshev.jl): at the
+ulp level the parity is UNPINNED (Julia cannot run in this image)."""
 import numpy as np
 
 PI = np.pi

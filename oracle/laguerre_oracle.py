@@ -19,7 +19,8 @@ because every node's value depends on (n, alpha, k) and on which region is selec
 
 Arithmetic outside /root/reference: besselj (AMOS zbesj; scipy.special.jv is the same routine),
 airyaiprime (AMOS zairy; scipy.special.airy on complex input).  evalpoly's muladd chain is plain
-multiply-add here.  Pin: golden values of test/test_gausslaguerre.jl:109-144.
+multiply-add here.  Pin: golden values of test/test_gausslaguerre.jl:66-144.  Julia cannot run in this
+image: below the 1e-13 absolute level of those tests the parity is UNPINNED.
 """
 from __future__ import annotations
 
