@@ -603,24 +603,30 @@ int legendre_asy_launch(int64_t n, int64_t kL0, int64_t kL1, double* xl, double*
 // (rec, gausslegendre.jl:233-267); n <= 5 are the closed forms (:27-60).
 // ---------------------------------------------------------------------------------------------
 
-// a / b for b = k + 1 (an exact small integer) without nvcc's slow-path scaffolding: same bits as
-// the IEEE quotient for every normal a (|P_k|, |P'_k| stay within [1e-300, 1e6] here; a signed zero
-// numerator is passed through, which is what IEEE gives for b > 0).
-__device__ __forceinline__ double div_by_count(double a, double b) {
-    const double q = fgq_div_fast(a, b);
-    return a == 0.0 ? a : q;
+// a / b for b = k + 1 (an exact small integer), given r = the correctly rounded 1/b: the last three
+// operations of the IEEE quotient's fast path (fgq_div_fast), so the same bits as a / b for every
+// normal a (|P_k|, |P'_k| stay within [1e-300, 1e6] here); a signed-zero numerator is passed through,
+// which is what IEEE gives for b > 0.  The reciprocals 1/2 .. 1/60 are shared by every lane, rule and
+// Newton step, so they are tabulated once per block in shared memory.
+__device__ __forceinline__ double div_by_count(double a, double b, double r) {
+    const double q = a * r;
+    const double rem = fma(-b, q, a);
+    const double res = fma(r, rem, q);
+    return a == 0.0 ? a : res;
 }
 
 // gausslegendre.jl:269-290 for one abscissa.  The loop counters are kept as doubles (exact), so the
 // quarter-rate I2F.F64 conversions of 2k+1, k, k+1 leave the inner loop.
-__device__ __forceinline__ void leg_inner_rec(int n, double xj, double& P, double& PP) {
+__device__ __forceinline__ void leg_inner_rec(int n, double xj, const double* __restrict__ rcp_tab, double& P,
+                                              double& PP) {
     double Pm2 = 1.0, Pm1 = xj, PPm1 = 1.0, PPm2 = 0.0;
     double tk = 3.0, dk = 1.0, dk1 = 2.0;
     for (int k = 1; k <= n - 1; ++k) {
-        const double newP = div_by_count(fma(tk * Pm1, xj, -dk * Pm2), dk1);
+        const double r = rcp_tab[k + 1];
+        const double newP = div_by_count(fma(tk * Pm1, xj, -dk * Pm2), dk1, r);
         Pm2 = Pm1;
         Pm1 = newP;
-        const double newPP = div_by_count(tk * fma(xj, PPm1, Pm2) - dk * PPm2, dk1);
+        const double newPP = div_by_count(tk * fma(xj, PPm1, Pm2) - dk * PPm2, dk1, r);
         PPm2 = PPm1;
         PPm1 = newPP;
         tk += 2.0;
@@ -673,6 +679,9 @@ __global__ void __launch_bounds__(REC_THREADS)
 legendre_rec_batch_kernel(int64_t nrules, const int32_t* __restrict__ n_i,
                           const int64_t* __restrict__ offsets, int n_single, int64_t lo, int64_t hi,
                           double* __restrict__ x, double* __restrict__ w) {
+    __shared__ double rcp_tab[64];
+    if (threadIdx.x < 64) rcp_tab[threadIdx.x] = fgq_rcp_fast((double)(threadIdx.x == 0 ? 1 : threadIdx.x));
+    __syncthreads();
     const int64_t rule = ((int64_t)blockIdx.x * REC_THREADS + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (rule >= nrules) return;
@@ -717,7 +726,7 @@ legendre_rec_batch_kernel(int64_t nrules, const int32_t* __restrict__ n_i,
     double P, PP;
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
-        leg_inner_rec(n, xj, P, PP);
+        leg_inner_rec(n, xj, rcp_tab, P, PP);
         xj -= P / PP;
     }
     // weights use P' of the LAST evaluation, i.e. at the pre-update iterate (:262-264)
