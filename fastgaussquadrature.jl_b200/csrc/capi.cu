@@ -64,6 +64,32 @@ int scratch_device(size_t bytes, int slot, void** out) {
     return FGQ_OK;
 }
 
+static void* g_pinned[2];
+static size_t g_pinned_bytes[2];
+// library-owned pinned staging (grow-only), for destinations that are ordinary pageable memory
+static int scratch_pinned(size_t bytes, int slot, void** out) {
+    if (g_pinned_bytes[slot] < bytes) {
+        if (g_pinned[slot]) {
+            FGQ_CUDA_TRY(cudaFreeHost(g_pinned[slot]));
+            g_pinned[slot] = nullptr;
+            g_pinned_bytes[slot] = 0;
+        }
+        FGQ_CUDA_TRY(cudaHostAlloc(&g_pinned[slot], bytes, cudaHostAllocDefault));
+        g_pinned_bytes[slot] = bytes;
+    }
+    *out = g_pinned[slot];
+    return FGQ_OK;
+}
+
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int scratch_stream(int which, cudaStream_t* out) {
     int dev;
     FGQ_TRY(cur_dev(&dev));
@@ -251,59 +277,101 @@ extern "C" int fgq_gausslegendre_host_pair(int64_t n, int64_t k_lo, int64_t k_hi
     cudaStream_t s_compute, s_copy;
     FGQ_TRY(scratch_stream(0, &s_compute));
     FGQ_TRY(scratch_stream(1, &s_copy));
+    // Pageable destination (a Julia Vector, a numpy array): DMA into library-owned pinned staging and let
+    // the host threads do the final copy as well as the mirroring — that also spreads the first-touch page
+    // faults of a freshly allocated 16 GB result over all threads instead of one driver thread.
+    const bool staged = !(is_pinned_host(xl) && is_pinned_host(wl));
+    double* stage[2] = {nullptr, nullptr};
+    if (staged) {
+        for (int b = 0; b < nbuf; ++b) {
+            void* p;
+            FGQ_TRY(scratch_pinned((size_t)chunk * 16, b, &p));
+            stage[b] = (double*)p;
+        }
+    }
     std::vector<cudaEvent_t> computed(nchunks), landed(nchunks);
     for (int64_t j = 0; j < nchunks; ++j) {
         FGQ_CUDA_TRY(cudaEventCreateWithFlags(&computed[j], cudaEventDisableTiming));
         FGQ_CUDA_TRY(cudaEventCreateWithFlags(&landed[j], cudaEventDisableTiming));
     }
     int rc = FGQ_OK;
-    for (int64_t j = 0; j < nchunks && rc == FGQ_OK; ++j) {
+    auto enqueue = [&](int64_t j) -> int {
         const int64_t lo = j * chunk, hi = lo + chunk < cnt ? lo + chunk : cnt;  // relative to k_lo
         const int b = (int)(j % nbuf);
         double* xd = buf[b];
         double* wd = buf[b] + chunk;
         if (j >= nbuf) cudaStreamWaitEvent(s_compute, landed[j - nbuf], 0);
         // left slice = output indices [k_lo-1+lo, k_lo-1+hi)
-        rc = fgq_gausslegendre_device(n, k_lo - 1 + lo, k_lo - 1 + hi, xd, wd, (void*)s_compute);
-        if (rc != FGQ_OK) break;
+        const int r = fgq_gausslegendre_device(n, k_lo - 1 + lo, k_lo - 1 + hi, xd, wd, (void*)s_compute);
+        if (r != FGQ_OK) return r;
         cudaEventRecord(computed[j], s_compute);
         cudaStreamWaitEvent(s_copy, computed[j], 0);
-        cudaMemcpyAsync(xl + lo, xd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy);
-        cudaMemcpyAsync(wl + lo, wd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy);
+        double* dx = staged ? stage[b] : xl + lo;
+        double* dw = staged ? stage[b] + chunk : wl + lo;
+        cudaMemcpyAsync(dx, xd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy);
+        cudaMemcpyAsync(dw, wd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy);
         cudaEventRecord(landed[j], s_copy);
-    }
-    if (rc == FGQ_OK) {
-        // element e of the left slice (half-index k = k_lo + e) mirrors to right-slice position cnt-1-e;
-        // the centre of an odd rule (k = m) has no mirror image
-        const int64_t mirror_cnt = (k_hi - 1 > mr) ? cnt - 1 : cnt;
-        unsigned hw = std::thread::hardware_concurrency();
-        const int T = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
-        std::vector<std::thread> workers;
-        std::atomic<int> failed{0};
-        for (int t = 0; t < T; ++t) {
-            workers.emplace_back([&, t]() {
-                cudaSetDevice(dev);
-                for (int64_t j = 0; j < nchunks; ++j) {
-                    if (cudaEventSynchronize(landed[j]) != cudaSuccess) {
-                        failed = 1;
-                        return;
-                    }
-                    const int64_t lo = j * chunk, hi0 = lo + chunk < cnt ? lo + chunk : cnt;
-                    const int64_t hi = hi0 < mirror_cnt ? hi0 : mirror_cnt;
-                    const int64_t len = hi - lo;
-                    if (len <= 0) continue;
-                    const int64_t a = lo + len * t / T, bnd = lo + len * (t + 1) / T;
-                    for (int64_t e = a; e < bnd; ++e) {
-                        xr[cnt - 1 - e] = -xl[e];
-                        wr[cnt - 1 - e] = wl[e];
-                    }
-                }
-            });
+        return FGQ_OK;
+    };
+    // element e of the left slice (half-index k = k_lo + e) mirrors to right-slice position cnt-1-e;
+    // the centre of an odd rule (k = m) has no mirror image
+    const int64_t mirror_cnt = (k_hi - 1 > mr) ? cnt - 1 : cnt;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int T = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+    auto host_part = [&](int64_t j, int t) {  // thread t's share of chunk j
+        const int64_t lo = j * chunk, hi0 = lo + chunk < cnt ? lo + chunk : cnt;
+        const int b = (int)(j % nbuf);
+        const double* sx = staged ? stage[b] - lo : xl;          // source indexed by e
+        const double* sw = staged ? stage[b] + chunk - lo : wl;
+        const int64_t len0 = hi0 - lo;
+        const int64_t a0 = lo + len0 * t / T, b0 = lo + len0 * (t + 1) / T;
+        if (staged) {
+            memcpy(xl + a0, sx + a0, (size_t)(b0 - a0) * 8);
+            memcpy(wl + a0, sw + a0, (size_t)(b0 - a0) * 8);
         }
-        for (auto& th : workers) th.join();
-        if (failed) {
-            set_error("device-to-host copy failed");
-            rc = FGQ_ECUDA;
+        const int64_t b1 = b0 < mirror_cnt ? b0 : mirror_cnt;
+        for (int64_t e = a0; e < b1; ++e) {
+            xr[cnt - 1 - e] = -sx[e];
+            wr[cnt - 1 - e] = sw[e];
+        }
+    };
+    if (!staged) {
+        // pinned destination: everything is enqueued up front, the workers only follow the copy events
+        for (int64_t j = 0; j < nchunks && rc == FGQ_OK; ++j) rc = enqueue(j);
+        if (rc == FGQ_OK) {
+            std::vector<std::thread> workers;
+            std::atomic<int> failed{0};
+            for (int t = 0; t < T; ++t) {
+                workers.emplace_back([&, t]() {
+                    cudaSetDevice(dev);
+                    for (int64_t j = 0; j < nchunks; ++j) {
+                        if (cudaEventSynchronize(landed[j]) != cudaSuccess) {
+                            failed = 1;
+                            return;
+                        }
+                        host_part(j, t);
+                    }
+                });
+            }
+            for (auto& th : workers) th.join();
+            if (failed) {
+                set_error("device-to-host copy failed");
+                rc = FGQ_ECUDA;
+            }
+        }
+    } else {
+        // staged: a staging buffer may only be refilled after the host threads have emptied it
+        for (int64_t j = 0; j < nchunks && j < nbuf && rc == FGQ_OK; ++j) rc = enqueue(j);
+        for (int64_t j = 0; j < nchunks && rc == FGQ_OK; ++j) {
+            if (cudaEventSynchronize(landed[j]) != cudaSuccess) {
+                set_error("device-to-host copy failed");
+                rc = FGQ_ECUDA;
+                break;
+            }
+            std::vector<std::thread> workers;
+            for (int t = 0; t < T; ++t) workers.emplace_back([&, t]() { host_part(j, t); });
+            for (auto& th : workers) th.join();
+            if (j + nbuf < nchunks) rc = enqueue(j + nbuf);
         }
     }
     cudaError_t e1 = cudaStreamSynchronize(s_compute);
