@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 METRIC = "gausslegendre_gnodes_per_s"
 UNIT = "Gnodes/s"
 N_DEFAULT = 10 ** 9
-CPU_SAMPLE_N = 2 * 10 ** 8     # bounded CPU sample: a full gausslegendre(2e8), same branch as 1e9
+CPU_SAMPLE_N = 5 * 10 ** 8     # bounded CPU sample: a full gausslegendre(5e8), same branch as 1e9 (~8 s on one core)
 PUBLISHED_JULIA_GNODES = 0.0428  # docs/src/benchmark.md:21-22 (n = 1e9+1, hardware unstated)
 
 
