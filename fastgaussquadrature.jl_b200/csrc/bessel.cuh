@@ -11,14 +11,9 @@
 #ifndef FGQ_BESSEL_CUH_
 #define FGQ_BESSEL_CUH_
 
-namespace fgq {
+#include "jacobi_plan.h"
 
-struct BesselOrder {
-    double nu;        // effective order (non-negative-integer reflection already applied)
-    double sign;      // J_{-m} = (-1)^m J_m for integer m: multiply the result by this
-    double rgamma;    // 1 / Gamma(nu + 1)
-    double cosc, sinc;  // cos, sin of (nu/2 + 1/4) pi
-};
+namespace fgq {
 
 struct ddv {
     double hi, lo;
@@ -48,23 +43,28 @@ __device__ __forceinline__ ddv dd_div(ddv a, ddv b) {
     return dd_add(dd_two_sum(q1, q2), {q3, 0.0});
 }
 
+// ascending series in double-double: any real order, x up to ~45 (cancellation e^x against 1e-32)
+__device__ inline double besselj_series_dd(const BesselOrder& o, double x) {
+    const double nu = o.nu;
+    if (x == 0.0) return nu == 0.0 ? 1.0 : 0.0;
+    const ddv q = dd_mul(dd_two_prod(x, x), {0.25, 0.0});
+    ddv term = {1.0, 0.0}, sum = {1.0, 0.0};
+    double maxterm = 1.0;
+    for (int k = 0; k < 400; ++k) {
+        const ddv den = dd_mul({(double)(k + 1), 0.0}, dd_two_sum(nu, (double)(k + 1)));
+        term = dd_div(dd_mul(term, q), den);
+        term.hi = -term.hi;
+        term.lo = -term.lo;
+        sum = dd_add(sum, term);
+        maxterm = fmax(maxterm, fabs(term.hi));
+        if (fabs(term.hi) < 1e-36 * maxterm && (double)k > 0.5 * x) break;
+    }
+    return o.sign * (pow(0.5 * x, nu) * o.rgamma) * sum.hi;
+}
+
 __device__ inline double besselj_dev(const BesselOrder& o, double x) {
     const double nu = o.nu;
-    if (x < 25.0) {
-        const ddv q = dd_mul(dd_two_prod(x, x), {0.25, 0.0});
-        ddv term = {1.0, 0.0}, sum = {1.0, 0.0};
-        double maxterm = 1.0;
-        for (int k = 0; k < 200; ++k) {
-            const ddv den = dd_mul({(double)(k + 1), 0.0}, dd_two_sum(nu, (double)(k + 1)));
-            term = dd_div(dd_mul(term, q), den);
-            term.hi = -term.hi;
-            term.lo = -term.lo;
-            sum = dd_add(sum, term);
-            maxterm = fmax(maxterm, fabs(term.hi));
-            if (fabs(term.hi) < 1e-36 * maxterm && (double)k > 0.5 * x) break;
-        }
-        return o.sign * (pow(0.5 * x, nu) * o.rgamma) * sum.hi;
-    }
+    if (x < 25.0) return besselj_series_dd(o, x);
     const double mu = 4.0 * nu * nu;
     const double i8x = 1.0 / (8.0 * x);
     double a = 1.0, P = 1.0, Q = 0.0, prev = 1.0;

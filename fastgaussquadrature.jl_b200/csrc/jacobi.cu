@@ -5,8 +5,8 @@
 //   gaussjacobi dispatch, jacobi_asy       src/gaussjacobi.jl:23-55, 170-194
 //   asy1, feval_asy1 (interior)            src/gaussjacobi.jl:196-361
 //   gaussradau(n), gausslobatto(n)         src/gaussradau.jl:31-49, src/gausslobatto.jl:31-52
-// (the 2 x 10 boundary nodes of asy2 and all parameter-only tables are planned on the host:
-//  jacobi_boundary.cu).
+//   asy2 and helpers (2 x 10 boundary nodes)   src/gaussjacobi.jl:363-667   (jacobi_boundary.cuh)
+// (parameter-only tables and constants are planned on the host: jacobi_boundary.cu).
 //
 // The reference materialises ~10 dense 20 x N arrays per evaluation and runs a BLAS gemv per
 // series term; here one thread owns one node and keeps the whole 20-term expansion in registers:
@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "fgq_math.h"
+#include "jacobi_boundary.cuh"
 #include "jacobi_plan.h"
 
 namespace fgq {
@@ -174,7 +175,8 @@ jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, doub
         t += dt;
         theta[ig] = t;
         if (interior) adt = (dt != dt) ? __longlong_as_double(0x7ff8000000000000LL) : fabs(dt);
-        if (ig >= p.lo && ig < p.hi) {
+        // the 10 nodes next to each end belong to the boundary kernel, which runs concurrently
+        if (ig >= p.lo && ig < p.hi && ig >= JAC_NBDY && ig < p.n - JAC_NBDY) {
             const double c = cos(t);
             x[ig - p.lo] = h ? -c : c;                   // vcat(-x_left, x_right) (:246)
             w[ig - p.lo] = (1.0 / (ders * ders)) * p.wc;  // 1 ./ ders.^2 (:222,:244), rmul! (:192)
@@ -560,13 +562,35 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
         set_error("internal: degenerate interior split (%lld of %lld)", (long long)n_left, (long long)n);
         return FGQ_EINVAL;
     }
+    const double wc = jacobi_weights_constant(n, a, b);
+    // Boundary nodes (:182-190): asy2 with (a, b) at the right end, with (b, a) mirrored at the left end (for
+    // a == b the reference reuses the right-end result; the same solve gives the same numbers).  Two
+    // single-block kernels, independent of the interior: forked onto a side stream and joined at the end
+    // (event dependencies only, so the call stays stream-ordered and graph-capturable).
+    cudaStream_t side;
+    FGQ_TRY(scratch_stream(1, &side));
+    cudaEvent_t ev_fork, ev_join;
+    FGQ_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    FGQ_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    FGQ_CUDA_TRY(cudaEventRecord(ev_fork, st));
+    FGQ_CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
+    for (int sd = 0; sd < 2; ++sd) {
+        JacobiBoundaryPlan bp;
+        jacobi_boundary_plan(n, sd == 0 ? a : b, sd == 0 ? b : a, &bp);
+        bp.wc = wc;
+        bp.side = sd;
+        bp.lo = lo;
+        bp.hi = hi;
+        jacobi_boundary_kernel<<<1, JB_THREADS, 0, side>>>(bp, x_dev, w_dev);
+        FGQ_LAUNCH_CHECK();
+    }
+    FGQ_CUDA_TRY(cudaEventRecord(ev_join, side));
     jacobi_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a, b, n_left, theta);
     FGQ_LAUNCH_CHECK();
 
     JacobiLaunch L[2];
     jacobi_interior_plan(n, a, b, &L[0].hp);
     jacobi_interior_plan(n, b, a, &L[1].hp);
-    const double wc = jacobi_weights_constant(n, a, b);
     for (int h = 0; h < 2; ++h) {
         L[h].half = h;
         L[h].n = n;
@@ -589,27 +613,9 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
             FGQ_LAUNCH_CHECK();
         }
     }
-    // boundary nodes (host-planned, O(1)): right end with (a,b), left end with (b,a) mirrored (:182-190)
-    JacobiPatch q;
-    q.n = n;
-    q.lo = lo;
-    q.hi = hi;
-    double xb[JAC_NBDY], wb[JAC_NBDY];
-    jacobi_asy2(n, a, b, JAC_NBDY, xb, wb);
-    for (int i = 0; i < JAC_NBDY; ++i) {
-        q.x[JAC_NBDY + i] = xb[i];
-        q.w[JAC_NBDY + i] = wb[i] * wc;
-    }
-    if (a != b) jacobi_asy2(n, b, a, JAC_NBDY, xb, wb);
-    for (int i = 0; i < JAC_NBDY; ++i) {
-        q.x[i] = -xb[JAC_NBDY - 1 - i];
-        q.w[i] = wb[JAC_NBDY - 1 - i] * wc;
-    }
-    for (int i = 0; i < 2 * JAC_NBDY; ++i) {
-        if (!(q.x[i] == q.x[i]) || !(q.w[i] == q.w[i])) add_warning(FGQ_WARN_NONFINITE);
-    }
-    jacobi_patch_kernel<<<1, 32, 0, st>>>(q, x_dev, w_dev);
-    FGQ_LAUNCH_CHECK();
+    FGQ_CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0));
+    cudaEventDestroy(ev_fork);
+    cudaEventDestroy(ev_join);
     return FGQ_OK;
 }
 
