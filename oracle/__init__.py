@@ -59,6 +59,10 @@ def lib():
         L.oracle_eval_laguerre_rec.restype = None
         L.oracle_innerjacobi_rec.argtypes = [_c_i64, _c_i64, _c_dp, ctypes.c_double, ctypes.c_double, _c_dp, _c_dp]
         L.oracle_innerjacobi_rec.restype = None
+        for nm in ("oracle_twin_sincos_q1", "oracle_twin_sincos_medium"):
+            f = getattr(L, nm)
+            f.argtypes = [_c_i64, _c_dp, _c_dp, _c_dp]
+            f.restype = None
         L.oracle_set_threads.argtypes = [ctypes.c_int]
         L.oracle_set_threads.restype = ctypes.c_int
         _lib = L
@@ -138,6 +142,16 @@ def innerjacobi_rec(n: int, x: np.ndarray, a: float, b: float):
     PP = np.empty_like(x)
     lib().oracle_innerjacobi_rec(int(n), len(x), _dp(x), float(a), float(b), _dp(P), _dp(PP))
     return P, PP
+
+
+def twin_sincos(t: np.ndarray, medium: bool = False):
+    """(sin t, cos t) from the library's fgq_math.h compiled for the host (first-quadrant or medium-range)."""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    s = np.empty_like(t)
+    c = np.empty_like(t)
+    f = lib().oracle_twin_sincos_medium if medium else lib().oracle_twin_sincos_q1
+    f(len(t), _dp(t), _dp(s), _dp(c))
+    return s, c
 
 
 def ulp_diff(got: np.ndarray, ref: np.ndarray) -> np.ndarray:

@@ -411,3 +411,14 @@ int oracle_set_threads(int nthreads) {
 #endif
 }
 #endif
+
+#ifdef FGQ_TWIN
+/* The library's own elementary functions (fgq_math.h), exported so that tests can measure their accuracy
+ * against a higher-precision libm on the host. */
+void oracle_twin_sincos_q1(int64_t cnt, const double* t, double* s, double* c) {
+    for (int64_t i = 0; i < cnt; ++i) fgq_sincos_q1(t[i], &s[i], &c[i]);
+}
+void oracle_twin_sincos_medium(int64_t cnt, const double* t, double* s, double* c) {
+    for (int64_t i = 0; i < cnt; ++i) fgq_sincos_medium(t[i], &s[i], &c[i]);
+}
+#endif
