@@ -25,7 +25,7 @@ _c_dp = ctypes.POINTER(ctypes.c_double)
 
 def build(force: bool = False) -> str:
     """Compile the C oracle (gcc, a few seconds)."""
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".c")]
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
     stale = os.path.exists(_LIB_PATH) and any(os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in srcs)
     if force or stale or not os.path.exists(_LIB_PATH):
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
@@ -38,7 +38,7 @@ def lib():
     if _lib is None:
         build()
         L = ctypes.CDLL(_LIB_PATH)
-        for sfx in ("", "_twin"):
+        for sfx in ("", "_twin", "_jl"):
             f = getattr(L, "oracle_gausslegendre" + sfx)
             f.argtypes = [_c_i64, _c_dp, _c_dp]
             f.restype = ctypes.c_int
@@ -63,6 +63,8 @@ def lib():
             f = getattr(L, nm)
             f.argtypes = [_c_i64, _c_dp, _c_dp, _c_dp]
             f.restype = None
+        L.oracle_jl_sincostan.argtypes = [_c_i64, _c_dp, _c_dp, _c_dp, _c_dp]
+        L.oracle_jl_sincostan.restype = None
         L.oracle_set_threads.argtypes = [ctypes.c_int]
         L.oracle_set_threads.restype = ctypes.c_int
         _lib = L
@@ -78,48 +80,60 @@ def set_threads(n: int) -> int:
     return lib().oracle_set_threads(int(n))
 
 
-def gausslegendre(n: int, twin: bool = False):
+def _sfx(twin) -> str:
+    """Elementary-function mode of the Legendre oracle: False / "libm" = glibc, True / "twin" = the
+    library's own fgq_math.h on the host, "julia" = the restated Julia Base sin/cos/tan (julia_libm.h)."""
+    if twin is True or twin == "twin":
+        return "_twin"
+    if twin == "julia":
+        return "_jl"
+    if twin is False or twin == "libm":
+        return ""
+    raise ValueError(f"unknown oracle libm mode {twin!r}")
+
+
+def gausslegendre(n: int, twin=False):
     """Oracle of ``gausslegendre(n)`` (reference src/gausslegendre.jl:22-68)."""
     if n < 0:
         raise ValueError("DomainError: Input n must be a non-negative integer")
     x = np.empty(n, dtype=np.float64)
     w = np.empty(n, dtype=np.float64)
-    f = lib().oracle_gausslegendre_twin if twin else lib().oracle_gausslegendre
+    f = getattr(lib(), "oracle_gausslegendre" + _sfx(twin))
     rc = f(n, _dp(x), _dp(w))
     if rc:
         raise RuntimeError(f"oracle_gausslegendre rc={rc}")
     return x, w
 
 
-def legendre_asy_half(n: int, k0: int, k1: int, twin: bool = False):
+def legendre_asy_half(n: int, k0: int, k1: int, twin=False):
     """cos(theta_k), w_k for half-indices k0..k1 (1-based, inclusive) of the asy path."""
     cnt = max(k1 - k0 + 1, 0)
     x = np.empty(cnt, dtype=np.float64)
     w = np.empty(cnt, dtype=np.float64)
-    f = lib().oracle_legendre_asy_half_twin if twin else lib().oracle_legendre_asy_half
+    f = getattr(lib(), "oracle_legendre_asy_half" + _sfx(twin))
     rc = f(n, k0, k1, _dp(x), _dp(w))
     if rc:
         raise MemoryError("oracle_legendre_asy_half")
     return x, w
 
 
-def legendre_theta(n: int, k0: int, k1: int, twin: bool = False):
+def legendre_theta(n: int, k0: int, k1: int, twin=False):
     cnt = max(k1 - k0 + 1, 0)
     t = np.empty(cnt, dtype=np.float64)
-    f = lib().oracle_legendre_theta_twin if twin else lib().oracle_legendre_theta
+    f = getattr(lib(), "oracle_legendre_theta" + _sfx(twin))
     if f(n, k0, k1, _dp(t)):
         raise MemoryError("oracle_legendre_theta")
     return t
 
 
-def gausslegendre_batch(n_i: np.ndarray, twin: bool = False):
+def gausslegendre_batch(n_i: np.ndarray, twin=False):
     """CSR batch of small rules: returns (offsets, x, w)."""
     n_i = np.ascontiguousarray(n_i, dtype=np.int32)
     offsets = np.zeros(len(n_i) + 1, dtype=np.int64)
     np.cumsum(n_i, out=offsets[1:])
     x = np.empty(int(offsets[-1]), dtype=np.float64)
     w = np.empty(int(offsets[-1]), dtype=np.float64)
-    f = lib().oracle_gausslegendre_batch_twin if twin else lib().oracle_gausslegendre_batch
+    f = getattr(lib(), "oracle_gausslegendre_batch" + _sfx(twin))
     rc = f(len(n_i), n_i.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
            offsets.ctypes.data_as(ctypes.POINTER(_c_i64)), _dp(x), _dp(w))
     if rc:
@@ -152,6 +166,16 @@ def twin_sincos(t: np.ndarray, medium: bool = False):
     f = lib().oracle_twin_sincos_medium if medium else lib().oracle_twin_sincos_q1
     f(len(t), _dp(t), _dp(s), _dp(c))
     return s, c
+
+
+def julia_sincostan(t: np.ndarray):
+    """(sin t, cos t, tan t) from julia_libm.h, the restatement of Julia Base's fdlibm-derived functions."""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    s = np.empty_like(t)
+    c = np.empty_like(t)
+    tn = np.empty_like(t)
+    lib().oracle_jl_sincostan(len(t), _dp(t), _dp(s), _dp(c), _dp(tn))
+    return s, c, tn
 
 
 def ulp_diff(got: np.ndarray, ref: np.ndarray) -> np.ndarray:

@@ -17,10 +17,12 @@
  * Julia cannot run in this image, so behaviour below 1e-14 absolute (the ulp
  * level of Julia's libm) is UNPINNED; see DESIGN.md.
  *
- * Two libm modes:
+ * Three libm modes:
  *   default      sin/cos/tan from the host libm (glibc) — the independent check.
  *   -DFGQ_TWIN   sin/cos/cot from the library's own fgq_math.h, so that the
  *                kernels can be pinned bit-for-bit against this file.
+ *   -DFGQ_JLIBM  sin/cos/tan from julia_libm.h: a restatement of the fdlibm-derived
+ *                algorithms Julia Base uses (the functions the reference really calls).
  */
 #include <math.h>
 #include <stdint.h>
@@ -33,6 +35,12 @@
 #define O_COS(x) fgq_cos_q1(x)
 #define O_COT(x) fgq_cot_q1(x)
 #define O_NAME(f) f##_twin
+#elif defined(FGQ_JLIBM)
+#include "julia_libm.h"
+#define O_SIN(x) jl_sin(x)
+#define O_COS(x) jl_cos(x)
+#define O_COT(x) jl_cot(x)
+#define O_NAME(f) f##_jl
 #else
 #define O_SIN(x) sin(x)
 #define O_COS(x) cos(x)
@@ -394,7 +402,7 @@ int O_NAME(oracle_legendre_theta)(int64_t n, int64_t k0, int64_t k1, double* the
     return 0;
 }
 
-#ifndef FGQ_TWIN
+#if !defined(FGQ_TWIN) && !defined(FGQ_JLIBM)
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -420,5 +428,17 @@ void oracle_twin_sincos_q1(int64_t cnt, const double* t, double* s, double* c) {
 }
 void oracle_twin_sincos_medium(int64_t cnt, const double* t, double* s, double* c) {
     for (int64_t i = 0; i < cnt; ++i) fgq_sincos_medium(t[i], &s[i], &c[i]);
+}
+#endif
+
+#ifdef FGQ_JLIBM
+/* The restated Julia Base sin/cos/tan, exported so that tests can measure them against a
+ * higher-precision libm. */
+void oracle_jl_sincostan(int64_t cnt, const double* t, double* s, double* c, double* tn) {
+    for (int64_t i = 0; i < cnt; ++i) {
+        s[i] = jl_sin(t[i]);
+        c[i] = jl_cos(t[i]);
+        tn[i] = jl_tan(t[i]);
+    }
 }
 #endif

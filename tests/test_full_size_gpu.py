@@ -97,7 +97,7 @@ def test_fused_moments(fgq, n):
 def test_legendre_1e9_every_index_against_the_oracle(fgq, oracle_mod):
     """at n = 1e9 compare EVERY index, not a sample.  The GPU rule is pulled back in
     chunks of 2.5e7 half-indices and compared with the C oracle: bit-for-bit against the twin mode;
-    against the libm mode nodes <= 1-2 ulp, weights <= 4 ulp except a ~1e-6 fraction at 5
+    against the libm and julia modes nodes <= 1-2 ulp, weights <= 4 ulp except a ~1e-6 fraction at 5
     (profiles/r01_parity_legendre_1e9.md holds the full histogram)."""
     import torch
     n = 10 ** 9
@@ -114,9 +114,10 @@ def test_legendre_1e9_every_index_against_the_oracle(fgq, oracle_mod):
         gw = wl[k0 - 1:k1].cpu().numpy()
         xt, wt = oracle_mod.legendre_asy_half(n, k0, k1, twin=True)
         assert np.array_equal(gx, xt) and np.array_equal(gw, wt), f"twin mismatch in half-indices {k0}..{k1}"
-        xo, wo = oracle_mod.legendre_asy_half(n, k0, k1)
-        assert oracle_mod.ulp_diff(gx, xo).max() <= 2
-        uw = oracle_mod.ulp_diff(gw, wo)
-        assert uw.max() <= 5
-        over4 += int(np.count_nonzero(uw > 4))
-    assert over4 <= 4e-6 * m
+        for md in ("libm", "julia"):   # glibc; the restated Julia Base sin/cos (oracle/julia_libm.h)
+            xo, wo = oracle_mod.legendre_asy_half(n, k0, k1, twin=md)
+            assert oracle_mod.ulp_diff(gx, xo).max() <= 2
+            uw = oracle_mod.ulp_diff(gw, wo)
+            assert uw.max() <= 5
+            over4 += int(np.count_nonzero(uw > 4))
+    assert over4 <= 8e-6 * m

@@ -80,6 +80,12 @@ def test_asy_parity(fgq, oracle_mod, n):
     uw = oracle_mod.ulp_diff(w, wo)
     assert uw.max() <= W_ULP + 1
     assert np.count_nonzero(uw > W_ULP) <= max(1, int(2e-7 * n))
+    # the same band against the restated Julia Base libm (oracle/julia_libm.h)
+    xj, wj = oracle_mod.gausslegendre(n, twin="julia")
+    assert _ulps(oracle_mod, x, xj) <= X_ULP
+    uw = oracle_mod.ulp_diff(w, wj)
+    assert uw.max() <= W_ULP + 1
+    assert np.count_nonzero(uw > W_ULP) <= max(1, int(2e-7 * n))
     if n % 2:
         assert x[n // 2] == 0.0
     assert np.all(np.diff(x) >= 0)

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "legendre_reference_tests.json")))
 
 
-@pytest.mark.parametrize("twin", [False, True])
+@pytest.mark.parametrize("twin", [False, True, "julia"])
 @pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: f"n{c['n']}")
 def test_golden_values(oracle_mod, case, twin):
     x, w = oracle_mod.gausslegendre(case["n"], twin=twin)
@@ -64,6 +64,43 @@ def test_twin_libm_gap(oracle_mod):
         nz = x != 0
         assert oracle_mod.ulp_diff(xt[nz], x[nz]).max() <= 1
         assert oracle_mod.ulp_diff(wt, w).max() <= 4
+
+
+def test_julia_libm_restatement_accuracy(oracle_mod):
+    """julia_libm.h (the restated Julia Base sin/cos/tan) is a < 1 ulp libm, as fdlibm documents, and
+    agrees with glibc to 1 ulp: checked against long double over the quadrant the Legendre angles
+    live in, the quadrant boundaries, the small-argument shortcuts and the medium range."""
+    rng = np.random.default_rng(7)
+    t = np.concatenate([rng.uniform(0, np.pi / 2, 200000), rng.uniform(-8, 8, 50000),
+                        10.0 ** rng.uniform(-10, 6, 50000),
+                        np.pi / 2 + rng.uniform(-1e-6, 1e-6, 5000), np.pi + rng.uniform(-1e-6, 1e-6, 5000),
+                        [np.pi / 4, np.nextafter(np.pi / 4, 0), np.pi / 2, np.pi, 0.6744, 0.67, 1e-9, 2e-8]])
+    s, c, tn = oracle_mod.julia_sincostan(t)
+    tl = t.astype(np.longdouble)
+    for got, ref in ((s, np.sin(tl)), (c, np.cos(tl)), (tn, np.tan(tl))):
+        err = np.abs(got.astype(np.longdouble) - ref) / np.spacing(np.abs(ref.astype(np.float64)))
+        assert float(err.max()) < 1.0
+    for got, ref in ((s, np.sin(t)), (c, np.cos(t)), (tn, np.tan(t))):
+        assert oracle_mod.ulp_diff(got, ref).max() <= 1
+
+
+def test_julia_libm_gap(oracle_mod):
+    """Legendre rules under the restated Julia libm against glibc and against the library's twin:
+    nodes <= 1 ulp, weights <= 4 ulp (5 on a ~1e-7 fraction) — three independent < 1 ulp libms give
+    rules inside the same band, which is what the 2 ulp / 4 ulp tolerance of the north star absorbs."""
+    for n in (61, 251, 1013, 10013, 100000, 1000003, 5000001):
+        xj, wj = oracle_mod.gausslegendre(n, twin="julia")
+        for mode in (False, True):
+            x, w = oracle_mod.gausslegendre(n, twin=mode)
+            nz = x != 0
+            assert np.array_equal(xj == 0, x == 0)
+            assert oracle_mod.ulp_diff(xj[nz], x[nz]).max() <= 1
+            uw = oracle_mod.ulp_diff(wj, w)
+            assert uw.max() <= 5 and np.count_nonzero(uw > 4) <= max(1, int(2e-7 * n))
+    # theta never depends on sin/cos, and on tan only through a correction ~1e-5 of its size:
+    for n in (100, 1013, 100000):
+        m = (n + 1) // 2
+        assert np.array_equal(oracle_mod.legendre_theta(n, 1, m, twin="julia"), oracle_mod.legendre_theta(n, 1, m))
 
 
 def test_theta_equals_a_beyond_2p25(oracle_mod):

@@ -1,6 +1,7 @@
 """Full-range parity report for the headline config: every half-index of gausslegendre(n) on the GPU
-against the C oracle (twin mode = bit-for-bit expectation; libm mode = glibc sin/cos/tan, the
-independent stand-in for Julia's libm).  Writes a markdown table of ulp histograms.
+against the C oracle (twin mode = bit-for-bit expectation; libm mode = glibc sin/cos/tan, an
+independent < 1 ulp libm; julia mode = oracle/julia_libm.h, the restated fdlibm-derived algorithms
+Julia Base uses, i.e. the functions the reference calls).  Writes a markdown table of ulp histograms.
 usage: python tools/parity_report.py [n] [out.md]"""
 import os
 import sys
@@ -24,8 +25,8 @@ m = (n + 1) // 2
 mr = n // 2
 assert bool(torch.equal(xl[:mr], -xr.flip(0))) and bool(torch.equal(wl[:mr], wr.flip(0))), "mirror symmetry"
 CH = 25_000_000
-hx = np.zeros(8, dtype=np.int64)
-hw = np.zeros(16, dtype=np.int64)
+hx = {md: np.zeros(8, dtype=np.int64) for md in ("libm", "julia")}
+hw = {md: np.zeros(8, dtype=np.int64) for md in ("libm", "julia")}
 twin_bad = 0
 t0 = time.time()
 for k0 in range(1, m + 1, CH):
@@ -38,24 +39,26 @@ for k0 in range(1, m + 1, CH):
     if n % 2 and k1 == m:
         xt[-1] = 0.0
     twin_bad += int(np.count_nonzero(gx != xt) + np.count_nonzero(gw != wt))
-    xo, wo = oracle.legendre_asy_half(n, k0, k1)
-    if n % 2 and k1 == m:
-        xo[-1] = 0.0
-    nz = xo != 0
-    ux = oracle.ulp_diff(gx[nz], xo[nz]).astype(np.int64)
-    uw = oracle.ulp_diff(gw, wo).astype(np.int64)
-    hx += np.bincount(np.minimum(ux, 7), minlength=8)
-    hw += np.bincount(np.minimum(uw, 15), minlength=16)
+    for md in ("libm", "julia"):
+        xo, wo = oracle.legendre_asy_half(n, k0, k1, twin=md)
+        if n % 2 and k1 == m:
+            xo[-1] = 0.0
+        nz = xo != 0
+        ux = oracle.ulp_diff(gx[nz], xo[nz]).astype(np.int64)
+        uw = oracle.ulp_diff(gw, wo).astype(np.int64)
+        hx[md] += np.bincount(np.minimum(ux, 7), minlength=8)
+        hw[md] += np.bincount(np.minimum(uw, 7), minlength=8)
 dt = time.time() - t0
 lines = [f"# Parity of gausslegendre({n}) on the B200 against the C oracle — every half-index ({m} of them)", "",
          f"* mirror symmetry x[i] == -x[n-1-i], w[i] == w[n-1-i]: exact over the whole rule",
          f"* twin oracle (library's own sin/cos compiled for the host): **{twin_bad} mismatching values** out of {2 * m} (bit-for-bit)",
-         f"* libm oracle (glibc sin/cos/tan), ulp distance |got-ref|/spacing(ref):", "",
-         "| ulp | nodes | weights |", "|---|---|---|"]
-for u in range(16):
-    a = hx[u] if u < 8 else 0
-    lines.append(f"| {u}{'+' if u in (7, 15) else ''} | {a if u < 8 else ''} | {hw[u]} |")
-lines += ["", f"max node ulp = {int(np.max(np.nonzero(hx)[0]))}, max weight ulp = {int(np.max(np.nonzero(hw)[0]))}; "
+         "* ulp distance |got-ref|/spacing(ref) against the two independent oracles — `libm`: glibc sin/cos/tan; "
+         "`julia`: oracle/julia_libm.h, the restated Julia Base (fdlibm-derived, FMA Horner) sin/cos/tan:", "",
+         "| ulp | nodes vs libm | weights vs libm | nodes vs julia | weights vs julia |", "|---|---|---|---|---|"]
+for u in range(8):
+    lines.append(f"| {u}{'+' if u == 7 else ''} | {hx['libm'][u]} | {hw['libm'][u]} | {hx['julia'][u]} | {hw['julia'][u]} |")
+mx = {md: (int(np.max(np.nonzero(hx[md])[0])), int(np.max(np.nonzero(hw[md])[0]))) for md in hx}
+lines += ["", f"max node / weight ulp: vs libm {mx['libm'][0]} / {mx['libm'][1]}, vs julia {mx['julia'][0]} / {mx['julia'][1]}; "
               f"oracle + compare time {dt:.1f} s on {os.cpu_count()} host threads."]
 open(out, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
