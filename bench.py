@@ -192,6 +192,25 @@ def time_other_configs(fgq_b200, cpu: bool):
     sf = fgq_b200.gausslegendre_moments_fused(nf).cpu().numpy()
     out["fused_moments_gausslegendre_1e9"] = {"device_ms": ms, "gnodes_per_s": nf / ms / 1e6,
                                               "sum_w_minus_2": float(sf[0] - 2), "sum_wx2_minus_2_3": float(sf[1] - 2 / 3)}
+    # C2 with odd n (docs/src/benchmark.md:21 times gausslegendre(1000000001)): the mirrored pair of a
+    # thread straddles a 16-byte boundary, handled with one warp shuffle
+    no = 10 ** 9 + 1
+    sh_odd = fgq_b200.gausslegendre_device(no, mode="pair")
+    ms = dev_time(lambda: fgq_b200.gausslegendre_device(no, mode="pair", out=sh_odd), reps=5)
+    out["C2_odd_gausslegendre_1e9p1"] = {"device_ms": ms, "gnodes_per_s": no / ms / 1e6}
+    del sh_odd
+    torch.cuda.empty_cache()
+
+    def host_wall(fn, reps=3):
+        fn()
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return best * 1e3
+
     # C3: gaussjacobi(1e7, 0.3, -0.7)
     n = 10_000_000
     x = torch.empty(n, dtype=torch.float64, device="cuda")
@@ -199,7 +218,8 @@ def time_other_configs(fgq_b200, cpu: bool):
     ws = torch.empty(int(L.fgq_gaussjacobi_workspace_bytes(n)) + 16, dtype=torch.uint8, device="cuda")
     ms = dev_time(lambda: chk(L.fgq_gaussjacobi_device(n, 0.3, -0.7, 0, n, x.data_ptr(), w.data_ptr(), ws.data_ptr(), sp)))
     out["C3_gaussjacobi_1e7"] = {"device_ms": ms, "mnodes_per_s": n / ms / 1e3,
-                                 "sum_w_err": float(w.sum().item() - 4.554443087962173)}
+                                 "sum_w_err": float(w.sum().item() - 4.554443087962173),
+                                 "host_call_ms": host_wall(lambda: fgq_b200.gaussjacobi(10_000_000, 0.3, -0.7))}
     # C4: gausshermite(1e6), gausslaguerre(1e6)
     n = 1_000_000
     x = torch.empty(n, dtype=torch.float64, device="cuda")
@@ -207,10 +227,12 @@ def time_other_configs(fgq_b200, cpu: bool):
     ws = torch.empty(int(L.fgq_gausshermite_workspace_bytes(n)) + 16, dtype=torch.uint8, device="cuda")
     ms = dev_time(lambda: chk(L.fgq_gausshermite_device(n, 0, 0, n, x.data_ptr(), w.data_ptr(), ws.data_ptr(), sp)))
     out["C4_gausshermite_1e6"] = {"device_ms": ms, "mnodes_per_s": n / ms / 1e3,
-                                  "sum_w_err": float(w.sum().item() - np.sqrt(np.pi))}
+                                  "sum_w_err": float(w.sum().item() - np.sqrt(np.pi)),
+                                  "host_call_ms": host_wall(lambda: fgq_b200.gausshermite(1_000_000))}
     ws = torch.empty(int(L.fgq_gausslaguerre_workspace_bytes(n)) + 16, dtype=torch.uint8, device="cuda")
     ms = dev_time(lambda: chk(L.fgq_gausslaguerre_device(n, 0.0, x.data_ptr(), w.data_ptr(), ws.data_ptr(), sp)))
-    out["C4_gausslaguerre_1e6"] = {"device_ms": ms, "mnodes_per_s": n / ms / 1e3, "sum_w_err": float(w.sum().item() - 1.0)}
+    out["C4_gausslaguerre_1e6"] = {"device_ms": ms, "mnodes_per_s": n / ms / 1e3, "sum_w_err": float(w.sum().item() - 1.0),
+                                   "host_call_ms": host_wall(lambda: fgq_b200.gausslaguerre(1_000_000))}
     # C5: 1e6 small rules, n in [2, 60]
     n_i = np.random.default_rng(0).integers(2, 61, size=1_000_000).astype(np.int32)
     off = np.zeros(len(n_i) + 1, dtype=np.int64)

@@ -1,12 +1,17 @@
 // capi.cu — status plumbing, library-owned scratch, host-returning entry points and the
 // rule-moments consumer of libfgq_cuda.so (see include/fgq.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "common.cuh"
 
@@ -16,6 +21,7 @@ static thread_local char t_err[512] = "";
 static thread_local int t_warn = 0;
 static std::atomic<int64_t> g_launches{0};
 static std::mutex g_host_mutex;
+static std::mutex g_res_mutex;  // lazily created per-device streams / events / scratch
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -51,6 +57,7 @@ static int cur_dev(int* dev) {
 int scratch_device(size_t bytes, int slot, void** out) {
     int dev;
     FGQ_TRY(cur_dev(&dev));
+    std::lock_guard<std::mutex> guard(g_res_mutex);
     if (g_scratch_bytes[dev][slot] < bytes) {
         if (g_scratch[dev][slot]) {
             FGQ_CUDA_TRY(cudaFree(g_scratch[dev][slot]));
@@ -64,8 +71,8 @@ int scratch_device(size_t bytes, int slot, void** out) {
     return FGQ_OK;
 }
 
-static void* g_pinned[2];
-static size_t g_pinned_bytes[2];
+static void* g_pinned[3];
+static size_t g_pinned_bytes[3];
 // library-owned pinned staging (grow-only), for destinations that are ordinary pageable memory
 static int scratch_pinned(size_t bytes, int slot, void** out) {
     if (g_pinned_bytes[slot] < bytes) {
@@ -93,6 +100,7 @@ static bool is_pinned_host(const void* p) {
 int scratch_stream(int which, cudaStream_t* out) {
     int dev;
     FGQ_TRY(cur_dev(&dev));
+    std::lock_guard<std::mutex> guard(g_res_mutex);
     if (!g_streams[dev][which])
         FGQ_CUDA_TRY(cudaStreamCreateWithFlags(&g_streams[dev][which], cudaStreamNonBlocking));
     *out = g_streams[dev][which];
@@ -102,6 +110,7 @@ int scratch_stream(int which, cudaStream_t* out) {
 int scratch_event(int which, cudaEvent_t* out) {
     int dev;
     FGQ_TRY(cur_dev(&dev));
+    std::lock_guard<std::mutex> guard(g_res_mutex);
     if (!g_events[dev][which])
         FGQ_CUDA_TRY(cudaEventCreateWithFlags(&g_events[dev][which], cudaEventDisableTiming));
     *out = g_events[dev][which];
@@ -140,6 +149,43 @@ rule_moments_kernel(const double* __restrict__ x, const double* __restrict__ w, 
         atomicAdd(sums, a);
         atomicAdd(sums + 1, b);
     }
+}
+
+// Mirror copy of the host-returning Legendre path: dst[cnt-1-e] = (negate ? -src[e] : src[e]) for e in
+// [a, b).  A pure data movement over up to 8 GB per array; the destination is written once and not read
+// again by this call, so the AVX2 form uses non-temporal stores (no write-allocate traffic competing
+// with the PCIe DMA for host memory bandwidth).
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void mirror_avx2(const double* src, double* dst, int64_t cnt, int64_t a,
+                                                         int64_t b, bool negate) {
+    // destination positions cnt-1-e descend as e ascends: walk e upwards, write blocks of 4 downwards
+    int64_t e = a;
+    // scalar until the 4-block [cnt-4-e, cnt-e) starts on a 32-byte boundary
+    while (e < b && ((uintptr_t)(dst + (cnt - e)) & 31) != 0) {
+        dst[cnt - 1 - e] = negate ? -src[e] : src[e];
+        ++e;
+    }
+    const __m256d sign = negate ? _mm256_set1_pd(-0.0) : _mm256_setzero_pd();
+    for (; e + 4 <= b; e += 4) {
+        __m256d v = _mm256_loadu_pd(src + e);
+        v = _mm256_permute4x64_pd(v, 0x1B);  // reverse the four lanes
+        v = _mm256_xor_pd(v, sign);
+        _mm256_stream_pd(dst + (cnt - 4 - e), v);
+    }
+    for (; e < b; ++e) dst[cnt - 1 - e] = negate ? -src[e] : src[e];
+    _mm_sfence();
+}
+#endif
+
+static void mirror_copy(const double* src, double* dst, int64_t cnt, int64_t a, int64_t b, bool negate) {
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) {
+        mirror_avx2(src, dst, cnt, a, b, negate);
+        return;
+    }
+#endif
+    for (int64_t e = a; e < b; ++e) dst[cnt - 1 - e] = negate ? -src[e] : src[e];
 }
 
 }  // namespace fgq
@@ -182,6 +228,90 @@ extern "C" int fgq_rule_moments_device(const double* x_dev, const double* w_dev,
 
 namespace fgq {
 
+// Device -> host copy of a finished result (x and w, cnt entries each), ordered after the work already
+// enqueued on `st`; returns when the data is in place.  A pinned destination is written by DMA directly.
+// A pageable one (a fresh Julia Vector, np.empty) would be staged by the driver through its own small
+// bounce buffer at 4-5 GB/s, one thread taking every first-touch page fault; instead the result is cut
+// into 2 MiB pieces that are DMA'd into a library-owned pinned ring and copied out by host threads as
+// they land (piece p by thread p mod T), which also spreads the page faults.
+int drain_to_host(double* x, double* w, const double* xd, const double* wd, int64_t cnt, cudaStream_t st) {
+    if (cnt <= 0) return FGQ_OK;
+    const int64_t PIECE = 1LL << 18;  // entries per piece and array
+    if (cnt < PIECE || (is_pinned_host(x) && is_pinned_host(w))) {
+        FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+        FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+        FGQ_CUDA_TRY(cudaStreamSynchronize(st));
+        return FGQ_OK;
+    }
+    constexpr int RING = 16;
+    void* ring_p;
+    FGQ_TRY(scratch_pinned((size_t)RING * 2 * PIECE * 8, 2, &ring_p));
+    double* ring = (double*)ring_p;
+    const int64_t pieces = (cnt + PIECE - 1) / PIECE;
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+    if (T > pieces) T = (int)pieces;
+    int dev;
+    FGQ_CUDA_TRY(cudaGetDevice(&dev));
+    cudaEvent_t ev[RING];
+    for (int i = 0; i < RING; ++i) FGQ_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    std::mutex mu;
+    std::condition_variable cv;
+    int64_t published = 0;            // pieces whose copies and event have been enqueued
+    std::vector<char> consumed((size_t)pieces, 0);
+    bool failed = false;
+    std::vector<std::thread> workers;
+    for (int t = 0; t < T; ++t) {
+        workers.emplace_back([&, t]() {
+            cudaSetDevice(dev);
+            for (int64_t p = t; p < pieces; p += T) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return published > p || failed; });
+                    if (failed) return;
+                }
+                const bool ok = cudaEventSynchronize(ev[p % RING]) == cudaSuccess;
+                if (ok) {
+                    const int64_t lo = p * PIECE, len = (lo + PIECE < cnt ? PIECE : cnt - lo);
+                    const double* sx = ring + (p % RING) * 2 * PIECE;
+                    memcpy(x + lo, sx, (size_t)len * 8);
+                    memcpy(w + lo, sx + PIECE, (size_t)len * 8);
+                }
+                std::lock_guard<std::mutex> lk(mu);
+                consumed[(size_t)p] = 1;
+                if (!ok) failed = true;
+                cv.notify_all();
+            }
+        });
+    }
+    cudaError_t err = cudaSuccess;
+    for (int64_t p = 0; p < pieces && err == cudaSuccess; ++p) {
+        if (p >= RING) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return consumed[(size_t)(p - RING)] != 0 || failed; });
+            if (failed) break;
+        }
+        const int64_t lo = p * PIECE, len = (lo + PIECE < cnt ? PIECE : cnt - lo);
+        double* sx = ring + (p % RING) * 2 * PIECE;
+        err = cudaMemcpyAsync(sx, xd + lo, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(sx + PIECE, wd + lo, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+        if (err == cudaSuccess) err = cudaEventRecord(ev[p % RING], st);
+        std::lock_guard<std::mutex> lk(mu);
+        if (err == cudaSuccess) published = p + 1; else failed = true;
+        cv.notify_all();
+    }
+    for (auto& th : workers) th.join();
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    for (int i = 0; i < RING; ++i) cudaEventDestroy(ev[i]);
+    FGQ_CUDA_TRY(err);
+    FGQ_CUDA_TRY(e2);
+    if (failed) {
+        set_error("device-to-host copy failed");
+        return FGQ_ECUDA;
+    }
+    return FGQ_OK;
+}
+
 int host_pipeline(int64_t lo_all, int64_t hi_all, double* x, double* w, SliceFn fn, void* ctx) {
     const int64_t n = hi_all - lo_all;
     if (n <= 0) return FGQ_OK;
@@ -208,20 +338,44 @@ int host_pipeline(int64_t lo_all, int64_t hi_all, double* x, double* w, SliceFn 
         FGQ_TRY(scratch_event(2 + b, &drained[b]));
     }
     int rc = FGQ_OK;
-    int64_t j = 0;
-    for (int64_t lo = 0; lo < n && rc == FGQ_OK; lo += chunk, ++j) {  // lo, hi relative to lo_all
-        const int64_t hi = lo + chunk < n ? lo + chunk : n;
-        const int b = (int)(j % nbuf);
-        double* xd = buf[b];
-        double* wd = buf[b] + chunk;
-        if (j >= nbuf) FGQ_CUDA_TRY(cudaStreamWaitEvent(s_compute, drained[b], 0));
-        rc = fn(ctx, lo_all + lo, lo_all + hi, xd, wd, s_compute);
-        if (rc != FGQ_OK) break;
-        FGQ_CUDA_TRY(cudaEventRecord(computed[b], s_compute));
-        FGQ_CUDA_TRY(cudaStreamWaitEvent(s_copy, computed[b], 0));
-        FGQ_CUDA_TRY(cudaMemcpyAsync(x + lo, xd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy));
-        FGQ_CUDA_TRY(cudaMemcpyAsync(w + lo, wd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy));
-        FGQ_CUDA_TRY(cudaEventRecord(drained[b], s_copy));
+    if (is_pinned_host(x) && is_pinned_host(w)) {
+        // pinned destination: DMA straight into it, everything enqueued up front
+        int64_t j = 0;
+        for (int64_t lo = 0; lo < n && rc == FGQ_OK; lo += chunk, ++j) {  // lo, hi relative to lo_all
+            const int64_t hi = lo + chunk < n ? lo + chunk : n;
+            const int b = (int)(j % nbuf);
+            double* xd = buf[b];
+            double* wd = buf[b] + chunk;
+            if (j >= nbuf) FGQ_CUDA_TRY(cudaStreamWaitEvent(s_compute, drained[b], 0));
+            rc = fn(ctx, lo_all + lo, lo_all + hi, xd, wd, s_compute);
+            if (rc != FGQ_OK) break;
+            FGQ_CUDA_TRY(cudaEventRecord(computed[b], s_compute));
+            FGQ_CUDA_TRY(cudaStreamWaitEvent(s_copy, computed[b], 0));
+            FGQ_CUDA_TRY(cudaMemcpyAsync(x + lo, xd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy));
+            FGQ_CUDA_TRY(cudaMemcpyAsync(w + lo, wd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy));
+            FGQ_CUDA_TRY(cudaEventRecord(drained[b], s_copy));
+        }
+    } else {
+        // pageable destination: chunk j+1 is computed while chunk j is drained through the pinned ring
+        // (drain_to_host returns when chunk j is in place, so its device buffer is free again)
+        const int64_t nchunks = (n + chunk - 1) / chunk;
+        auto launch = [&](int64_t j) -> int {
+            const int64_t lo = j * chunk, hi = lo + chunk < n ? lo + chunk : n;
+            const int b = (int)(j % nbuf);
+            const int r = fn(ctx, lo_all + lo, lo_all + hi, buf[b], buf[b] + chunk, s_compute);
+            if (r != FGQ_OK) return r;
+            FGQ_CUDA_TRY(cudaEventRecord(computed[b], s_compute));
+            return FGQ_OK;
+        };
+        rc = launch(0);
+        for (int64_t j = 0; j < nchunks && rc == FGQ_OK; ++j) {
+            const int64_t lo = j * chunk, hi = lo + chunk < n ? lo + chunk : n;
+            const int b = (int)(j % nbuf);
+            FGQ_CUDA_TRY(cudaStreamWaitEvent(s_copy, computed[b], 0));
+            if (j + 1 < nchunks) rc = launch(j + 1);
+            if (rc != FGQ_OK) break;
+            rc = drain_to_host(x + lo, w + lo, buf[b], buf[b] + chunk, hi - lo, s_copy);
+        }
     }
     cudaError_t e1 = cudaStreamSynchronize(s_compute);
     cudaError_t e2 = cudaStreamSynchronize(s_copy);
@@ -264,7 +418,13 @@ extern "C" int fgq_gausslegendre_host_pair(int64_t n, int64_t k_lo, int64_t k_hi
     HostPathLock lock;
     int dev;
     FGQ_CUDA_TRY(cudaGetDevice(&dev));
-    const int64_t CHUNK = 1LL << 24;
+    // half-indices per pipeline stage; FGQ_HOST_CHUNK_LOG2 is a tuning aid (tools/host_call_timing.py)
+    static const int chunk_log2 = []() {
+        const char* e = getenv("FGQ_HOST_CHUNK_LOG2");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 16 && v <= 28) ? v : 24;
+    }();
+    const int64_t CHUNK = 1LL << chunk_log2;
     const int64_t chunk = cnt < CHUNK ? cnt : CHUNK;
     const int64_t nchunks = (cnt + chunk - 1) / chunk;
     const int nbuf = nchunks > 1 ? 2 : 1;
@@ -330,10 +490,8 @@ extern "C" int fgq_gausslegendre_host_pair(int64_t n, int64_t k_lo, int64_t k_hi
             memcpy(wl + a0, sw + a0, (size_t)(b0 - a0) * 8);
         }
         const int64_t b1 = b0 < mirror_cnt ? b0 : mirror_cnt;
-        for (int64_t e = a0; e < b1; ++e) {
-            xr[cnt - 1 - e] = -sx[e];
-            wr[cnt - 1 - e] = sw[e];
-        }
+        mirror_copy(sx, xr, cnt, a0, b1, true);
+        mirror_copy(sw, wr, cnt, a0, b1, false);
     };
     if (!staged) {
         // pinned destination: everything is enqueued up front, the workers only follow the copy events
@@ -457,8 +615,6 @@ extern "C" int fgq_gausslegendre_batch_host(int64_t nrules, const int32_t* n_i,
     FGQ_CUDA_TRY(cudaMemcpyAsync(p_n, n_i, (size_t)nrules * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     FGQ_CUDA_TRY(cudaMemcpyAsync(p_off, offsets, (size_t)nrules * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FGQ_TRY(fgq_gausslegendre_batch_device(nrules, (const int32_t*)p_n, (const int64_t*)p_off, xd, wd, (void*)st));
-    FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
-    FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
-    FGQ_CUDA_TRY(cudaStreamSynchronize(st));
+    FGQ_TRY(drain_to_host(x, w, xd, wd, total, st));
     return FGQ_OK;
 }

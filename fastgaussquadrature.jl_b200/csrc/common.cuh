@@ -59,6 +59,10 @@ int scratch_device(size_t bytes, int slot, void** out);   // grow-only, per (dev
 int scratch_stream(int which, cudaStream_t* out);          // two library streams
 int scratch_event(int which, cudaEvent_t* out);
 
+// D2H of a finished result, ordered after `st`; blocks until the data is in place.  Pageable destinations
+// go through a pinned ring drained by host threads (capi.cu).  Caller holds HostPathLock.
+int drain_to_host(double* x, double* w, const double* x_dev, const double* w_dev, int64_t cnt, cudaStream_t st);
+
 // Chunked compute -> D2H pipeline shared by every *_host entry point: fn fills device
 // buffers with output indices [lo, hi) of the rule; x/w receive hi-lo entries.
 typedef int (*SliceFn)(void* ctx, int64_t lo, int64_t hi, double* x_dev, double* w_dev,

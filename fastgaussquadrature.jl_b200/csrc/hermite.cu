@@ -456,9 +456,7 @@ extern "C" int fgq_gausshermite_host(int64_t n, int normalize, double* x, double
     double* xd = (double*)out;
     double* wd = xd + n;
     FGQ_TRY(fgq_gausshermite_device(n, normalize, 0, n, xd, wd, ws, (void*)st));
-    FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    FGQ_CUDA_TRY(cudaStreamSynchronize(st));
+    FGQ_TRY(drain_to_host(x, w, xd, wd, n, st));
     return FGQ_OK;
 }
 

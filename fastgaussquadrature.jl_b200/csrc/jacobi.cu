@@ -739,9 +739,7 @@ static int jacobi_family_host(int which, int64_t n, double a, double b, double* 
     else if (which == 3) rc = fgq_gaussradau_jacobi_device(n, a, b, xd, wd, ws, (void*)st);
     else rc = fgq_gausslobatto_device(n, xd, wd, ws, (void*)st);
     if (rc != FGQ_OK) return rc;
-    FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    FGQ_CUDA_TRY(cudaStreamSynchronize(st));
+    FGQ_TRY(drain_to_host(x, w, xd, wd, n, st));
     return FGQ_OK;
 }
 

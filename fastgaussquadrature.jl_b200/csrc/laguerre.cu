@@ -650,9 +650,7 @@ extern "C" int fgq_gausslaguerre_host(int64_t n, double alpha, int reduced, doub
     FGQ_CUDA_TRY(cudaMemcpyAsync(&h, ws, sizeof(h), cudaMemcpyDeviceToHost, st));
     FGQ_CUDA_TRY(cudaStreamSynchronize(st));
     const int64_t cnt = reduced ? (int64_t)h.n_out : n;
-    FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
-    FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
-    FGQ_CUDA_TRY(cudaStreamSynchronize(st));
+    FGQ_TRY(drain_to_host(x, w, xd, wd, cnt, st));
     if (n_out) *n_out = cnt;
     add_warning(warn0 | (int)h.warn);
     return FGQ_OK;

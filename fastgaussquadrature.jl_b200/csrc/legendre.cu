@@ -671,6 +671,32 @@ __device__ __forceinline__ void leg_closed_form(int n, int i, double& x, double&
     }
 }
 
+// One Newton iterate of rec (gausslegendre.jl:233-267): initial guess j (0-based) of the n-point rule,
+// two Newton steps on the recurrence, weight from P' of the LAST evaluation, i.e. at the pre-update
+// iterate (:262-264).
+__device__ __forceinline__ void leg_rec_iterate(int n, int j, const double* __restrict__ rcp_tab, double& xj,
+                                                double& wv) {
+    // leg_initial_guess (:299-309): asymptotic nodes with the n <= 255 series, negated
+    LegConsts c;
+    c.vn = 1.0 / ((double)n + 0.5);
+    c.vn2 = c.vn * c.vn;
+    c.vn4 = c.vn2 * c.vn2;
+    c.vn6 = c.vn4 * c.vn2;
+    c.inv_vn2 = 0.0;
+    double jk, j1sq;
+    bessel_pair<true>(j + 1, jk, j1sq);
+    const double a = jk * c.vn;
+    const double u = fgq_cot_q1(a);
+    xj = fgq_cos_q1(leg_theta<3>(a, u, c)) * -1.0;
+    double P, PP;
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+        leg_inner_rec(n, xj, rcp_tab, P, PP);
+        xj -= P / PP;
+    }
+    wv = 2.0 / ((1.0 - xj * xj) * (PP * PP));
+}
+
 constexpr int REC_THREADS = 128;
 
 // n_i == nullptr: a single rule of n_single nodes, of which output indices [lo, hi) are
@@ -710,27 +736,10 @@ legendre_rec_batch_kernel(int64_t nrules, const int32_t* __restrict__ n_i,
         return;
     }
     const int m = n / 2 + 1;
-    if (lane >= m) return;
-    // leg_initial_guess (:299-309): asymptotic nodes with the n <= 255 series, negated
-    LegConsts c;
-    c.vn = 1.0 / ((double)n + 0.5);
-    c.vn2 = c.vn * c.vn;
-    c.vn4 = c.vn2 * c.vn2;
-    c.vn6 = c.vn4 * c.vn2;
-    c.inv_vn2 = 0.0;
-    double jk, j1sq;
-    bessel_pair<true>(lane + 1, jk, j1sq);
-    const double a = jk * c.vn;
-    const double u = fgq_cot_q1(a);
-    double xj = fgq_cos_q1(leg_theta<3>(a, u, c)) * -1.0;
-    double P, PP;
-#pragma unroll 1
-    for (int it = 0; it < 2; ++it) {
-        leg_inner_rec(n, xj, rcp_tab, P, PP);
-        xj -= P / PP;
-    }
-    // weights use P' of the LAST evaluation, i.e. at the pre-update iterate (:262-264)
-    const double wv = 2.0 / ((1.0 - xj * xj) * (PP * PP));
+    // for even n the m-th iterate is overwritten by the mirror (:258-261): never computed here
+    if (lane >= (n + 1) / 2) return;
+    double xj, wv;
+    leg_rec_iterate(n, lane, rcp_tab, xj, wv);
     const int i = lane;  // 0-based output index of the left copy
     if (i < m - 1) {
         if (i >= lo && i < hi) {
@@ -742,10 +751,105 @@ legendre_rec_batch_kernel(int64_t nrules, const int32_t* __restrict__ n_i,
             xr[j] = -xj;
             wr[j] = wv;
         }
-    } else if (n & 1) {  // i == m-1: the centre of an odd rule; for even n this lane's value is overwritten by the mirror (:258-261)
+    } else {  // i == m-1: the centre of an odd rule
         if (i >= lo && i < hi) {
             xr[i] = xj;
             wr[i] = wv;
+        }
+    }
+}
+
+// The batched form.  One warp per rule leaves 32 - (n/2+1) lanes idle (37 % of them for n uniform on
+// [2, 60]); here a block takes a TILE of 128 consecutive rules, sorts them by n in shared memory
+// (counting sort, longest first) and deals the (rule, iterate) pairs of the sorted list out to its
+// threads as one flat index space: every lane works, and the lanes of a warp hold iterates of rules
+// with (nearly) equal n, so the recurrence loops of a warp end together.  Per-iterate arithmetic is
+// leg_rec_iterate, the same as above: results do not depend on the packing.
+constexpr int TILE = 128;
+
+__global__ void __launch_bounds__(TILE)
+legendre_rec_tile_kernel(int64_t nrules, const int32_t* __restrict__ n_i, const int64_t* __restrict__ offsets,
+                         double* __restrict__ x, double* __restrict__ w) {
+    __shared__ double rcp_tab[64];
+    __shared__ int s_bucket[64];         // histogram over key = 60 - n, then bucket starts
+    __shared__ int s_n[TILE];            // n of the s-th rule of the sorted tile
+    __shared__ int s_start[TILE + 1];    // first flat index of the s-th rule
+    __shared__ long long s_off[TILE];    // its output offset
+    __shared__ int s_warp[TILE / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < 64) {
+        rcp_tab[tid] = fgq_rcp_fast((double)(tid == 0 ? 1 : tid));
+        s_bucket[tid] = 0;
+    }
+    __syncthreads();
+    const int64_t rule = (int64_t)blockIdx.x * TILE + tid;
+    int n = 0;
+    long long off = 0;
+    if (rule < nrules) {
+        n = n_i[rule];
+        off = offsets[rule];
+        if (n < 0 || n > 60) n = 0;
+    }
+    const int key = 60 - n;
+    const int rank = atomicAdd(&s_bucket[key], 1);
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the 64 bucket counts, two per lane
+        const int v0 = s_bucket[2 * tid], v1 = s_bucket[2 * tid + 1];
+        int incl = v0 + v1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const int excl = incl - (v0 + v1);
+        s_bucket[2 * tid] = excl;
+        s_bucket[2 * tid + 1] = excl + v0;
+    }
+    __syncthreads();
+    const int pos = s_bucket[key] + rank;
+    s_n[pos] = n;
+    s_off[pos] = off;
+    __syncthreads();
+    // threads a rule needs: n <= 5 closed forms, one per node; otherwise one per kept Newton iterate
+    const int ns = s_n[tid];
+    const int need = ns <= 5 ? ns : (ns + 1) / 2;
+    int incl = need;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int q = 0; q < wid; ++q) before += s_warp[q];
+    s_start[tid] = before + incl - need;
+    if (tid == TILE - 1) s_start[TILE] = before + incl;
+    __syncthreads();
+    const int total = s_start[TILE];
+    for (int f = tid; f < total; f += TILE) {
+        int s = 0;  // largest s with s_start[s] <= f (empty rules sort last, at s_start == total)
+#pragma unroll
+        for (int step = TILE / 2; step > 0; step >>= 1)
+            if (s_start[s + step] <= f) s += step;
+        const int nr = s_n[s];
+        const int i = f - s_start[s];
+        double* xr = x + s_off[s];
+        double* wr = w + s_off[s];
+        if (nr <= 5) {
+            double xv, wv;
+            leg_closed_form(nr, i, xv, wv);
+            xr[i] = xv;
+            wr[i] = wv;
+            continue;
+        }
+        double xj, wv;
+        leg_rec_iterate(nr, i, rcp_tab, xj, wv);
+        xr[i] = xj;
+        wr[i] = wv;
+        if (i < nr / 2) {  // not the centre of an odd rule
+            xr[nr - 1 - i] = -xj;
+            wr[nr - 1 - i] = wv;
         }
     }
 }
@@ -822,14 +926,13 @@ extern "C" int fgq_gausslegendre_batch_device(int64_t nrules, const int32_t* n_i
         return FGQ_EINVAL;
     }
     if (nrules == 0) return FGQ_OK;
-    const int64_t warps_per_block = REC_THREADS / 32;
-    const int64_t blocks = (nrules + warps_per_block - 1) / warps_per_block;
+    const int64_t blocks = (nrules + TILE - 1) / TILE;
     if (blocks > 0x7fffffffLL) {
         set_error("batch too large");
         return FGQ_EINVAL;
     }
-    legendre_rec_batch_kernel<<<(unsigned)blocks, REC_THREADS, 0, as_stream(stream)>>>(
-        nrules, n_i_dev, offsets_dev, 0, 0, 0, x_dev, w_dev);
+    legendre_rec_tile_kernel<<<(unsigned)blocks, TILE, 0, as_stream(stream)>>>(nrules, n_i_dev, offsets_dev,
+                                                                                 x_dev, w_dev);
     FGQ_LAUNCH_CHECK();
     return FGQ_OK;
 }
