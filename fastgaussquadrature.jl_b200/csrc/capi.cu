@@ -2,10 +2,14 @@
 // rule-moments consumer of libfgq_cuda.so (see include/fgq.h).
 #include <stdarg.h>
 #include <stdlib.h>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 #include <string.h>
 
 #include <atomic>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -151,43 +155,6 @@ rule_moments_kernel(const double* __restrict__ x, const double* __restrict__ w, 
     }
 }
 
-// Mirror copy of the host-returning Legendre path: dst[cnt-1-e] = (negate ? -src[e] : src[e]) for e in
-// [a, b).  A pure data movement over up to 8 GB per array; the destination is written once and not read
-// again by this call, so the AVX2 form uses non-temporal stores (no write-allocate traffic competing
-// with the PCIe DMA for host memory bandwidth).
-#if defined(__x86_64__)
-__attribute__((target("avx2"))) static void mirror_avx2(const double* src, double* dst, int64_t cnt, int64_t a,
-                                                         int64_t b, bool negate) {
-    // destination positions cnt-1-e descend as e ascends: walk e upwards, write blocks of 4 downwards
-    int64_t e = a;
-    // scalar until the 4-block [cnt-4-e, cnt-e) starts on a 32-byte boundary
-    while (e < b && ((uintptr_t)(dst + (cnt - e)) & 31) != 0) {
-        dst[cnt - 1 - e] = negate ? -src[e] : src[e];
-        ++e;
-    }
-    const __m256d sign = negate ? _mm256_set1_pd(-0.0) : _mm256_setzero_pd();
-    for (; e + 4 <= b; e += 4) {
-        __m256d v = _mm256_loadu_pd(src + e);
-        v = _mm256_permute4x64_pd(v, 0x1B);  // reverse the four lanes
-        v = _mm256_xor_pd(v, sign);
-        _mm256_stream_pd(dst + (cnt - 4 - e), v);
-    }
-    for (; e < b; ++e) dst[cnt - 1 - e] = negate ? -src[e] : src[e];
-    _mm_sfence();
-}
-#endif
-
-static void mirror_copy(const double* src, double* dst, int64_t cnt, int64_t a, int64_t b, bool negate) {
-#if defined(__x86_64__)
-    static const bool have_avx2 = __builtin_cpu_supports("avx2");
-    if (have_avx2) {
-        mirror_avx2(src, dst, cnt, a, b, negate);
-        return;
-    }
-#endif
-    for (int64_t e = a; e < b; ++e) dst[cnt - 1 - e] = negate ? -src[e] : src[e];
-}
-
 }  // namespace fgq
 
 using namespace fgq;
@@ -228,81 +195,234 @@ extern "C" int fgq_rule_moments_device(const double* x_dev, const double* w_dev,
 
 namespace fgq {
 
-// Device -> host copy of a finished result (x and w, cnt entries each), ordered after the work already
-// enqueued on `st`; returns when the data is in place.  A pinned destination is written by DMA directly.
-// A pageable one (a fresh Julia Vector, np.empty) would be staged by the driver through its own small
-// bounce buffer at 4-5 GB/s, one thread taking every first-touch page fault; instead the result is cut
-// into 2 MiB pieces that are DMA'd into a library-owned pinned ring and copied out by host threads as
-// they land (piece p by thread p mod T), which also spreads the page faults.
-int drain_to_host(double* x, double* w, const double* xd, const double* wd, int64_t cnt, cudaStream_t st) {
+// Mirror copy of the host-returning Legendre path: dst[cnt-1-e] = (negate ? -src[e] : src[e]) for e in
+// [a, b).  A pure data movement over up to 8 GB per array; the destination is written once and not read
+// again by this call, so the AVX2 form uses non-temporal stores (no write-allocate traffic competing
+// with the PCIe DMA for host memory bandwidth).
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void mirror_avx2(const double* src, double* dst, int64_t cnt, int64_t a,
+                                                         int64_t b, bool negate) {
+    // destination positions cnt-1-e descend as e ascends: walk e upwards, write blocks of 4 downwards
+    int64_t e = a;
+    // scalar until the 4-block [cnt-4-e, cnt-e) starts on a 32-byte boundary
+    while (e < b && ((uintptr_t)(dst + (cnt - e)) & 31) != 0) {
+        dst[cnt - 1 - e] = negate ? -src[e] : src[e];
+        ++e;
+    }
+    const __m256d sign = negate ? _mm256_set1_pd(-0.0) : _mm256_setzero_pd();
+    for (; e + 4 <= b; e += 4) {
+        __m256d v = _mm256_loadu_pd(src + e);
+        v = _mm256_permute4x64_pd(v, 0x1B);  // reverse the four lanes
+        v = _mm256_xor_pd(v, sign);
+        _mm256_stream_pd(dst + (cnt - 4 - e), v);
+    }
+    for (; e < b; ++e) dst[cnt - 1 - e] = negate ? -src[e] : src[e];
+    _mm_sfence();
+}
+#endif
+
+static void mirror_copy(const double* src, double* dst, int64_t cnt, int64_t a, int64_t b, bool negate) {
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) {
+        mirror_avx2(src, dst, cnt, a, b, negate);
+        return;
+    }
+#endif
+    for (int64_t e = a; e < b; ++e) dst[cnt - 1 - e] = negate ? -src[e] : src[e];
+}
+
+// Host worker threads of the host-returning entry points: created once, parked on a condition variable
+// between calls (spawning 16 threads per call costs ~0.5 ms, more than a whole gausshermite(1e6)).  Only
+// used under HostPathLock, i.e. by one call at a time.  Deliberately leaked: parked threads must not
+// outlive the synchronisation objects they wait on during static destruction.
+class WorkerPool {
+  public:
+    static WorkerPool& get() {
+        static WorkerPool* pool = new WorkerPool();
+        return *pool;
+    }
+    int max_threads() const { return (int)threads_; }
+    // runs job(t) for t in [0, T): t = 0 on the calling thread, the others on pool threads; returns when
+    // all of them have finished
+    void run(int T, const std::function<void(int)>& job) {
+        if (T > 1) {
+            std::unique_lock<std::mutex> lk(mu_);
+            while ((int)spawned_ < T - 1) {
+                const int id = (int)spawned_++;
+                std::thread([this, id]() { loop(id); }).detach();
+            }
+            job_ = &job;
+            active_ = T - 1;
+            remaining_ = T - 1;
+            ++generation_;
+            cv_start_.notify_all();
+        }
+        job(0);
+        if (T > 1) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_done_.wait(lk, [&] { return remaining_ == 0; });
+            job_ = nullptr;
+        }
+    }
+
+  private:
+    WorkerPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        threads_ = hw == 0 ? 4 : (hw > 16 ? 16 : hw);
+    }
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_start_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (id >= active_) continue;
+                job = job_;
+            }
+            (*job)(id + 1);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--remaining_ == 0) cv_done_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_start_, cv_done_;
+    const std::function<void(int)>* job_ = nullptr;
+    uint64_t generation_ = 0;
+    int active_ = 0, remaining_ = 0;
+    unsigned threads_ = 4, spawned_ = 0;
+};
+
+// A freshly allocated multi-GB result (Julia `Vector{Float64}(undef, n)`, np.empty) is untouched
+// anonymous memory: with 4 KiB pages its first touch costs ~4e6 page faults per 16 GB.  Ask for
+// transparent huge pages on the interior of the range (a hint; a no-op where THP is off or the memory
+// is already populated).
+static void hint_huge_pages(void* p, size_t bytes) {
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+    if (bytes < (64u << 20)) return;
+    const uintptr_t HP = 2u << 20;
+    const uintptr_t lo = ((uintptr_t)p + HP - 1) & ~(HP - 1), hi = ((uintptr_t)p + bytes) & ~(HP - 1);
+    if (hi > lo) madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
+#else
+    (void)p;
+    (void)bytes;
+#endif
+}
+
+// Device -> host copy of a result (x and w, cnt entries each) on stream `st`; returns when the data is in
+// place.  The result is cut into pieces; before the copies of piece [lo, hi) are enqueued `src` names the
+// device addresses holding it (and may enqueue the kernels that produce it: see ChunkedProducer), so the
+// whole transfer is one uninterrupted queue of DMA copies.
+//  * Pinned destination: DMA straight into it.
+//  * Pageable destination (a fresh Julia Vector, np.empty): the driver would stage it through its own
+//    small bounce buffer at 4-5 GB/s, one thread taking every first-touch page fault; instead 2 MiB
+//    pieces are DMA'd into a library-owned pinned ring and copied out by host threads as they land
+//    (piece p by thread p mod T), which also spreads the page faults.
+//  * Optional mirror (the Legendre +-x symmetry): entry i of this call is element e = m.e0 + i of a left
+//    slice of m.cnt half-indices; the threads also write m.xr[m.cnt-1-e] = -x, m.wr[m.cnt-1-e] = w for
+//    e < m.mirror_cnt.
+int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const PieceSource& src, const MirrorSpec* m) {
     if (cnt <= 0) return FGQ_OK;
-    const int64_t PIECE = 1LL << 18;  // entries per piece and array
-    if (cnt < PIECE || (is_pinned_host(x) && is_pinned_host(w))) {
+    if (!m && cnt < DRAIN_PIECE) {  // small result: one plain copy, no threads
+        const double *xd = nullptr, *wd = nullptr;
+        FGQ_TRY(src(0, cnt, &xd, &wd));
         FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
         FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
         FGQ_CUDA_TRY(cudaStreamSynchronize(st));
         return FGQ_OK;
     }
+    const bool direct = is_pinned_host(x) && is_pinned_host(w);
+    const int64_t PIECE = direct ? DRAIN_PIECE_PINNED : DRAIN_PIECE;  // entries per piece and array
     constexpr int RING = 16;
-    void* ring_p;
-    FGQ_TRY(scratch_pinned((size_t)RING * 2 * PIECE * 8, 2, &ring_p));
-    double* ring = (double*)ring_p;
+    double* ring = nullptr;
+    if (!direct) {
+        void* ring_p;
+        FGQ_TRY(scratch_pinned((size_t)RING * 2 * PIECE * 8, 2, &ring_p));
+        ring = (double*)ring_p;
+    }
     const int64_t pieces = (cnt + PIECE - 1) / PIECE;
-    unsigned hw = std::thread::hardware_concurrency();
-    int T = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+    const bool threaded = m || !direct;  // a pinned destination without mirror needs no host work
+    WorkerPool& pool = WorkerPool::get();
+    int T = threaded ? pool.max_threads() : 0;
     if (T > pieces) T = (int)pieces;
     int dev;
     FGQ_CUDA_TRY(cudaGetDevice(&dev));
     cudaEvent_t ev[RING];
-    for (int i = 0; i < RING; ++i) FGQ_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    if (threaded)
+        for (int i = 0; i < RING; ++i) FGQ_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
     std::mutex mu;
     std::condition_variable cv;
     int64_t published = 0;            // pieces whose copies and event have been enqueued
     std::vector<char> consumed((size_t)pieces, 0);
     bool failed = false;
-    std::vector<std::thread> workers;
-    for (int t = 0; t < T; ++t) {
-        workers.emplace_back([&, t]() {
-            cudaSetDevice(dev);
-            for (int64_t p = t; p < pieces; p += T) {
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return published > p || failed; });
-                    if (failed) return;
-                }
-                const bool ok = cudaEventSynchronize(ev[p % RING]) == cudaSuccess;
-                if (ok) {
-                    const int64_t lo = p * PIECE, len = (lo + PIECE < cnt ? PIECE : cnt - lo);
-                    const double* sx = ring + (p % RING) * 2 * PIECE;
-                    memcpy(x + lo, sx, (size_t)len * 8);
-                    memcpy(w + lo, sx + PIECE, (size_t)len * 8);
-                }
+    int rc = FGQ_OK;
+    cudaError_t err = cudaSuccess;
+    // the calling thread feeds the copy queue, the pool threads drain it
+    auto feeder = [&]() {
+        for (int64_t p = 0; p < pieces && err == cudaSuccess && rc == FGQ_OK; ++p) {
+            if (threaded && p >= RING) {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return consumed[(size_t)(p - RING)] != 0 || failed; });
+                if (failed) break;
+            }
+            const int64_t lo = p * PIECE, len = (lo + PIECE < cnt ? PIECE : cnt - lo);
+            const double *xd = nullptr, *wd = nullptr;
+            rc = src(lo, lo + len, &xd, &wd);
+            if (rc == FGQ_OK) {
+                double* dx = direct ? x + lo : ring + (p % RING) * 2 * PIECE;
+                double* dw = direct ? w + lo : dx + PIECE;
+                err = cudaMemcpyAsync(dx, xd, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+                if (err == cudaSuccess) err = cudaMemcpyAsync(dw, wd, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+                if (err == cudaSuccess && threaded) err = cudaEventRecord(ev[p % RING], st);
+            }
+            if (threaded) {
                 std::lock_guard<std::mutex> lk(mu);
-                consumed[(size_t)p] = 1;
-                if (!ok) failed = true;
+                if (err == cudaSuccess && rc == FGQ_OK) published = p + 1; else failed = true;
                 cv.notify_all();
             }
-        });
-    }
-    cudaError_t err = cudaSuccess;
-    for (int64_t p = 0; p < pieces && err == cudaSuccess; ++p) {
-        if (p >= RING) {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return consumed[(size_t)(p - RING)] != 0 || failed; });
-            if (failed) break;
         }
-        const int64_t lo = p * PIECE, len = (lo + PIECE < cnt ? PIECE : cnt - lo);
-        double* sx = ring + (p % RING) * 2 * PIECE;
-        err = cudaMemcpyAsync(sx, xd + lo, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
-        if (err == cudaSuccess) err = cudaMemcpyAsync(sx + PIECE, wd + lo, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
-        if (err == cudaSuccess) err = cudaEventRecord(ev[p % RING], st);
-        std::lock_guard<std::mutex> lk(mu);
-        if (err == cudaSuccess) published = p + 1; else failed = true;
-        cv.notify_all();
-    }
-    for (auto& th : workers) th.join();
+    };
+    auto drainer = [&](int t) {
+        cudaSetDevice(dev);
+        for (int64_t p = t; p < pieces; p += T) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return published > p || failed; });
+                if (failed) return;
+            }
+            const bool ok = cudaEventSynchronize(ev[p % RING]) == cudaSuccess;
+            if (ok) {
+                const int64_t lo = p * PIECE, len = (lo + PIECE < cnt ? PIECE : cnt - lo);
+                const double* sx = direct ? x + lo : ring + (p % RING) * 2 * PIECE;
+                const double* sw = direct ? w + lo : sx + PIECE;
+                if (!direct) {
+                    memcpy(x + lo, sx, (size_t)len * 8);
+                    memcpy(w + lo, sw, (size_t)len * 8);
+                }
+                if (m) {
+                    const int64_t e0 = m->e0 + lo;  // element index of sx[0]
+                    const int64_t e1 = e0 + len < m->mirror_cnt ? e0 + len : m->mirror_cnt;
+                    if (e1 > e0) {
+                        mirror_copy(sx - e0, m->xr, m->cnt, e0, e1, true);
+                        mirror_copy(sw - e0, m->wr, m->cnt, e0, e1, false);
+                    }
+                }
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            consumed[(size_t)p] = 1;
+            if (!ok) failed = true;
+            cv.notify_all();
+        }
+    };
+    pool.run(T + 1, [&](int t) {
+        if (t == 0) feeder(); else drainer(t - 1);
+    });
     cudaError_t e2 = cudaStreamSynchronize(st);
-    for (int i = 0; i < RING; ++i) cudaEventDestroy(ev[i]);
+    if (threaded)
+        for (int i = 0; i < RING; ++i) cudaEventDestroy(ev[i]);
+    if (rc != FGQ_OK) return rc;
     FGQ_CUDA_TRY(err);
     FGQ_CUDA_TRY(e2);
     if (failed) {
@@ -312,6 +432,87 @@ int drain_to_host(double* x, double* w, const double* xd, const double* wd, int6
     return FGQ_OK;
 }
 
+// A finished result in device memory.
+int drain_to_host(double* x, double* w, const double* xd, const double* wd, int64_t cnt, cudaStream_t st) {
+    if (cnt <= 0) return FGQ_OK;
+    if (cnt < DRAIN_PIECE) {
+        FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+        FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+        FGQ_CUDA_TRY(cudaStreamSynchronize(st));
+        return FGQ_OK;
+    }
+    hint_huge_pages(x, (size_t)cnt * 8);
+    hint_huge_pages(w, (size_t)cnt * 8);
+    return drain_to_host(x, w, cnt, st, [&](int64_t lo, int64_t, const double** px, const double** pw) {
+        *px = xd + lo;
+        *pw = wd + lo;
+        return (int)FGQ_OK;
+    }, nullptr);
+}
+
+// A result produced chunk by chunk into two library-owned device buffers: produce(lo, hi, x_dev, w_dev, st)
+// enqueues the kernels for entries [lo, hi).  As a PieceSource it launches chunk j+1 when the first piece of
+// chunk j is about to be copied, with event dependencies only (a buffer is refilled after its copies have
+// run), so kernels, DMA and host threads all overlap and nothing blocks between chunks.
+struct ChunkedProducer {
+    int64_t cnt, chunk, nchunks;
+    int nbuf;
+    double* buf[2];
+    cudaStream_t s_compute, s_copy;
+    cudaEvent_t computed[2], drained[2];
+    std::function<int(int64_t, int64_t, double*, double*, cudaStream_t)> produce;
+    int64_t launched = 0;
+
+    int init(int64_t cnt_, int64_t max_chunk) {
+        cnt = cnt_;
+        chunk = cnt < max_chunk ? cnt : max_chunk;
+        nchunks = (cnt + chunk - 1) / chunk;
+        nbuf = nchunks > 1 ? 2 : 1;
+        buf[0] = buf[1] = nullptr;
+        for (int b = 0; b < nbuf; ++b) {
+            void* p;
+            FGQ_TRY(scratch_device((size_t)chunk * 16, b, &p));
+            buf[b] = (double*)p;
+        }
+        FGQ_TRY(scratch_stream(0, &s_compute));
+        FGQ_TRY(scratch_stream(1, &s_copy));
+        for (int b = 0; b < 2; ++b) {
+            FGQ_TRY(scratch_event(b, &computed[b]));
+            FGQ_TRY(scratch_event(2 + b, &drained[b]));
+        }
+        return FGQ_OK;
+    }
+    int launch(int64_t j) {
+        const int64_t lo = j * chunk, hi = lo + chunk < cnt ? lo + chunk : cnt;
+        const int b = (int)(j % nbuf);
+        if (j >= nbuf) FGQ_CUDA_TRY(cudaStreamWaitEvent(s_compute, drained[b], 0));
+        FGQ_TRY(produce(lo, hi, buf[b], buf[b] + chunk, s_compute));
+        FGQ_CUDA_TRY(cudaEventRecord(computed[b], s_compute));
+        return FGQ_OK;
+    }
+    int piece(int64_t lo, int64_t, const double** px, const double** pw) {
+        const int64_t j = lo / chunk;
+        const int b = (int)(j % nbuf);
+        if (lo == j * chunk) {  // first piece of chunk j: every copy of chunk j-1 has been enqueued
+            if (j >= 1) FGQ_CUDA_TRY(cudaEventRecord(drained[(j - 1) % nbuf], s_copy));
+            while (launched <= j) FGQ_TRY(launch(launched++));
+            FGQ_CUDA_TRY(cudaStreamWaitEvent(s_copy, computed[b], 0));
+            if (j + 1 < nchunks && launched <= j + 1) FGQ_TRY(launch(launched++));
+        }
+        *px = buf[b] + (lo - j * chunk);
+        *pw = buf[b] + chunk + (lo - j * chunk);
+        return FGQ_OK;
+    }
+    int finish(int rc) {
+        cudaError_t e1 = cudaStreamSynchronize(s_compute);
+        cudaError_t e2 = cudaStreamSynchronize(s_copy);
+        if (rc != FGQ_OK) return rc;
+        FGQ_CUDA_TRY(e1);
+        FGQ_CUDA_TRY(e2);
+        return FGQ_OK;
+    }
+};
+
 int host_pipeline(int64_t lo_all, int64_t hi_all, double* x, double* w, SliceFn fn, void* ctx) {
     const int64_t n = hi_all - lo_all;
     if (n <= 0) return FGQ_OK;
@@ -320,69 +521,18 @@ int host_pipeline(int64_t lo_all, int64_t hi_all, double* x, double* w, SliceFn 
         return FGQ_EINVAL;
     }
     HostPathLock lock;
-    const int64_t CHUNK = 1LL << 24;  // nodes per chunk: 128 MiB of x + 128 MiB of w
-    const int64_t chunk = n < CHUNK ? n : CHUNK;
-    const int nbuf = n > CHUNK ? 2 : 1;
-    double* buf[2] = {nullptr, nullptr};
-    for (int b = 0; b < nbuf; ++b) {
-        void* p;
-        FGQ_TRY(scratch_device((size_t)chunk * 16, b, &p));
-        buf[b] = (double*)p;
-    }
-    cudaStream_t s_compute, s_copy;
-    FGQ_TRY(scratch_stream(0, &s_compute));
-    FGQ_TRY(scratch_stream(1, &s_copy));
-    cudaEvent_t computed[2], drained[2];
-    for (int b = 0; b < 2; ++b) {
-        FGQ_TRY(scratch_event(b, &computed[b]));
-        FGQ_TRY(scratch_event(2 + b, &drained[b]));
-    }
-    int rc = FGQ_OK;
-    if (is_pinned_host(x) && is_pinned_host(w)) {
-        // pinned destination: DMA straight into it, everything enqueued up front
-        int64_t j = 0;
-        for (int64_t lo = 0; lo < n && rc == FGQ_OK; lo += chunk, ++j) {  // lo, hi relative to lo_all
-            const int64_t hi = lo + chunk < n ? lo + chunk : n;
-            const int b = (int)(j % nbuf);
-            double* xd = buf[b];
-            double* wd = buf[b] + chunk;
-            if (j >= nbuf) FGQ_CUDA_TRY(cudaStreamWaitEvent(s_compute, drained[b], 0));
-            rc = fn(ctx, lo_all + lo, lo_all + hi, xd, wd, s_compute);
-            if (rc != FGQ_OK) break;
-            FGQ_CUDA_TRY(cudaEventRecord(computed[b], s_compute));
-            FGQ_CUDA_TRY(cudaStreamWaitEvent(s_copy, computed[b], 0));
-            FGQ_CUDA_TRY(cudaMemcpyAsync(x + lo, xd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy));
-            FGQ_CUDA_TRY(cudaMemcpyAsync(w + lo, wd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy));
-            FGQ_CUDA_TRY(cudaEventRecord(drained[b], s_copy));
-        }
-    } else {
-        // pageable destination: chunk j+1 is computed while chunk j is drained through the pinned ring
-        // (drain_to_host returns when chunk j is in place, so its device buffer is free again)
-        const int64_t nchunks = (n + chunk - 1) / chunk;
-        auto launch = [&](int64_t j) -> int {
-            const int64_t lo = j * chunk, hi = lo + chunk < n ? lo + chunk : n;
-            const int b = (int)(j % nbuf);
-            const int r = fn(ctx, lo_all + lo, lo_all + hi, buf[b], buf[b] + chunk, s_compute);
-            if (r != FGQ_OK) return r;
-            FGQ_CUDA_TRY(cudaEventRecord(computed[b], s_compute));
-            return FGQ_OK;
-        };
-        rc = launch(0);
-        for (int64_t j = 0; j < nchunks && rc == FGQ_OK; ++j) {
-            const int64_t lo = j * chunk, hi = lo + chunk < n ? lo + chunk : n;
-            const int b = (int)(j % nbuf);
-            FGQ_CUDA_TRY(cudaStreamWaitEvent(s_copy, computed[b], 0));
-            if (j + 1 < nchunks) rc = launch(j + 1);
-            if (rc != FGQ_OK) break;
-            rc = drain_to_host(x + lo, w + lo, buf[b], buf[b] + chunk, hi - lo, s_copy);
-        }
-    }
-    cudaError_t e1 = cudaStreamSynchronize(s_compute);
-    cudaError_t e2 = cudaStreamSynchronize(s_copy);
-    if (rc != FGQ_OK) return rc;
-    FGQ_CUDA_TRY(e1);
-    FGQ_CUDA_TRY(e2);
-    return FGQ_OK;
+    hint_huge_pages(x, (size_t)n * 8);
+    hint_huge_pages(w, (size_t)n * 8);
+    ChunkedProducer cp;
+    FGQ_TRY(cp.init(n, 1LL << 24));  // nodes per chunk: 128 MiB of x + 128 MiB of w
+    cp.produce = [&](int64_t lo, int64_t hi, double* xd, double* wd, cudaStream_t st) {
+        return fn(ctx, lo_all + lo, lo_all + hi, xd, wd, st);
+    };
+    const int rc = drain_to_host(x, w, n, cp.s_copy,
+                                 [&](int64_t lo, int64_t hi, const double** px, const double** pw) {
+                                     return cp.piece(lo, hi, px, pw);
+                                 }, nullptr);
+    return cp.finish(rc);
 }
 
 }  // namespace fgq
@@ -416,132 +566,31 @@ extern "C" int fgq_gausslegendre_host_pair(int64_t n, int64_t k_lo, int64_t k_hi
         return FGQ_EINVAL;
     }
     HostPathLock lock;
-    int dev;
-    FGQ_CUDA_TRY(cudaGetDevice(&dev));
     // half-indices per pipeline stage; FGQ_HOST_CHUNK_LOG2 is a tuning aid (tools/host_call_timing.py)
     static const int chunk_log2 = []() {
         const char* e = getenv("FGQ_HOST_CHUNK_LOG2");
         const int v = e ? atoi(e) : 0;
-        return (v >= 16 && v <= 28) ? v : 24;
+        return (v >= 21 && v <= 28) ? v : 24;
     }();
-    const int64_t CHUNK = 1LL << chunk_log2;
-    const int64_t chunk = cnt < CHUNK ? cnt : CHUNK;
-    const int64_t nchunks = (cnt + chunk - 1) / chunk;
-    const int nbuf = nchunks > 1 ? 2 : 1;
-    double* buf[2] = {nullptr, nullptr};
-    for (int b = 0; b < nbuf; ++b) {
-        void* p;
-        FGQ_TRY(scratch_device((size_t)chunk * 16, b, &p));
-        buf[b] = (double*)p;
-    }
-    cudaStream_t s_compute, s_copy;
-    FGQ_TRY(scratch_stream(0, &s_compute));
-    FGQ_TRY(scratch_stream(1, &s_copy));
-    // Pageable destination (a Julia Vector, a numpy array): DMA into library-owned pinned staging and let
-    // the host threads do the final copy as well as the mirroring — that also spreads the first-touch page
-    // faults of a freshly allocated 16 GB result over all threads instead of one driver thread.
-    const bool staged = !(is_pinned_host(xl) && is_pinned_host(wl));
-    double* stage[2] = {nullptr, nullptr};
-    if (staged) {
-        for (int b = 0; b < nbuf; ++b) {
-            void* p;
-            FGQ_TRY(scratch_pinned((size_t)chunk * 16, b, &p));
-            stage[b] = (double*)p;
-        }
-    }
-    std::vector<cudaEvent_t> computed(nchunks), landed(nchunks);
-    for (int64_t j = 0; j < nchunks; ++j) {
-        FGQ_CUDA_TRY(cudaEventCreateWithFlags(&computed[j], cudaEventDisableTiming));
-        FGQ_CUDA_TRY(cudaEventCreateWithFlags(&landed[j], cudaEventDisableTiming));
-    }
-    int rc = FGQ_OK;
-    auto enqueue = [&](int64_t j) -> int {
-        const int64_t lo = j * chunk, hi = lo + chunk < cnt ? lo + chunk : cnt;  // relative to k_lo
-        const int b = (int)(j % nbuf);
-        double* xd = buf[b];
-        double* wd = buf[b] + chunk;
-        if (j >= nbuf) cudaStreamWaitEvent(s_compute, landed[j - nbuf], 0);
+    for (double* p : {xl, wl, xr, wr}) hint_huge_pages(p, (size_t)cnt * 8);
+    // The kernel of chunk j+1 runs while chunk j crosses PCIe and is mirrored.  A pinned destination
+    // receives the DMA directly and the host threads only write the mirror image; a pageable one (a Julia
+    // Vector, a numpy array) is filled through the pinned ring by the same threads, which also spreads
+    // the first-touch page faults of a freshly allocated 16 GB result over all of them.
+    ChunkedProducer cp;
+    FGQ_TRY(cp.init(cnt, 1LL << chunk_log2));
+    cp.produce = [&](int64_t lo, int64_t hi, double* xd, double* wd, cudaStream_t st) {
         // left slice = output indices [k_lo-1+lo, k_lo-1+hi)
-        const int r = fgq_gausslegendre_device(n, k_lo - 1 + lo, k_lo - 1 + hi, xd, wd, (void*)s_compute);
-        if (r != FGQ_OK) return r;
-        cudaEventRecord(computed[j], s_compute);
-        cudaStreamWaitEvent(s_copy, computed[j], 0);
-        double* dx = staged ? stage[b] : xl + lo;
-        double* dw = staged ? stage[b] + chunk : wl + lo;
-        cudaMemcpyAsync(dx, xd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy);
-        cudaMemcpyAsync(dw, wd, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s_copy);
-        cudaEventRecord(landed[j], s_copy);
-        return FGQ_OK;
+        return fgq_gausslegendre_device(n, k_lo - 1 + lo, k_lo - 1 + hi, xd, wd, (void*)st);
     };
     // element e of the left slice (half-index k = k_lo + e) mirrors to right-slice position cnt-1-e;
     // the centre of an odd rule (k = m) has no mirror image
-    const int64_t mirror_cnt = (k_hi - 1 > mr) ? cnt - 1 : cnt;
-    unsigned hw = std::thread::hardware_concurrency();
-    const int T = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
-    auto host_part = [&](int64_t j, int t) {  // thread t's share of chunk j
-        const int64_t lo = j * chunk, hi0 = lo + chunk < cnt ? lo + chunk : cnt;
-        const int b = (int)(j % nbuf);
-        const double* sx = staged ? stage[b] - lo : xl;          // source indexed by e
-        const double* sw = staged ? stage[b] + chunk - lo : wl;
-        const int64_t len0 = hi0 - lo;
-        const int64_t a0 = lo + len0 * t / T, b0 = lo + len0 * (t + 1) / T;
-        if (staged) {
-            memcpy(xl + a0, sx + a0, (size_t)(b0 - a0) * 8);
-            memcpy(wl + a0, sw + a0, (size_t)(b0 - a0) * 8);
-        }
-        const int64_t b1 = b0 < mirror_cnt ? b0 : mirror_cnt;
-        mirror_copy(sx, xr, cnt, a0, b1, true);
-        mirror_copy(sw, wr, cnt, a0, b1, false);
-    };
-    if (!staged) {
-        // pinned destination: everything is enqueued up front, the workers only follow the copy events
-        for (int64_t j = 0; j < nchunks && rc == FGQ_OK; ++j) rc = enqueue(j);
-        if (rc == FGQ_OK) {
-            std::vector<std::thread> workers;
-            std::atomic<int> failed{0};
-            for (int t = 0; t < T; ++t) {
-                workers.emplace_back([&, t]() {
-                    cudaSetDevice(dev);
-                    for (int64_t j = 0; j < nchunks; ++j) {
-                        if (cudaEventSynchronize(landed[j]) != cudaSuccess) {
-                            failed = 1;
-                            return;
-                        }
-                        host_part(j, t);
-                    }
-                });
-            }
-            for (auto& th : workers) th.join();
-            if (failed) {
-                set_error("device-to-host copy failed");
-                rc = FGQ_ECUDA;
-            }
-        }
-    } else {
-        // staged: a staging buffer may only be refilled after the host threads have emptied it
-        for (int64_t j = 0; j < nchunks && j < nbuf && rc == FGQ_OK; ++j) rc = enqueue(j);
-        for (int64_t j = 0; j < nchunks && rc == FGQ_OK; ++j) {
-            if (cudaEventSynchronize(landed[j]) != cudaSuccess) {
-                set_error("device-to-host copy failed");
-                rc = FGQ_ECUDA;
-                break;
-            }
-            std::vector<std::thread> workers;
-            for (int t = 0; t < T; ++t) workers.emplace_back([&, t]() { host_part(j, t); });
-            for (auto& th : workers) th.join();
-            if (j + nbuf < nchunks) rc = enqueue(j + nbuf);
-        }
-    }
-    cudaError_t e1 = cudaStreamSynchronize(s_compute);
-    cudaError_t e2 = cudaStreamSynchronize(s_copy);
-    for (int64_t j = 0; j < nchunks; ++j) {
-        cudaEventDestroy(computed[j]);
-        cudaEventDestroy(landed[j]);
-    }
-    if (rc != FGQ_OK) return rc;
-    FGQ_CUDA_TRY(e1);
-    FGQ_CUDA_TRY(e2);
-    return FGQ_OK;
+    const MirrorSpec mir{xr, wr, cnt, 0, (k_hi - 1 > mr) ? cnt - 1 : cnt};
+    const int rc = drain_to_host(xl, wl, cnt, cp.s_copy,
+                                 [&](int64_t lo, int64_t hi, const double** px, const double** pw) {
+                                     return cp.piece(lo, hi, px, pw);
+                                 }, &mir);
+    return cp.finish(rc);
 }
 
 extern "C" int fgq_gausslegendre_host(int64_t n, double* x, double* w) {

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <functional>
+
 #include "../../include/fgq.h"
 
 namespace fgq {
@@ -61,7 +63,18 @@ int scratch_event(int which, cudaEvent_t* out);
 
 // D2H of a finished result, ordered after `st`; blocks until the data is in place.  Pageable destinations
 // go through a pinned ring drained by host threads (capi.cu).  Caller holds HostPathLock.
+struct MirrorSpec {      // optional +-x mirroring done by the same host threads (Legendre pair shards)
+    double *xr, *wr;     // right slice: xr[cnt-1-e] = -x_e, wr[cnt-1-e] = w_e
+    int64_t cnt;         // half-indices of the whole left slice
+    int64_t e0;          // element index (within the left slice) of this call's first entry
+    int64_t mirror_cnt;  // elements e < mirror_cnt have a mirror image (the centre of an odd rule has none)
+};
 int drain_to_host(double* x, double* w, const double* x_dev, const double* w_dev, int64_t cnt, cudaStream_t st);
+// general form: src(lo, hi, &x_dev, &w_dev) names (and may produce) the device data of piece [lo, hi)
+typedef std::function<int(int64_t, int64_t, const double**, const double**)> PieceSource;
+constexpr int64_t DRAIN_PIECE = 1LL << 18;         // entries per piece through the pinned ring (2 MiB)
+constexpr int64_t DRAIN_PIECE_PINNED = 1LL << 20;  // entries per piece into a pinned destination (8 MiB)
+int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const PieceSource& src, const MirrorSpec* mirror);
 
 // Chunked compute -> D2H pipeline shared by every *_host entry point: fn fills device
 // buffers with output indices [lo, hi) of the rule; x/w receive hi-lo entries.

@@ -24,6 +24,8 @@ __constant__ double c_airy_roots[10] = {
     -7.944133587120853, -9.022650853340981, -10.04017434155809, -11.00852430373326,
     -11.93601556323626, -12.828776752865757};
 
+constexpr int HERMITE_SUM_BLOCKS = 64;
+
 struct HermiteState {   // lives at the start of the workspace
     unsigned long long maxdt_bits[20];
     unsigned int ticket[20];
@@ -31,7 +33,9 @@ struct HermiteState {   // lives at the start of the workspace
     int sweeps;
     double norm_sum;
     unsigned int sum_ticket;
+    double norm_part[HERMITE_SUM_BLOCKS];  // per-block partial sums, added in block order by the last block
 };
+static_assert(sizeof(HermiteState) <= 1024, "state must fit the workspace header");
 
 struct HermiteParams {
     int64_t n;
@@ -167,13 +171,16 @@ __device__ __forceinline__ void hermpoly_asy_airy(const HermiteParams& p, double
 
 constexpr int HERM_THREADS = 128;
 
-// One Newton sweep (gausshermite.jl:75-86) over the half range.
-__global__ void __launch_bounds__(HERM_THREADS)
+// One Newton sweep (gausshermite.jl:75-86) over the half range.  Persistent grid (grid stride over the
+// node tiles): the pre-enqueued sweeps that find the rule converged then cost ~2 us instead of the time to
+// schedule and retire thousands of empty blocks.
+constexpr int64_t HERM_GRID = 148 * 4;
+
+__global__ void __launch_bounds__(HERM_THREADS, 4)
 hermite_sweep_kernel(HermiteParams p, int sweep, HermiteState* st, double* theta, double* xh, double* wh) {
     if (*((volatile int*)&st->done)) return;
-    const int64_t t = (int64_t)blockIdx.x * HERM_THREADS + threadIdx.x;
-    double adt = 0.0;
-    if (t < p.nh) {
+    unsigned long long bits = 0ull;
+    for (int64_t t = (int64_t)blockIdx.x * HERM_THREADS + threadIdx.x; t < p.nh; t += (int64_t)gridDim.x * HERM_THREADS) {
         double th = theta[t];
         double s, c;
         sincos(th, &s, &c);
@@ -182,15 +189,16 @@ hermite_sweep_kernel(HermiteParams p, int sweep, HermiteState* st, double* theta
         const double dth = -val / (1.4142135623730951 * p.sq_musq * dval * s);
         th = th - dth;
         theta[t] = th;
-        adt = fabs(dth);
+        double adt = fabs(dth);
         if (dth != dth) adt = __longlong_as_double(0x7ff8000000000000LL);  // NaN poisons the norm, as norm() does
+        const unsigned long long b = (unsigned long long)__double_as_longlong(adt);
+        bits = b > bits ? b : bits;
         const double x = p.sq_musq * cos(th);
         const double w = x * val + 1.4142135623730951 * dval;
         xh[t] = x;
         wh[t] = 1.0 / (w * w);
     }
     // block max of |dtheta| through the bit pattern (non-negative doubles order like integers; NaN sorts last)
-    unsigned long long bits = (unsigned long long)__double_as_longlong(adt);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long other = __shfl_down_sync(0xffffffffu, bits, o);
@@ -292,7 +300,10 @@ __global__ void hermite_gw_kernel(HermiteParams p, double* xh, double* wh) {
 
 // sum over the FOLDED rule of exp(-x^2) w (gausshermite.jl:62): twice the half-range sum, the centre
 // node of an odd rule counted once.
-__global__ void __launch_bounds__(256)
+// Deterministic: fixed grid-stride assignment, per-block partials summed in block order by the last block
+// to arrive (an atomicAdd of the partials would make the last bit of every weight depend on the order in
+// which the blocks finish).
+__global__ void __launch_bounds__(512)
 hermite_normsum_kernel(HermiteParams p, HermiteState* st, const double* xh, const double* wh) {
     double s = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -303,13 +314,20 @@ hermite_normsum_kernel(HermiteParams p, HermiteState* st, const double* xh, cons
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    __shared__ double sh[8];
+    __shared__ double sh[16];
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0.0;
-        for (int i = 0; i < 8; ++i) a += sh[i];
-        atomicAdd(&st->norm_sum, a);
+        for (int i = 0; i < 16; ++i) a += sh[i];
+        st->norm_part[blockIdx.x] = a;
+        __threadfence();
+        if (atomicAdd(&st->sum_ticket, 1u) == gridDim.x - 1) {
+            __threadfence();
+            double tot = 0.0;
+            for (unsigned i = 0; i < gridDim.x; ++i) tot += ((volatile double*)st->norm_part)[i];
+            st->norm_sum = tot;
+        }
     }
 }
 
@@ -419,14 +437,15 @@ extern "C" int fgq_gausshermite_device(int64_t n, int normalize, int64_t lo, int
         hermite_rec_kernel<<<1, 128, 0, st>>>(p, xh, wh);  // :46-48
         FGQ_LAUNCH_CHECK();
     } else {
+        const unsigned bsweep = (unsigned)(b128 < HERM_GRID ? b128 : HERM_GRID);
         for (int s = 0; s < 20; ++s) {
-            hermite_sweep_kernel<<<b128, HERM_THREADS, 0, st>>>(p, s, state, theta, xh, wh);
+            hermite_sweep_kernel<<<bsweep, HERM_THREADS, 0, st>>>(p, s, state, theta, xh, wh);
             FGQ_LAUNCH_CHECK();
         }
     }
-    int64_t rb = (p.nh + 255) / 256;
-    if (rb > 148 * 4) rb = 148 * 4;
-    hermite_normsum_kernel<<<(unsigned)rb, 256, 0, st>>>(p, state, xh, wh);
+    int64_t rb = (p.nh + 511) / 512;
+    if (rb > HERMITE_SUM_BLOCKS) rb = HERMITE_SUM_BLOCKS;
+    hermite_normsum_kernel<<<(unsigned)rb, 512, 0, st>>>(p, state, xh, wh);
     FGQ_LAUNCH_CHECK();
     if (hi > lo) {
         hermite_fold_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, st>>>(p, normalize, state, xh, wh,

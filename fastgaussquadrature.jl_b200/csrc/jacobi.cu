@@ -48,11 +48,12 @@ struct JacobiLaunch {
 };
 
 constexpr int JAC_THREADS = 128;
+constexpr int64_t JAC_GRID = 148 * 5;  // persistent grid: 5 blocks of 128 threads fit one SM at 96 registers
 
 // gaussjacobi.jl:254-361 for one node.  NORM: only the truncation norms of terms 12..20 are produced.
 template <bool NORM>
 __device__ __forceinline__ void feval_asy1_node(const JacobiHalfPlan& P, double nn, double t, int mbreak,
-                                                double& vals, double& ders, double* tnorm) {
+                                                double& vals, double& ders, double* tnorm, bool take_norm = false) {
     const double PI = 3.141592653589793;
     const double a = P.a, b = P.b;
     double sinT_, cosT_;
@@ -87,7 +88,12 @@ __device__ __forceinline__ void feval_asy1_node(const JacobiHalfPlan& P, double 
             d1 *= cA;
             d2 *= sA;
             if (NORM) {
-                tnorm[m - 12] = fabs(d1 + d2);
+                // running max over the bit patterns (as the block/grid reduction): a NaN norm, whose
+                // pattern lies above +inf, wins
+                const double v = fabs(d1 + d2);
+                const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
+                const unsigned long long cb = (unsigned long long)__double_as_longlong(tnorm[m - 12]);
+                if (take_norm && vb > cb) tnorm[m - 12] = v;
             } else {
                 const double cA2 = cA * cosT_ + sA * sinT_;
                 const double sA2 = sA * cosT_ - cA * sinT_;
@@ -136,24 +142,34 @@ __global__ void jacobi_init_kernel(int64_t n, double a, double b, int64_t n_left
     theta[i] = (i < n_left) ? PI - tt : tt;
 }
 
+// Persistent form: a fixed grid (a few blocks per SM) walks the node tiles with a grid stride, so the
+// pre-enqueued launches that find their half already converged cost ~2 us instead of the ~42 us it takes
+// to schedule and retire 39 063 empty blocks (n = 1e7; those were 30 % of the call), and every block
+// reduces its norms once instead of once per tile.
 template <bool NORM>
-__global__ void __launch_bounds__(JAC_THREADS)
+__global__ void __launch_bounds__(JAC_THREADS, 5)
 jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, double* theta, double* x, double* w) {
     const int h = p.half;
     const int phase = *((volatile int*)&st->phase[h]);
     if (phase == 2) return;
-    const int64_t r = (int64_t)blockIdx.x * JAC_THREADS + threadIdx.x;
-    const int64_t ig = p.first + r;
-    const bool active = r < p.count;
-    const bool interior = active && ig >= p.idx_lo && ig < p.idx_hi;
     const double nn = (double)p.n;
-    double t = active ? theta[ig] : 1.0;
+    const int64_t ntiles = (p.count + JAC_THREADS - 1) / JAC_THREADS;
     if (NORM) {
-        double tn[9];
-        double dummy_v, dummy_d;
-        feval_asy1_node<true>(p.hp, nn, t, 0, dummy_v, dummy_d, tn);
+        double tmax[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) tmax[q] = 0.0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t r = tile * JAC_THREADS + threadIdx.x;
+            const int64_t ig = p.first + r;
+            const bool active = r < p.count;
+            const bool interior = active && ig >= p.idx_lo && ig < p.idx_hi;
+            const double t = active ? theta[ig] : 1.0;
+            double dummy_v, dummy_d;
+            feval_asy1_node<true>(p.hp, nn, t, 0, dummy_v, dummy_d, tmax, interior);
+        }
+#pragma unroll
         for (int q = 0; q < 9; ++q) {
-            const unsigned long long bits = block_max_bits(interior ? tn[q] : 0.0);
+            const unsigned long long bits = block_max_bits(tmax[q]);
             if (threadIdx.x == 0) atomicMax(&st->termnorm[h][p.sweep][q], bits);
         }
         return;
@@ -167,14 +183,23 @@ jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, doub
             break;
         }
     }
-    double adt = 0.0;
-    if (active) {
+    unsigned long long adt_bits = 0ull;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r = tile * JAC_THREADS + threadIdx.x;
+        const int64_t ig = p.first + r;
+        if (r >= p.count) continue;
+        const bool interior = ig >= p.idx_lo && ig < p.idx_hi;
+        double t = theta[ig];
         double vals, ders;
         feval_asy1_node<false>(p.hp, nn, t, mbreak, vals, ders, nullptr);
         const double dt = vals / ders;
         t += dt;
         theta[ig] = t;
-        if (interior) adt = (dt != dt) ? __longlong_as_double(0x7ff8000000000000LL) : fabs(dt);
+        if (interior) {
+            const double adt = (dt != dt) ? __longlong_as_double(0x7ff8000000000000LL) : fabs(dt);
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(adt);
+            adt_bits = bits > adt_bits ? bits : adt_bits;
+        }
         // the 10 nodes next to each end belong to the boundary kernel, which runs concurrently
         if (ig >= p.lo && ig < p.hi && ig >= JAC_NBDY && ig < p.n - JAC_NBDY) {
             const double c = cos(t);
@@ -182,7 +207,7 @@ jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, doub
             w[ig - p.lo] = (1.0 / (ders * ders)) * p.wc;  // 1 ./ ders.^2 (:222,:244), rmul! (:192)
         }
     }
-    const unsigned long long bits = block_max_bits(adt);
+    const unsigned long long bits = block_max_bits(__longlong_as_double((long long)adt_bits));
     if (threadIdx.x == 0) {
         atomicMax(&st->dtnorm[h][p.sweep], bits);
         __threadfence();
@@ -606,7 +631,8 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
     for (int s = 0; s < 11; ++s) {
         for (int h = 0; h < 2; ++h) {
             L[h].sweep = s;
-            const unsigned blocks = (unsigned)((L[h].count + JAC_THREADS - 1) / JAC_THREADS);
+            const int64_t tiles = (L[h].count + JAC_THREADS - 1) / JAC_THREADS;
+            const unsigned blocks = (unsigned)(tiles < JAC_GRID ? tiles : JAC_GRID);
             jacobi_pass_kernel<true><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
             FGQ_LAUNCH_CHECK();
             jacobi_pass_kernel<false><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
