@@ -270,6 +270,11 @@ class WorkerPool {
     WorkerPool() {
         unsigned hw = std::thread::hardware_concurrency();
         threads_ = hw == 0 ? 4 : (hw > 16 ? 16 : hw);
+        // several processes on one host (one per GPU) share its cores: FGQ_HOST_THREADS caps this process
+        if (const char* e = getenv("FGQ_HOST_THREADS")) {
+            const int v = atoi(e);
+            if (v >= 1 && v <= 64) threads_ = (unsigned)v;
+        }
     }
     void loop(int id) {
         uint64_t seen = 0;
