@@ -373,6 +373,9 @@ def main():
         for _ in range(2):  # warm-up (scratch allocation, host worker threads)
             call()
         barrier()
+        import ctypes
+        st_p, st_d, st_l, st_s = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+        fgq_b200.lib().fgq_debug_drain_stats(ctypes.byref(st_p), ctypes.byref(st_d), ctypes.byref(st_l), ctypes.byref(st_s))
         per_call = []
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -385,12 +388,15 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
+        fgq_b200.lib().fgq_debug_drain_stats(ctypes.byref(st_p), ctypes.byref(st_d), ctypes.byref(st_l), ctypes.byref(st_s))
         e2e = {"value": n * args.e2e_steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 0,
                "d2h_bytes_per_step": 8 * (n + n % 2), "steps": args.e2e_steps,
                "call_s_min": min(per_call), "call_s_median": float(np.median(per_call)),
                "what": "host-returning C-ABI call into pinned host buffers: kernel + PCIe D2H of the left half of each "
                        "shard, chunk-pipelined; the mirrored half is written by host threads (+-x symmetry)",
                "mode": args.e2e_mode,
+               "drain_rank0": {"pieces": st_p.value, "mirror_by_dma": st_d.value, "landed_before_pickup": st_l.value,
+                               "last_dma_share": st_s.value / 1000.0},
                "check_sum_w_minus_2": float(np.float64(hw.sum().item()) - 2.0) if hw is not None else None}
 
     if rank == 0:

@@ -316,6 +316,9 @@ static void hint_huge_pages(void* p, size_t bytes) {
 #endif
 }
 
+static std::atomic<int64_t> g_drain_pieces{0}, g_drain_dma{0}, g_drain_landed{0};
+static std::atomic<int> g_drain_share_milli{0};
+
 // Device -> host copy of a result (x and w, cnt entries each) on stream `st`; returns when the data is in
 // place.  The result is cut into pieces; before the copies of piece [lo, hi) are enqueued `src` names the
 // device addresses holding it (and may enqueue the kernels that produce it: see ChunkedProducer), so the
@@ -331,16 +334,22 @@ static void hint_huge_pages(void* p, size_t bytes) {
 int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const PieceSource& src, const MirrorSpec* m) {
     if (cnt <= 0) return FGQ_OK;
     if (!m && cnt < DRAIN_PIECE) {  // small result: one plain copy, no threads
-        const double *xd = nullptr, *wd = nullptr;
-        FGQ_TRY(src(0, cnt, &xd, &wd));
-        FGQ_CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
-        FGQ_CUDA_TRY(cudaMemcpyAsync(w, wd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+        PieceDev pd{};
+        FGQ_TRY(src(0, cnt, &pd));
+        FGQ_CUDA_TRY(cudaMemcpyAsync(x, pd.x, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+        FGQ_CUDA_TRY(cudaMemcpyAsync(w, pd.w, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
         FGQ_CUDA_TRY(cudaStreamSynchronize(st));
         return FGQ_OK;
     }
     const bool direct = is_pinned_host(x) && is_pinned_host(w);
+    // the mirror image of a piece may travel by DMA instead (see below) when everything is pinned
+    const bool dma_mirror_ok = m && direct && is_pinned_host(m->xr) && is_pinned_host(m->wr);
     const int64_t PIECE = direct ? DRAIN_PIECE_PINNED : DRAIN_PIECE;  // entries per piece and array
-    constexpr int RING = 16;
+    // pieces in flight: 16 ring slots for a pageable destination; 64 when the DMA goes straight to pinned
+    // memory (no ring), so that PCIe can run well ahead of the host threads and a thread can tell a piece
+    // that has been waiting for it from one it has to wait for
+    constexpr int MAX_RING = 64;
+    const int RING = direct ? MAX_RING : 16;
     double* ring = nullptr;
     if (!direct) {
         void* ring_p;
@@ -354,51 +363,99 @@ int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const Piec
     if (T > pieces) T = (int)pieces;
     int dev;
     FGQ_CUDA_TRY(cudaGetDevice(&dev));
-    cudaEvent_t ev[RING];
+    cudaEvent_t ev[MAX_RING];
     if (threaded)
         for (int i = 0; i < RING; ++i) FGQ_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
     std::mutex mu;
     std::condition_variable cv;
     int64_t published = 0;            // pieces whose copies and event have been enqueued
+    int64_t claimed = 0;              // pieces taken by a host thread (in order)
     std::vector<char> consumed((size_t)pieces, 0);
+    std::vector<char> by_dma((size_t)pieces, 0);
     bool failed = false;
     int rc = FGQ_OK;
     cudaError_t err = cudaSuccess;
+    // Who writes the mirror image of a piece?  The host threads (8 B/node over PCIe, but 24 B/node of host
+    // memory traffic) or a second pair of DMA copies of the image the kernel left in device memory
+    // (16 B/node over PCIe, 16 B/node of host traffic, no host work).  One GPU on its own is PCIe-bound and
+    // wants the former; several processes sharing one host's memory and cores want more of the latter.
+    // `dma_share` is the fraction of pieces sent the second way, steered by what the host threads see:
+    // a piece that had already landed when a thread picked it up means the host side is behind (raise the
+    // share); a piece the thread had to wait for means PCIe is behind (lower it).
+    double dma_share = 0.0, dma_acc = 0.0;
+    bool adapt = true;
+    if (const char* e = getenv("FGQ_HOST_MIRROR_DMA_SHARE")) {  // tests / tuning: a fixed share in [0, 1]
+        const double v = atof(e);
+        if (v >= 0.0 && v <= 1.0) {
+            dma_share = v;
+            adapt = false;
+        }
+    }
     // the calling thread feeds the copy queue, the pool threads drain it
     auto feeder = [&]() {
         for (int64_t p = 0; p < pieces && err == cudaSuccess && rc == FGQ_OK; ++p) {
-            if (threaded && p >= RING) {
+            bool use_dma = false;
+            if (threaded) {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return consumed[(size_t)(p - RING)] != 0 || failed; });
+                if (p >= RING) cv.wait(lk, [&] { return consumed[(size_t)(p - RING)] != 0 || failed; });
                 if (failed) break;
+                if (dma_mirror_ok) {
+                    dma_acc += dma_share;
+                    if (dma_acc >= 1.0) {
+                        dma_acc -= 1.0;
+                        use_dma = true;
+                    }
+                }
             }
             const int64_t lo = p * PIECE, len = (lo + PIECE < cnt ? PIECE : cnt - lo);
-            const double *xd = nullptr, *wd = nullptr;
-            rc = src(lo, lo + len, &xd, &wd);
+            PieceDev pd{};
+            rc = src(lo, lo + len, &pd);
             if (rc == FGQ_OK) {
                 double* dx = direct ? x + lo : ring + (p % RING) * 2 * PIECE;
                 double* dw = direct ? w + lo : dx + PIECE;
-                err = cudaMemcpyAsync(dx, xd, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
-                if (err == cudaSuccess) err = cudaMemcpyAsync(dw, wd, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+                err = cudaMemcpyAsync(dx, pd.x, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+                if (err == cudaSuccess) err = cudaMemcpyAsync(dw, pd.w, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+                use_dma = use_dma && pd.xr && pd.wr;
+                if (use_dma && err == cudaSuccess) {
+                    // elements [e0, e1) of the left slice <-> right positions [cnt - e1, cnt - e0), ascending;
+                    // pd.xr points at the image of position cnt - (e0 + len)
+                    const int64_t e0 = m->e0 + lo;
+                    const int64_t e1 = e0 + len < m->mirror_cnt ? e0 + len : m->mirror_cnt;
+                    const int64_t skip = e0 + len - e1;  // the centre of an odd rule has no image
+                    if (e1 > e0) {
+                        err = cudaMemcpyAsync(m->xr + (m->cnt - e1), pd.xr + skip, (size_t)(e1 - e0) * 8,
+                                              cudaMemcpyDeviceToHost, st);
+                        if (err == cudaSuccess)
+                            err = cudaMemcpyAsync(m->wr + (m->cnt - e1), pd.wr + skip, (size_t)(e1 - e0) * 8,
+                                                  cudaMemcpyDeviceToHost, st);
+                    }
+                }
                 if (err == cudaSuccess && threaded) err = cudaEventRecord(ev[p % RING], st);
             }
             if (threaded) {
                 std::lock_guard<std::mutex> lk(mu);
+                by_dma[(size_t)p] = use_dma;
                 if (err == cudaSuccess && rc == FGQ_OK) published = p + 1; else failed = true;
                 cv.notify_all();
             }
         }
     };
-    auto drainer = [&](int t) {
+    auto drainer = [&](int) {
         cudaSetDevice(dev);
-        for (int64_t p = t; p < pieces; p += T) {
+        for (;;) {
+            int64_t p;
+            bool dma;
             {
                 std::unique_lock<std::mutex> lk(mu);
+                if (claimed >= pieces || failed) return;
+                p = claimed++;
                 cv.wait(lk, [&] { return published > p || failed; });
                 if (failed) return;
+                dma = by_dma[(size_t)p] != 0;
             }
-            const bool ok = cudaEventSynchronize(ev[p % RING]) == cudaSuccess;
-            if (ok) {
+            const bool landed = cudaEventQuery(ev[p % RING]) == cudaSuccess;
+            const bool ok = landed || cudaEventSynchronize(ev[p % RING]) == cudaSuccess;
+            if (ok && !dma) {
                 const int64_t lo = p * PIECE, len = (lo + PIECE < cnt ? PIECE : cnt - lo);
                 const double* sx = direct ? x + lo : ring + (p % RING) * 2 * PIECE;
                 const double* sw = direct ? w + lo : sx + PIECE;
@@ -418,6 +475,13 @@ int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const Piec
             std::lock_guard<std::mutex> lk(mu);
             consumed[(size_t)p] = 1;
             if (!ok) failed = true;
+            g_drain_pieces++;
+            g_drain_dma += dma;
+            g_drain_landed += landed;
+            if (adapt) {
+                dma_share += landed ? 1.0 / 16 : -1.0 / 16;
+                dma_share = dma_share < 0.0 ? 0.0 : (dma_share > 1.0 ? 1.0 : dma_share);
+            }
             cv.notify_all();
         }
     };
@@ -425,6 +489,7 @@ int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const Piec
         if (t == 0) feeder(); else drainer(t - 1);
     });
     cudaError_t e2 = cudaStreamSynchronize(st);
+    g_drain_share_milli = (int)(dma_share * 1000);
     if (threaded)
         for (int i = 0; i < RING; ++i) cudaEventDestroy(ev[i]);
     if (rc != FGQ_OK) return rc;
@@ -448,9 +513,9 @@ int drain_to_host(double* x, double* w, const double* xd, const double* wd, int6
     }
     hint_huge_pages(x, (size_t)cnt * 8);
     hint_huge_pages(w, (size_t)cnt * 8);
-    return drain_to_host(x, w, cnt, st, [&](int64_t lo, int64_t, const double** px, const double** pw) {
-        *px = xd + lo;
-        *pw = wd + lo;
+    return drain_to_host(x, w, cnt, st, [&](int64_t lo, int64_t, PieceDev* pd) {
+        pd->x = xd + lo;
+        pd->w = wd + lo;
         return (int)FGQ_OK;
     }, nullptr);
 }
@@ -465,10 +530,14 @@ struct ChunkedProducer {
     double* buf[2];
     cudaStream_t s_compute, s_copy;
     cudaEvent_t computed[2], drained[2];
-    std::function<int(int64_t, int64_t, double*, double*, cudaStream_t)> produce;
+    // produce(lo, hi, x_dev, w_dev, xr_dev, wr_dev, st): xr_dev/wr_dev (null unless `mirrored`) receive the
+    // +-x image of the chunk in ascending order, xr_dev[(hi-lo)-1-i] = -x_dev[i]
+    std::function<int(int64_t, int64_t, double*, double*, double*, double*, cudaStream_t)> produce;
     int64_t launched = 0;
+    bool mirrored = false;
 
-    int init(int64_t cnt_, int64_t max_chunk) {
+    int init(int64_t cnt_, int64_t max_chunk, bool mirrored_ = false) {
+        mirrored = mirrored_;
         cnt = cnt_;
         chunk = cnt < max_chunk ? cnt : max_chunk;
         nchunks = (cnt + chunk - 1) / chunk;
@@ -476,7 +545,7 @@ struct ChunkedProducer {
         buf[0] = buf[1] = nullptr;
         for (int b = 0; b < nbuf; ++b) {
             void* p;
-            FGQ_TRY(scratch_device((size_t)chunk * 16, b, &p));
+            FGQ_TRY(scratch_device((size_t)chunk * (mirrored ? 32 : 16), b, &p));
             buf[b] = (double*)p;
         }
         FGQ_TRY(scratch_stream(0, &s_compute));
@@ -491,11 +560,12 @@ struct ChunkedProducer {
         const int64_t lo = j * chunk, hi = lo + chunk < cnt ? lo + chunk : cnt;
         const int b = (int)(j % nbuf);
         if (j >= nbuf) FGQ_CUDA_TRY(cudaStreamWaitEvent(s_compute, drained[b], 0));
-        FGQ_TRY(produce(lo, hi, buf[b], buf[b] + chunk, s_compute));
+        FGQ_TRY(produce(lo, hi, buf[b], buf[b] + chunk, mirrored ? buf[b] + 2 * chunk : nullptr,
+                        mirrored ? buf[b] + 3 * chunk : nullptr, s_compute));
         FGQ_CUDA_TRY(cudaEventRecord(computed[b], s_compute));
         return FGQ_OK;
     }
-    int piece(int64_t lo, int64_t, const double** px, const double** pw) {
+    int piece(int64_t lo, int64_t hi, PieceDev* pd) {
         const int64_t j = lo / chunk;
         const int b = (int)(j % nbuf);
         if (lo == j * chunk) {  // first piece of chunk j: every copy of chunk j-1 has been enqueued
@@ -504,8 +574,13 @@ struct ChunkedProducer {
             FGQ_CUDA_TRY(cudaStreamWaitEvent(s_copy, computed[b], 0));
             if (j + 1 < nchunks && launched <= j + 1) FGQ_TRY(launch(launched++));
         }
-        *px = buf[b] + (lo - j * chunk);
-        *pw = buf[b] + chunk + (lo - j * chunk);
+        pd->x = buf[b] + (lo - j * chunk);
+        pd->w = buf[b] + chunk + (lo - j * chunk);
+        if (mirrored) {  // image of [lo, hi) within the chunk's image of length len_j
+            const int64_t len_j = (j * chunk + chunk < cnt ? chunk : cnt - j * chunk);
+            pd->xr = buf[b] + 2 * chunk + (len_j - (hi - j * chunk));
+            pd->wr = buf[b] + 3 * chunk + (len_j - (hi - j * chunk));
+        }
         return FGQ_OK;
     }
     int finish(int rc) {
@@ -530,13 +605,11 @@ int host_pipeline(int64_t lo_all, int64_t hi_all, double* x, double* w, SliceFn 
     hint_huge_pages(w, (size_t)n * 8);
     ChunkedProducer cp;
     FGQ_TRY(cp.init(n, 1LL << 24));  // nodes per chunk: 128 MiB of x + 128 MiB of w
-    cp.produce = [&](int64_t lo, int64_t hi, double* xd, double* wd, cudaStream_t st) {
+    cp.produce = [&](int64_t lo, int64_t hi, double* xd, double* wd, double*, double*, cudaStream_t st) {
         return fn(ctx, lo_all + lo, lo_all + hi, xd, wd, st);
     };
     const int rc = drain_to_host(x, w, n, cp.s_copy,
-                                 [&](int64_t lo, int64_t hi, const double** px, const double** pw) {
-                                     return cp.piece(lo, hi, px, pw);
-                                 }, nullptr);
+                                 [&](int64_t lo, int64_t hi, PieceDev* pd) { return cp.piece(lo, hi, pd); }, nullptr);
     return cp.finish(rc);
 }
 
@@ -582,20 +655,33 @@ extern "C" int fgq_gausslegendre_host_pair(int64_t n, int64_t k_lo, int64_t k_hi
     // receives the DMA directly and the host threads only write the mirror image; a pageable one (a Julia
     // Vector, a numpy array) is filled through the pinned ring by the same threads, which also spreads
     // the first-touch page faults of a freshly allocated 16 GB result over all of them.
+    // everything pinned: the kernel also leaves the +-x image in device memory, so that drain_to_host can
+    // balance the mirror work between PCIe and the host threads
+    const bool all_pinned = is_pinned_host(xl) && is_pinned_host(wl) && is_pinned_host(xr) && is_pinned_host(wr);
     ChunkedProducer cp;
-    FGQ_TRY(cp.init(cnt, 1LL << chunk_log2));
-    cp.produce = [&](int64_t lo, int64_t hi, double* xd, double* wd, cudaStream_t st) {
-        // left slice = output indices [k_lo-1+lo, k_lo-1+hi)
+    FGQ_TRY(cp.init(cnt, 1LL << chunk_log2, all_pinned));
+    cp.produce = [&](int64_t lo, int64_t hi, double* xd, double* wd, double* xrd, double* wrd, cudaStream_t st) {
+        // left slice = output indices [k_lo-1+lo, k_lo-1+hi) = half-indices [k_lo+lo, k_lo+hi)
+        if (xrd) return fgq_gausslegendre_device_pair(n, k_lo + lo, k_lo + hi, xd, wd, xrd, wrd, (void*)st);
         return fgq_gausslegendre_device(n, k_lo - 1 + lo, k_lo - 1 + hi, xd, wd, (void*)st);
     };
     // element e of the left slice (half-index k = k_lo + e) mirrors to right-slice position cnt-1-e;
     // the centre of an odd rule (k = m) has no mirror image
     const MirrorSpec mir{xr, wr, cnt, 0, (k_hi - 1 > mr) ? cnt - 1 : cnt};
     const int rc = drain_to_host(xl, wl, cnt, cp.s_copy,
-                                 [&](int64_t lo, int64_t hi, const double** px, const double** pw) {
-                                     return cp.piece(lo, hi, px, pw);
-                                 }, &mir);
+                                 [&](int64_t lo, int64_t hi, PieceDev* pd) { return cp.piece(lo, hi, pd); }, &mir);
     return cp.finish(rc);
+}
+
+// counters of the threaded drains since the last call of this function: pieces handled by host threads,
+// pieces whose mirror image went by DMA, pieces that had landed before a thread picked them up, and the
+// last value of the adaptive DMA share (x 1000)
+extern "C" int fgq_debug_drain_stats(int64_t* pieces, int64_t* dma_pieces, int64_t* landed, int* share_milli) {
+    if (pieces) *pieces = g_drain_pieces.exchange(0);
+    if (dma_pieces) *dma_pieces = g_drain_dma.exchange(0);
+    if (landed) *landed = g_drain_landed.exchange(0);
+    if (share_milli) *share_milli = g_drain_share_milli.load();
+    return FGQ_OK;
 }
 
 extern "C" int fgq_gausslegendre_host(int64_t n, double* x, double* w) {

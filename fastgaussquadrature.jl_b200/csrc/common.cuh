@@ -71,7 +71,11 @@ struct MirrorSpec {      // optional +-x mirroring done by the same host threads
 };
 int drain_to_host(double* x, double* w, const double* x_dev, const double* w_dev, int64_t cnt, cudaStream_t st);
 // general form: src(lo, hi, &x_dev, &w_dev) names (and may produce) the device data of piece [lo, hi)
-typedef std::function<int(int64_t, int64_t, const double**, const double**)> PieceSource;
+struct PieceDev {
+    const double *x, *w;    // device data of the piece
+    const double *xr, *wr;  // optional: its +-x image (ascending, i.e. reversed and negated), or null
+};
+typedef std::function<int(int64_t, int64_t, PieceDev*)> PieceSource;
 constexpr int64_t DRAIN_PIECE = 1LL << 18;         // entries per piece through the pinned ring (2 MiB)
 constexpr int64_t DRAIN_PIECE_PINNED = 1LL << 20;  // entries per piece into a pinned destination (8 MiB)
 int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const PieceSource& src, const MirrorSpec* mirror);

@@ -207,6 +207,11 @@ int fgq_debug_legendre_theta_device(int64_t n, int64_t k_lo, int64_t k_hi, doubl
  * IEEE operators.  Expected 0. */
 int fgq_debug_fastdiv_check(int64_t n, int64_t k_lo, int64_t k_hi,
                             unsigned long long* mismatches_dev, void* stream);
+/* Counters of the threaded device->host drains since the previous call of this function: pieces handled,
+ * pieces whose mirror image travelled by DMA instead of being written by a host thread, pieces that had
+ * already landed when a thread picked them up, and the last adaptive DMA share x 1000 (bench.py reports
+ * them beside e2e).  Any pointer may be NULL. */
+int fgq_debug_drain_stats(int64_t* pieces, int64_t* dma_pieces, int64_t* landed, int* share_milli);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t fgq_launch_count(void);
 

@@ -263,3 +263,28 @@ def test_host_symmetric_path(fgq, oracle_mod, n):
                 xa[lo:hi] = xs
                 wa[lo:hi] = ws
         assert np.array_equal(xa, xt) and np.array_equal(wa, wt)
+
+
+@pytest.mark.parametrize("share", ["0", "1", "0.37", None])
+@pytest.mark.parametrize("n", [(1 << 21) + 5, 3 * (1 << 24) + 7, 3 * (1 << 24) + 8])
+def test_host_symmetric_path_pinned(fgq, oracle_mod, n, share, monkeypatch):
+    """Pinned destinations: the mirror image of a piece is written either by host threads or by a second
+    pair of DMA copies of the image the kernel left in device memory; the split is adaptive at run time
+    (share=None) and pinned here to 0, 1 and a mixed value: the bits must not depend on it."""
+    if share is None:
+        monkeypatch.delenv("FGQ_HOST_MIRROR_DMA_SHARE", raising=False)
+    else:
+        monkeypatch.setenv("FGQ_HOST_MIRROR_DMA_SHARE", share)
+    xt, wt = oracle_mod.gausslegendre(n, twin=True)
+    x, w = fgq.gausslegendre(n, pinned=True)
+    assert np.array_equal(x, xt) and np.array_equal(w, wt)
+    world = 3
+    xa = np.full(n, np.nan)
+    wa = np.full(n, np.nan)
+    for r in range(world):
+        segs, _ = fgq.gausslegendre_host_pair(n, r, world, pinned=True)
+        for lo, hi, xs, ws in segs:
+            assert np.all(np.isnan(xa[lo:hi]))
+            xa[lo:hi] = xs
+            wa[lo:hi] = ws
+    assert np.array_equal(xa, xt) and np.array_equal(wa, wt)
