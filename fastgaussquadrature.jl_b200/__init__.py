@@ -19,8 +19,13 @@ from .api import (  # noqa: F401
     gausslaguerre_device,
     gausshermite,
     gausshermite_device,
+    gausshermite_reduced,
+    gausshermite_reduced_device,
     gausslegendre,
     gausslegendre_batch,
+    gaussjacobi_batch,
+    gausshermite_batch,
+    gausslaguerre_batch,
     gausslegendre_device,
     gausslegendre_host_pair,
     gausslegendre_moments_fused,

@@ -57,6 +57,18 @@ SIGNATURES = {
     "fgq_gausslaguerre_workspace_bytes": (_i64, [_i64]),
     "fgq_gausslaguerre_device": (ctypes.c_int, [_i64, ctypes.c_double, _vp, _vp, _vp, _vp]),
     "fgq_gausslaguerre_stats": (ctypes.c_int, [_vp, _i64p, _i64p, _i64p, _i64p]),
+    "fgq_gausshermite_reduced_bound": (_i64, [_i64]),
+    "fgq_gausshermite_reduced_device": (ctypes.c_int, [_i64, ctypes.c_int, _vp, _vp, _vp, _vp, _i64p, _i64p]),
+    "fgq_gausshermite_reduced_host": (ctypes.c_int, [_i64, ctypes.c_int, _vp, _vp, _i64p, _i64p]),
+    "fgq_gaussjacobi_batch_workspace_bytes": (_i64, [_i64]),
+    "fgq_gaussjacobi_batch_device": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fgq_gaussjacobi_batch_host": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fgq_gausshermite_batch_workspace_bytes": (_i64, [_i64]),
+    "fgq_gausshermite_batch_device": (ctypes.c_int, [_i64, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "fgq_gausshermite_batch_host": (ctypes.c_int, [_i64, _vp, _vp, ctypes.c_int, _vp, _vp]),
+    "fgq_gausslaguerre_batch_workspace_bytes": (_i64, [_i64]),
+    "fgq_gausslaguerre_batch_device": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fgq_gausslaguerre_batch_host": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "fgq_rule_moments_device": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "fgq_gausslegendre_moments_fused_device": (ctypes.c_int, [_i64, _i64, _i64, ctypes.c_int, _vp, _vp]),
     "fgq_measure_dfma_peak": (ctypes.c_int, [_dp]),

@@ -116,6 +116,55 @@ def gausslegendre_batch(n_i, offsets=None):
     return offsets, x, w
 
 
+def _batch_layout(n_i, offsets):
+    n_i = np.ascontiguousarray(n_i, dtype=np.int32)
+    if n_i.ndim != 1:
+        raise ValueError("n_i must be one-dimensional")
+    if offsets is None:
+        offsets = np.zeros(len(n_i) + 1, dtype=np.int64)
+        np.cumsum(np.maximum(n_i, 0), out=offsets[1:])
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    total = int(offsets[-1]) if len(offsets) else 0
+    return n_i, offsets, np.empty(total, dtype=np.float64), np.empty(total, dtype=np.float64)
+
+
+def _batch_param(v, count):
+    a = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (count,)))
+    return a
+
+
+def gaussjacobi_batch(n_i, alpha, beta, offsets=None):
+    """Batch of small rules ``gaussjacobi(n_i[r], alpha[r], beta[r])``, 0 <= n_i <= 100, CSR layout
+    (``alpha`` / ``beta`` broadcast against ``n_i``).  Returns ``(offsets, x, w)``.  Every rule takes the
+    branch gaussjacobi.jl:23-55 dispatches it to; one block per ``jacobi_rec`` rule (:61-155), bit-identical
+    to the single calls."""
+    n_i, offsets, x, w = _batch_layout(n_i, offsets)
+    a, b = _batch_param(alpha, len(n_i)), _batch_param(beta, len(n_i))
+    if len(n_i):
+        check(lib().fgq_gaussjacobi_batch_host(len(n_i), _ptr(n_i), _ptr(a), _ptr(b), _ptr(offsets), _ptr(x), _ptr(w)))
+    return offsets, x, w
+
+
+def gausshermite_batch(n_i, offsets=None, normalize=False):
+    """Batch of small rules ``gausshermite(n_i[r]; normalize)``, 0 <= n_i <= 200, CSR layout; one block per
+    rule (hermite_gw / hermite_rec, gausshermite.jl:91-137,325-341), bit-identical to the single calls."""
+    n_i, offsets, x, w = _batch_layout(n_i, offsets)
+    if len(n_i):
+        check(lib().fgq_gausshermite_batch_host(len(n_i), _ptr(n_i), _ptr(offsets), int(bool(normalize)), _ptr(x), _ptr(w)))
+    return offsets, x, w
+
+
+def gausslaguerre_batch(n_i, alpha=0.0, offsets=None):
+    """Batch of small rules ``gausslaguerre(n_i[r], alpha[r])``, 0 <= n_i <= 127, CSR layout; one thread per
+    rule (closed forms, gausslaguerre_GW, gausslaguerre_rec: gausslaguerre.jl:70-95), bit-identical to the
+    single calls."""
+    n_i, offsets, x, w = _batch_layout(n_i, offsets)
+    a = _batch_param(alpha, len(n_i))
+    if len(n_i):
+        check(lib().fgq_gausslaguerre_batch_host(len(n_i), _ptr(n_i), _ptr(a), _ptr(offsets), _ptr(x), _ptr(w)))
+    return offsets, x, w
+
+
 # ---- device-resident, sharded -----------------------------------------------------------------
 
 def index_partition(n: int, world: int) -> List[Tuple[int, int]]:
@@ -330,6 +379,44 @@ def gausshermite(n, *, normalize: bool = False):
         return x, w
     check(lib().fgq_gausshermite_host(n, int(bool(normalize)), _ptr(x), _ptr(w)))
     return x, w
+
+
+def gausshermite_reduced(n, *, normalize: bool = False):
+    """Truncated Gauss-Hermite rule: ``(first, x, w)``, the centre block ``first : first+len(x)`` (0-based) of
+    ``gausshermite(n)`` holding every weight >= 10 floatmin; all omitted weights are 0.0 in the full rule
+    (exp(-x^2) underflows, gausshermite.jl:30).  Only that block is computed (2.4 % of the nodes at n = 1e6);
+    the analogue of ``gausslaguerre(n; reduced=true)`` (gausslaguerre.jl:163-169)."""
+    import ctypes
+    n = _as_int(n)
+    if n < 0:
+        raise DomainError(f"DomainError({n}): Input n must be a non-negative integer")
+    L = lib()
+    bound = int(L.fgq_gausshermite_reduced_bound(n))
+    x, w = _host_pair(bound, False)
+    first, n_out = ctypes.c_int64(0), ctypes.c_int64(0)
+    if n > 0:
+        check(L.fgq_gausshermite_reduced_host(n, int(bool(normalize)), _ptr(x), _ptr(w), ctypes.byref(first),
+                                              ctypes.byref(n_out)))
+    return int(first.value), x[:n_out.value], w[:n_out.value]
+
+
+def gausshermite_reduced_device(n, *, normalize: bool = False, stream=None):
+    """Device-resident truncated rule: ``(first, x, w, workspace)`` with x, w torch CUDA tensors holding the
+    entries ``first : first+len(x)`` of the full rule (the block inside |x| <= 27.5, untrimmed)."""
+    import ctypes
+    import torch
+    n = _as_int(n)
+    if n < 0:
+        raise DomainError(f"DomainError({n}): Input n must be a non-negative integer")
+    L = lib()
+    bound = int(L.fgq_gausshermite_reduced_bound(n))
+    x = torch.empty(bound, dtype=torch.float64, device="cuda")
+    w = torch.empty(bound, dtype=torch.float64, device="cuda")
+    ws = torch.empty(max(int(L.fgq_gausshermite_workspace_bytes(n)), 8), dtype=torch.uint8, device="cuda")
+    first, count = ctypes.c_int64(0), ctypes.c_int64(0)
+    check(L.fgq_gausshermite_reduced_device(n, int(bool(normalize)), x.data_ptr(), w.data_ptr(), ws.data_ptr(),
+                                            _stream_ptr(stream), ctypes.byref(first), ctypes.byref(count)))
+    return int(first.value), x[:count.value], w[:count.value], ws
 
 
 def gausshermite_device(n, *, normalize: bool = False, stream=None):

@@ -713,6 +713,43 @@ extern "C" int fgq_gausslegendre_host_slice(int64_t n, int64_t lo, int64_t hi, d
     return host_pipeline(lo, hi, x, w, legendre_slice, &n);
 }
 
+namespace fgq {
+int small_batch_rules(int64_t nrules, const int32_t* n_i, const int64_t* offsets, int n_max, const char* what,
+                      std::vector<SmallRule>* rules, int64_t* total) {
+    *total = 0;
+    if (nrules < 0 || (nrules > 0 && (!n_i || !offsets))) {
+        set_error("invalid batch description");
+        return FGQ_EINVAL;
+    }
+    if (nrules > 0x7fffffffLL) {
+        set_error("batch too large");
+        return FGQ_EINVAL;
+    }
+    if (rules) rules->resize((size_t)nrules);
+    int64_t tot = 0;
+    for (int64_t i = 0; i < nrules; ++i) {
+        if (n_i[i] < 0) {
+            set_error("DomainError(%d): %s rule %lld of the batch: n must be non-negative", n_i[i], what, (long long)i);
+            return FGQ_EDOMAIN;
+        }
+        if (n_i[i] > n_max) {
+            set_error("batched %s rules are limited to n <= %d (rule %lld has n=%d): use the single-rule call",
+                      what, n_max, (long long)i, n_i[i]);
+            return FGQ_EINVAL;
+        }
+        if (offsets[i] < 0) {
+            set_error("negative offset");
+            return FGQ_EINVAL;
+        }
+        const int64_t end = offsets[i] + n_i[i];
+        if (end > tot) tot = end;
+        if (rules) (*rules)[(size_t)i] = SmallRule{n_i[i], 0, offsets[i]};
+    }
+    *total = tot;
+    return FGQ_OK;
+}
+}  // namespace fgq
+
 extern "C" int fgq_gausslegendre_batch_host(int64_t nrules, const int32_t* n_i,
                                             const int64_t* offsets, double* x, double* w) {
     clear_status();

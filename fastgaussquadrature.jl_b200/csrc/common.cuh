@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <functional>
+#include <vector>
 
 #include "../../include/fgq.h"
 
@@ -85,6 +86,20 @@ int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const Piec
 typedef int (*SliceFn)(void* ctx, int64_t lo, int64_t hi, double* x_dev, double* w_dev,
                        cudaStream_t st);
 int host_pipeline(int64_t lo, int64_t hi, double* x, double* w, SliceFn fn, void* ctx);
+
+// Batched small rules of the Jacobi / Hermite / Laguerre families.  The caller describes
+// the batch with HOST arrays (n_i, parameters, CSR offsets): the per-rule constants need host libm
+// (gamma functions, Bessel-zero guesses), exactly like the single-rule calls, and are uploaded into the
+// workspace before the launch.
+struct SmallRule {   // one rule of a batch: n nodes written at x[off .. off+n)
+    int32_t n;
+    int32_t kind;
+    int64_t off;
+};
+// Validates (n_i, offsets): n < 0 -> FGQ_EDOMAIN, n > n_max or a negative offset -> FGQ_EINVAL.  Fills
+// `rules` (may be null) and the output length `total` = max(off + n).
+int small_batch_rules(int64_t nrules, const int32_t* n_i, const int64_t* offsets, int n_max, const char* what,
+                      std::vector<SmallRule>* rules, int64_t* total);
 
 }  // namespace fgq
 #endif

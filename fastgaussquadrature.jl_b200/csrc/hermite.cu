@@ -17,6 +17,11 @@
 #include "common.cuh"
 #include "gw.cuh"
 
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
 namespace fgq {
 
 __constant__ double c_airy_roots[10] = {
@@ -41,6 +46,8 @@ struct HermiteParams {
     int64_t n;
     int64_t m;        // (n-1)>>1 (odd) or n>>1 (even): count of Tricomi/Airy guesses
     int64_t nh;       // half-range length: m+1 (odd, leading 0) or m
+    int64_t nact;     // half-range nodes actually computed, counted from the centre: nh, or fewer for the
+                      // truncated rule (fgq_gausshermite_reduced_*)
     int odd;
     double a;         // +-0.5
     double nu;        // 4m + 2a + 2
@@ -114,7 +121,7 @@ __global__ void hermite_init_kernel(HermiteParams p, HermiteState* st, double* t
         st->norm_sum = 0.0;
         st->sum_ticket = 0u;
     }
-    if (t >= p.nh) return;
+    if (t >= p.nact) return;
     double x0;
     if (p.odd) {
         x0 = (t == 0) ? 0.0 : hermite_guess(p, t);  // [0; x_init][1:m+1]
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(HERM_THREADS, 4)
 hermite_sweep_kernel(HermiteParams p, int sweep, HermiteState* st, double* theta, double* xh, double* wh) {
     if (*((volatile int*)&st->done)) return;
     unsigned long long bits = 0ull;
-    for (int64_t t = (int64_t)blockIdx.x * HERM_THREADS + threadIdx.x; t < p.nh; t += (int64_t)gridDim.x * HERM_THREADS) {
+    for (int64_t t = (int64_t)blockIdx.x * HERM_THREADS + threadIdx.x; t < p.nact; t += (int64_t)gridDim.x * HERM_THREADS) {
         double th = theta[t];
         double s, c;
         sincos(th, &s, &c);
@@ -248,7 +255,7 @@ __device__ void hermpoly_rec(int n, double x0, double& val, double& dval) {
 
 // hermite_rec (gausshermite.jl:91-111), 21 <= n <= 200: one block, one thread per half-range node,
 // at most 10 Newton steps with the global stopping rule ||dx||_inf < sqrt(eps).
-__global__ void __launch_bounds__(128) hermite_rec_kernel(HermiteParams p, double* xh, double* wh) {
+__device__ __forceinline__ void hermite_rec_block(const HermiteParams& p, double* xh, double* wh) {
     const int t = threadIdx.x;
     const bool active = t < p.nh;
     const double SQ2 = 1.4142135623730951;
@@ -281,9 +288,12 @@ __global__ void __launch_bounds__(128) hermite_rec_kernel(HermiteParams p, doubl
     }
 }
 
+__global__ void __launch_bounds__(128) hermite_rec_kernel(HermiteParams p, double* xh, double* wh) {
+    hermite_rec_block(p, xh, wh);
+}
+
 // hermite_gw (gausshermite.jl:325-341), 2 <= n <= 20: eigenvalues of the Jacobi matrix, upper half.
-__global__ void hermite_gw_kernel(HermiteParams p, double* xh, double* wh) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void hermite_gw_thread(const HermiteParams& p, double* xh, double* wh) {
     const int n = (int)p.n;
     double d[GW_MAX], e[GW_MAX], z[GW_MAX];
     for (int i = 0; i < n; ++i) d[i] = 0.0;
@@ -298,19 +308,29 @@ __global__ void hermite_gw_kernel(HermiteParams p, double* xh, double* wh) {
     }
 }
 
+__global__ void hermite_gw_kernel(HermiteParams p, double* xh, double* wh) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    hermite_gw_thread(p, xh, wh);
+}
+
 // sum over the FOLDED rule of exp(-x^2) w (gausshermite.jl:62): twice the half-range sum, the centre
 // node of an odd rule counted once.
 // Deterministic: fixed grid-stride assignment, per-block partials summed in block order by the last block
 // to arrive (an atomicAdd of the partials would make the last bit of every weight depend on the order in
 // which the blocks finish).
+__device__ __forceinline__ double hermite_norm_term(const HermiteParams& p, int64_t t, const double* xh,
+                                                    const double* wh) {
+    const double x = xh[t];
+    const double term = exp(-(x * x)) * wh[t];
+    return (p.odd && t == 0) ? term : 2.0 * term;
+}
+
 __global__ void __launch_bounds__(512)
 hermite_normsum_kernel(HermiteParams p, HermiteState* st, const double* xh, const double* wh) {
     double s = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < p.nh; t += stride) {
-        const double x = xh[t];
-        const double term = exp(-(x * x)) * wh[t];
-        s += (p.odd && t == 0) ? term : 2.0 * term;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < p.nact; t += stride) {
+        s += hermite_norm_term(p, t, xh, wh);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
@@ -332,11 +352,10 @@ hermite_normsum_kernel(HermiteParams p, HermiteState* st, const double* xh, cons
 }
 
 // fold out (:55-61), global scale (:62), exp(-x^2) (:30), optional normalize (:31)
-__global__ void __launch_bounds__(256)
-hermite_fold_kernel(HermiteParams p, int normalize, const HermiteState* st, const double* xh,
-                    const double* wh, int64_t lo, int64_t hi, double* x, double* w) {
-    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // output index
-    if (i >= hi) return;
+// output entry i of the folded rule from the half-range arrays
+__device__ __forceinline__ void hermite_fold_one(const HermiteParams& p, int normalize, double norm_sum,
+                                                 const double* xh, const double* wh, int64_t i, double& xo,
+                                                 double& wo) {
     // half index: odd n: centre at nh-1 (output) <-> xh[0]; even: outputs nh-1 and nh <-> xh[0]
     int64_t h;
     bool neg;
@@ -348,16 +367,69 @@ hermite_fold_kernel(HermiteParams p, int normalize, const HermiteState* st, cons
         neg = false;
     }
     const double xv = xh[h];
-    const double scale = 1.7724538509055159 / st->norm_sum;
+    const double scale = 1.7724538509055159 / norm_sum;
     double wv = wh[h] * scale;
     wv = wv * exp(-(xv * xv));
-    double xo = neg ? -xv : xv;
+    xo = neg ? -xv : xv;
     if (normalize) {
         xo = 1.4142135623730951 * xo;
         wv = wv / 1.7724538509055159;
     }
+    wo = wv;
+}
+
+__global__ void __launch_bounds__(256)
+hermite_fold_kernel(HermiteParams p, int normalize, const HermiteState* st, const double* xh,
+                    const double* wh, int64_t lo, int64_t hi, double* x, double* w) {
+    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // output index
+    if (i >= hi) return;
+    double xo, wo;
+    hermite_fold_one(p, normalize, st->norm_sum, xh, wh, i, xo, wo);
     x[i - lo] = xo;
-    w[i - lo] = wv;
+    w[i - lo] = wo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched small rules (n <= 200): one block per rule runs the whole single-rule
+// pipeline — hermite_gw / hermite_rec, the normalisation sum, the fold — out of shared memory, with the
+// same device functions and the same summation order as the single-rule launches above, so a batch
+// is bit-identical to the concatenation of single calls.  The parameter sets depend on n only and are
+// read from a table of the 201 possible ones.
+// ---------------------------------------------------------------------------------------------
+constexpr int HERMITE_BATCH_MAX_N = 200;
+
+__global__ void __launch_bounds__(128)
+hermite_small_batch_kernel(const SmallRule* __restrict__ rules, const HermiteParams* __restrict__ table,
+                           int normalize, double* __restrict__ x, double* __restrict__ w) {
+    __shared__ double xh[128], wh[128];
+    __shared__ double sh[4];
+    const SmallRule r = rules[blockIdx.x];
+    if (r.n <= 0 || r.n > HERMITE_BATCH_MAX_N) return;
+    const HermiteParams p = table[r.n];
+    const int t = threadIdx.x;
+    if (r.n <= 20) {
+        if (t == 0) hermite_gw_thread(p, xh, wh);
+    } else {
+        hermite_rec_block(p, xh, wh);
+    }
+    __syncthreads();
+    // hermite_normsum_kernel with one block: thread t holds term t, warp sums, partials in warp order
+    double s = 0.0;
+    if (t < p.nh) s += hermite_norm_term(p, t, xh, wh);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((t & 31) == 0) sh[t >> 5] = s;
+    __syncthreads();
+    double a = 0.0;
+    for (int i = 0; i < 4; ++i) a += sh[i];
+    double tot = 0.0;
+    tot += a;
+    for (int i = t; i < r.n; i += 128) {
+        double xo, wo;
+        hermite_fold_one(p, normalize, tot, xh, wh, i, xo, wo);
+        x[r.off + i] = xo;
+        w[r.off + i] = wo;
+    }
 }
 
 }  // namespace fgq
@@ -377,6 +449,7 @@ static HermiteParams hermite_params(int64_t n) {
         p.a = -0.5;
         p.nh = p.m;
     }
+    p.nact = p.nh;
     p.nu = (double)(4 * p.m) + 2.0 * p.a + 2.0;
     p.musq = (double)(2 * n + 1);
     p.sq_musq = sqrt(p.musq);
@@ -405,6 +478,43 @@ extern "C" int64_t fgq_gausshermite_workspace_bytes(int64_t n) {
     return 1024 + 3 * 8 * nh;
 }
 
+// nact: half-range nodes to compute (from the centre); the output slice [lo, hi) must lie within them
+static int hermite_device_impl(int64_t n, int normalize, int64_t lo, int64_t hi, int64_t nact, double* x_dev,
+                               double* w_dev, void* workspace_dev, cudaStream_t st) {
+    HermiteParams p = hermite_params(n);
+    p.nact = nact;
+    HermiteState* state = (HermiteState*)workspace_dev;
+    double* theta = (double*)((char*)workspace_dev + 1024);
+    double* xh = theta + p.nh;
+    double* wh = xh + p.nh;
+    const unsigned b128 = (unsigned)((p.nact + HERM_THREADS - 1) / HERM_THREADS);
+    hermite_init_kernel<<<b128, HERM_THREADS, 0, st>>>(p, state, theta);  // also resets the state
+    FGQ_LAUNCH_CHECK();
+    if (n <= 20) {  // :41-45; n = 1 (x = 0, w = sqrt(pi), :41-42) is the 1 x 1 case of the same kernel
+        hermite_gw_kernel<<<1, 32, 0, st>>>(p, xh, wh);
+        FGQ_LAUNCH_CHECK();
+    } else if (n <= 200) {
+        hermite_rec_kernel<<<1, 128, 0, st>>>(p, xh, wh);  // :46-48
+        FGQ_LAUNCH_CHECK();
+    } else {
+        const unsigned bsweep = (unsigned)(b128 < HERM_GRID ? b128 : HERM_GRID);
+        for (int s = 0; s < 20; ++s) {
+            hermite_sweep_kernel<<<bsweep, HERM_THREADS, 0, st>>>(p, s, state, theta, xh, wh);
+            FGQ_LAUNCH_CHECK();
+        }
+    }
+    int64_t rb = (p.nact + 511) / 512;
+    if (rb > HERMITE_SUM_BLOCKS) rb = HERMITE_SUM_BLOCKS;
+    hermite_normsum_kernel<<<(unsigned)rb, 512, 0, st>>>(p, state, xh, wh);
+    FGQ_LAUNCH_CHECK();
+    if (hi > lo) {
+        hermite_fold_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, st>>>(p, normalize, state, xh, wh,
+                                                                             lo, hi, x_dev, w_dev);
+        FGQ_LAUNCH_CHECK();
+    }
+    return FGQ_OK;
+}
+
 extern "C" int fgq_gausshermite_device(int64_t n, int normalize, int64_t lo, int64_t hi, double* x_dev,
                                        double* w_dev, void* workspace_dev, void* stream) {
     clear_status();
@@ -421,37 +531,96 @@ extern "C" int fgq_gausshermite_device(int64_t n, int normalize, int64_t lo, int
         set_error("null pointer");
         return FGQ_EINVAL;
     }
-    cudaStream_t st = as_stream(stream);
-    HermiteParams p = hermite_params(n);
-    HermiteState* state = (HermiteState*)workspace_dev;
-    double* theta = (double*)((char*)workspace_dev + 1024);
-    double* xh = theta + p.nh;
-    double* wh = xh + p.nh;
-    const unsigned b128 = (unsigned)((p.nh + HERM_THREADS - 1) / HERM_THREADS);
-    hermite_init_kernel<<<b128, HERM_THREADS, 0, st>>>(p, state, theta);  // also resets the state
-    FGQ_LAUNCH_CHECK();
-    if (n <= 20) {  // :41-45; n = 1 (x = 0, w = sqrt(pi), :41-42) is the 1 x 1 case of the same kernel
-        hermite_gw_kernel<<<1, 32, 0, st>>>(p, xh, wh);
-        FGQ_LAUNCH_CHECK();
-    } else if (n <= 200) {
-        hermite_rec_kernel<<<1, 128, 0, st>>>(p, xh, wh);  // :46-48
-        FGQ_LAUNCH_CHECK();
-    } else {
-        const unsigned bsweep = (unsigned)(b128 < HERM_GRID ? b128 : HERM_GRID);
-        for (int s = 0; s < 20; ++s) {
-            hermite_sweep_kernel<<<bsweep, HERM_THREADS, 0, st>>>(p, s, state, theta, xh, wh);
-            FGQ_LAUNCH_CHECK();
-        }
+    return hermite_device_impl(n, normalize, lo, hi, hermite_params(n).nh, x_dev, w_dev, workspace_dev,
+                               as_stream(stream));
+}
+
+// ---- truncated rule ----
+// exp(-x^2) is exactly 0 in double precision for x^2 > 745.14, and the unweighted weights it multiplies
+// (gausshermite.jl:30) are below 1: every node beyond |x| = 27.5 carries the weight 0.0.  The positive
+// zeros of H_n are spaced at least pi / sqrt(2n+1) apart and the first one lies at least half that from
+// the origin (Sturm comparison of y'' + (2n + 1 - x^2) y = 0 with the constant-coefficient equation), so
+// the half-range nodes with index >= 27.5 sqrt(2n+1) / pi + 1 all lie beyond the cut.
+static int64_t hermite_active_half(int64_t n) {
+    const int64_t nh = hermite_params(n).nh;
+    if (n <= 200) return nh;  // the small-n branches always compute the whole rule
+    const double bound = 27.5 * sqrt(2.0 * (double)n + 1.0) / 3.141592653589793 + 2.0;
+    return bound < (double)nh ? (int64_t)bound : nh;
+}
+
+// output range [first, first + count) of the full rule covered by the computed half-range nodes
+static void hermite_reduced_range(int64_t n, int64_t* first, int64_t* count) {
+    const HermiteParams p = hermite_params(n);
+    const int64_t nact = hermite_active_half(n);
+    *first = p.nh - nact;
+    *count = n - 2 * (p.nh - nact);
+}
+
+extern "C" int64_t fgq_gausshermite_reduced_bound(int64_t n) {
+    if (n <= 0) return 0;
+    int64_t first, count;
+    hermite_reduced_range(n, &first, &count);
+    return count;
+}
+
+extern "C" int fgq_gausshermite_reduced_device(int64_t n, int normalize, double* x_dev, double* w_dev,
+                                               void* workspace_dev, void* stream, int64_t* first,
+                                               int64_t* count) {
+    clear_status();
+    if (n < 0) {
+        set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);
+        return FGQ_EDOMAIN;
     }
-    int64_t rb = (p.nh + 511) / 512;
-    if (rb > HERMITE_SUM_BLOCKS) rb = HERMITE_SUM_BLOCKS;
-    hermite_normsum_kernel<<<(unsigned)rb, 512, 0, st>>>(p, state, xh, wh);
-    FGQ_LAUNCH_CHECK();
-    if (hi > lo) {
-        hermite_fold_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, st>>>(p, normalize, state, xh, wh,
-                                                                             lo, hi, x_dev, w_dev);
-        FGQ_LAUNCH_CHECK();
+    int64_t f = 0, c = 0;
+    if (n > 0) hermite_reduced_range(n, &f, &c);
+    if (first) *first = f;
+    if (count) *count = c;
+    if (n == 0) return FGQ_OK;
+    if (!workspace_dev || !x_dev || !w_dev) {
+        set_error("null pointer");
+        return FGQ_EINVAL;
     }
+    return hermite_device_impl(n, normalize, f, f + c, hermite_active_half(n), x_dev, w_dev, workspace_dev,
+                               as_stream(stream));
+}
+
+extern "C" int fgq_gausshermite_reduced_host(int64_t n, int normalize, double* x, double* w, int64_t* first,
+                                             int64_t* n_out) {
+    clear_status();
+    if (n < 0) {
+        set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);
+        return FGQ_EDOMAIN;
+    }
+    if (first) *first = 0;
+    if (n_out) *n_out = 0;
+    if (n == 0) return FGQ_OK;
+    if (!x || !w) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    HostPathLock lock;
+    int64_t f, c;
+    hermite_reduced_range(n, &f, &c);
+    void *ws, *out;
+    FGQ_TRY(scratch_device((size_t)fgq_gausshermite_workspace_bytes(n), 6, &ws));
+    FGQ_TRY(scratch_device((size_t)c * 16, 0, &out));
+    cudaStream_t st;
+    FGQ_TRY(scratch_stream(0, &st));
+    double* xd = (double*)out;
+    double* wd = xd + c;
+    FGQ_TRY(hermite_device_impl(n, normalize, f, f + c, hermite_active_half(n), xd, wd, ws, st));
+    FGQ_TRY(drain_to_host(x, w, xd, wd, c, st));
+    // keep the centre block of weights >= 10 floatmin (the threshold of the reference's reduced Laguerre rule,
+    // gausslaguerre.jl:163-169); the rule is symmetric, so the same number of entries leaves at both ends
+    int64_t drop = 0;
+    while (2 * drop < c && fabs(w[drop]) < 10 * 2.2250738585072014e-308) ++drop;
+    if (2 * drop >= c) drop = 0;  // cannot happen for a Hermite rule (the centre weights are O(1/sqrt(n)))
+    if (drop > 0) {
+        memmove(x, x + drop, (size_t)(c - 2 * drop) * 8);
+        memmove(w, w + drop, (size_t)(c - 2 * drop) * 8);
+    }
+    if (first) *first = f + drop;
+    if (n_out) *n_out = c - 2 * drop;
     return FGQ_OK;
 }
 
@@ -486,5 +655,69 @@ extern "C" int fgq_gausshermite_sweeps(const void* workspace_dev, int* sweeps) {
     HermiteState h;
     FGQ_CUDA_TRY(cudaMemcpy(&h, workspace_dev, sizeof(h), cudaMemcpyDeviceToHost));
     *sweeps = h.sweeps;
+    return FGQ_OK;
+}
+
+// ---- batched small rules ----
+static const HermiteParams* hermite_param_table() {
+    static HermiteParams table[HERMITE_BATCH_MAX_N + 1];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (int n = 0; n <= HERMITE_BATCH_MAX_N; ++n) table[n] = hermite_params(n);
+    });
+    return table;
+}
+
+constexpr size_t HERMITE_TABLE_BYTES = ((HERMITE_BATCH_MAX_N + 1) * sizeof(HermiteParams) + 255) / 256 * 256;
+
+extern "C" int64_t fgq_gausshermite_batch_workspace_bytes(int64_t nrules) {
+    if (nrules < 0) return 0;
+    return (int64_t)HERMITE_TABLE_BYTES + nrules * (int64_t)sizeof(SmallRule);
+}
+
+extern "C" int fgq_gausshermite_batch_device(int64_t nrules, const int32_t* n_i, const int64_t* offsets,
+                                             int normalize, double* x_dev, double* w_dev, void* workspace_dev,
+                                             void* stream) {
+    clear_status();
+    std::vector<SmallRule> rules;
+    int64_t total = 0;
+    FGQ_TRY(small_batch_rules(nrules, n_i, offsets, HERMITE_BATCH_MAX_N, "gausshermite", &rules, &total));
+    if (nrules == 0 || total == 0) return FGQ_OK;
+    if (!x_dev || !w_dev || !workspace_dev) {
+        set_error("null pointer");
+        return FGQ_EINVAL;
+    }
+    cudaStream_t st = as_stream(stream);
+    char* ws = (char*)workspace_dev;
+    FGQ_CUDA_TRY(cudaMemcpyAsync(ws, hermite_param_table(), (HERMITE_BATCH_MAX_N + 1) * sizeof(HermiteParams),
+                                 cudaMemcpyHostToDevice, st));
+    FGQ_CUDA_TRY(cudaMemcpyAsync(ws + HERMITE_TABLE_BYTES, rules.data(), rules.size() * sizeof(SmallRule),
+                                 cudaMemcpyHostToDevice, st));
+    hermite_small_batch_kernel<<<(unsigned)nrules, 128, 0, st>>>((const SmallRule*)(ws + HERMITE_TABLE_BYTES),
+                                                                 (const HermiteParams*)ws, normalize, x_dev, w_dev);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+extern "C" int fgq_gausshermite_batch_host(int64_t nrules, const int32_t* n_i, const int64_t* offsets, int normalize,
+                                           double* x, double* w) {
+    clear_status();
+    int64_t total = 0;
+    FGQ_TRY(small_batch_rules(nrules, n_i, offsets, HERMITE_BATCH_MAX_N, "gausshermite", nullptr, &total));
+    if (total == 0) return FGQ_OK;
+    if (!x || !w) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    HostPathLock lock;
+    void *ws, *out;
+    FGQ_TRY(scratch_device((size_t)fgq_gausshermite_batch_workspace_bytes(nrules), 6, &ws));
+    FGQ_TRY(scratch_device((size_t)total * 16, 0, &out));
+    cudaStream_t st;
+    FGQ_TRY(scratch_stream(0, &st));
+    double* xd = (double*)out;
+    double* wd = xd + total;
+    FGQ_TRY(fgq_gausshermite_batch_device(nrules, n_i, offsets, normalize, xd, wd, ws, (void*)st));
+    FGQ_TRY(drain_to_host(x, w, xd, wd, total, st));
     return FGQ_OK;
 }

@@ -302,7 +302,7 @@ __device__ __forceinline__ void jacobi_inner_rec(int n, double xj, double a, dou
     PP = PPj;
 }
 
-__global__ void __launch_bounds__(128) jacobi_rec_kernel(const JacobiRecParams p, double* x, double* w) {
+__device__ __forceinline__ void jacobi_rec_block(const JacobiRecParams& p, double* x, double* w) {
     const double PI = 3.141592653589793;
     const int tid = threadIdx.x;
     const int h = tid >> 6;          // 0: HalfRec(n, alpha, beta, 1); 1: HalfRec(n, beta, alpha, 0)
@@ -377,6 +377,42 @@ __global__ void __launch_bounds__(128) jacobi_rec_kernel(const JacobiRecParams p
         x[tid - p.lo] = xs[tid];
         w[tid - p.lo] = wsum[tid] * s_scale;
     }
+}
+
+__global__ void __launch_bounds__(128) jacobi_rec_kernel(const JacobiRecParams p, double* x, double* w) {
+    jacobi_rec_block(p, x, w);
+}
+
+// Batched small rules: one block per rule, the same device function as the single-rule
+// launch, so a batch is bit-identical to the concatenation of single calls.  kind 1: the one-node rule
+// (gaussjacobi.jl:42-43; node in `alpha`, weight in `c`); kind 2: jacobi_rec (:61-155); kind 0: nothing
+// to do here (empty, or served by the Legendre / Chebyshev / Golub-Welsch routes from the host loop).
+struct JacobiBatchRule {
+    int32_t n;
+    int32_t kind;
+    int64_t off;
+    double alpha, beta, c;
+};
+
+__global__ void __launch_bounds__(128)
+jacobi_small_batch_kernel(const JacobiBatchRule* __restrict__ rules, double* __restrict__ x, double* __restrict__ w) {
+    const JacobiBatchRule r = rules[blockIdx.x];
+    if (r.kind == 1) {
+        if (threadIdx.x == 0) {
+            x[r.off] = r.alpha;
+            w[r.off] = r.c;
+        }
+        return;
+    }
+    if (r.kind != 2) return;
+    JacobiRecParams p;
+    p.n = r.n;
+    p.alpha = r.alpha;
+    p.beta = r.beta;
+    p.c = r.c;
+    p.lo = 0;
+    p.hi = r.n;
+    jacobi_rec_block(p, x + r.off, w + r.off);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -528,6 +564,17 @@ static int jacobi_gw_device(int64_t n, double a, double b, int radau, int64_t lo
     return FGQ_OK;
 }
 
+// :42-43: x = (b-a)/(a+b+2), w = 2^(a+b+1) beta(a+1, b+1)
+static void jacobi_one_node(double a, double b, double* x, double* w) {
+    *x = (b - a) / (a + b + 2);
+    *w = pow(2.0, a + b + 1) * (tgamma(a + 1) * tgamma(b + 1) / tgamma(a + b + 2));
+}
+
+// the weight normalisation of jacobi_rec (:89)
+static double jacobi_rec_const(double a, double b) {
+    return pow(2.0, a + b + 1) * tgamma(2 + a) * tgamma(2 + b) / (tgamma(2 + a + b) * (a + 1) * (b + 1));
+}
+
 static int jacobi_rec_device(int64_t n, double a, double b, int64_t lo, int64_t hi, double* x_dev, double* w_dev,
                              cudaStream_t st) {
     JacobiRecParams p;
@@ -543,14 +590,13 @@ static int jacobi_rec_device(int64_t n, double a, double b, int64_t lo, int64_t 
         q.lo = lo;
         q.hi = hi;
         for (int i = 0; i < 2 * JAC_NBDY; ++i) q.x[i] = q.w[i] = 0.0;
-        q.x[0] = (b - a) / (a + b + 2);
-        q.w[0] = pow(2.0, a + b + 1) * (tgamma(a + 1) * tgamma(b + 1) / tgamma(a + b + 2));
+        jacobi_one_node(a, b, &q.x[0], &q.w[0]);
         if (hi > 1) q.hi = 1;
         jacobi_patch_kernel<<<1, 32, 0, st>>>(q, x_dev, w_dev);
         FGQ_LAUNCH_CHECK();
         return FGQ_OK;
     }
-    p.c = pow(2.0, a + b + 1) * tgamma(2 + a) * tgamma(2 + b) / (tgamma(2 + a + b) * (a + 1) * (b + 1));
+    p.c = jacobi_rec_const(a, b);
     jacobi_rec_kernel<<<1, 128, 0, st>>>(p, x_dev, w_dev);
     FGQ_LAUNCH_CHECK();
     return FGQ_OK;
@@ -683,6 +729,103 @@ extern "C" int fgq_gaussjacobi_device(int64_t n, double a, double b, int64_t lo,
         return FGQ_EINVAL;
     }
     return jacobi_asy_device(n, a, b, lo, hi, x_dev, w_dev, workspace_dev, as_stream(stream));
+}
+
+// ---- batched small rules: n <= 100 ----
+constexpr int JACOBI_BATCH_MAX_N = 100;
+constexpr size_t JACOBI_BATCH_GW_BYTES = 8192;  // workspace of one Golub-Welsch rule (4096 + 16 n)
+
+extern "C" int64_t fgq_gaussjacobi_batch_workspace_bytes(int64_t nrules) {
+    if (nrules < 0) return 0;
+    return (int64_t)JACOBI_BATCH_GW_BYTES + nrules * (int64_t)sizeof(JacobiBatchRule);
+}
+
+// Classifies every rule the way fgq_gaussjacobi_device dispatches it.  `others` receives the rules served
+// by single-rule launches (the Legendre / Chebyshev routes of (0,0), (+-1/2,+-1/2) and the Golub-Welsch
+// region max(a,b) >= 5).
+static int jacobi_batch_plan(int64_t nrules, const int32_t* n_i, const double* alpha_i, const double* beta_i,
+                             const int64_t* offsets, std::vector<JacobiBatchRule>* rules,
+                             std::vector<int64_t>* others, int64_t* total) {
+    std::vector<SmallRule> base;
+    FGQ_TRY(small_batch_rules(nrules, n_i, offsets, JACOBI_BATCH_MAX_N, "gaussjacobi", rules ? &base : nullptr, total));
+    if (nrules > 0 && (!alpha_i || !beta_i)) {
+        set_error("invalid batch description");
+        return FGQ_EINVAL;
+    }
+    if (rules) rules->resize((size_t)nrules);
+    for (int64_t i = 0; i < nrules; ++i) {
+        const int n = n_i[i];
+        const double a = alpha_i[i], b = beta_i[i];
+        JacobiBatchRule r{n, 0, offsets[i], a, b, 0.0};
+        const bool special = (a == 0.0 && b == 0.0) || (fabs(a) == 0.5 && fabs(b) == 0.5);
+        if (special) {
+            if (n > 0 && others) others->push_back(i);
+        } else if (n > 0) {
+            const int rc = jacobi_check_args(n, a, b);
+            if (rc != FGQ_OK) return rc;
+            if (n == 1) {
+                r.kind = 1;
+                jacobi_one_node(a, b, &r.alpha, &r.c);
+            } else if ((a > b ? a : b) >= 5.0) {
+                if (others) others->push_back(i);
+            } else {
+                r.kind = 2;
+                r.c = jacobi_rec_const(a, b);
+            }
+        }
+        if (rules) (*rules)[(size_t)i] = r;
+    }
+    return FGQ_OK;
+}
+
+extern "C" int fgq_gaussjacobi_batch_device(int64_t nrules, const int32_t* n_i, const double* alpha_i,
+                                            const double* beta_i, const int64_t* offsets, double* x_dev,
+                                            double* w_dev, void* workspace_dev, void* stream) {
+    clear_status();
+    std::vector<JacobiBatchRule> rules;
+    std::vector<int64_t> others;
+    int64_t total = 0;
+    FGQ_TRY(jacobi_batch_plan(nrules, n_i, alpha_i, beta_i, offsets, &rules, &others, &total));
+    if (nrules == 0 || total == 0) return FGQ_OK;
+    if (!x_dev || !w_dev || !workspace_dev) {
+        set_error("null pointer");
+        return FGQ_EINVAL;
+    }
+    cudaStream_t st = as_stream(stream);
+    char* ws = (char*)workspace_dev;
+    FGQ_CUDA_TRY(cudaMemcpyAsync(ws + JACOBI_BATCH_GW_BYTES, rules.data(), rules.size() * sizeof(JacobiBatchRule),
+                                 cudaMemcpyHostToDevice, st));
+    jacobi_small_batch_kernel<<<(unsigned)nrules, 128, 0, st>>>((const JacobiBatchRule*)(ws + JACOBI_BATCH_GW_BYTES),
+                                                                x_dev, w_dev);
+    FGQ_LAUNCH_CHECK();
+    for (int64_t i : others) {
+        const JacobiBatchRule& r = rules[(size_t)i];
+        FGQ_TRY(fgq_gaussjacobi_device(r.n, r.alpha, r.beta, 0, r.n, x_dev + r.off, w_dev + r.off, ws, stream));
+    }
+    return FGQ_OK;
+}
+
+extern "C" int fgq_gaussjacobi_batch_host(int64_t nrules, const int32_t* n_i, const double* alpha_i,
+                                          const double* beta_i, const int64_t* offsets, double* x, double* w) {
+    clear_status();
+    int64_t total = 0;
+    FGQ_TRY(jacobi_batch_plan(nrules, n_i, alpha_i, beta_i, offsets, nullptr, nullptr, &total));
+    if (total == 0) return FGQ_OK;
+    if (!x || !w) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    HostPathLock lock;
+    void *ws, *out;
+    FGQ_TRY(scratch_device((size_t)fgq_gaussjacobi_batch_workspace_bytes(nrules), 6, &ws));
+    FGQ_TRY(scratch_device((size_t)total * 16, 0, &out));
+    cudaStream_t st;
+    FGQ_TRY(scratch_stream(0, &st));
+    double* xd = (double*)out;
+    double* wd = xd + total;
+    FGQ_TRY(fgq_gaussjacobi_batch_device(nrules, n_i, alpha_i, beta_i, offsets, xd, wd, ws, (void*)st));
+    FGQ_TRY(drain_to_host(x, w, xd, wd, total, st));
+    return FGQ_OK;
 }
 
 // mode 1 = gaussradau(n), mode 2 = gausslobatto(n); the inner Jacobi rule has n - mode nodes and is

@@ -16,6 +16,9 @@
 // by Newton on the O(n) recurrence, one thread per flagged node (about 35 nodes at n = 1e6).
 #include <math.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "airy.cuh"
 #include "bessel.cuh"
 #include "common.cuh"
@@ -372,7 +375,8 @@ __device__ void eval_laguerre_rec(int64_t n, double alpha, double pn0, double x,
 }
 
 // gl_rec_newton (:547-579)
-__device__ void gl_rec_newton_dev(const LaguerreParams& p, double x0, bool computeweight, double& xk_out,
+template <class P>
+__device__ void gl_rec_newton_dev(const P& p, double x0, bool computeweight, double& xk_out,
                                   double& wk_out, unsigned int* warn) {
     const double eps = 2.220446049250313e-16;
     double step = x0, xk = x0, xk_prev = x0, pn_prev = 1.7976931348623157e308, pn_deriv = 0.0;
@@ -431,8 +435,8 @@ struct LaguerreSmall {
     double jak_pre[7];  // approx_besselroots(alpha, min(n, 7))
 };
 
-__global__ void laguerre_small_kernel(const LaguerreParams p, const LaguerreSmall q, LaguerreState* st, double* x, double* w) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+template <class P>
+__device__ void laguerre_small_rule(const P& p, const LaguerreSmall& q, unsigned int* warn_word, double* x, double* w) {
     const int n = (int)p.n;
     const double al = p.alpha;
     if (n == 1) {
@@ -476,7 +480,35 @@ __global__ void laguerre_small_kernel(const LaguerreParams p, const LaguerreSmal
         x[k - 1] = xk;
         w[k - 1] = wk;
     }
-    if (warn) atomicOr(&st->warn, warn);
+    if (warn) atomicOr(warn_word, warn);
+}
+
+__global__ void laguerre_small_kernel(const LaguerreParams p, const LaguerreSmall q, LaguerreState* st, double* x, double* w) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    laguerre_small_rule(p, q, &st->warn, x, w);
+}
+
+// Batched small rules (n < 128): the small-rule branches are sequential per rule (each
+// Newton start is extrapolated from the previous nodes), so the batch runs one THREAD per rule through
+// the same device function as the single-rule launch: bit-identical to the concatenation of single
+// calls.  Only the fields the small-rule branches read travel with a rule.
+struct LaguerreBatchRule {
+    int64_t n;
+    int64_t off;
+    double alpha, pn0, wnorm, xmax;
+    LaguerreSmall q;
+};
+
+constexpr int LAG_BATCH_THREADS = 32;
+
+__global__ void __launch_bounds__(LAG_BATCH_THREADS)
+laguerre_small_batch_kernel(int64_t nrules, const LaguerreBatchRule* __restrict__ rules, unsigned int* warn_word,
+                            double* __restrict__ x, double* __restrict__ w) {
+    const int64_t i = (int64_t)blockIdx.x * LAG_BATCH_THREADS + threadIdx.x;
+    if (i >= nrules) return;
+    const LaguerreBatchRule r = rules[i];
+    if (r.n <= 0) return;
+    laguerre_small_rule(r, r.q, warn_word, x + r.off, w + r.off);
 }
 
 // reduced rule (:163-169 ...): the rule ends before the first weight below 10 floatmin
@@ -652,6 +684,105 @@ extern "C" int fgq_gausslaguerre_host(int64_t n, double alpha, int reduced, doub
     const int64_t cnt = reduced ? (int64_t)h.n_out : n;
     FGQ_TRY(drain_to_host(x, w, xd, wd, cnt, st));
     if (n_out) *n_out = cnt;
+    add_warning(warn0 | (int)h.warn);
+    return FGQ_OK;
+}
+
+// ---- batched small rules: n < 128 ----
+constexpr int LAGUERRE_BATCH_MAX_N = 127;
+
+extern "C" int64_t fgq_gausslaguerre_batch_workspace_bytes(int64_t nrules) {
+    if (nrules < 0) return 0;
+    return 256 + nrules * (int64_t)sizeof(LaguerreBatchRule);
+}
+
+static int laguerre_batch_plan(int64_t nrules, const int32_t* n_i, const double* alpha_i, const int64_t* offsets,
+                               std::vector<LaguerreBatchRule>* rules, int64_t* total, int* warn) {
+    FGQ_TRY(small_batch_rules(nrules, n_i, offsets, LAGUERRE_BATCH_MAX_N, "gausslaguerre", nullptr, total));
+    if (nrules > 0 && !alpha_i) {
+        set_error("invalid batch description");
+        return FGQ_EINVAL;
+    }
+    if (rules) rules->resize((size_t)nrules);
+    for (int64_t i = 0; i < nrules; ++i) {
+        const int64_t n = n_i[i];
+        const double alpha = alpha_i[i];
+        FGQ_TRY(laguerre_check(n, alpha));  // alpha <= -1 is a DomainError for every n, as in the reference (:61)
+        if (n > 0 && alpha * alpha / (double)n > 1) *warn |= FGQ_WARN_LARGE_ALPHA;
+        if (!rules) continue;
+        LaguerreBatchRule r;
+        r.n = n;
+        r.off = offsets[i];
+        r.alpha = alpha;
+        // the same expressions as laguerre_params / fgq_gausslaguerre_device
+        r.pn0 = 1 / sqrt(tgamma(alpha + 1));
+        r.wnorm = pow((double)n * (double)n + alpha * (double)n, -0.5);
+        r.xmax = 4 * (double)n + 2 * alpha + 2;
+        r.q.g1 = tgamma(1 + alpha);
+        r.q.g2 = tgamma(alpha + 2);
+        for (int k = 0; k < 7; ++k) r.q.jak_pre[k] = 0.0;
+        if (n >= 15) approx_besselroots(alpha, 7, r.q.jak_pre);
+        (*rules)[(size_t)i] = r;
+    }
+    // one thread per rule: the cost of a rule grows like n^2, so rules of (nearly) equal n share a warp,
+    // longest first (the output position travels with the rule, the processing order is free)
+    if (rules)
+        std::stable_sort(rules->begin(), rules->end(),
+                         [](const LaguerreBatchRule& a, const LaguerreBatchRule& b) { return a.n > b.n; });
+    return FGQ_OK;
+}
+
+extern "C" int fgq_gausslaguerre_batch_device(int64_t nrules, const int32_t* n_i, const double* alpha_i,
+                                              const int64_t* offsets, double* x_dev, double* w_dev,
+                                              void* workspace_dev, void* stream) {
+    clear_status();
+    std::vector<LaguerreBatchRule> rules;
+    int64_t total = 0;
+    int warn = 0;
+    FGQ_TRY(laguerre_batch_plan(nrules, n_i, alpha_i, offsets, &rules, &total, &warn));
+    if (warn) add_warning(warn);
+    if (nrules == 0 || total == 0) return FGQ_OK;
+    if (!x_dev || !w_dev || !workspace_dev) {
+        set_error("null pointer");
+        return FGQ_EINVAL;
+    }
+    cudaStream_t st = as_stream(stream);
+    char* ws = (char*)workspace_dev;
+    laguerre_state_init_kernel<<<1, 1, 0, st>>>((LaguerreState*)ws, 0);
+    FGQ_LAUNCH_CHECK();
+    FGQ_CUDA_TRY(cudaMemcpyAsync(ws + 256, rules.data(), rules.size() * sizeof(LaguerreBatchRule),
+                                 cudaMemcpyHostToDevice, st));
+    const int64_t blocks = (nrules + LAG_BATCH_THREADS - 1) / LAG_BATCH_THREADS;
+    laguerre_small_batch_kernel<<<(unsigned)blocks, LAG_BATCH_THREADS, 0, st>>>(
+        nrules, (const LaguerreBatchRule*)(ws + 256), &((LaguerreState*)ws)->warn, x_dev, w_dev);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+extern "C" int fgq_gausslaguerre_batch_host(int64_t nrules, const int32_t* n_i, const double* alpha_i,
+                                            const int64_t* offsets, double* x, double* w) {
+    clear_status();
+    int64_t total = 0;
+    int warn = 0;
+    FGQ_TRY(laguerre_batch_plan(nrules, n_i, alpha_i, offsets, nullptr, &total, &warn));
+    if (total == 0) return FGQ_OK;
+    if (!x || !w) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    HostPathLock lock;
+    void *ws, *out;
+    FGQ_TRY(scratch_device((size_t)fgq_gausslaguerre_batch_workspace_bytes(nrules), 6, &ws));
+    FGQ_TRY(scratch_device((size_t)total * 16, 0, &out));
+    cudaStream_t st;
+    FGQ_TRY(scratch_stream(0, &st));
+    double* xd = (double*)out;
+    double* wd = xd + total;
+    FGQ_TRY(fgq_gausslaguerre_batch_device(nrules, n_i, alpha_i, offsets, xd, wd, ws, (void*)st));
+    const int warn0 = fgq_warnings();
+    LaguerreState h;
+    FGQ_CUDA_TRY(cudaMemcpyAsync(&h, ws, sizeof(h), cudaMemcpyDeviceToHost, st));
+    FGQ_TRY(drain_to_host(x, w, xd, wd, total, st));
     add_warning(warn0 | (int)h.warn);
     return FGQ_OK;
 }

@@ -174,6 +174,61 @@ int fgq_gausslaguerre_device(int64_t n, double alpha, double* x_dev, double* w_d
 int fgq_gausslaguerre_stats(const void* workspace_dev, int64_t* k_b, int64_t* k_a, int64_t* n_flagged,
                             int64_t* n_reduced);
 
+/* ---- truncated Gauss-Hermite rule ------------------------------------------ */
+
+/* The analogue of gausslaguerre(n; reduced = true) (gausslaguerre.jl:163-169) for Gauss-Hermite: at
+ * n = 1e6 only 2.4 % of the weights gausshermite returns (gausshermite.jl:28-33) are non-zero, because
+ * exp(-x^2) (:30) is exactly 0.0 beyond |x| = 27.3.  These calls compute only the centre block of the rule:
+ * the half-range nodes inside |x| <= 27.5 (bounded a priori through the Sturm spacing pi / sqrt(2n+1) of
+ * the zeros), with the same kernels, Newton stopping rule (:79) and normalisation sum (:62) taken over
+ * that block.  The entries agree with the full rule to the Newton tolerance (not bit for bit: the global
+ * stopping rule sees fewer nodes); every omitted weight is 0.0 in the full rule.  n <= 200: the whole rule.
+ *   *first  receives the 0-based index, within the full n-point rule, of the first entry written,
+ *   *count / *n_out the number of entries.  fgq_gausshermite_reduced_bound(n) bounds it (size of x, w).
+ * The host variant also drops the entries below 10 * floatmin at both ends (the reference's threshold for
+ * the reduced Laguerre rule).  workspace_dev: fgq_gausshermite_workspace_bytes(n) bytes. */
+int64_t fgq_gausshermite_reduced_bound(int64_t n);
+int fgq_gausshermite_reduced_device(int64_t n, int normalize, double* x_dev, double* w_dev, void* workspace_dev,
+                                    void* stream, int64_t* first, int64_t* count);
+int fgq_gausshermite_reduced_host(int64_t n, int normalize, double* x, double* w, int64_t* first, int64_t* n_out);
+
+/* ---- batched small rules of the other families ------------------------- */
+
+/* Batches of small rules in the CSR layout of fgq_gausslegendre_batch_*: rule i occupies
+ * [offsets[i], offsets[i] + n_i[i]) of x and w.  Each rule is computed by the small-n branch the
+ * reference dispatches it to, with the same device code as the single-rule call, so a batch is
+ * bit-identical to the concatenation of single calls:
+ *   gaussjacobi   0 <= n_i <= 100   jacobi_rec (gaussjacobi.jl:61-155), one 128-thread block per rule; n = 1
+ *                                   closed form (:42-43); (0,0) / (+-1/2,+-1/2) / max(a,b) >= 5 rules go
+ *                                   through their Legendre / Chebyshev / Golub-Welsch routes (:28-39, :50-51)
+ *   gausshermite  0 <= n_i <= 200   hermite_gw n <= 20 (gausshermite.jl:325-341), hermite_rec (:91-137); one block
+ *                                   per rule incl. normalisation sum and fold (:55-62)
+ *   gausslaguerre 0 <= n_i <= 127   closed forms (gausslaguerre.jl:70-78), gausslaguerre_GW n < 15 (:535-542),
+ *                                   gausslaguerre_rec (:582-641); one thread per rule (the branch is sequential)
+ * n_i, alpha_i, beta_i and offsets are HOST arrays in both variants: the per-rule constants (gamma
+ * functions, Bessel-zero guesses) are planned on the host exactly as in the single-rule calls and uploaded
+ * into workspace_dev (>= fgq_*_batch_workspace_bytes(nrules)) ahead of the launch.  The device variants
+ * fill device buffers asynchronously on `stream` and never synchronise.
+ *   n_i < 0 or an inadmissible parameter -> FGQ_EDOMAIN (as the single-rule call);
+ *   n_i above the limit                  -> FGQ_EINVAL  (use the single-rule call). */
+int64_t fgq_gaussjacobi_batch_workspace_bytes(int64_t nrules);
+int fgq_gaussjacobi_batch_device(int64_t nrules, const int32_t* n_i, const double* alpha_i, const double* beta_i,
+                                 const int64_t* offsets, double* x_dev, double* w_dev, void* workspace_dev,
+                                 void* stream);
+int fgq_gaussjacobi_batch_host(int64_t nrules, const int32_t* n_i, const double* alpha_i, const double* beta_i,
+                               const int64_t* offsets, double* x, double* w);
+int64_t fgq_gausshermite_batch_workspace_bytes(int64_t nrules);
+int fgq_gausshermite_batch_device(int64_t nrules, const int32_t* n_i, const int64_t* offsets, int normalize,
+                                  double* x_dev, double* w_dev, void* workspace_dev, void* stream);
+int fgq_gausshermite_batch_host(int64_t nrules, const int32_t* n_i, const int64_t* offsets, int normalize,
+                                double* x, double* w);
+int64_t fgq_gausslaguerre_batch_workspace_bytes(int64_t nrules);
+int fgq_gausslaguerre_batch_device(int64_t nrules, const int32_t* n_i, const double* alpha_i,
+                                   const int64_t* offsets, double* x_dev, double* w_dev, void* workspace_dev,
+                                   void* stream);
+int fgq_gausslaguerre_batch_host(int64_t nrules, const int32_t* n_i, const double* alpha_i, const int64_t* offsets,
+                                 double* x, double* w);
+
 /* ---- consumers / checks ------------------------------------------------------------------ */
 
 /* sums_dev[0] += sum w_i, sums_dev[1] += sum w_i x_i^2 over count entries (device buffers;

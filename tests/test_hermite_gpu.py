@@ -120,3 +120,51 @@ def test_normalize_and_slices(fgq):
         fgq._lib.check(L.fgq_gausshermite_device(n, 0, lo, hi, xs.data_ptr(), wsl.data_ptr(), ws.data_ptr(), 0))
         torch.cuda.synchronize()
         assert np.array_equal(xs.cpu().numpy(), x[lo:hi]) and np.array_equal(wsl.cpu().numpy(), w[lo:hi])
+
+
+@pytest.mark.parametrize("n", [1, 2, 20, 21, 200, 201, 251, 372, 373, 5000, 100_001, 1_000_000])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_reduced_rule_is_the_centre_block_of_the_full_rule(fgq, n, normalize):
+    """Truncated rule: the returned block matches the full rule to the Newton tolerance,
+    every omitted weight of the full rule is below 10 floatmin, and the moments still hold."""
+    xf, wf = fgq.gausshermite(n, normalize=normalize)
+    first, x, w = fgq.gausshermite_reduced(n, normalize=normalize)
+    m = len(x)
+    assert first >= 0 and first + m <= n and first == n - (first + m)  # symmetric block
+    assert np.all(wf[:first] < 10 * np.finfo(float).tiny) and np.all(wf[first + m:] < 10 * np.finfo(float).tiny)
+    assert np.all(w >= 10 * np.finfo(float).tiny)
+    if first > 0:   # maximal: the next weight outside is below the threshold in the full rule too
+        assert wf[first - 1] < 10 * np.finfo(float).tiny
+    xs, ws = xf[first:first + m], wf[first:first + m]
+    scale = np.sqrt(2.0 * n + 1) * (np.sqrt(2.0) if normalize else 1.0)
+    assert np.abs(x - xs).max() <= 8 * np.spacing(scale)
+    big = ws > 1e-280
+    # One ulp of theta moves a node by ~ulp(scale) (the two runs may stop Newton one sweep apart); through
+    # exp(-x^2) and the residual term x*val of the weight formula (gausshermite.jl:83-86) that shows up
+    # ~4|x| times larger, relatively, in the weight
+    dx = np.maximum(np.abs(x - xs), 2 * np.spacing(scale))
+    assert np.all(np.abs(w[big] / ws[big] - 1) <= 5e-12 + 8 * np.abs(xs[big]) * dx[big])
+    half = m // 2   # (the centre node of an odd rule is whatever Newton left of cos(pi/2): not compared)
+    assert np.array_equal(x[:half], -x[::-1][:half]) and np.array_equal(w, w[::-1])
+    if n <= 200 or fgq.lib().fgq_gausshermite_reduced_bound(n) == n:
+        assert np.array_equal(x, xs) and np.array_equal(w, ws)  # nothing truncated: the very same launches
+    mu0 = 1.0 if normalize else np.sqrt(np.pi)
+    mu2 = 1.0 if normalize else np.sqrt(np.pi) / 2
+    assert abs(w.sum() - mu0) < 2e-13 * max(1.0, mu0)
+    if n >= 2:
+        assert abs(np.dot(w, x * x) - mu2) < 3e-12
+
+
+def test_reduced_rule_size(fgq):
+    """2.4 % of the nodes at n = 1e6."""
+    first, x, w = fgq.gausshermite_reduced(1_000_000)
+    assert 0.02 * 1e6 < len(x) < 0.03 * 1e6
+    assert fgq.lib().fgq_gausshermite_reduced_bound(1_000_000) < 0.03 * 1e6
+    f2, xd, wd, _ = fgq.gausshermite_reduced_device(1_000_000)
+    xd, wd = xd.cpu().numpy(), wd.cpu().numpy()
+    off = first - f2
+    assert off >= 0 and np.array_equal(xd[off:off + len(x)], x) and np.array_equal(wd[off:off + len(x)], w)
+    assert np.all(wd[:off] < 10 * np.finfo(float).tiny)
+    with pytest.raises(fgq.DomainError):
+        fgq.gausshermite_reduced(-1)
+    assert len(fgq.gausshermite_reduced(0)[1]) == 0
