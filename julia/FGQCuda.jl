@@ -44,6 +44,48 @@ function gausslegendre_batch(ns::Vector{Int32})
     return offsets, x, w
 end
 
+# Batches of small rules of the other families (same CSR layout; n_i <= 100 / 200 / 127)
+function _offsets(ns::Vector{Int32})
+    offsets = Vector{Int64}(undef, length(ns) + 1); offsets[1] = 0
+    cumsum!(view(offsets, 2:length(offsets)), Int64.(ns))
+    return offsets
+end
+function gaussjacobi_batch(ns::Vector{Int32}, α::Vector{Float64}, β::Vector{Float64})
+    offsets = _offsets(ns); x = Vector{Float64}(undef, offsets[end]); w = similar(x)
+    GC.@preserve ns α β offsets x w check(ccall((:fgq_gaussjacobi_batch_host, libfgq), Cint,
+        (Int64, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+        length(ns), ns, α, β, offsets, x, w), length(ns))
+    return offsets, x, w
+end
+function gausshermite_batch(ns::Vector{Int32}; normalize::Bool=false)
+    offsets = _offsets(ns); x = Vector{Float64}(undef, offsets[end]); w = similar(x)
+    GC.@preserve ns offsets x w check(ccall((:fgq_gausshermite_batch_host, libfgq), Cint,
+        (Int64, Ptr{Int32}, Ptr{Int64}, Cint, Ptr{Float64}, Ptr{Float64}),
+        length(ns), ns, offsets, normalize, x, w), length(ns))
+    return offsets, x, w
+end
+function gausslaguerre_batch(ns::Vector{Int32}, α::Vector{Float64})
+    offsets = _offsets(ns); x = Vector{Float64}(undef, offsets[end]); w = similar(x)
+    GC.@preserve ns α offsets x w check(ccall((:fgq_gausslaguerre_batch_host, libfgq), Cint,
+        (Int64, Ptr{Int32}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+        length(ns), ns, α, offsets, x, w), length(ns))
+    return offsets, x, w
+end
+
+# Truncated Gauss-Hermite rule: (first, x, w) with x, w = entries first+1 : first+length(x) (1-based) of
+# gausshermite(n); every omitted weight is 0.0 in the full rule
+function gausshermite_reduced(n::Integer; normalize::Bool=false)
+    n < 0 && throw(DomainError(n, "Input n must be a non-negative integer"))
+    bound = ccall((:fgq_gausshermite_reduced_bound, libfgq), Int64, (Int64,), n)
+    x = Vector{Float64}(undef, bound); w = similar(x)
+    first = Ref{Int64}(0); n_out = Ref{Int64}(0)
+    n == 0 && return 0, x, w
+    GC.@preserve x w check(ccall((:fgq_gausshermite_reduced_host, libfgq), Cint,
+        (Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}), n, normalize, x, w, first, n_out), n)
+    resize!(x, n_out[]); resize!(w, n_out[])
+    return first[], x, w
+end
+
 # gaussjacobi(n, α, β) — src/gaussjacobi.jl:23-55 (asymptotic branch n > 100, max(α,β) < 5; (0,0) and
 # (±1/2, ±1/2) are routed to the Legendre / Chebyshev kernels by the library, as the reference does)
 function gaussjacobi(n::Integer, α::Real, β::Real)
