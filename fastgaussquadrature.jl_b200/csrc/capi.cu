@@ -382,7 +382,10 @@ int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const Piec
     // `dma_share` is the fraction of pieces sent the second way, steered by what the host threads see:
     // a piece that had already landed when a thread picked it up means the host side is behind (raise the
     // share); a piece the thread had to wait for means PCIe is behind (lower it).
-    double dma_share = 0.0, dma_acc = 0.0;
+    // The share carries over from call to call (the caller holds HostPathLock): the feeder runs up to RING
+    // pieces ahead of the host threads, so a short drain is over before its own observations can act.
+    static double s_dma_share = 0.0;
+    double dma_share = s_dma_share, dma_acc = 0.0;
     bool adapt = true;
     if (const char* e = getenv("FGQ_HOST_MIRROR_DMA_SHARE")) {  // tests / tuning: a fixed share in [0, 1]
         const double v = atof(e);
@@ -490,6 +493,7 @@ int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const Piec
     });
     cudaError_t e2 = cudaStreamSynchronize(st);
     g_drain_share_milli = (int)(dma_share * 1000);
+    if (adapt && dma_mirror_ok) s_dma_share = dma_share;
     if (threaded)
         for (int i = 0; i < RING; ++i) cudaEventDestroy(ev[i]);
     if (rc != FGQ_OK) return rc;
@@ -714,6 +718,24 @@ extern "C" int fgq_gausslegendre_host_slice(int64_t n, int64_t lo, int64_t hi, d
 }
 
 namespace fgq {
+void host_parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& f) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int64_t T = hw == 0 ? 4 : (hw > 16 ? 16 : hw);
+    if (const char* e = getenv("FGQ_HOST_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 64) T = v;
+    }
+    if (n < (1 << 13) || T <= 1) {  // not worth ~50 us per thread
+        f(0, n);
+        return;
+    }
+    if (T > n / 2048) T = n / 2048;
+    std::vector<std::thread> th;
+    for (int64_t t = 1; t < T; ++t) th.emplace_back([&, t] { f(n * t / T, n * (t + 1) / T); });
+    f(0, n / T);
+    for (auto& x : th) x.join();
+}
+
 int small_batch_rules(int64_t nrules, const int32_t* n_i, const int64_t* offsets, int n_max, const char* what,
                       std::vector<SmallRule>* rules, int64_t* total) {
     *total = 0;

@@ -101,5 +101,9 @@ struct SmallRule {   // one rule of a batch: n nodes written at x[off .. off+n)
 int small_batch_rules(int64_t nrules, const int32_t* n_i, const int64_t* offsets, int n_max, const char* what,
                       std::vector<SmallRule>* rules, int64_t* total);
 
+// f(lo, hi) over [0, n) cut into contiguous ranges, on up to 16 short-lived host threads when n is large
+// (per-rule planning of a big batch: gamma functions, Bessel-zero guesses); f must not fail.
+void host_parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& f);
+
 }  // namespace fgq
 #endif

@@ -15,6 +15,7 @@
 // normalisation sum (:62) and a fold/scale kernel that also applies exp(-x^2) (:30).
 #include "airy.cuh"
 #include "common.cuh"
+#include "fgq_math.h"
 #include "gw.cuh"
 
 #include <string.h>
@@ -30,6 +31,7 @@ __constant__ double c_airy_roots[10] = {
     -11.93601556323626, -12.828776752865757};
 
 constexpr int HERMITE_SUM_BLOCKS = 64;
+constexpr int HERMITE_REC_MAX_N = 200;   // hermite_rec serves 21 <= n <= 200 (gausshermite.jl:46-48)
 
 struct HermiteState {   // lives at the start of the workspace
     unsigned long long maxdt_bits[20];
@@ -230,13 +232,40 @@ hermite_sweep_kernel(HermiteParams p, int sweep, HermiteState* st, double* theta
 
 // hermpoly_rec(n, x0) (gausshermite.jl:113-137): scaled Hermite polynomial and derivative by the
 // recurrence, regularised by powers of exp(-x0^2/(4n)) whenever |H| >= 100.
-__device__ void hermpoly_rec(int n, double x0, double& val, double& dval) {
+// The divisors sqrt(k+1) and sqrt((k+1)/k) of a step do not depend on x0: the block tabulates them once,
+// together with their correctly rounded reciprocals, and every quotient a / b becomes the last three
+// operations of the IEEE quotient's fast path (fgq_div_fast) — the same bits as a / b for every operand
+// here (|H| stays within [1e-200, 1e4]; a signed zero passes through as IEEE division would return it) —
+// instead of two square roots and two full divisions per step and thread.
+struct HermiteRecTables {
+    double s1[HERMITE_REC_MAX_N], r1[HERMITE_REC_MAX_N];  // sqrt(k+1), 1/sqrt(k+1)         at [k]
+    double s2[HERMITE_REC_MAX_N], r2[HERMITE_REC_MAX_N];  // sqrt((k+1)/k), its reciprocal  at [k]
+};
+
+__device__ __forceinline__ double div_tab(double a, double b, double r) {
+    const double q = a * r;
+    const double rem = fma(-b, q, a);
+    const double res = fma(r, rem, q);
+    return a == 0.0 ? a : res;
+}
+
+__device__ __forceinline__ void hermite_rec_tables(int n, HermiteRecTables& T) {
+    for (int k = 1 + (int)threadIdx.x; k <= n - 1; k += (int)blockDim.x) {
+        const double k1 = (double)(k + 1);
+        const double a = sqrt(k1), b = sqrt(k1 / (double)k);
+        T.s1[k] = a;
+        T.r1[k] = fgq_rcp_fast(a);
+        T.s2[k] = b;
+        T.r2[k] = fgq_rcp_fast(b);
+    }
+}
+
+__device__ void hermpoly_rec(int n, double x0, const HermiteRecTables& T, double& val, double& dval) {
     const double w = exp(-(x0 * x0) / (4 * (double)n));
     int wc = 0;
     double Hold = 1.0, H = x0;
     for (int k = 1; k <= n - 1; ++k) {
-        const double k1 = (double)(k + 1);
-        const double Hnew = x0 * H / sqrt(k1) - Hold / sqrt(k1 / (double)k);
+        const double Hnew = div_tab(x0 * H, T.s1[k], T.r1[k]) - div_tab(Hold, T.s2[k], T.r2[k]);
         Hold = H;
         H = Hnew;
         while (fabs(H) >= 100 && wc < n) {
@@ -265,10 +294,13 @@ __device__ __forceinline__ void hermite_rec_block(const HermiteParams& p, double
         x0 *= SQ2;
     }
     __shared__ double s_mx[4];
+    __shared__ HermiteRecTables s_tab;
+    hermite_rec_tables((int)p.n, s_tab);
+    __syncthreads();
     for (int it = 0; it < 10; ++it) {
         double adx = 0.0;
         if (active) {
-            hermpoly_rec((int)p.n, x0, val, dval);
+            hermpoly_rec((int)p.n, x0, s_tab, val, dval);
             double dx = val / dval;
             if (dx != dx) dx = 0.0;
             x0 = x0 - dx;

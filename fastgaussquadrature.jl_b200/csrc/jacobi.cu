@@ -274,27 +274,55 @@ struct JacobiRecParams {
     int64_t lo, hi;  // output slice
 };
 
-// innerjacobi_rec! for one abscissa (:129-155)
-__device__ __forceinline__ void jacobi_inner_rec(int n, double xj, double a, double b, double& P, double& PP) {
-    double Pj = (a - b + (a + b + 2) * xj) / 2;
-    double Pm1 = 1.0;
-    double PPj = (a + b + 2) / 2;
-    double PPm1 = 0.0;
-    for (int k = 1; k <= n - 1; ++k) {
+// innerjacobi_rec! for one abscissa (:129-155).  The recurrence coefficients of step k
+//   A = 2(k+1)(k+a+b+1)(2k+a+b), B = (2k+a+b+1)(a^2-b^2), C = (2k+a+b)(2k+a+b+1)(2k+a+b+2), D = 2(k+a)(k+b)(2k+a+b+2)
+// do not depend on the abscissa: the block tabulates them once (with the correctly rounded 1/A, so that both
+// quotients of a step become the last three operations of the IEEE quotient's fast path: the same bits as
+// x / A, see fgq_div_fast).  The mirrored half works with (b, a): every coefficient is unchanged bit for bit
+// (sums and products of two numbers commute in floating point too) except B, which changes sign.
+constexpr int JACOBI_REC_MAX_N = 100;
+struct JacobiRecTables {
+    double A[JACOBI_REC_MAX_N], rA[JACOBI_REC_MAX_N], B[JACOBI_REC_MAX_N], C[JACOBI_REC_MAX_N], D[JACOBI_REC_MAX_N];
+};
+
+__device__ __forceinline__ void jacobi_rec_tables(int n, double a, double b, JacobiRecTables& T) {
+    for (int k = 1 + (int)threadIdx.x; k <= n - 1; k += (int)blockDim.x) {
         const double dk = (double)k;
         const double k0 = fma(2.0, dk, a + b);
         const double k1 = k0 + 1;
         const double k2 = k0 + 2;
         const double A = 2 * (dk + 1) * (dk + (a + b + 1)) * k0;
-        const double B = k1 * (a * a - b * b);
-        const double C = k0 * k1 * k2;
-        const double D = 2 * (dk + a) * (dk + b) * k2;
+        T.A[k] = A;
+        T.rA[k] = fgq_rcp_fast(A);
+        T.B[k] = k1 * (a * a - b * b);
+        T.C[k] = k0 * k1 * k2;
+        T.D[k] = 2 * (dk + a) * (dk + b) * k2;
+    }
+}
+
+__device__ __forceinline__ double jacobi_div_tab(double x, double A, double rA) {
+    const double q = x * rA;
+    const double rem = fma(-A, q, x);
+    const double res = fma(rA, rem, q);
+    return x == 0.0 ? x : res;
+}
+
+// bsign = +1 for the half that works with the tabulated (a, b), -1 for the mirrored one
+__device__ __forceinline__ void jacobi_inner_rec(int n, double xj, double a, double b, double bsign,
+                                                 const JacobiRecTables& T, double& P, double& PP) {
+    double Pj = (a - b + (a + b + 2) * xj) / 2;
+    double Pm1 = 1.0;
+    double PPj = (a + b + 2) / 2;
+    double PPm1 = 0.0;
+    for (int k = 1; k <= n - 1; ++k) {
+        const double A = T.A[k], rA = T.rA[k], C = T.C[k], D = T.D[k];
+        const double B = bsign * T.B[k];
         const double c1 = fma(C, xj, B);
-        const double newP = fma(-D, Pm1, c1 * Pj) / A;
+        const double newP = jacobi_div_tab(fma(-D, Pm1, c1 * Pj), A, rA);
         const double oldP = Pj;
         Pm1 = oldP;   // (Pm1, Pj) = (Pj, ...): the right-hand side uses the OLD Pm1
         Pj = newP;
-        const double newPP = fma(c1, PPj, fma(-D, PPm1, C * Pm1)) / A;  // C * Pm1 uses the NEW Pm1 (= old Pj), as in :148-149
+        const double newPP = jacobi_div_tab(fma(c1, PPj, fma(-D, PPm1, C * Pm1)), A, rA);  // C * Pm1 uses the NEW Pm1 (= old Pj), as in :148-149
         PPm1 = PPj;
         PPj = newPP;
     }
@@ -316,6 +344,9 @@ __device__ __forceinline__ void jacobi_rec_block(const JacobiRecParams& p, doubl
     __shared__ double s_dx2[4];
     __shared__ int s_done[2];
     __shared__ double xs[128], wsum[128];
+    __shared__ JacobiRecTables s_tab;
+    jacobi_rec_tables(n, p.alpha, p.beta, s_tab);
+    const double bsign = h == 0 ? 1.0 : -1.0;
     if (tid < 2) s_done[tid] = 0;
     // initial guess (:97-109)
     const double c1 = 1 / (2 * (double)n + a + b + 1);
@@ -332,7 +363,7 @@ __device__ __forceinline__ void jacobi_rec_block(const JacobiRecParams& p, doubl
         const bool run = !s_done[h];
         double dx2 = 0.0;
         if (run && active) {
-            jacobi_inner_rec(n, xj, a, b, P1, P2);
+            jacobi_inner_rec(n, xj, a, b, bsign, s_tab, P1, P2);
             const double dx = P1 / P2;
             dx2 = dx * dx;
             xj = xj - dx;
@@ -356,7 +387,7 @@ __device__ __forceinline__ void jacobi_rec_block(const JacobiRecParams& p, doubl
         if (s_done[0] && s_done[1]) break;
     }
     // once more for derivatives (:127)
-    if (active) jacobi_inner_rec(n, xj, a, b, P1, P2);
+    if (active) jacobi_inner_rec(n, xj, a, b, bsign, s_tab, P1, P2);
     // assemble (:69-88): left half mirrored, sum in the reference's order
     if (active) {
         const double xi = h == 0 ? xj : -xj;
@@ -765,16 +796,24 @@ static int jacobi_batch_plan(int64_t nrules, const int32_t* n_i, const double* a
             if (rc != FGQ_OK) return rc;
             if (n == 1) {
                 r.kind = 1;
-                jacobi_one_node(a, b, &r.alpha, &r.c);
             } else if ((a > b ? a : b) >= 5.0) {
                 if (others) others->push_back(i);
             } else {
                 r.kind = 2;
-                r.c = jacobi_rec_const(a, b);
             }
         }
         if (rules) (*rules)[(size_t)i] = r;
     }
+    // the gamma-function constants (4 tgamma + pow per rule), on host threads for a large batch
+    if (rules)
+        host_parallel_for(nrules, [&](int64_t lo, int64_t hi) {
+            for (int64_t i = lo; i < hi; ++i) {
+                JacobiBatchRule& r = (*rules)[(size_t)i];
+                const double a = r.alpha, b = r.beta;
+                if (r.kind == 1) jacobi_one_node(a, b, &r.alpha, &r.c);
+                if (r.kind == 2) r.c = jacobi_rec_const(a, b);
+            }
+        });
     return FGQ_OK;
 }
 

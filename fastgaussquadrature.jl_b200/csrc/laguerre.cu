@@ -703,32 +703,41 @@ static int laguerre_batch_plan(int64_t nrules, const int32_t* n_i, const double*
         set_error("invalid batch description");
         return FGQ_EINVAL;
     }
-    if (rules) rules->resize((size_t)nrules);
     for (int64_t i = 0; i < nrules; ++i) {
         const int64_t n = n_i[i];
         const double alpha = alpha_i[i];
         FGQ_TRY(laguerre_check(n, alpha));  // alpha <= -1 is a DomainError for every n, as in the reference (:61)
         if (n > 0 && alpha * alpha / (double)n > 1) *warn |= FGQ_WARN_LARGE_ALPHA;
-        if (!rules) continue;
-        LaguerreBatchRule r;
-        r.n = n;
-        r.off = offsets[i];
-        r.alpha = alpha;
-        // the same expressions as laguerre_params / fgq_gausslaguerre_device
-        r.pn0 = 1 / sqrt(tgamma(alpha + 1));
-        r.wnorm = pow((double)n * (double)n + alpha * (double)n, -0.5);
-        r.xmax = 4 * (double)n + 2 * alpha + 2;
-        r.q.g1 = tgamma(1 + alpha);
-        r.q.g2 = tgamma(alpha + 2);
-        for (int k = 0; k < 7; ++k) r.q.jak_pre[k] = 0.0;
-        if (n >= 15) approx_besselroots(alpha, 7, r.q.jak_pre);
-        (*rules)[(size_t)i] = r;
     }
-    // one thread per rule: the cost of a rule grows like n^2, so rules of (nearly) equal n share a warp,
-    // longest first (the output position travels with the rule, the processing order is free)
-    if (rules)
-        std::stable_sort(rules->begin(), rules->end(),
-                         [](const LaguerreBatchRule& a, const LaguerreBatchRule& b) { return a.n > b.n; });
+    if (!rules) return FGQ_OK;
+    rules->resize((size_t)nrules);
+    // One thread per rule on the device, and the cost of a rule grows like n^2: rules of equal n share a
+    // warp, longest first (the output position travels with the rule, the processing order is free).
+    // Counting sort over n: slot[i] = position of rule i in the launch order.
+    std::vector<int64_t> start(LAGUERRE_BATCH_MAX_N + 2, 0), slot((size_t)nrules);
+    for (int64_t i = 0; i < nrules; ++i) start[LAGUERRE_BATCH_MAX_N - n_i[i] + 1]++;
+    for (int k = 0; k <= LAGUERRE_BATCH_MAX_N; ++k) start[k + 1] += start[k];
+    for (int64_t i = 0; i < nrules; ++i) slot[(size_t)i] = start[LAGUERRE_BATCH_MAX_N - n_i[i]]++;
+    // per-rule constants (3 tgamma, pow, the Bessel-zero guesses), on host threads for a large batch
+    host_parallel_for(nrules, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const int64_t n = n_i[i];
+            const double alpha = alpha_i[i];
+            LaguerreBatchRule r;
+            r.n = n;
+            r.off = offsets[i];
+            r.alpha = alpha;
+            // the same expressions as laguerre_params / fgq_gausslaguerre_device
+            r.pn0 = 1 / sqrt(tgamma(alpha + 1));
+            r.wnorm = pow((double)n * (double)n + alpha * (double)n, -0.5);
+            r.xmax = 4 * (double)n + 2 * alpha + 2;
+            r.q.g1 = tgamma(1 + alpha);
+            r.q.g2 = tgamma(alpha + 2);
+            for (int k = 0; k < 7; ++k) r.q.jak_pre[k] = 0.0;
+            if (n >= 15) approx_besselroots(alpha, 7, r.q.jak_pre);
+            (*rules)[(size_t)slot[(size_t)i]] = r;
+        }
+    });
     return FGQ_OK;
 }
 
