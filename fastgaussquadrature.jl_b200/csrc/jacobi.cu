@@ -48,12 +48,19 @@ struct JacobiLaunch {
 };
 
 constexpr int JAC_THREADS = 128;
+constexpr int JAC_NORM_STAGE1 = 4;  // truncation candidates (terms 12, 13, ...) examined by the first norm stage
 constexpr int64_t JAC_GRID = 148 * 5;  // persistent grid: 5 blocks of 128 threads fit one SM at 96 registers
 
-// gaussjacobi.jl:254-361 for one node.  NORM: only the truncation norms of terms 12..20 are produced.
-template <bool NORM>
+// gaussjacobi.jl:254-361 for one node.  MODE 0: the evaluation.  MODE 1 / 2: only the truncation norms of
+// terms 12..15 / 16..20 are produced (the norm pass is staged: the second stage runs only if none of the
+// first four candidates falls below the threshold; large rules are cut at term 15: n t >= ~10 pi on the
+// interior set whatever n is).
+template <int MODE>
 __device__ __forceinline__ void feval_asy1_node(const JacobiHalfPlan& P, double nn, double t, int mbreak,
                                                 double& vals, double& ders, double* tnorm, bool take_norm = false) {
+    constexpr bool NORM = MODE != 0;
+    constexpr int M_FIRST = MODE == 0 ? 1 : (MODE == 1 ? 12 : 12 + JAC_NORM_STAGE1);
+    constexpr int M_LAST = MODE == 1 ? 11 + JAC_NORM_STAGE1 : JAC_M;
     const double PI = 3.141592653589793;
     const double a = P.a, b = P.b;
     double sinT_, cosT_;
@@ -68,8 +75,8 @@ __device__ __forceinline__ void feval_asy1_node(const JacobiHalfPlan& P, double 
     const double shift = (a + 0.5) * PI / 2;
     double S = 0.0, S2 = 0.0;
 #pragma unroll
-    for (int m = 1; m <= JAC_M; ++m) {
-        if (!NORM || m >= 12) {
+    for (int m = 1; m <= M_LAST; ++m) {
+        if (m >= M_FIRST) {
             if (!NORM && m == mbreak) break;
             const double A = (c0 + m) * t / 2 - shift;
             double sA, cA;
@@ -146,15 +153,22 @@ __global__ void jacobi_init_kernel(int64_t n, double a, double b, int64_t n_left
 // pre-enqueued launches that find their half already converged cost ~2 us instead of the ~42 us it takes
 // to schedule and retire 39 063 empty blocks (n = 1e7; those were 30 % of the call), and every block
 // reduces its norms once instead of once per tile.
-template <bool NORM>
+template <int MODE>
 __global__ void __launch_bounds__(JAC_THREADS, 5)
 jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, double* theta, double* x, double* w) {
+    constexpr bool NORM = MODE != 0;
     const int h = p.half;
     const int phase = *((volatile int*)&st->phase[h]);
     if (phase == 2) return;
     const double nn = (double)p.n;
     const int64_t ntiles = (p.count + JAC_THREADS - 1) / JAC_THREADS;
     if (NORM) {
+        if (MODE == 2) {  // second stage: only if the series is not already cut at one of terms 12..15
+            for (int q = 0; q < JAC_NORM_STAGE1; ++q) {
+                const double nm = __longlong_as_double((long long)st->termnorm[h][p.sweep][q]);
+                if (nm < 2.220446049250313e-16 / 100) return;
+            }
+        }
         double tmax[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) tmax[q] = 0.0;
@@ -165,10 +179,10 @@ jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, doub
             const bool interior = active && ig >= p.idx_lo && ig < p.idx_hi;
             const double t = active ? theta[ig] : 1.0;
             double dummy_v, dummy_d;
-            feval_asy1_node<true>(p.hp, nn, t, 0, dummy_v, dummy_d, tmax, interior);
+            feval_asy1_node<MODE>(p.hp, nn, t, 0, dummy_v, dummy_d, tmax, interior);
         }
 #pragma unroll
-        for (int q = 0; q < 9; ++q) {
+        for (int q = (MODE == 1 ? 0 : JAC_NORM_STAGE1); q < (MODE == 1 ? JAC_NORM_STAGE1 : 9); ++q) {
             const unsigned long long bits = block_max_bits(tmax[q]);
             if (threadIdx.x == 0) atomicMax(&st->termnorm[h][p.sweep][q], bits);
         }
@@ -191,7 +205,7 @@ jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, doub
         const bool interior = ig >= p.idx_lo && ig < p.idx_hi;
         double t = theta[ig];
         double vals, ders;
-        feval_asy1_node<false>(p.hp, nn, t, mbreak, vals, ders, nullptr);
+        feval_asy1_node<0>(p.hp, nn, t, mbreak, vals, ders, nullptr);
         const double dt = vals / ders;
         t += dt;
         theta[ig] = t;
@@ -710,9 +724,11 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
             L[h].sweep = s;
             const int64_t tiles = (L[h].count + JAC_THREADS - 1) / JAC_THREADS;
             const unsigned blocks = (unsigned)(tiles < JAC_GRID ? tiles : JAC_GRID);
-            jacobi_pass_kernel<true><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
+            jacobi_pass_kernel<1><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
             FGQ_LAUNCH_CHECK();
-            jacobi_pass_kernel<false><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
+            jacobi_pass_kernel<2><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
+            FGQ_LAUNCH_CHECK();
+            jacobi_pass_kernel<0><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
             FGQ_LAUNCH_CHECK();
         }
     }

@@ -9,6 +9,9 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fgq_b200  # noqa: E402
 
+if os.environ.get("FGQ_DIGEST_LIB"):  # compare against another build of the library
+    sys.modules[fgq_b200.lib.__module__].LIB_PATH = os.environ["FGQ_DIGEST_LIB"]
+
 rng = np.random.default_rng(5)
 
 
@@ -37,3 +40,11 @@ x, w = fgq_b200.gaussjacobi(77, 0.3, -0.7)
 print("jacobi single 77   ", digest([x, w]))
 _, xb, wb = fgq_b200.gausslegendre_batch(np.arange(0, 61))
 print("legendre batch     ", digest([xb, wb]))
+# the asymptotic Jacobi path (+ Radau / Lobatto epilogues), Hermite and Laguerre asymptotics
+for n, a, b in ((101, 0.3, -0.7), (1000, -0.9, 2.5), (12345, 4.9, 4.9), (1_000_000, 0.3, -0.7), (200_001, 1.0, 0.0)):
+    print(f"jacobi asy {n} {a} {b}".ljust(34), digest(fgq_b200.gaussjacobi(n, a, b)))
+print("radau 5000".ljust(34), digest(fgq_b200.gaussradau(5000)))
+print("lobatto 5000".ljust(34), digest(fgq_b200.gausslobatto(5000)))
+print("hermite 100000".ljust(34), digest(fgq_b200.gausshermite(100_000)))
+print("laguerre 100000".ljust(34), digest(fgq_b200.gausslaguerre(100_000, 0.5)))
+print("legendre 1000001".ljust(34), digest(fgq_b200.gausslegendre(1_000_001)))
