@@ -45,9 +45,11 @@ struct JacobiLaunch {
     double wc;             // weightsConstant
     int64_t lo, hi;        // output slice
     double tol;
+    double tskip;          // norm passes: nodes with theta >= tskip provably stay below the truncation threshold
 };
 
 constexpr int JAC_THREADS = 128;
+constexpr double JAC_SKIP_TMAX = 1.5718;  // pi/2 + 1e-3: the bound behind tskip assumes 1/(2 cos(t/2)) <= 0.7079
 constexpr int JAC_NORM_STAGE1 = 4;  // truncation candidates (terms 12, 13, ...) examined by the first norm stage
 constexpr int64_t JAC_GRID = 148 * 5;  // persistent grid: 5 blocks of 128 threads fit one SM at 96 registers
 
@@ -178,8 +180,11 @@ jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, doub
             const bool active = r < p.count;
             const bool interior = active && ig >= p.idx_lo && ig < p.idx_hi;
             const double t = active ? theta[ig] : 1.0;
+            // jacobi_norm_skip_angle: for these angles every candidate term is below eps/100 whatever its
+            // phase, so the node cannot change the outcome of the comparison the norms are used for
+            if (!interior || (t >= p.tskip && t <= JAC_SKIP_TMAX)) continue;
             double dummy_v, dummy_d;
-            feval_asy1_node<MODE>(p.hp, nn, t, 0, dummy_v, dummy_d, tmax, interior);
+            feval_asy1_node<MODE>(p.hp, nn, t, 0, dummy_v, dummy_d, tmax, true);
         }
 #pragma unroll
         for (int q = (MODE == 1 ? 0 : JAC_NORM_STAGE1); q < (MODE == 1 ? JAC_NORM_STAGE1 : 9); ++q) {
@@ -652,6 +657,37 @@ extern "C" int64_t fgq_gaussjacobi_workspace_bytes(int64_t n) {
     return 4096 + 16 * n;
 }
 
+// The truncation rule (:309) only asks whether max over the interior set of |dS1 + dS2| of a term m >= 12 is
+// below eps/100.  |dS1 + dS2| <= sum_l |PHI[l][m-1]| csc^l sec^(m-1-l) with csc = 1/(2 sin(t/2)) decreasing in t
+// and sec = 1/(2 cos(t/2)) <= 0.7079 up to t = pi/2 + 1e-3: beyond the angle returned here every candidate term
+// is below a QUARTER of the threshold (the margin covers the rounding of the device sums by orders of
+// magnitude), so such a node can never make a norm reach the threshold and the norm passes skip it.  The
+// comparison, hence the truncation index and every result bit, is unchanged; the stored norms become the
+// maxima over the nodes that were looked at.  +inf: no node may be skipped (small n).
+static double jacobi_norm_skip_angle(const JacobiHalfPlan& hp) {
+    const double thr = 2.220446049250313e-16 / 100 / 4;
+    auto bound = [&](double t) {
+        const double csc = (1.0 / sin(t / 2)) / 2 * (1 + 1e-9);
+        const double sec = 0.7079;
+        double worst = 0.0;
+        for (int m = 12; m <= JAC_M; ++m) {
+            double sum = 0.0;
+            for (int l = 0; l < m; ++l) sum += fabs(hp.PHI[l][m - 1]) * pow(csc, l) * pow(sec, m - 1 - l);
+            if (!(sum <= worst)) worst = sum;  // a NaN table entry disables skipping
+        }
+        return worst * (1 + 1e-9);
+    };
+    const double PIO2 = 3.141592653589793 / 2;
+    if (!(bound(PIO2) < thr)) return HUGE_VAL;
+    double lo = 1e-300, hi = PIO2;  // bound(lo) >= thr (or overflow), bound(hi) < thr
+    if (bound(lo) < thr) return lo;
+    for (int it = 0; it < 200 && hi - lo > 1e-12 * hi; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (bound(mid) < thr) hi = mid; else lo = mid;
+    }
+    return hi;
+}
+
 // Core: the (alpha, beta) != (0,0), (+-1/2, +-1/2) asymptotic branch.
 static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t hi, double* x_dev, double* w_dev,
                              void* workspace_dev, cudaStream_t st) {
@@ -714,6 +750,7 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
         L[h].lo = lo;
         L[h].hi = hi;
         L[h].tol = sqrt(2.220446049250313e-16) / 100;
+        L[h].tskip = jacobi_norm_skip_angle(L[h].hp);
     }
     L[0].first = n_left;          L[0].count = n - n_left;
     L[0].idx_lo = n_left;         L[0].idx_hi = n - (JAC_NBDY - 1);   // all but the last 9 (:206)

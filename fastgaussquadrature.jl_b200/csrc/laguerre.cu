@@ -292,16 +292,23 @@ __global__ void laguerre_state_init_kernel(LaguerreState* st, int64_t n) {
     st->warn = 0;
 }
 
-// first k where delta_bulk < delta_bessel (:138-151)
+// first k where delta_bulk < delta_bessel (:138-151), searched over k in [k_first, k_last] with a grid
+// stride.  The hand-over happens at k = O(sqrt(n)) (the reference itself only prepares ceil(sqrt(n)) Bessel
+// zeros before falling back to McMahon's expansion), so the search is staged: a first launch over a window
+// of a few sqrt(n) — one evaluation per thread, few enough blocks that each warp has an SM sub-partition
+// to itself — and a second launch over the rest, whose threads return at once when the window held it.
+// (A single launch over all k had every resident thread, 150 000 of them, evaluate both expansions before
+// the first result could stop anybody: 124 us at n = 1e6.)
 __global__ void __launch_bounds__(LAG_THREADS)
-laguerre_handover_bessel_kernel(const LaguerreParams p, LaguerreState* st) {
-    const int64_t k = 1 + (int64_t)blockIdx.x * LAG_THREADS + threadIdx.x;
-    if (k > p.n) return;
-    if ((unsigned long long)k >= *((volatile unsigned long long*)&st->k_b)) return;  // already beaten by a smaller k
-    double xb, wb, db, xu, wu, du;
-    laguerre_bessel(p, laguerre_jak(p, k), xb, wb, db);
-    laguerre_bulk(p, k, xu, wu, du, nullptr);
-    if (du < db) atomicMin(&st->k_b, (unsigned long long)k);
+laguerre_handover_bessel_kernel(const LaguerreParams p, LaguerreState* st, int64_t k_first, int64_t k_last) {
+    const int64_t stride = (int64_t)gridDim.x * LAG_THREADS;
+    for (int64_t k = k_first + (int64_t)blockIdx.x * LAG_THREADS + threadIdx.x; k <= k_last; k += stride) {
+        if ((unsigned long long)k >= *((volatile unsigned long long*)&st->k_b)) return;  // already beaten by a smaller k
+        double xb, wb, db, xu, wu, du;
+        laguerre_bessel(p, laguerre_jak(p, k), xb, wb, db);
+        laguerre_bulk(p, k, xu, wu, du, nullptr);
+        if (du < db) atomicMin(&st->k_b, (unsigned long long)k);
+    }
 }
 
 // first k >= max(k_b + 1, k_airy) where delta_airy < delta_bulk (:201-209)
@@ -627,8 +634,20 @@ extern "C" int fgq_gausslaguerre_device(int64_t n, double alpha, double* x_dev, 
         return FGQ_OK;
     }
     const unsigned blocks = (unsigned)((n + LAG_THREADS - 1) / LAG_THREADS);
-    laguerre_handover_bessel_kernel<<<blocks, LAG_THREADS, 0, st>>>(p, state);
-    FGQ_LAUNCH_CHECK();
+    {
+        int64_t window = 8 * (int64_t)ceil(sqrt((double)n));
+        if (window < 1024) window = 1024;
+        if (window > n) window = n;
+        laguerre_handover_bessel_kernel<<<(unsigned)((window + LAG_THREADS - 1) / LAG_THREADS), LAG_THREADS, 0, st>>>(
+            p, state, 1, window);
+        FGQ_LAUNCH_CHECK();
+        if (window < n) {
+            const int64_t rest = (n - window + LAG_THREADS - 1) / LAG_THREADS;
+            laguerre_handover_bessel_kernel<<<(unsigned)(rest < 148 * 6 ? rest : 148 * 6), LAG_THREADS, 0, st>>>(
+                p, state, window + 1, n);
+            FGQ_LAUNCH_CHECK();
+        }
+    }
     // candidates k >= k_airy (the kernel skips those <= k_b)
     const int64_t cand = n - (p.k_airy < 1 ? 1 : p.k_airy) + 1;
     laguerre_handover_airy_kernel<<<(unsigned)((cand + LAG_THREADS - 1) / LAG_THREADS), LAG_THREADS, 0, st>>>(p, state);
