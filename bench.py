@@ -244,6 +244,52 @@ def time_other_configs(fgq_b200, cpu: bool):
     w = torch.empty(tot, dtype=torch.float64, device="cuda")
     ms = dev_time(lambda: chk(L.fgq_gausslegendre_batch_device(len(n_i), dn.data_ptr(), do.data_ptr(), x.data_ptr(), w.data_ptr(), sp)))
     out["C5_batch_1e6_rules"] = {"device_ms": ms, "mrules_per_s": len(n_i) / ms / 1e3, "mnodes_per_s": tot / ms / 1e3, "nodes": tot}
+    # truncated Gauss-Hermite rule (only the centre block of non-zero weights is computed)
+    n = 1_000_000
+    nb = int(L.fgq_gausshermite_reduced_bound(n))
+    xr = torch.empty(nb, dtype=torch.float64, device="cuda")
+    wr = torch.empty(nb, dtype=torch.float64, device="cuda")
+    ws = torch.empty(int(L.fgq_gausshermite_workspace_bytes(n)) + 16, dtype=torch.uint8, device="cuda")
+    ms = dev_time(lambda: chk(L.fgq_gausshermite_reduced_device(n, 0, xr.data_ptr(), wr.data_ptr(), ws.data_ptr(), sp, None, None)))
+    out["reduced_gausshermite_1e6"] = {"device_ms": ms, "entries": nb, "sum_w_err": float(wr.sum().item() - np.sqrt(np.pi)),
+                                       "host_call_ms": host_wall(lambda: fgq_b200.gausshermite_reduced(1_000_000))}
+    # batches of small rules of the other families (1e5 rules each, host-side planning included
+    # in host_call_ms; device_ms spans descriptor upload + kernel on the stream)
+    nr = 100_000
+    rng = np.random.default_rng(0)
+
+    def batch_entry(n_i, wsbytes, launch, host_call):
+        off = np.zeros(len(n_i) + 1, dtype=np.int64)
+        np.cumsum(n_i, out=off[1:])
+        tot = int(off[-1])
+        xb = torch.empty(tot, dtype=torch.float64, device="cuda")
+        wb = torch.empty(tot, dtype=torch.float64, device="cuda")
+        wsb = torch.empty(int(wsbytes), dtype=torch.uint8, device="cuda")
+        ms = dev_time(lambda: chk(launch(off, xb, wb, wsb)))
+        return {"rules": len(n_i), "nodes": tot, "stream_ms_incl_host_planning": ms, "mrules_per_s": len(n_i) / ms / 1e3,
+                "host_call_ms": host_wall(host_call)}
+
+    n_j = rng.integers(2, 101, nr).astype(np.int32)
+    a_j, b_j = rng.uniform(-0.9, 4.9, nr), rng.uniform(-0.9, 4.9, nr)
+    out["batch_gaussjacobi_1e5_rules"] = batch_entry(
+        n_j, L.fgq_gaussjacobi_batch_workspace_bytes(nr),
+        lambda off, xb, wb, wsb: L.fgq_gaussjacobi_batch_device(nr, n_j.ctypes.data, a_j.ctypes.data, b_j.ctypes.data,
+                                                                off.ctypes.data, xb.data_ptr(), wb.data_ptr(),
+                                                                wsb.data_ptr(), sp),
+        lambda: fgq_b200.gaussjacobi_batch(n_j, a_j, b_j))
+    n_h = rng.integers(2, 201, nr).astype(np.int32)
+    out["batch_gausshermite_1e5_rules"] = batch_entry(
+        n_h, L.fgq_gausshermite_batch_workspace_bytes(nr),
+        lambda off, xb, wb, wsb: L.fgq_gausshermite_batch_device(nr, n_h.ctypes.data, off.ctypes.data, 0, xb.data_ptr(),
+                                                                 wb.data_ptr(), wsb.data_ptr(), sp),
+        lambda: fgq_b200.gausshermite_batch(n_h))
+    n_l = rng.integers(2, 128, nr).astype(np.int32)
+    a_l = rng.uniform(-0.9, 4.9, nr)
+    out["batch_gausslaguerre_1e5_rules"] = batch_entry(
+        n_l, L.fgq_gausslaguerre_batch_workspace_bytes(nr),
+        lambda off, xb, wb, wsb: L.fgq_gausslaguerre_batch_device(nr, n_l.ctypes.data, a_l.ctypes.data, off.ctypes.data,
+                                                                  xb.data_ptr(), wb.data_ptr(), wsb.data_ptr(), sp),
+        lambda: fgq_b200.gausslaguerre_batch(n_l, a_l))
     if cpu:
         import oracle
         from oracle import hermite_oracle, jacobi_oracle, laguerre_oracle
