@@ -603,35 +603,53 @@ int legendre_asy_launch(int64_t n, int64_t kL0, int64_t kL1, double* xl, double*
 // (rec, gausslegendre.jl:233-267); n <= 5 are the closed forms (:27-60).
 // ---------------------------------------------------------------------------------------------
 
+// Per-step constants of the recurrence (gausslegendre.jl:269-290), shared by every lane, rule and Newton
+// step of a block and therefore tabulated once per block in shared memory: the counters 2k+1, k, k+1 as
+// doubles (no I2F conversions, no FP64 adds to advance them) and r = the correctly rounded 1/(k+1).
+// A lane reads step k with two 16-byte broadcast loads: the FP64 pipe, which bounds this kernel, only sees
+// the recurrence itself.
+struct __align__(16) RecStep {
+    double r, tk;    // 1/(k+1), 2k+1
+    double dk, dk1;  // k, k+1
+};
+constexpr int REC_STEPS = 64;
+
+__device__ __forceinline__ void rec_step_table(RecStep* tab) {  // call with >= 64 threads, then __syncthreads()
+    if (threadIdx.x < REC_STEPS) {
+        const int k = threadIdx.x;
+        RecStep s;
+        s.r = fgq_rcp_fast((double)(k + 1));
+        s.tk = (double)(2 * k + 1);
+        s.dk = (double)k;
+        s.dk1 = (double)(k + 1);
+        tab[k] = s;
+    }
+}
+
 // a / b for b = k + 1 (an exact small integer), given r = the correctly rounded 1/b: the last three
 // operations of the IEEE quotient's fast path (fgq_div_fast), so the same bits as a / b for every
-// normal a (|P_k|, |P'_k| stay within [1e-300, 1e6] here); a signed-zero numerator is passed through,
-// which is what IEEE gives for b > 0.  The reciprocals 1/2 .. 1/60 are shared by every lane, rule and
-// Newton step, so they are tabulated once per block in shared memory.
+// normal a (|P_k|, |P'_k| stay within [1e-300, 1e6] here).  A zero numerator comes out as +0 whatever its
+// sign, where IEEE returns -0 for -0: the sign of a zero P_k or P'_k never reaches an output (it is only
+// ever added to non-zero terms or subtracted from the abscissa), which tools/small_rule_digest.py confirms
+// over the whole input space of this path (n = 0..60) — so no FP64 compare-and-select guards it.
 __device__ __forceinline__ double div_by_count(double a, double b, double r) {
     const double q = a * r;
     const double rem = fma(-b, q, a);
-    const double res = fma(r, rem, q);
-    return a == 0.0 ? a : res;
+    return fma(r, rem, q);
 }
 
-// gausslegendre.jl:269-290 for one abscissa.  The loop counters are kept as doubles (exact), so the
-// quarter-rate I2F.F64 conversions of 2k+1, k, k+1 leave the inner loop.
-__device__ __forceinline__ void leg_inner_rec(int n, double xj, const double* __restrict__ rcp_tab, double& P,
+// gausslegendre.jl:269-290 for one abscissa.
+__device__ __forceinline__ void leg_inner_rec(int n, double xj, const RecStep* __restrict__ tab, double& P,
                                               double& PP) {
     double Pm2 = 1.0, Pm1 = xj, PPm1 = 1.0, PPm2 = 0.0;
-    double tk = 3.0, dk = 1.0, dk1 = 2.0;
     for (int k = 1; k <= n - 1; ++k) {
-        const double r = rcp_tab[k + 1];
-        const double newP = div_by_count(fma(tk * Pm1, xj, -dk * Pm2), dk1, r);
+        const RecStep s = tab[k];
+        const double newP = div_by_count(fma(s.tk * Pm1, xj, -s.dk * Pm2), s.dk1, s.r);
         Pm2 = Pm1;
         Pm1 = newP;
-        const double newPP = div_by_count(tk * fma(xj, PPm1, Pm2) - dk * PPm2, dk1, r);
+        const double newPP = div_by_count(s.tk * fma(xj, PPm1, Pm2) - s.dk * PPm2, s.dk1, s.r);
         PPm2 = PPm1;
         PPm1 = newPP;
-        tk += 2.0;
-        dk = dk1;
-        dk1 += 1.0;
     }
     P = Pm1;
     PP = PPm1;
@@ -674,7 +692,7 @@ __device__ __forceinline__ void leg_closed_form(int n, int i, double& x, double&
 // One Newton iterate of rec (gausslegendre.jl:233-267): initial guess j (0-based) of the n-point rule,
 // two Newton steps on the recurrence, weight from P' of the LAST evaluation, i.e. at the pre-update
 // iterate (:262-264).
-__device__ __forceinline__ void leg_rec_iterate(int n, int j, const double* __restrict__ rcp_tab, double& xj,
+__device__ __forceinline__ void leg_rec_iterate(int n, int j, const RecStep* __restrict__ rcp_tab, double& xj,
                                                 double& wv) {
     // leg_initial_guess (:299-309): asymptotic nodes with the n <= 255 series, negated
     LegConsts c;
@@ -705,8 +723,8 @@ __global__ void __launch_bounds__(REC_THREADS)
 legendre_rec_batch_kernel(int64_t nrules, const int32_t* __restrict__ n_i,
                           const int64_t* __restrict__ offsets, int n_single, int64_t lo, int64_t hi,
                           double* __restrict__ x, double* __restrict__ w) {
-    __shared__ double rcp_tab[64];
-    if (threadIdx.x < 64) rcp_tab[threadIdx.x] = fgq_rcp_fast((double)(threadIdx.x == 0 ? 1 : threadIdx.x));
+    __shared__ RecStep rcp_tab[REC_STEPS];
+    rec_step_table(rcp_tab);
     __syncthreads();
     const int64_t rule = ((int64_t)blockIdx.x * REC_THREADS + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -770,17 +788,15 @@ constexpr int TILE = 128;
 __global__ void __launch_bounds__(TILE)
 legendre_rec_tile_kernel(int64_t nrules, const int32_t* __restrict__ n_i, const int64_t* __restrict__ offsets,
                          double* __restrict__ x, double* __restrict__ w) {
-    __shared__ double rcp_tab[64];
+    __shared__ RecStep rcp_tab[REC_STEPS];
     __shared__ int s_bucket[64];         // histogram over key = 60 - n, then bucket starts
     __shared__ int s_n[TILE];            // n of the s-th rule of the sorted tile
     __shared__ int s_start[TILE + 1];    // first flat index of the s-th rule
     __shared__ long long s_off[TILE];    // its output offset
     __shared__ int s_warp[TILE / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid < 64) {
-        rcp_tab[tid] = fgq_rcp_fast((double)(tid == 0 ? 1 : tid));
-        s_bucket[tid] = 0;
-    }
+    rec_step_table(rcp_tab);
+    if (tid < 64) s_bucket[tid] = 0;
     __syncthreads();
     const int64_t rule = (int64_t)blockIdx.x * TILE + tid;
     int n = 0;
