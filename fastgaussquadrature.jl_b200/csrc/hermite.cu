@@ -369,17 +369,26 @@ hermite_normsum_kernel(HermiteParams p, HermiteState* st, const double* xh, cons
     __shared__ double sh[16];
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
+    __shared__ bool s_last;
+    __shared__ double s_part[HERMITE_SUM_BLOCKS];
     if (threadIdx.x == 0) {
         double a = 0.0;
         for (int i = 0; i < 16; ++i) a += sh[i];
         st->norm_part[blockIdx.x] = a;
         __threadfence();
-        if (atomicAdd(&st->sum_ticket, 1u) == gridDim.x - 1) {
-            __threadfence();
-            double tot = 0.0;
-            for (unsigned i = 0; i < gridDim.x; ++i) tot += ((volatile double*)st->norm_part)[i];
-            st->norm_sum = tot;
-        }
+        s_last = atomicAdd(&st->sum_ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // last block: fetch the partials in parallel (64 dependent L2 round trips by one thread cost ~10 us),
+    // add them in block order as before
+    __threadfence();
+    if (threadIdx.x < gridDim.x) s_part[threadIdx.x] = ((volatile double*)st->norm_part)[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (unsigned i = 0; i < gridDim.x; ++i) tot += s_part[i];
+        st->norm_sum = tot;
     }
 }
 

@@ -521,8 +521,9 @@ laguerre_small_batch_kernel(int64_t nrules, const LaguerreBatchRule* __restrict_
 // reduced rule (:163-169 ...): the rule ends before the first weight below 10 floatmin
 __global__ void laguerre_reduced_kernel(int64_t n, const double* w, LaguerreState* st) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // ~98 % of the weights underflow at n = 1e6: aggregate per warp and skip indices that cannot
-    // lower the minimum any more, instead of a million atomics on one address
+    // ~98 % of the weights underflow at n = 1e6: one candidate per BLOCK (warp shuffles, then shared memory),
+    // and blocks that cannot lower the minimum any more skip the atomic — instead of a million atomics, or
+    // 31 000 polls, on one address
     unsigned long long cand = ~0ull;
     if (i < n && fabs(w[i]) < 10 * 2.2250738585072014e-308) cand = (unsigned long long)i;
 #pragma unroll
@@ -530,7 +531,13 @@ __global__ void laguerre_reduced_kernel(int64_t n, const double* w, LaguerreStat
         const unsigned long long other = __shfl_down_sync(0xffffffffu, cand, o);
         cand = other < cand ? other : cand;
     }
-    if ((threadIdx.x & 31) == 0 && cand < *((volatile unsigned long long*)&st->n_out)) atomicMin(&st->n_out, cand);
+    __shared__ unsigned long long s_cand[32];
+    if ((threadIdx.x & 31) == 0) s_cand[threadIdx.x >> 5] = cand;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned q = 1; q < (blockDim.x + 31) / 32; ++q) cand = s_cand[q] < cand ? s_cand[q] : cand;
+        if (cand < *((volatile unsigned long long*)&st->n_out)) atomicMin(&st->n_out, cand);
+    }
 }
 
 }  // namespace fgq
