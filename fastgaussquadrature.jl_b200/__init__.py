@@ -7,6 +7,8 @@ path (reference src/FastGaussQuadrature.jl:7-19), over the C ABI of ``libfgq_cud
 from ._lib import DomainError, FGQError, NotImplementedOnDevice, build, lib  # noqa: F401
 from .api import (  # noqa: F401
     approx_besselroots,
+    besselroots,
+    gausschebyshev,
     gausschebyshevt,
     gausschebyshevu,
     gausschebyshevv,

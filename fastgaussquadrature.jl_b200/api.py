@@ -351,6 +351,30 @@ def gausschebyshevw(n):
     return _chebyshev(4, n)
 
 
+def gausschebyshev(n, kind=1):
+    """Deprecated ``gausschebyshev(n, kind=1)`` (reference src/gausschebyshev.jl:117-144): kind 1..4 forwards to
+    gausschebyshevt/u/v/w with a DeprecationWarning (the reference's ``Base.depwarn``); any other kind raises
+    ``ValueError`` (the reference's ``ArgumentError``); n < 0 is a DomainError first, as there."""
+    import warnings
+    n = _as_int(n)
+    if n < 0:
+        raise DomainError(f"DomainError({n}): Input n must be a non-negative integer")
+    if kind not in (1, 2, 3, 4):
+        raise ValueError("Chebyshev kind should be 1, 2, 3, or 4")
+    name = "tuvw"[kind - 1]
+    warnings.warn(f"`gausschebyshev(n, {kind})` is deprecated and will be removed in the next breaking release. "
+                  f"Please use `gausschebyshev{name}(n)` instead.", DeprecationWarning, stacklevel=2)
+    return _chebyshev(int(kind), n)
+
+
+def besselroots(nu, n):
+    """Deprecated alias of ``approx_besselroots`` (reference src/besselroots.jl:247)."""
+    import warnings
+    warnings.warn("`besselroots(nu, n)` is deprecated, use `approx_besselroots(nu, n)` instead.", DeprecationWarning,
+                  stacklevel=2)
+    return approx_besselroots(nu, n)
+
+
 def approx_besselroots(nu, n):
     """``approx_besselroots(ν, n)`` (reference src/besselroots.jl:23-67)."""
     n = _as_int(n)

@@ -128,6 +128,26 @@ for (f, kind) in ((:gausschebyshevt, 1), (:gausschebyshevu, 2), (:gausschebyshev
     end
 end
 
+# deprecated dispatcher gausschebyshev(n, kind) — src/gausschebyshev.jl:117-144
+function gausschebyshev(n::Integer, kind::Integer = 1)
+    n < 0 && throw(DomainError(n, "Input n must be a non-negative integer"))
+    1 <= kind <= 4 || throw(ArgumentError("Chebyshev kind should be 1, 2, 3, or 4"))
+    f = (gausschebyshevt, gausschebyshevu, gausschebyshevv, gausschebyshevw)[kind]
+    Base.depwarn("`gausschebyshev(n, $kind)` is deprecated and will be removed in the next breaking release. Please use `$(nameof(f))(n)` instead.", :gausschebyshev)
+    return f(n)
+end
+
+# approx_besselroots(ν, n) — src/besselroots.jl:23-67; besselroots is its deprecated alias (:247)
+function approx_besselroots(ν::Real, n::Integer)
+    n < 0 && throw(DomainError(n, "Input n must be a non-negative integer"))
+    x = Vector{Float64}(undef, n)
+    n == 0 && return x
+    GC.@preserve x check(ccall((:fgq_approx_besselroots, libfgq), Cint,
+        (Float64, Int64, Ptr{Float64}), Float64(ν), n, x), n)
+    return x
+end
+Base.@deprecate besselroots(ν::Real, n::Integer) approx_besselroots(ν, n)
+
 # gausshermite(n; normalize) — src/gausshermite.jl:28-33 (asymptotic branch n > 200)
 function gausshermite(n::Integer; normalize = false)
     n < 0 && throw(DomainError(n, "Input n must be a non-negative integer"))

@@ -48,3 +48,25 @@ def test_gpu_parity(fgq, oracle_mod, kind, n):
     a, b = {1: (-0.5, -0.5), 2: (0.5, 0.5), 3: (-0.5, 0.5), 4: (0.5, -0.5)}[kind]
     xj, wj = fgq.gaussjacobi(n, a, b)
     assert np.array_equal(xj, x) and np.array_equal(wj, w)
+
+
+@pytest.mark.gpu
+def test_deprecated_aliases(fgq):
+    """gausschebyshev(n, kind) (src/gausschebyshev.jl:117-144) and besselroots (src/besselroots.jl:247) keep working,
+    with a deprecation warning, exactly as in the reference."""
+    rules = {1: fgq.gausschebyshevt, 2: fgq.gausschebyshevu, 3: fgq.gausschebyshevv, 4: fgq.gausschebyshevw}
+    for kind, f in rules.items():
+        with pytest.warns(DeprecationWarning):
+            x, w = fgq.gausschebyshev(17, kind)
+        xs, ws = f(17)
+        assert np.array_equal(x, xs) and np.array_equal(w, ws)
+    with pytest.warns(DeprecationWarning):
+        x, _ = fgq.gausschebyshev(5)          # kind defaults to 1
+    assert np.array_equal(x, fgq.gausschebyshevt(5)[0])
+    with pytest.raises(ValueError):           # ArgumentError in the reference
+        fgq.gausschebyshev(5, 7)
+    with pytest.raises(fgq.DomainError):      # checked before the kind, as in the reference
+        fgq.gausschebyshev(-1, 7)
+    with pytest.warns(DeprecationWarning):
+        r = fgq.besselroots(0.3, 12)
+    assert np.array_equal(r, fgq.approx_besselroots(0.3, 12))
