@@ -46,6 +46,7 @@ SIGNATURES = {
     "fgq_gaussradau_jacobi_host": (ctypes.c_int, [_i64, ctypes.c_double, ctypes.c_double, _vp, _vp]),
     "fgq_gaussradau_jacobi_device": (ctypes.c_int, [_i64, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp, _vp]),
     "fgq_approx_besselroots": (ctypes.c_int, [ctypes.c_double, _i64, _vp]),
+    "fgq_approx_besselroots_device": (ctypes.c_int, [ctypes.c_double, _i64, _vp, _vp]),
     "fgq_besselj": (ctypes.c_double, [ctypes.c_double, ctypes.c_double]),
     "fgq_gausschebyshev_host": (ctypes.c_int, [ctypes.c_int, _i64, _vp, _vp]),
     "fgq_gausschebyshev_device": (ctypes.c_int, [ctypes.c_int, _i64, _i64, _i64, _vp, _vp, _vp]),

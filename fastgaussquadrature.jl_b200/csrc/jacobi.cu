@@ -1080,14 +1080,4 @@ extern "C" int fgq_gaussjacobi_stats(const void* workspace_dev, int* sweeps, int
 }
 
 // host-planned Bessel pieces, exported for tests (test_besselroots.jl:7-12)
-extern "C" int fgq_approx_besselroots(double nu, int64_t n, double* x) {
-    clear_status();
-    if (n < 0) {
-        set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);  // besselroots.jl:41-43
-        return FGQ_EDOMAIN;
-    }
-    if (n > 0 && !x) return FGQ_EINVAL;
-    approx_besselroots(nu, (int)n, x);
-    return FGQ_OK;
-}
 extern "C" double fgq_besselj(double nu, double x) { return besselj_real(nu, x); }

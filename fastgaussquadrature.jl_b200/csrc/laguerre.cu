@@ -88,6 +88,16 @@ __device__ __forceinline__ double laguerre_jak(const LaguerreParams& p, int64_t 
     return k <= p.head_count ? p.jak_head[k - 1] : mcmahon_dev(p, k);
 }
 
+// approx_besselroots(nu, n) as a rule of its own (besselroots.jl:23-67): the first 20 (nu = 0, table) or 6
+// (-1 <= nu <= 5, Piessens' Chebyshev series) zeros are parameter-only and planned on the host, every other
+// zero is McMahon's expansion of its index — one thread per zero.  zero_all: nu < -1, where the reference
+// returns zeros.
+__global__ void besselroots_kernel(const LaguerreParams p, int zero_all, int64_t n, double* out) {
+    const int64_t k = 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n) return;
+    out[k - 1] = zero_all ? 0.0 : laguerre_jak(p, k);
+}
+
 // gl_bulk_solve_t (:411-427)
 __device__ __forceinline__ double gl_bulk_solve_t(const LaguerreParams& p, int64_t k, unsigned int* warn) {
     const double PI = 3.141592653589793;
@@ -819,5 +829,48 @@ extern "C" int fgq_gausslaguerre_batch_host(int64_t nrules, const int32_t* n_i, 
     FGQ_CUDA_TRY(cudaMemcpyAsync(&h, ws, sizeof(h), cudaMemcpyDeviceToHost, st));
     FGQ_TRY(drain_to_host(x, w, xd, wd, total, st));
     add_warning(warn0 | (int)h.warn);
+    return FGQ_OK;
+}
+
+// ---- approx_besselroots(nu, n) on the device ----
+extern "C" int fgq_approx_besselroots_device(double nu, int64_t n, double* x_dev, void* stream) {
+    clear_status();
+    if (n < 0) {
+        set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);  // besselroots.jl:41-43
+        return FGQ_EDOMAIN;
+    }
+    if (n == 0) return FGQ_OK;
+    if (!x_dev) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    // laguerre_params plans exactly the nu-only data this needs: the table / Piessens head and McMahon's
+    // coefficients (its n-dependent fields are not read by the kernel)
+    const bool zero_all = !(nu >= -1.0);
+    const LaguerreParams p = laguerre_params(1, zero_all ? 0.0 : nu);
+    besselroots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(p, zero_all ? 1 : 0, n, x_dev);
+    FGQ_LAUNCH_CHECK();
+    return FGQ_OK;
+}
+
+extern "C" int fgq_approx_besselroots(double nu, int64_t n, double* x) {
+    clear_status();
+    if (n < 0) {
+        set_error("DomainError(%lld): Input n must be a non-negative integer", (long long)n);
+        return FGQ_EDOMAIN;
+    }
+    if (n == 0) return FGQ_OK;
+    if (!x) {
+        set_error("null output pointer");
+        return FGQ_EINVAL;
+    }
+    HostPathLock lock;
+    void* out;
+    FGQ_TRY(scratch_device((size_t)n * 8, 0, &out));
+    cudaStream_t st;
+    FGQ_TRY(scratch_stream(0, &st));
+    FGQ_TRY(fgq_approx_besselroots_device(nu, n, (double*)out, (void*)st));
+    FGQ_CUDA_TRY(cudaMemcpyAsync(x, out, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    FGQ_CUDA_TRY(cudaStreamSynchronize(st));
     return FGQ_OK;
 }

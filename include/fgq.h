@@ -125,8 +125,11 @@ int fgq_gaussradau_jacobi_host(int64_t n, double a, double b, double* x, double*
 int fgq_gaussradau_jacobi_device(int64_t n, double a, double b, double* x_dev, double* w_dev,
                                  void* workspace_dev, void* stream);
 
-/* approx_besselroots(nu, n) — src/besselroots.jl:23-67 (host-planned; 12-digit zeros of J_nu). */
+/* approx_besselroots(nu, n) — src/besselroots.jl:23-67 (12-digit zeros of J_nu): one thread per zero
+ * (McMahon's expansion, :74-116); the first 20 (nu = 0, table) / 6 (-1 <= nu <= 5, Piessens, :118-165) zeros
+ * are parameter-only data planned on the host.  n < 0 -> FGQ_EDOMAIN (:41-43). */
 int fgq_approx_besselroots(double nu, int64_t n, double* x);
+int fgq_approx_besselroots_device(double nu, int64_t n, double* x_dev, void* stream);
 /* J_nu(x), real order, moderate x: the host planner's stand-in for the reference's besselj. */
 double fgq_besselj(double nu, double x);
 

@@ -69,6 +69,13 @@ def test_no_cpu_fallback(fgq_cpu):
         fgq_cpu.gausslegendre(100)
     with pytest.raises(fgq_cpu.FGQError):
         fgq_cpu.gausslegendre_batch(np.array([5, 6, 7]))
+    for call in (lambda: fgq_cpu.gaussjacobi(50, 0.3, -0.7), lambda: fgq_cpu.gausshermite(50),
+                 lambda: fgq_cpu.gausslaguerre(50), lambda: fgq_cpu.gausschebyshevt(50),
+                 lambda: fgq_cpu.approx_besselroots(0.3, 50), lambda: fgq_cpu.gausshermite_reduced(500),
+                 lambda: fgq_cpu.gaussjacobi_batch([5, 6], 0.3, 0.2), lambda: fgq_cpu.gausshermite_batch([5, 6]),
+                 lambda: fgq_cpu.gausslaguerre_batch([5, 6], 0.0)):
+        with pytest.raises(fgq_cpu.FGQError):
+            call()
 
 
 def test_product_never_imports_the_oracle():

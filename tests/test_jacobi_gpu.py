@@ -67,11 +67,27 @@ def test_dispatch_and_errors(fgq):
 
 
 def test_besselroots_and_besselj(fgq):
-    # test/test_besselroots.jl:7-12 on the library's host planner
+    # test/test_besselroots.jl:7-12 on the library's approx_besselroots (one thread per zero on the device)
     for nu in np.arange(0, 5.01, 0.1):
         r = fgq.approx_besselroots(float(nu), 10)
         assert np.max(np.abs(jv(nu, r))) < 1e-11
         assert np.allclose(r, jo.approx_besselroots(float(nu), 10), rtol=1e-14, atol=0)
+    # every branch of besselroots.jl:28-67 at lengths beyond the host-planned head
+    for nu in (0.0, -1.0, -0.5, 0.3, 5.0, 5.5, 12.25):
+        for n in (0, 1, 5, 6, 7, 20, 21, 1000, 100003):
+            r = fgq.approx_besselroots(nu, n)
+            ro = jo.approx_besselroots(nu, n)
+            assert r.shape == ro.shape
+            assert np.all(np.abs(r - ro) <= 2 * np.spacing(np.abs(ro))), (nu, n)
+    assert np.array_equal(fgq.approx_besselroots(-1.5, 8), np.zeros(8))   # no branch of the reference matches: zeros
+    with pytest.raises(fgq.DomainError):
+        fgq.approx_besselroots(0.0, -1)
+    # device-resident variant
+    import torch
+    out = torch.empty(1000, dtype=torch.float64, device="cuda")
+    assert fgq.lib().fgq_approx_besselroots_device(0.3, 1000, out.data_ptr(), 0) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), fgq.approx_besselroots(0.3, 1000))
     # besselj stand-in (double-double ascending series) against mpmath; AMOS (scipy.special.jv, what
     # the reference calls) is itself only good to ~5e-14 of the local amplitude on this grid
     import mpmath as mp
