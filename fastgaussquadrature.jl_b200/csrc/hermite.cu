@@ -13,6 +13,8 @@
 // kernel reduces its max into the workspace, the last block to finish sets a `done` flag, and the
 // remaining (pre-enqueued) sweep launches exit immediately.  Then a reduction for the global
 // normalisation sum (:62) and a fold/scale kernel that also applies exp(-x^2) (:30).
+#include <cooperative_groups.h>
+
 #include "airy.cuh"
 #include "common.cuh"
 #include "fgq_math.h"
@@ -22,6 +24,8 @@
 
 #include <mutex>
 #include <vector>
+
+namespace cg = cooperative_groups;
 
 namespace fgq {
 
@@ -111,26 +115,33 @@ __device__ double hermite_guess(const HermiteParams& p, int64_t i) {
     return sqrt(fabs(v));
 }
 
-__global__ void hermite_init_kernel(HermiteParams p, HermiteState* st, double* theta) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t == 0) {
-        for (int i = 0; i < 20; ++i) {
-            st->maxdt_bits[i] = 0ull;
-            st->ticket[i] = 0u;
-        }
-        st->done = 0;
-        st->sweeps = 0;
-        st->norm_sum = 0.0;
-        st->sum_ticket = 0u;
-    }
-    if (t >= p.nact) return;
+// initial theta of half-range node t (0-based, from the centre)
+__device__ __forceinline__ double hermite_theta0(const HermiteParams& p, int64_t t) {
     double x0;
     if (p.odd) {
         x0 = (t == 0) ? 0.0 : hermite_guess(p, t);  // [0; x_init][1:m+1]
     } else {
         x0 = hermite_guess(p, t + 1);
     }
-    theta[t] = acos(x0 / p.sq_musq);
+    return acos(x0 / p.sq_musq);
+}
+
+__device__ __forceinline__ void hermite_state_reset(HermiteState* st) {
+    for (int i = 0; i < 20; ++i) {
+        st->maxdt_bits[i] = 0ull;
+        st->ticket[i] = 0u;
+    }
+    st->done = 0;
+    st->sweeps = 0;
+    st->norm_sum = 0.0;
+    st->sum_ticket = 0u;
+}
+
+__global__ void hermite_init_kernel(HermiteParams p, HermiteState* st, double* theta) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) hermite_state_reset(st);
+    if (t >= p.nact) return;
+    theta[t] = hermite_theta0(p, t);
 }
 
 // gausshermite.jl:171-250 at one theta
@@ -180,6 +191,28 @@ __device__ __forceinline__ void hermpoly_asy_airy(const HermiteParams& p, double
 
 constexpr int HERM_THREADS = 128;
 
+// One Newton step (gausshermite.jl:75-86) of half-range node t; returns the bit pattern of |dtheta| (non-negative
+// doubles order like integers; a NaN update returns the NaN pattern, which sorts last: it poisons the norm, as
+// norm() does)
+__device__ __forceinline__ unsigned long long hermite_sweep_node(const HermiteParams& p, int64_t t, double* theta,
+                                                                 double* xh, double* wh) {
+    double th = theta[t];
+    double s, c;
+    sincos(th, &s, &c);
+    double val, dval;
+    hermpoly_asy_airy(p, th, s, c, val, dval);
+    const double dth = -val / (1.4142135623730951 * p.sq_musq * dval * s);
+    th = th - dth;
+    theta[t] = th;
+    double adt = fabs(dth);
+    if (dth != dth) adt = __longlong_as_double(0x7ff8000000000000LL);
+    const double x = p.sq_musq * cos(th);
+    const double w = x * val + 1.4142135623730951 * dval;
+    xh[t] = x;
+    wh[t] = 1.0 / (w * w);
+    return (unsigned long long)__double_as_longlong(adt);
+}
+
 // One Newton sweep (gausshermite.jl:75-86) over the half range.  Persistent grid (grid stride over the
 // node tiles): the pre-enqueued sweeps that find the rule converged then cost ~2 us instead of the time to
 // schedule and retire thousands of empty blocks.
@@ -190,22 +223,8 @@ hermite_sweep_kernel(HermiteParams p, int sweep, HermiteState* st, double* theta
     if (*((volatile int*)&st->done)) return;
     unsigned long long bits = 0ull;
     for (int64_t t = (int64_t)blockIdx.x * HERM_THREADS + threadIdx.x; t < p.nact; t += (int64_t)gridDim.x * HERM_THREADS) {
-        double th = theta[t];
-        double s, c;
-        sincos(th, &s, &c);
-        double val, dval;
-        hermpoly_asy_airy(p, th, s, c, val, dval);
-        const double dth = -val / (1.4142135623730951 * p.sq_musq * dval * s);
-        th = th - dth;
-        theta[t] = th;
-        double adt = fabs(dth);
-        if (dth != dth) adt = __longlong_as_double(0x7ff8000000000000LL);  // NaN poisons the norm, as norm() does
-        const unsigned long long b = (unsigned long long)__double_as_longlong(adt);
+        const unsigned long long b = hermite_sweep_node(p, t, theta, xh, wh);
         bits = b > bits ? b : bits;
-        const double x = p.sq_musq * cos(th);
-        const double w = x * val + 1.4142135623730951 * dval;
-        xh[t] = x;
-        wh[t] = 1.0 / (w * w);
     }
     // block max of |dtheta| through the bit pattern (non-negative doubles order like integers; NaN sorts last)
 #pragma unroll
@@ -431,6 +450,117 @@ hermite_fold_kernel(HermiteParams p, int normalize, const HermiteState* st, cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// The whole asymptotic rule in ONE cooperative launch (n > 200).  The multi-launch form above pre-enqueues
+// init, 20 sweeps, the normalisation sum and the fold — 23 launches of which 17 find the rule converged and
+// return, and at n = 1e6 those empty launches plus the kernel boundaries are a quarter of the call.  Here a
+// persistent grid (every block co-resident: cudaLaunchCooperativeKernel) keeps each half-range node with one
+// thread from the initial guess to the last sweep; the only global steps are the reference's stopping rule
+// (a grid barrier per sweep, then everybody reads the same max) and the normalisation sum.  Same device
+// functions per node and the same summation order as hermite_normsum_kernel (virtual blocks of 512 threads,
+// grid-stride terms, shuffle tree per warp, warp partials and block partials added in index order), so the
+// results are bit-identical to the multi-launch form (FGQ_HERMITE_FUSED=0 selects it; the digest tool
+// compares the two).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HERM_THREADS, 4)
+hermite_fused_kernel(HermiteParams p, int normalize, HermiteState* st, double* theta, double* xh, double* wh,
+                     int64_t lo, int64_t hi, double* x, double* w) {
+    cg::grid_group grid = cg::this_grid();
+    const int64_t gid = (int64_t)blockIdx.x * HERM_THREADS + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * HERM_THREADS;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (gid == 0) hermite_state_reset(st);
+    for (int64_t t = gid; t < p.nact; t += stride) theta[t] = hermite_theta0(p, t);
+    grid.sync();  // the reset is visible before anybody reduces into the state
+    __shared__ unsigned long long sh_bits[HERM_THREADS / 32];
+    for (int sweep = 0; sweep < 20; ++sweep) {
+        unsigned long long bits = 0ull;
+        for (int64_t t = gid; t < p.nact; t += stride) {
+            const unsigned long long b = hermite_sweep_node(p, t, theta, xh, wh);
+            bits = b > bits ? b : bits;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_down_sync(0xffffffffu, bits, o);
+            bits = other > bits ? other : bits;
+        }
+        if (lane == 0) sh_bits[wid] = bits;
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 1; i < HERM_THREADS / 32; ++i) bits = sh_bits[i] > bits ? sh_bits[i] : bits;
+            atomicMax(&st->maxdt_bits[sweep], bits);
+        }
+        grid.sync();
+        const double mx = __longlong_as_double((long long)*((volatile unsigned long long*)&st->maxdt_bits[sweep]));
+        if (gid == 0) st->sweeps = sweep + 1;
+        if (mx < p.tol) break;  // the reference's stopping rule (:79); the same value everywhere
+    }
+    // normalisation sum: real block b plays virtual block b of hermite_normsum_kernel (512 threads = 16 warps;
+    // each of the 4 real warps takes 4 of them)
+    int64_t vb = (p.nact + 511) / 512;
+    if (vb > HERMITE_SUM_BLOCKS) vb = HERMITE_SUM_BLOCKS;
+    __shared__ double sh_sum[16];
+    __shared__ double s_part[HERMITE_SUM_BLOCKS];
+    __shared__ double s_tot;
+    // the terms themselves (an exp each) are computed by the whole grid, into theta, which has served its
+    // purpose; the fixed-order sums below then only add
+    for (int64_t t = gid; t < p.nact; t += stride) theta[t] = hermite_norm_term(p, t, xh, wh);
+    grid.sync();
+    for (int64_t b = blockIdx.x; b < vb; b += gridDim.x) {
+        // real warp `wid` plays virtual warps wid, wid + 4, wid + 8, wid + 12 at once, four strides per round:
+        // 16 independent loads in flight, then the adds of each virtual thread in its fixed order (a term
+        // past the end is replaced by +0.0, which leaves a non-negative sum unchanged)
+        const int64_t vstride = vb * 512;
+        const int64_t t0 = b * 512 + wid * 32 + lane;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int64_t base = 0; b * 512 + base < p.nact; base += 4 * vstride) {
+            double v[4][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t t = t0 + 128 * k + base + j * vstride;
+                    v[k][j] = t < p.nact ? theta[t] : 0.0;
+                }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[k] += v[k][j];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double s = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+            if (lane == 0) sh_sum[wid + 4 * k] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0.0;
+            for (int i = 0; i < 16; ++i) a += sh_sum[i];
+            st->norm_part[b] = a;
+        }
+        __syncthreads();
+    }
+    grid.sync();
+    if (tid < vb) s_part[tid] = ((volatile double*)st->norm_part)[tid];
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int64_t i = 0; i < vb; ++i) tot += s_part[i];
+        s_tot = tot;
+        if (blockIdx.x == 0) st->norm_sum = tot;
+    }
+    __syncthreads();
+    const double tot = s_tot;
+    for (int64_t i = lo + gid; i < hi; i += stride) {
+        double xo, wo;
+        hermite_fold_one(p, normalize, tot, xh, wh, i, xo, wo);
+        x[i - lo] = xo;
+        w[i - lo] = wo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batched small rules (n <= 200): one block per rule runs the whole single-rule
 // pipeline — hermite_gw / hermite_rec, the normalisation sum, the fold — out of shared memory, with the
 // same device functions and the same summation order as the single-rule launches above, so a batch
@@ -519,6 +649,19 @@ extern "C" int64_t fgq_gausshermite_workspace_bytes(int64_t n) {
     return 1024 + 3 * 8 * nh;
 }
 
+// FGQ_HERMITE_FUSED=0: the multi-launch form (regression checks); default: one cooperative launch
+static bool hermite_use_fused() {
+    static const bool on = []() {
+        const char* e = getenv("FGQ_HERMITE_FUSED");
+        if (e && atoi(e) == 0) return false;
+        int dev = 0, coop = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) return false;
+        return coop != 0;
+    }();
+    return on;
+}
+
 // nact: half-range nodes to compute (from the centre); the output slice [lo, hi) must lie within them
 static int hermite_device_impl(int64_t n, int normalize, int64_t lo, int64_t hi, int64_t nact, double* x_dev,
                                double* w_dev, void* workspace_dev, cudaStream_t st) {
@@ -529,6 +672,21 @@ static int hermite_device_impl(int64_t n, int normalize, int64_t lo, int64_t hi,
     double* xh = theta + p.nh;
     double* wh = xh + p.nh;
     const unsigned b128 = (unsigned)((p.nact + HERM_THREADS - 1) / HERM_THREADS);
+    if (n > 200 && hermite_use_fused()) {
+        int dev = 0, per_sm = 0, sms = 0;
+        FGQ_CUDA_TRY(cudaGetDevice(&dev));
+        FGQ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hermite_fused_kernel, HERM_THREADS, 0));
+        FGQ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int64_t grid = (int64_t)per_sm * sms;
+        if (grid > b128) grid = b128;
+        if (grid < 1) grid = 1;
+        void* args[] = {(void*)&p, (void*)&normalize, (void*)&state, (void*)&theta, (void*)&xh, (void*)&wh,
+                        (void*)&lo, (void*)&hi, (void*)&x_dev, (void*)&w_dev};
+        FGQ_CUDA_TRY(cudaLaunchCooperativeKernel((void*)hermite_fused_kernel, dim3((unsigned)grid), dim3(HERM_THREADS),
+                                                 args, 0, st));
+        count_launch();
+        return FGQ_OK;
+    }
     hermite_init_kernel<<<b128, HERM_THREADS, 0, st>>>(p, state, theta);  // also resets the state
     FGQ_LAUNCH_CHECK();
     if (n <= 20) {  // :41-45; n = 1 (x = 0, w = sqrt(pi), :41-42) is the 1 x 1 case of the same kernel

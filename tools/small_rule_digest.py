@@ -48,3 +48,7 @@ print("lobatto 5000".ljust(34), digest(fgq_b200.gausslobatto(5000)))
 print("hermite 100000".ljust(34), digest(fgq_b200.gausshermite(100_000)))
 print("laguerre 100000".ljust(34), digest(fgq_b200.gausslaguerre(100_000, 0.5)))
 print("legendre 1000001".ljust(34), digest(fgq_b200.gausslegendre(1_000_001)))
+for n in (201, 5001, 1_000_000):
+    print(f"hermite asy {n}".ljust(34), digest(fgq_b200.gausshermite(n)))
+print("hermite asy 100001 normalize".ljust(34), digest(fgq_b200.gausshermite(100_001, normalize=True)))
+print("hermite reduced 1000000".ljust(34), digest(fgq_b200.gausshermite_reduced(1_000_000)[1:]))
