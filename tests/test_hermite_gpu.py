@@ -168,3 +168,28 @@ def test_reduced_rule_size(fgq):
     with pytest.raises(fgq.DomainError):
         fgq.gausshermite_reduced(-1)
     assert len(fgq.gausshermite_reduced(0)[1]) == 0
+
+
+def test_fused_launch_equals_multi_launch_form():
+    """n > 200 runs as one cooperative launch (hermite_fused_kernel); FGQ_HERMITE_FUSED=0 selects the
+    multi-launch form it replaced.  Both must give the same bits (full and truncated rule, both normalisations,
+    even and odd n) — checked in two subprocesses because the switch is read once per process."""
+    import subprocess
+    import sys
+    code = (
+        "import hashlib, sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(HERE)!r})\n"
+        "import fgq_b200\n"
+        "h = hashlib.sha256()\n"
+        "for n in (201, 1000, 5001, 100000, 1000001):\n"
+        "    for nz in (False, True):\n"
+        "        for a in fgq_b200.gausshermite(n, normalize=nz): h.update(a.tobytes())\n"
+        "        for a in fgq_b200.gausshermite_reduced(n, normalize=nz)[1:]: h.update(a.tobytes())\n"
+        "print(h.hexdigest())\n")
+    outs = []
+    for fused in ("0", "1"):
+        env = dict(os.environ, FGQ_HERMITE_FUSED=fused)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1] and len(outs[0]) == 64
