@@ -76,6 +76,8 @@ SIGNATURES = {
     "fgq_measure_store_peak": (ctypes.c_int, [_i64, _dp]),
     "fgq_debug_legendre_theta_device": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp]),
     "fgq_debug_fastdiv_check": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp]),
+    "fgq_debug_codec_stats": (ctypes.c_int, [_i64p, _i64p]),
+    "fgq_debug_codec_roundtrip_host": (ctypes.c_int, [_vp, _i64, _vp, _i64p]),
     "fgq_debug_drain_stats": (ctypes.c_int, [_i64p, _i64p, _i64p, ctypes.POINTER(ctypes.c_int)]),
 }
 

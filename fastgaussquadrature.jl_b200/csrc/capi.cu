@@ -18,6 +18,7 @@
 #endif
 
 #include "common.cuh"
+#include "delta_codec.h"
 
 namespace fgq {
 
@@ -241,7 +242,7 @@ __attribute__((target("avx2"))) static void copy_stream_avx2(double* dst, const 
 static void copy_stream(double* dst, const double* src, int64_t n) {
 #if defined(__x86_64__)
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
-    if (have_avx2 && n >= 4096) {
+    if (have_avx2 && n >= 256) {
         copy_stream_avx2(dst, src, n);
         return;
     }
@@ -645,6 +646,292 @@ int host_pipeline(int64_t lo_all, int64_t hi_all, double* x, double* w, SliceFn 
     return cp.finish(rc);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Compressed transport of a mirror-pair shard (delta_codec.h): the kernel's output is packed on the device
+// into second-difference streams (~1 byte per value instead of 8), those cross PCIe into pinned staging, and
+// the host threads unpack them straight into the caller's left slice and its mirror image.  PCIe stops being
+// the bound (1-2 GB instead of 8 GB per 1e9-node rule); what remains is the host writing its own 16 GB.
+// Works the same for pinned and pageable destinations (no ring copy: the decoder's output IS the result).
+// Pipeline: chunk j+1 is generated and packed while chunk j is in flight / being decoded; a chunk's streams
+// are cut into batches that fit a staging slot (normally one batch per chunk; incompressible data — never
+// produced by the rule kernels, but the codec does not assume that — just takes more batches).
+// ---------------------------------------------------------------------------------------------
+static std::atomic<int64_t> g_codec_bytes{0}, g_codec_values{0};
+
+struct CodecBatch {
+    int64_t chunk_lo;      // first element (of the left slice) of the chunk this batch belongs to
+    int64_t b0, b1;        // block range within the chunk
+    int64_t chunk_len;     // elements in the chunk
+    const uint32_t* dir[2];
+    const uint8_t* stage[2];  // staging address of the first byte of block b0's stream, per array
+    uint32_t base8[2];        // stream offset (8-byte units) of block b0, per array
+    int slot;
+};
+
+static int codec_pair_pipeline(int64_t n, int64_t k_lo, int64_t cnt, double* xl, double* wl, const MirrorSpec& mir) {
+    constexpr int64_t CHUNK = 1LL << 24;
+    constexpr int64_t NB = CHUNK / CODEC_BLOCK;
+    constexpr size_t STAGE_BYTES = 64u << 20;            // per staging slot (both arrays of a batch)
+    const size_t pay_bytes = (size_t)codec_worst_bytes(CHUNK);  // per array, per device slot
+    const int64_t nch = (cnt + CHUNK - 1) / CHUNK;
+    const int nslot = nch > 1 ? 2 : 1;
+    const int64_t cap = cnt < CHUNK ? cnt : CHUNK;  // values per array in a raw slot; w starts 16-byte aligned after x
+    // device memory: raw chunk (scratch slots 0/1 as the plain pipeline), codec arrays (slot 7)
+    const size_t dev_per_slot = 2 * pay_bytes + 4 * (size_t)NB * 4 + 64;
+    void* dev_all;
+    FGQ_TRY(scratch_device(dev_per_slot * 2, 7, &dev_all));
+    double* raw[2] = {nullptr, nullptr};
+    for (int s = 0; s < nslot; ++s) {
+        void* p;
+        FGQ_TRY(scratch_device((size_t)(cap + 2) * 16, s, &p));
+        raw[s] = (double*)p;
+    }
+    // pinned: 2 staging slots + per device slot the directories and totals
+    void* pin_all;
+    const size_t dir_bytes = 2 * (size_t)NB * 4 + 64;
+    FGQ_TRY(scratch_pinned(2 * STAGE_BYTES + 2 * dir_bytes, 0, &pin_all));
+    uint8_t* stage[2] = {(uint8_t*)pin_all, (uint8_t*)pin_all + STAGE_BYTES};
+    uint8_t* dir_h[2] = {(uint8_t*)pin_all + 2 * STAGE_BYTES, (uint8_t*)pin_all + 2 * STAGE_BYTES + dir_bytes};
+    CodecArrays ca[2];
+    for (int s = 0; s < 2; ++s) {
+        uint8_t* base = (uint8_t*)dev_all + (size_t)s * dev_per_slot;
+        ca[s].payload[0] = base;
+        ca[s].payload[1] = base + pay_bytes;
+        ca[s].size8[0] = (uint32_t*)(base + 2 * pay_bytes);
+        ca[s].size8[1] = ca[s].size8[0] + NB;
+        ca[s].dir[0] = ca[s].size8[1] + NB;
+        ca[s].dir[1] = ca[s].dir[0] + NB;   // dir[0], dir[1] contiguous: one copy
+        ca[s].total8 = (unsigned long long*)(ca[s].dir[1] + NB);
+        ca[s].capacity8 = pay_bytes / 8;
+    }
+    cudaStream_t s_compute, s_copy;
+    FGQ_TRY(scratch_stream(0, &s_compute));
+    FGQ_TRY(scratch_stream(1, &s_copy));
+    cudaEvent_t packed[2], sent[2], landed[2];  // per device slot: packed / all payload copied; per staging slot: landed
+    for (int i = 0; i < 2; ++i) {
+        FGQ_CUDA_TRY(cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming));
+        FGQ_CUDA_TRY(cudaEventCreateWithFlags(&sent[i], cudaEventDisableTiming));
+        FGQ_CUDA_TRY(cudaEventCreateWithFlags(&landed[i], cudaEventDisableTiming));
+    }
+    WorkerPool& pool = WorkerPool::get();
+    const int T = pool.max_threads() > 1 ? pool.max_threads() : 1;
+    int dev;
+    FGQ_CUDA_TRY(cudaGetDevice(&dev));
+
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<CodecBatch> batches;     // published batches, in order
+    int64_t next_group = 0;              // next block group to claim within batches[cur]
+    size_t cur = 0;                      // batch being decoded
+    int64_t groups_done = 0;             // finished groups of batches[cur]
+    size_t batches_done = 0;
+    bool all_published = false, failed = false;
+    int rc = FGQ_OK;
+    cudaError_t err = cudaSuccess;
+    constexpr int64_t GROUP = 16;        // blocks per claim
+
+    auto launch_chunk = [&](int64_t j) -> int {
+        const int s = (int)(j % nslot);
+        const int64_t lo = j * CHUNK, len = lo + CHUNK < cnt ? CHUNK : cnt - lo;
+        if (j >= nslot) FGQ_CUDA_TRY(cudaStreamWaitEvent(s_compute, sent[s], 0));  // device slot drained
+        double* xd = raw[s];
+        double* wd = raw[s] + ((cap + 1) & ~1LL);
+        FGQ_TRY(fgq_gausslegendre_device(n, k_lo - 1 + lo, k_lo - 1 + lo + len, xd, wd, (void*)s_compute));
+        ca[s].values[0] = xd;
+        ca[s].values[1] = wd;
+        FGQ_TRY(codec_encode_launch(ca[s], len, s_compute));
+        FGQ_CUDA_TRY(cudaEventRecord(packed[s], s_compute));
+        return FGQ_OK;
+    };
+
+    auto feeder = [&]() {
+        int64_t launched = 0;
+        size_t published = 0;
+        auto fail = [&](int r, cudaError_t e) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (r != FGQ_OK) rc = r;
+            if (e != cudaSuccess) err = e;
+            failed = true;
+            cv.notify_all();
+        };
+        for (int64_t j = 0; j < nch; ++j) {
+            const int s = (int)(j % nslot);
+            while (launched <= j + 1 && launched < nch) {
+                const int r = launch_chunk(launched);
+                if (r != FGQ_OK) return fail(r, cudaSuccess);
+                ++launched;
+            }
+            const int64_t lo = j * CHUNK, len = lo + CHUNK < cnt ? CHUNK : cnt - lo;
+            const int64_t nb = (len + CODEC_BLOCK - 1) / CODEC_BLOCK;
+            // the host copy of chunk j-2's directory is still in use until that chunk is decoded
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] {
+                    if (failed) return true;
+                    // every batch of chunk j - nslot (same slot) consumed?
+                    for (size_t q = batches_done; q < batches.size(); ++q)
+                        if (batches[q].chunk_lo == (j - nslot) * CHUNK && j >= nslot) return false;
+                    return true;
+                });
+                if (failed) return;
+            }
+            cudaError_t e = cudaStreamWaitEvent(s_copy, packed[s], 0);
+            uint32_t* dh = (uint32_t*)dir_h[s];
+            if (e == cudaSuccess)  // dir[0], dir[1], total8[2] are contiguous on the device
+                e = cudaMemcpyAsync(dh, ca[s].dir[0], 2 * (size_t)NB * 4 + 16, cudaMemcpyDeviceToHost, s_copy);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s_copy);
+            if (e != cudaSuccess) return fail(FGQ_OK, e);
+            const uint32_t* d[2] = {dh, dh + NB};
+            unsigned long long tot8[2];
+            memcpy(tot8, dh + 2 * NB, 16);
+            if (tot8[0] > ca[s].capacity8 || tot8[1] > ca[s].capacity8) return fail(FGQ_EINVAL, cudaSuccess);
+            g_codec_bytes += (int64_t)(tot8[0] + tot8[1]) * 8;
+            g_codec_values += 2 * len;
+            auto off8 = [&](int a, int64_t b) -> uint64_t { return b < nb ? (uint64_t)(d[a][b] >> 2) : (uint64_t)tot8[a]; };
+            int64_t b0 = 0;
+            while (b0 < nb) {
+                // largest b1 with both ranges fitting one staging slot
+                int64_t b1 = b0;
+                while (b1 < nb) {
+                    const uint64_t bytes = ((off8(0, b1 + 1) - off8(0, b0)) + (off8(1, b1 + 1) - off8(1, b0))) * 8;
+                    if (bytes > STAGE_BYTES) break;
+                    ++b1;
+                }
+                if (b1 == b0) return fail(FGQ_EINVAL, cudaSuccess);  // cannot happen: a block is <= 8.2 KB
+                const int slot = (int)(published & 1);
+                {   // staging slot free: the batch that used it two publications ago is decoded
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return failed || published < 2 || batches_done + 2 > published; });
+                    if (failed) return;
+                }
+                const size_t bx = (size_t)(off8(0, b1) - off8(0, b0)) * 8, bw = (size_t)(off8(1, b1) - off8(1, b0)) * 8;
+                e = cudaMemcpyAsync(stage[slot], ca[s].payload[0] + off8(0, b0) * 8, bx, cudaMemcpyDeviceToHost, s_copy);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(stage[slot] + bx, ca[s].payload[1] + off8(1, b0) * 8, bw, cudaMemcpyDeviceToHost, s_copy);
+                if (e == cudaSuccess) e = cudaEventRecord(landed[slot], s_copy);
+                if (e == cudaSuccess && b1 == nb) e = cudaEventRecord(sent[s], s_copy);
+                if (e != cudaSuccess) return fail(FGQ_OK, e);
+                CodecBatch B;
+                B.chunk_lo = lo;
+                B.chunk_len = len;
+                B.b0 = b0;
+                B.b1 = b1;
+                B.dir[0] = d[0];
+                B.dir[1] = d[1];
+                B.stage[0] = stage[slot];
+                B.stage[1] = stage[slot] + bx;
+                B.base8[0] = (uint32_t)off8(0, b0);
+                B.base8[1] = (uint32_t)off8(1, b0);
+                B.slot = slot;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    batches.push_back(B);
+                    ++published;
+                    cv.notify_all();
+                }
+                b0 = b1;
+            }
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        all_published = true;
+        cv.notify_all();
+    };
+
+    auto decoder = [&]() {
+        cudaSetDevice(dev);
+        int64_t tmp[CODEC_BLOCK];
+        size_t synced = (size_t)-1;  // batch whose landing this thread has already waited for
+        for (;;) {
+            CodecBatch B;
+            int64_t g0, g1;
+            size_t my;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                for (;;) {
+                    if (failed) return;
+                    if (cur < batches.size()) {
+                        const int64_t ngroups = (batches[cur].b1 - batches[cur].b0 + GROUP - 1) / GROUP;
+                        if (next_group < ngroups) break;
+                        // this batch is fully claimed: wait until it is finished, then move on
+                        cv.wait(lk);
+                        continue;
+                    }
+                    if (all_published) return;
+                    cv.wait(lk);
+                }
+                my = cur;
+                B = batches[cur];
+                g0 = B.b0 + next_group * GROUP;
+                g1 = g0 + GROUP < B.b1 ? g0 + GROUP : B.b1;
+                ++next_group;
+            }
+            if (synced != my) {
+                if (cudaEventSynchronize(landed[B.slot]) != cudaSuccess) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    failed = true;
+                    cv.notify_all();
+                    return;
+                }
+                synced = my;
+            }
+            for (int64_t b = g0; b < g1; ++b) {
+                const int64_t e0 = B.chunk_lo + b * CODEC_BLOCK;  // element index within the left slice
+                const int len = (int)(B.chunk_len - b * CODEC_BLOCK < CODEC_BLOCK ? B.chunk_len - b * CODEC_BLOCK : CODEC_BLOCK);
+                const int64_t e1m = e0 + len < mir.mirror_cnt ? e0 + len : mir.mirror_cnt;
+                for (int a = 0; a < 2; ++a) {
+                    const uint32_t ent = B.dir[a][b];
+                    const uint8_t* p = B.stage[a] + (size_t)((ent >> 2) - B.base8[a]) * 8;
+                    codec_decode_block(p, (int)(ent & 3u), len, tmp);
+                    double* dst = a == 0 ? xl : wl;
+                    double* dstr = a == 0 ? mir.xr : mir.wr;
+                    copy_stream(dst + e0, (const double*)tmp, len);
+                    if (e1m > e0) mirror_copy((const double*)tmp - e0, dstr, mir.cnt, e0, e1m, a == 0);
+                }
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ++groups_done;
+                const int64_t ngroups = (batches[my].b1 - batches[my].b0 + GROUP - 1) / GROUP;
+                if (my == cur && groups_done == ngroups) {  // batch finished
+                    ++cur;
+                    ++batches_done;
+                    next_group = 0;
+                    groups_done = 0;
+                }
+                cv.notify_all();
+            }
+        }
+    };
+    pool.run(T + 1, [&](int t) {
+        if (t == 0) feeder(); else decoder();
+    });
+    cudaError_t e1 = cudaStreamSynchronize(s_compute);
+    cudaError_t e2 = cudaStreamSynchronize(s_copy);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(packed[i]);
+        cudaEventDestroy(sent[i]);
+        cudaEventDestroy(landed[i]);
+    }
+    if (rc != FGQ_OK) {
+        set_error("internal: transport coding failed");
+        return rc;
+    }
+    FGQ_CUDA_TRY(err);
+    FGQ_CUDA_TRY(e1);
+    FGQ_CUDA_TRY(e2);
+    if (failed) {
+        set_error("device-to-host transfer failed");
+        return FGQ_ECUDA;
+    }
+    return FGQ_OK;
+}
+
+// FGQ_HOST_CODEC=0 sends the plain values instead (comparison runs, tests)
+static bool use_host_codec() {
+    const char* e = getenv("FGQ_HOST_CODEC");
+    return !(e && atoi(e) == 0);
+}
+
 }  // namespace fgq
 
 static int legendre_slice(void* ctx, int64_t lo, int64_t hi, double* xd, double* wd,
@@ -689,6 +976,10 @@ extern "C" int fgq_gausslegendre_host_pair(int64_t n, int64_t k_lo, int64_t k_hi
     // the first-touch page faults of a freshly allocated 16 GB result over all of them.
     // everything pinned: the kernel also leaves the +-x image in device memory, so that drain_to_host can
     // balance the mirror work between PCIe and the host threads
+    if (use_host_codec() && cnt >= (1LL << 20)) {
+        const MirrorSpec mirc{xr, wr, cnt, 0, (k_hi - 1 > mr) ? cnt - 1 : cnt};
+        return codec_pair_pipeline(n, k_lo, cnt, xl, wl, mirc);
+    }
     const bool all_pinned = is_pinned_host(xl) && is_pinned_host(wl) && is_pinned_host(xr) && is_pinned_host(wr);
     ChunkedProducer cp;
     FGQ_TRY(cp.init(cnt, 1LL << chunk_log2, all_pinned));
@@ -708,6 +999,30 @@ extern "C" int fgq_gausslegendre_host_pair(int64_t n, int64_t k_lo, int64_t k_hi
 // counters of the threaded drains since the last call of this function: pieces handled by host threads,
 // pieces whose mirror image went by DMA, pieces that had landed before a thread picked them up, and the
 // last value of the adaptive DMA share (x 1000)
+// bytes that crossed PCIe in coded form and the values they carried, since the last call of this function
+extern "C" int fgq_debug_codec_stats(int64_t* bytes, int64_t* values) {
+    if (bytes) *bytes = g_codec_bytes.exchange(0);
+    if (values) *values = g_codec_values.exchange(0);
+    return FGQ_OK;
+}
+
+// Round trip of the transport coding on the HOST (tests without a GPU): decode(encode(in)) -> out, stream size
+// through *stream_bytes.  The product packs on the device; this is the reference encoder of delta_codec.h.
+extern "C" int fgq_debug_codec_roundtrip_host(const double* in, int64_t cnt, double* out, int64_t* stream_bytes) {
+    if (cnt < 0 || (cnt > 0 && (!in || !out))) return FGQ_EINVAL;
+    const int64_t nb = (cnt + CODEC_BLOCK - 1) / CODEC_BLOCK;
+    std::vector<uint8_t> payload((size_t)codec_worst_bytes(cnt) + 8);
+    std::vector<uint32_t> dir((size_t)nb + 1);
+    const int64_t bytes = codec_encode_host((const int64_t*)in, cnt, payload.data(), dir.data());
+    for (int64_t b = 0; b < nb; ++b) {
+        const int len = (int)(cnt - b * CODEC_BLOCK < CODEC_BLOCK ? cnt - b * CODEC_BLOCK : CODEC_BLOCK);
+        codec_decode_block(payload.data() + (size_t)(dir[(size_t)b] >> 2) * 8, (int)(dir[(size_t)b] & 3u), len,
+                           (int64_t*)out + b * CODEC_BLOCK);
+    }
+    if (stream_bytes) *stream_bytes = bytes;
+    return FGQ_OK;
+}
+
 extern "C" int fgq_debug_drain_stats(int64_t* pieces, int64_t* dma_pieces, int64_t* landed, int* share_milli) {
     if (pieces) *pieces = g_drain_pieces.exchange(0);
     if (dma_pieces) *dma_pieces = g_drain_dma.exchange(0);

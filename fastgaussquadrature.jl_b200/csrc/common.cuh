@@ -101,6 +101,18 @@ struct SmallRule {   // one rule of a batch: n nodes written at x[off .. off+n)
 int small_batch_rules(int64_t nrules, const int32_t* n_i, const int64_t* offsets, int n_max, const char* what,
                       std::vector<SmallRule>* rules, int64_t* total);
 
+// Transport coding of a chunk of (x, w) before it crosses PCIe (delta_codec.h, codec.cu).  Index 0 = x, 1 = w.
+constexpr int64_t CODEC_MAX_BLOCKS = 1LL << 15;  // 1024-value blocks per chunk (2^25 values)
+struct CodecArrays {
+    const double* values[2];     // the chunk in device memory
+    uint32_t* size8[2];          // per block: (stream size in 8-byte units << 2) | width class
+    uint32_t* dir[2];            // per block: (stream offset in 8-byte units << 2) | width class
+    uint8_t* payload[2];         // the streams (worst case: 8 B per value + 16 B per block)
+    unsigned long long* total8;  // [2]: stream sizes in 8-byte units
+    uint64_t capacity8;          // capacity of each payload buffer in 8-byte units
+};
+int codec_encode_launch(const CodecArrays& a, int64_t cnt, cudaStream_t st);
+
 // f(lo, hi) over [0, n) cut into contiguous ranges, on up to 16 short-lived host threads when n is large
 // (per-rule planning of a big batch: gamma functions, Bessel-zero guesses); f must not fail.
 void host_parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& f);

@@ -270,6 +270,12 @@ int fgq_debug_fastdiv_check(int64_t n, int64_t k_lo, int64_t k_hi,
  * already landed when a thread picked them up, and the last adaptive DMA share x 1000 (bench.py reports
  * them beside e2e).  Any pointer may be NULL. */
 int fgq_debug_drain_stats(int64_t* pieces, int64_t* dma_pieces, int64_t* landed, int* share_milli);
+/* Transport coding of large host-returning Legendre calls (csrc/delta_codec.h): bytes that crossed PCIe in
+ * coded form and the number of values they carried, since the previous call of this function. */
+int fgq_debug_codec_stats(int64_t* bytes, int64_t* values);
+/* decode(encode(in)) on the host with the reference encoder of csrc/delta_codec.h (tests; no GPU needed):
+ * out must equal in bit for bit for ANY content; *stream_bytes receives the coded size. */
+int fgq_debug_codec_roundtrip_host(const double* in, int64_t cnt, double* out, int64_t* stream_bytes);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t fgq_launch_count(void);
 

@@ -1,0 +1,50 @@
+"""Transport coding of large host-returning calls (csrc/delta_codec.h): the reference encoder + the product's
+decoder on the HOST must round-trip ANY 64-bit content bit for bit, and smooth rule data must compress to about
+one byte per value.  (The device packer is checked on the GPU by the host-path parity tests, which compare whole
+rules against the oracle.)"""
+import ctypes
+
+import numpy as np
+import pytest
+
+
+def _roundtrip(lib, a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    out = np.full_like(a, np.nan)
+    nbytes = ctypes.c_int64(0)
+    rc = lib.fgq_debug_codec_roundtrip_host(a.ctypes.data, len(a), out.ctypes.data, ctypes.byref(nbytes))
+    assert rc == 0
+    assert np.array_equal(a.view(np.int64), out.view(np.int64))   # bit patterns (NaN payloads, signed zeros too)
+    return nbytes.value
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import fgq_b200
+    return fgq_b200.lib()
+
+
+@pytest.mark.parametrize("cnt", [0, 1, 2, 3, 1023, 1024, 1025, 5000, 1 << 16])
+def test_roundtrip_arbitrary_content(lib, cnt):
+    rng = np.random.default_rng(cnt)
+    bits = rng.integers(-2 ** 63, 2 ** 63 - 1, cnt, dtype=np.int64)   # random patterns incl. NaN / inf / denormals
+    nbytes = _roundtrip(lib, bits.view(np.float64))
+    assert nbytes <= cnt * 8 + 16 * ((cnt + 1023) // 1024)           # never worse than raw + headers
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 1.0, -1.0] * 300)[:cnt]
+    _roundtrip(lib, special)
+
+
+@pytest.mark.parametrize("n,limit", [(4_000_000, 2.1), (40_000_000, 1.1)])
+def test_rule_data_compresses(lib, oracle_mod, n, limit):
+    """Left half of gausslegendre(n): the second difference of the bit patterns is the curvature of the rule
+    in ulps, ~(pi/n)^2 / 2^-53 = 5500 at n = 4e6 (16-bit class, 2 B/value), 55 at n = 4e7 and below 1 at n = 1e9
+    (8-bit class, 1 B/value), plus a few ulp of rounding noise; the first blocks of the weights and the blocks
+    with a binade crossing take a wider class."""
+    x, w = oracle_mod.gausslegendre(n)
+    m = n // 2
+    bx = _roundtrip(lib, x[:m])
+    bw = _roundtrip(lib, w[:m])
+    assert bx < limit * m and bw < limit * m, (bx / m, bw / m)
+    if n <= 4_000_000:  # the whole rule at once (crosses the centre: sign change of x) still round-trips
+        _roundtrip(lib, x)
+        _roundtrip(lib, w)
