@@ -422,6 +422,8 @@ def main():
         import ctypes
         st_p, st_d, st_l, st_s = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
         fgq_b200.lib().fgq_debug_drain_stats(ctypes.byref(st_p), ctypes.byref(st_d), ctypes.byref(st_l), ctypes.byref(st_s))
+        cd_b, cd_v = ctypes.c_int64(0), ctypes.c_int64(0)
+        fgq_b200.lib().fgq_debug_codec_stats(ctypes.byref(cd_b), ctypes.byref(cd_v))  # reset
         per_call = []
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -435,11 +437,23 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         fgq_b200.lib().fgq_debug_drain_stats(ctypes.byref(st_p), ctypes.byref(st_d), ctypes.byref(st_l), ctypes.byref(st_s))
+        fgq_b200.lib().fgq_debug_codec_stats(ctypes.byref(cd_b), ctypes.byref(cd_v))
+        coded = torch.tensor([float(cd_b.value), float(cd_v.value)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(coded)
+        coded_bytes, coded_values = float(coded[0].item()), float(coded[1].item())
+        # bytes that really crossed PCIe per step: the coded streams when the transport coding is active
+        # (FGQ_HOST_CODEC, default on), otherwise the plain left half
+        d2h = int(coded_bytes / args.e2e_steps) if coded_values > 0 else 8 * (n + n % 2)
         e2e = {"value": n * args.e2e_steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 0,
-               "d2h_bytes_per_step": 8 * (n + n % 2), "steps": args.e2e_steps,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+               "transport": ({"coding": "second differences of the bit patterns, lossless (csrc/delta_codec.h)",
+                              "bytes_per_value": coded_bytes / coded_values} if coded_values > 0 else
+                             {"coding": "none"}),
                "call_s_min": min(per_call), "call_s_median": float(np.median(per_call)),
-               "what": "host-returning C-ABI call into pinned host buffers: kernel + PCIe D2H of the left half of each "
-                       "shard, chunk-pipelined; the mirrored half is written by host threads (+-x symmetry)",
+               "what": "host-returning C-ABI call into pinned host buffers: kernel + device-side packing + PCIe D2H of the "
+                       "coded left half of each shard, chunk-pipelined; host threads unpack it into the left half and write "
+                       "the mirrored half (+-x symmetry)",
                "mode": args.e2e_mode,
                "drain_rank0": {"pieces": st_p.value, "mirror_by_dma": st_d.value, "landed_before_pickup": st_l.value,
                                "last_dma_share": st_s.value / 1000.0},
