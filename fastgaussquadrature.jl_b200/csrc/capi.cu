@@ -797,7 +797,7 @@ static int codec_pair_pipeline(int64_t n, int64_t k_lo, int64_t cnt, double* xl,
                     if (bytes > STAGE_BYTES) break;
                     ++b1;
                 }
-                if (b1 == b0) return fail(FGQ_EINVAL, cudaSuccess);  // cannot happen: a block is <= 8.2 KB
+                if (b1 == b0) return fail(FGQ_EINVAL, cudaSuccess);  // cannot happen: a block is <= 8.3 KB
                 const int slot = (int)(published & 1);
                 {   // staging slot free: the batch that used it two publications ago is decoded
                     std::unique_lock<std::mutex> lk(mu);
@@ -1011,7 +1011,7 @@ extern "C" int fgq_debug_codec_stats(int64_t* bytes, int64_t* values) {
 extern "C" int fgq_debug_codec_roundtrip_host(const double* in, int64_t cnt, double* out, int64_t* stream_bytes) {
     if (cnt < 0 || (cnt > 0 && (!in || !out))) return FGQ_EINVAL;
     const int64_t nb = (cnt + CODEC_BLOCK - 1) / CODEC_BLOCK;
-    std::vector<uint8_t> payload((size_t)codec_worst_bytes(cnt) + 8);
+    std::vector<uint8_t> payload((size_t)codec_worst_bytes(cnt) + 64);
     std::vector<uint32_t> dir((size_t)nb + 1);
     const int64_t bytes = codec_encode_host((const int64_t*)in, cnt, payload.data(), dir.data());
     for (int64_t b = 0; b < nb; ++b) {

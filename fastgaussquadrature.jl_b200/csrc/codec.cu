@@ -32,9 +32,8 @@ codec_class_kernel(CodecArrays a, int64_t cnt, int64_t nb) {
     if (threadIdx.x == 0) s_cls = 0;
     const int len = codec_load_block((const uint64_t*)a.values[arr], cnt, b, sh);
     int cls = 0;
-    for (int i = 2 + threadIdx.x; i < len; i += CODEC_THREADS) {
-        const int64_t d2 = (int64_t)((sh[i] - sh[i - 1]) - (sh[i - 1] - sh[i - 2]));
-        const int c = codec_class_of(d2);
+    for (int i = 2 * CODEC_STRIDE + threadIdx.x; i < len; i += CODEC_THREADS) {
+        const int c = codec_class_of((int64_t)codec_d2(sh, i));
         cls = c > cls ? c : cls;
     }
     if (cls) atomicMax(&s_cls, cls);
@@ -95,25 +94,26 @@ codec_pack_kernel(CodecArrays a, int64_t cnt, int64_t nb) {
     if ((uint64_t)off8 + size8 > a.capacity8) return;  // the host sees total8 > capacity8 and takes the plain path
     uint8_t* p = a.payload[arr] + (size_t)off8 * 8;
     uint64_t* p64 = (uint64_t*)p;
-    if (threadIdx.x == 0) {
-        p64[0] = sh[0];
-        p64[1] = len > 1 ? sh[1] - sh[0] : 0ull;
+    if (threadIdx.x < CODEC_STRIDE) {
+        const int i = threadIdx.x;
+        p64[i] = i < len ? sh[i] : 0ull;
+        p64[CODEC_STRIDE + i] = i + CODEC_STRIDE < len ? sh[i + CODEC_STRIDE] - sh[i] : 0ull;
     }
     // each thread assembles whole 8-byte words of the packed stream: 8 >> cls second differences per word
     const int per = 8 >> cls;
-    const int nd2 = len > 2 ? len - 2 : 0;
+    const int nd2 = len > 2 * CODEC_STRIDE ? len - 2 * CODEC_STRIDE : 0;
     const int nwords = (nd2 + per - 1) / per;
     for (int wd = threadIdx.x; wd < nwords; wd += CODEC_THREADS) {
         uint64_t word = 0;
         for (int j = 0; j < per; ++j) {
-            const int i = 2 + wd * per + j;
+            const int i = 2 * CODEC_STRIDE + wd * per + j;
             if (i < len) {
-                const uint64_t d2 = (sh[i] - sh[i - 1]) - (sh[i - 1] - sh[i - 2]);
+                const uint64_t d2 = codec_d2(sh, i);
                 const uint64_t mask = cls == 3 ? ~0ull : ((1ull << (8 << cls)) - 1ull);
                 word |= (d2 & mask) << (j * (8 << cls));
             }
         }
-        p64[2 + wd] = word;
+        p64[CODEC_HEADER8 + wd] = word;
     }
 }
 

@@ -29,17 +29,17 @@ def test_roundtrip_arbitrary_content(lib, cnt):
     rng = np.random.default_rng(cnt)
     bits = rng.integers(-2 ** 63, 2 ** 63 - 1, cnt, dtype=np.int64)   # random patterns incl. NaN / inf / denormals
     nbytes = _roundtrip(lib, bits.view(np.float64))
-    assert nbytes <= cnt * 8 + 16 * ((cnt + 1023) // 1024)           # never worse than raw + headers
+    assert nbytes <= cnt * 8 + 64 * ((cnt + 1023) // 1024)           # never worse than raw + headers
     special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 1.0, -1.0] * 300)[:cnt]
     _roundtrip(lib, special)
 
 
-@pytest.mark.parametrize("n,limit", [(4_000_000, 2.1), (40_000_000, 1.1)])
+@pytest.mark.parametrize("n,limit", [(4_000_000, 4.2), (40_000_000, 2.1)])
 def test_rule_data_compresses(lib, oracle_mod, n, limit):
-    """Left half of gausslegendre(n): the second difference of the bit patterns is the curvature of the rule
-    in ulps, ~(pi/n)^2 / 2^-53 = 5500 at n = 4e6 (16-bit class, 2 B/value), 55 at n = 4e7 and below 1 at n = 1e9
-    (8-bit class, 1 B/value), plus a few ulp of rounding noise; the first blocks of the weights and the blocks
-    with a binade crossing take a wider class."""
+    """Left half of gausslegendre(n): the (stride-4) second difference of the bit patterns is 16 x the curvature
+    of the rule in ulps, 16 (pi/n)^2 / 2^-53 = 88000 at n = 4e6 (32-bit class), 880 at n = 4e7 (16-bit class) and
+    1.4 at n = 1e9 (8-bit class, 1 B/value), plus a few ulp of rounding noise; the first blocks of the weights
+    and the blocks with a binade crossing take a wider class."""
     x, w = oracle_mod.gausslegendre(n)
     m = n // 2
     bx = _roundtrip(lib, x[:m])
@@ -48,3 +48,13 @@ def test_rule_data_compresses(lib, oracle_mod, n, limit):
     if n <= 4_000_000:  # the whole rule at once (crosses the centre: sign change of x) still round-trips
         _roundtrip(lib, x)
         _roundtrip(lib, w)
+
+
+def test_headline_size_compresses_to_one_byte(lib):
+    """A window of the n = 1e9 rule (nodes -cos(theta_k), weights ~ (pi/n) sin(theta_k), correctly rounded here):
+    one byte per value."""
+    n = 10 ** 9
+    k = np.arange(2 * 10 ** 8, 2 * 10 ** 8 + (1 << 20), dtype=np.float64)
+    th = (k + 0.75) * np.pi / (n + 0.5)
+    for v in (-np.cos(th), np.pi / (n + 0.5) * np.sin(th)):
+        assert _roundtrip(lib, v) < 1.08 * len(v)
