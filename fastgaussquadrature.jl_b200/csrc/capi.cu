@@ -1016,8 +1016,16 @@ extern "C" int fgq_debug_codec_roundtrip_host(const double* in, int64_t cnt, dou
     const int64_t bytes = codec_encode_host((const int64_t*)in, cnt, payload.data(), dir.data());
     for (int64_t b = 0; b < nb; ++b) {
         const int len = (int)(cnt - b * CODEC_BLOCK < CODEC_BLOCK ? cnt - b * CODEC_BLOCK : CODEC_BLOCK);
-        codec_decode_block(payload.data() + (size_t)(dir[(size_t)b] >> 2) * 8, (int)(dir[(size_t)b] & 3u), len,
-                           (int64_t*)out + b * CODEC_BLOCK);
+        const uint8_t* p = payload.data() + (size_t)(dir[(size_t)b] >> 2) * 8;
+        const int cls = (int)(dir[(size_t)b] & 3u);
+        codec_decode_block(p, cls, len, (int64_t*)out + b * CODEC_BLOCK);
+        // the portable decoder must agree with the dispatched (AVX2) one
+        int64_t ref[CODEC_BLOCK];
+        codec_decode_block_scalar(p, cls, len, ref);
+        if (memcmp(ref, (const int64_t*)out + b * CODEC_BLOCK, (size_t)len * 8) != 0) {
+            set_error("internal: scalar and vector decoders disagree in block %lld", (long long)b);
+            return FGQ_EINVAL;
+        }
     }
     if (stream_bytes) *stream_bytes = bytes;
     return FGQ_OK;
