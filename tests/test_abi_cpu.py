@@ -111,3 +111,33 @@ def test_partitions_cover_the_rule(fgq_cpu):
             assert total == n
             if cover is not None:
                 assert np.all(cover == 1)
+
+
+def test_batch_descriptions_are_validated_before_any_device_work(fgq_cpu):
+    """Host logic of the small-rule batches: argument errors map onto the reference's exceptions (DomainError) or
+    ValueError without needing a device."""
+    i64 = np.int64
+    with pytest.raises(fgq_cpu.DomainError):
+        fgq_cpu.gaussjacobi_batch([5, -1], 0.3, 0.2, offsets=np.array([0, 5, 5], dtype=i64))
+    with pytest.raises(fgq_cpu.DomainError):
+        fgq_cpu.gaussjacobi_batch([5, 6], [0.3, -1.0], 0.2)     # non-integrable weight (gaussjacobi.jl:44-45)
+    with pytest.raises(ValueError):
+        fgq_cpu.gaussjacobi_batch([5, 101], 0.3, 0.2)           # beyond the batched branch
+    with pytest.raises(ValueError):
+        fgq_cpu.gausshermite_batch([5, 201])
+    with pytest.raises(fgq_cpu.DomainError):
+        fgq_cpu.gausshermite_batch([5, -2], offsets=np.array([0, 5, 5], dtype=i64))
+    with pytest.raises(ValueError):
+        fgq_cpu.gausslaguerre_batch([5, 128], 0.0)
+    with pytest.raises(fgq_cpu.DomainError):
+        fgq_cpu.gausslaguerre_batch([5, 6], [-1.0, 0.0])        # gausslaguerre.jl:61
+    for off, x, w in (fgq_cpu.gaussjacobi_batch([], 0.1, 0.2), fgq_cpu.gausshermite_batch([]),
+                      fgq_cpu.gausslaguerre_batch([]), fgq_cpu.gausshermite_batch([0, 0])):
+        assert len(x) == 0 and len(w) == 0
+    # truncated Hermite rule: the a-priori size bound needs no device
+    L = fgq_cpu.lib()
+    assert L.fgq_gausshermite_reduced_bound(0) == 0
+    assert L.fgq_gausshermite_reduced_bound(150) == 150          # small rules are never truncated
+    b = L.fgq_gausshermite_reduced_bound(1_000_000)
+    assert 24_000 < b < 25_000 and b % 2 == 0
+    assert L.fgq_gausshermite_reduced_bound(1_000_001) % 2 == 1  # odd rules keep their centre node
