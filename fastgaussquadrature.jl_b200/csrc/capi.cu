@@ -202,7 +202,7 @@ namespace fgq {
 // with the PCIe DMA for host memory bandwidth).
 #if defined(__x86_64__)
 __attribute__((target("avx2"))) static void mirror_avx2(const double* src, double* dst, int64_t cnt, int64_t a,
-                                                         int64_t b, bool negate) {
+                                                         int64_t b, bool negate, bool fence) {
     // destination positions cnt-1-e descend as e ascends: walk e upwards, write blocks of 4 downwards
     int64_t e = a;
     // scalar until the 4-block [cnt-4-e, cnt-e) starts on a 32-byte boundary
@@ -218,7 +218,7 @@ __attribute__((target("avx2"))) static void mirror_avx2(const double* src, doubl
         _mm256_stream_pd(dst + (cnt - 4 - e), v);
     }
     for (; e < b; ++e) dst[cnt - 1 - e] = negate ? -src[e] : src[e];
-    _mm_sfence();
+    if (fence) _mm_sfence();
 }
 #endif
 
@@ -227,7 +227,7 @@ __attribute__((target("avx2"))) static void mirror_avx2(const double* src, doubl
 // memcpy only switches to them for copies far larger than a 2 MiB piece), i.e. a third of the host-memory
 // traffic of this step, on a path that is host-memory bound.
 #if defined(__x86_64__)
-__attribute__((target("avx2"))) static void copy_stream_avx2(double* dst, const double* src, int64_t n) {
+__attribute__((target("avx2"))) static void copy_stream_avx2(double* dst, const double* src, int64_t n, bool fence) {
     int64_t i = 0;
     while (i < n && ((uintptr_t)(dst + i) & 31) != 0) {
         dst[i] = src[i];
@@ -235,26 +235,35 @@ __attribute__((target("avx2"))) static void copy_stream_avx2(double* dst, const 
     }
     for (; i + 4 <= n; i += 4) _mm256_stream_pd(dst + i, _mm256_loadu_pd(src + i));
     for (; i < n; ++i) dst[i] = src[i];
-    _mm_sfence();
+    if (fence) _mm_sfence();
 }
 #endif
 
-static void copy_stream(double* dst, const double* src, int64_t n) {
+// fence = false: the caller issues one store fence for a whole run of calls (stream_fence), instead of draining
+// the write-combining buffers after every 8 KB
+static void stream_fence() {
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
+}
+
+static void copy_stream(double* dst, const double* src, int64_t n, bool fence = true) {
 #if defined(__x86_64__)
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
     if (have_avx2 && n >= 256) {
-        copy_stream_avx2(dst, src, n);
+        copy_stream_avx2(dst, src, n, fence);
         return;
     }
 #endif
     memcpy(dst, src, (size_t)n * 8);
 }
 
-static void mirror_copy(const double* src, double* dst, int64_t cnt, int64_t a, int64_t b, bool negate) {
+static void mirror_copy(const double* src, double* dst, int64_t cnt, int64_t a, int64_t b, bool negate,
+                        bool fence = true) {
 #if defined(__x86_64__)
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
     if (have_avx2) {
-        mirror_avx2(src, dst, cnt, a, b, negate);
+        mirror_avx2(src, dst, cnt, a, b, negate, fence);
         return;
     }
 #endif
@@ -884,10 +893,11 @@ static int codec_pair_pipeline(int64_t n, int64_t k_lo, int64_t cnt, double* xl,
                     codec_decode_block(p, (int)(ent & 3u), len, tmp);
                     double* dst = a == 0 ? xl : wl;
                     double* dstr = a == 0 ? mir.xr : mir.wr;
-                    copy_stream(dst + e0, (const double*)tmp, len);
-                    if (e1m > e0) mirror_copy((const double*)tmp - e0, dstr, mir.cnt, e0, e1m, a == 0);
+                    copy_stream(dst + e0, (const double*)tmp, len, false);
+                    if (e1m > e0) mirror_copy((const double*)tmp - e0, dstr, mir.cnt, e0, e1m, a == 0, false);
                 }
             }
+            stream_fence();  // one fence per group of blocks, before the group is reported done
             {
                 std::lock_guard<std::mutex> lk(mu);
                 ++groups_done;
