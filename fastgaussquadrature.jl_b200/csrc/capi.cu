@@ -667,6 +667,72 @@ int host_pipeline(int64_t lo_all, int64_t hi_all, double* x, double* w, SliceFn 
 // ---------------------------------------------------------------------------------------------
 static std::atomic<int64_t> g_codec_bytes{0}, g_codec_values{0};
 
+#if defined(__x86_64__)
+// Decodes a block straight into its two destinations from the vector registers (no bounce buffer): dl[i] = u_i,
+// dr_end[-1 - i] = +-u_i.  Requires len >= 8, len % 4 == 0 and both dl and dr_end 32-byte aligned.
+__attribute__((target("avx2"))) static void codec_unpack_fused_avx2(const uint8_t* p, int cls, int len, double* dl,
+                                                                     double* dr_end, bool negate) {
+    __m256i v = _mm256_loadu_si256((const __m256i*)p);
+    __m256i d1 = _mm256_loadu_si256((const __m256i*)(p + 32));
+    const __m256d sign = negate ? _mm256_set1_pd(-0.0) : _mm256_setzero_pd();
+#define FGQ_EMIT4(i, vv)                                                                              \
+    do {                                                                                              \
+        const __m256d f_ = _mm256_castsi256_pd(vv);                                                   \
+        _mm256_stream_pd(dl + (i), f_);                                                               \
+        _mm256_stream_pd(dr_end - 4 - (i), _mm256_xor_pd(_mm256_permute4x64_pd(f_, 0x1B), sign));     \
+    } while (0)
+    FGQ_EMIT4(0, v);
+    v = _mm256_add_epi64(v, d1);
+    FGQ_EMIT4(4, v);
+    const uint8_t* q = p + 64;
+    for (int i = 8; i < len; i += 4) {
+        __m256i d2;
+        switch (cls) {
+            case 0: {
+                int32_t four;
+                memcpy(&four, q + (i - 8), 4);
+                d2 = _mm256_cvtepi8_epi64(_mm_cvtsi32_si128(four));
+                break;
+            }
+            case 1: d2 = _mm256_cvtepi16_epi64(_mm_loadl_epi64((const __m128i*)(q + 2 * (size_t)(i - 8)))); break;
+            case 2: d2 = _mm256_cvtepi32_epi64(_mm_loadu_si128((const __m128i*)(q + 4 * (size_t)(i - 8)))); break;
+            default: d2 = _mm256_loadu_si256((const __m256i*)(q + 8 * (size_t)(i - 8)));
+        }
+        d1 = _mm256_add_epi64(d1, d2);
+        v = _mm256_add_epi64(v, d1);
+        FGQ_EMIT4(i, v);
+    }
+#undef FGQ_EMIT4
+}
+#endif
+
+// One block of the left slice (elements [e0, e0 + len)) from its coded form into dst[e0 ..] and, for the elements
+// below e1m, into the mirror image dstr[mcnt - 1 - e].  No store fence: the caller fences once per run of blocks.
+// fused = true takes the register-to-destination path where its alignment conditions hold (off by default:
+// FGQ_CODEC_FUSED=1), otherwise the block goes through the 8 KB bounce buffer `tmp`.
+static void codec_unpack_block(const uint8_t* p, int cls, int len, double* dst, double* dstr, int64_t mcnt, int64_t e0,
+                               int64_t e1m, bool negate, bool fused, int64_t* tmp) {
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (fused && have_avx2 && len >= 8 && (len & 3) == 0 && e1m == e0 + len &&
+        ((uintptr_t)(dst + e0) & 31) == 0 && ((uintptr_t)(dstr + (mcnt - e0)) & 31) == 0) {
+        codec_unpack_fused_avx2(p, cls, len, dst + e0, dstr + (mcnt - e0), negate);
+        return;
+    }
+#endif
+    codec_decode_block(p, cls, len, tmp);
+    copy_stream(dst + e0, (const double*)tmp, len, false);
+    if (e1m > e0) mirror_copy((const double*)tmp - e0, dstr, mcnt, e0, e1m, negate, false);
+}
+
+static bool codec_fused_default() {
+    static const bool on = []() {
+        const char* e = getenv("FGQ_CODEC_FUSED");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+
 struct CodecBatch {
     int64_t chunk_lo;      // first element (of the left slice) of the chunk this batch belongs to
     int64_t b0, b1;        // block range within the chunk
@@ -846,6 +912,7 @@ static int codec_pair_pipeline(int64_t n, int64_t k_lo, int64_t cnt, double* xl,
         cv.notify_all();
     };
 
+    const bool fused_unpack = codec_fused_default();
     auto decoder = [&]() {
         cudaSetDevice(dev);
         int64_t tmp[CODEC_BLOCK];
@@ -890,11 +957,8 @@ static int codec_pair_pipeline(int64_t n, int64_t k_lo, int64_t cnt, double* xl,
                 for (int a = 0; a < 2; ++a) {
                     const uint32_t ent = B.dir[a][b];
                     const uint8_t* p = B.stage[a] + (size_t)((ent >> 2) - B.base8[a]) * 8;
-                    codec_decode_block(p, (int)(ent & 3u), len, tmp);
-                    double* dst = a == 0 ? xl : wl;
-                    double* dstr = a == 0 ? mir.xr : mir.wr;
-                    copy_stream(dst + e0, (const double*)tmp, len, false);
-                    if (e1m > e0) mirror_copy((const double*)tmp - e0, dstr, mir.cnt, e0, e1m, a == 0, false);
+                    codec_unpack_block(p, (int)(ent & 3u), len, a == 0 ? xl : wl, a == 0 ? mir.xr : mir.wr, mir.cnt, e0,
+                                       e1m, a == 0, fused_unpack, tmp);
                 }
             }
             stream_fence();  // one fence per group of blocks, before the group is reported done
@@ -1038,6 +1102,28 @@ extern "C" int fgq_debug_codec_roundtrip_host(const double* in, int64_t cnt, dou
         }
     }
     if (stream_bytes) *stream_bytes = bytes;
+    return FGQ_OK;
+}
+
+// The host half of the coded transfer without a device (tests): `in` (cnt values, the left slice) is coded with the
+// reference encoder and unpacked block by block through codec_unpack_block — the routine the pipeline's host threads
+// run — into left[0 .. cnt) and the mirror image right[cnt - 1 - e] = (negate ? -in[e] : in[e]) for e < mirror_cnt.
+extern "C" int fgq_debug_codec_unpack_host(const double* in, int64_t cnt, double* left, double* right, int64_t mirror_cnt,
+                                           int negate, int fused) {
+    if (cnt < 0 || mirror_cnt < 0 || mirror_cnt > cnt || (cnt > 0 && (!in || !left || !right))) return FGQ_EINVAL;
+    const int64_t nb = (cnt + CODEC_BLOCK - 1) / CODEC_BLOCK;
+    std::vector<uint8_t> payload((size_t)codec_worst_bytes(cnt) + 64);
+    std::vector<uint32_t> dir((size_t)nb + 1);
+    codec_encode_host((const int64_t*)in, cnt, payload.data(), dir.data());
+    int64_t tmp[CODEC_BLOCK];
+    for (int64_t b = 0; b < nb; ++b) {
+        const int64_t e0 = b * CODEC_BLOCK;
+        const int len = (int)(cnt - e0 < CODEC_BLOCK ? cnt - e0 : CODEC_BLOCK);
+        const int64_t e1m = e0 + len < mirror_cnt ? e0 + len : mirror_cnt;
+        codec_unpack_block(payload.data() + (size_t)(dir[(size_t)b] >> 2) * 8, (int)(dir[(size_t)b] & 3u), len, left,
+                           right, cnt, e0, e1m, negate != 0, fused != 0, tmp);
+    }
+    stream_fence();
     return FGQ_OK;
 }
 

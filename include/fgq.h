@@ -276,6 +276,11 @@ int fgq_debug_codec_stats(int64_t* bytes, int64_t* values);
 /* decode(encode(in)) on the host with the reference encoder of csrc/delta_codec.h (tests; no GPU needed):
  * out must equal in bit for bit for ANY content; *stream_bytes receives the coded size. */
 int fgq_debug_codec_roundtrip_host(const double* in, int64_t cnt, double* out, int64_t* stream_bytes);
+/* The host half of a coded transfer without a device (tests): codes `in` with the reference encoder and unpacks it
+ * through the routine the pipeline's host threads run: left[e] = in[e], right[cnt-1-e] = +-in[e] for e < mirror_cnt.
+ * fused != 0 selects the register-to-destination variant (FGQ_CODEC_FUSED=1 in the product; off by default). */
+int fgq_debug_codec_unpack_host(const double* in, int64_t cnt, double* left, double* right, int64_t mirror_cnt,
+                                int negate, int fused);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t fgq_launch_count(void);
 

@@ -58,3 +58,33 @@ def test_headline_size_compresses_to_one_byte(lib):
     th = (k + 0.75) * np.pi / (n + 0.5)
     for v in (-np.cos(th), np.pi / (n + 0.5) * np.sin(th)):
         assert _roundtrip(lib, v) < 1.08 * len(v)
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("negate", [0, 1])
+def test_unpack_into_slice_and_mirror(lib, fused, negate):
+    """The routine the pipeline's host threads run (decode a block into the left slice and its mirror image), for
+    every destination alignment, lengths that are not multiples of the block / vector size, a rule with and without
+    a centre node, smooth (8-bit class) and random (64-bit class) content; with the bounce buffer and with the
+    register-to-destination variant."""
+    rng = np.random.default_rng(7 + fused + 2 * negate)
+    for cnt in (1, 7, 8, 1023, 1024, 1028, 4096, 5 * 1024 + 3, 40_000):
+        k = np.arange(3 * 10 ** 8, 3 * 10 ** 8 + cnt, dtype=np.float64)
+        smooth = -np.cos((k + 0.75) * np.pi / (10 ** 9 + 0.5))
+        noisy = rng.integers(-2 ** 62, 2 ** 62, cnt, dtype=np.int64).view(np.float64)
+        for src in (smooth, noisy):
+            for mirror_cnt in (cnt, cnt - 1):
+                for off_l in range(4):
+                    for off_r in (0, 1, 3):
+                        left = np.full(cnt + 8, 7.25)
+                        right = np.full(cnt + 8, 7.25)
+                        lv, rv = left[off_l:off_l + cnt], right[off_r:off_r + cnt]
+                        rc = lib.fgq_debug_codec_unpack_host(src.ctypes.data, cnt, lv.ctypes.data, rv.ctypes.data,
+                                                             mirror_cnt, negate, fused)
+                        assert rc == 0
+                        assert np.array_equal(lv.view(np.int64), src.view(np.int64))
+                        want = (-src if negate else src)[:mirror_cnt][::-1]
+                        assert np.array_equal(rv[cnt - mirror_cnt:].view(np.int64), want.view(np.int64))
+                        # nothing outside the destinations was touched (guard bands, and the centre slot)
+                        assert np.all(left[:off_l] == 7.25) and np.all(left[off_l + cnt:] == 7.25)
+                        assert np.all(right[:off_r + cnt - mirror_cnt] == 7.25) and np.all(right[off_r + cnt:] == 7.25)
