@@ -61,7 +61,11 @@ int fgq_gausslegendre_host_slice(int64_t n, int64_t lo, int64_t hi, double* x, d
  * fgq_gausslegendre_device_pair; only the left slice crosses PCIe, the mirrored slice
  * (x[n-1-i] = -x[i], w[n-1-i] = w[i]) is written by host threads while the next chunk is in flight.
  * xl/wl and xr/wr receive k_hi-k_lo entries each (element 0 of xr/wr is left untouched when the shard
- * holds the centre of an odd rule).  fgq_gausslegendre_host uses it for n >= 2^21. */
+ * holds the centre of an odd rule).  fgq_gausslegendre_host uses it for n >= 2^21.
+ * Shards of >= 2^20 half-indices cross PCIe as a lossless second-difference coding of their bit patterns
+ * (~1 byte per value at n = 1e9 instead of 8; csrc/delta_codec.h) that library-owned host threads unpack
+ * straight into xl/wl and the mirror image; the result is bit-identical to the plain transfer
+ * (environment FGQ_HOST_CODEC=0).  Destinations may be pinned or pageable. */
 int fgq_gausslegendre_host_pair(int64_t n, int64_t k_lo, int64_t k_hi, double* xl, double* wl,
                                 double* xr, double* wr);
 
