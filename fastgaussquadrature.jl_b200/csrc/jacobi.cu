@@ -19,6 +19,8 @@
 //     pre-enqueued launches return immediately.
 #include <math.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "fgq_math.h"
 #include "jacobi_boundary.cuh"
@@ -1067,6 +1069,22 @@ extern "C" int fgq_gaussradau_jacobi_host(int64_t n, double a, double b, double*
 }
 
 // sweeps[2] (right, left), terms[2] (series terms kept in the last evaluation): for tests/reporting
+// The angles beyond which the norm passes skip a node (jacobi_norm_skip_angle), for the right half (a, b) and the
+// mirrored left half (b, a) of gaussjacobi(n, a, b): host-only, exported so that the bound can be checked against
+// the oracle's series terms without a device.  +inf = nothing may be skipped.
+extern "C" int fgq_debug_jacobi_skip_angles(int64_t n, double a, double b, double* t_right, double* t_left) {
+    clear_status();
+    if (n < 2 || !t_right || !t_left) return FGQ_EINVAL;
+    static JacobiHalfPlan hp;  // 6.5 KB: off the stack
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    jacobi_interior_plan(n, a, b, &hp);
+    *t_right = jacobi_norm_skip_angle(hp);
+    jacobi_interior_plan(n, b, a, &hp);
+    *t_left = jacobi_norm_skip_angle(hp);
+    return FGQ_OK;
+}
+
 extern "C" int fgq_gaussjacobi_stats(const void* workspace_dev, int* sweeps, int* terms) {
     clear_status();
     if (!workspace_dev || !sweeps || !terms) return FGQ_EINVAL;

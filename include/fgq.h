@@ -280,6 +280,10 @@ int fgq_debug_codec_stats(int64_t* bytes, int64_t* values);
 /* decode(encode(in)) on the host with the reference encoder of csrc/delta_codec.h (tests; no GPU needed):
  * out must equal in bit for bit for ANY content; *stream_bytes receives the coded size. */
 int fgq_debug_codec_roundtrip_host(const double* in, int64_t cnt, double* out, int64_t* stream_bytes);
+/* Angles beyond which the Jacobi truncation-norm passes skip a node (every candidate series term is provably below
+ * a quarter of the reference's eps/100 threshold there), for the right half (a, b) and the mirrored left half (b, a);
+ * +inf = no skipping.  Host-only; tests check the bound against the oracle's series terms. */
+int fgq_debug_jacobi_skip_angles(int64_t n, double a, double b, double* t_right, double* t_left);
 /* The host half of a coded transfer without a device (tests): codes `in` with the reference encoder and unpacks it
  * through the routine the pipeline's host threads run: left[e] = in[e], right[cnt-1-e] = +-in[e] for e < mirror_cnt.
  * fused != 0 selects the register-to-destination variant (FGQ_CODEC_FUSED=1 in the product; off by default). */
