@@ -37,3 +37,22 @@ def test_structure_and_sweeps():
     assert abs(wn.sum() - 1) < 1e-13 and abs(np.dot(wn, xn * xn) - 1) < 1e-11
     with pytest.raises(ValueError):
         ho.gausshermite(-1)
+
+
+@pytest.mark.parametrize("n", [201, 5000, 100_001, 1_000_000])
+def test_truncated_rule_bound_is_safe(n):
+    """The a-priori size of the truncated rule (fgq_gausshermite_reduced_bound: Sturm spacing of the zeros of H_n,
+    DESIGN.md 8.8) against the oracle's full rule: every node outside the centre block lies beyond |x| = 27.5 and
+    carries the weight 0.0; needs no device."""
+    import fgq_b200
+    from oracle import hermite_oracle as ho
+    bound = int(fgq_b200.lib().fgq_gausshermite_reduced_bound(n))
+    assert 0 < bound <= n and (n - bound) % 2 == 0
+    x, w = ho.gausshermite(n)
+    first = (n - bound) // 2
+    if first:
+        assert np.all(np.abs(x[:first]) > 27.5) and np.all(np.abs(x[first + bound:]) > 27.5)
+        assert np.all(w[:first] == 0.0) and np.all(w[first + bound:] == 0.0)
+        # and it is not wasteful: the block reaches at most a few nodes beyond the cut
+        assert np.abs(x[first + 8]) > 27.3
+    assert abs(w[first:first + bound].sum() - np.sqrt(np.pi)) < 1e-13
