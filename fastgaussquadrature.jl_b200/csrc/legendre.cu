@@ -179,7 +179,7 @@ __device__ __forceinline__ void leg_half_index(int64_t k, const LegConsts& c, do
     fgq_sincos_q1(a, &s, &ca);
     constexpr bool FAST = !HEAD && NT <= 1 && WT <= 1;  // tail launches of the large-n branches
     double u = 0.0;
-    if (NT > 0 || WT > 0) u = dv<FAST>(ca, s);  // cot(a)
+    if (NT > 0 || WT > 0) u = rc<FAST>(fgq_tan_q1(a));  // cot(a) = inv(tan(a)), :100,158
     if (NT == 0) {
         cx = ca;
         if (theta_out) *theta_out = a;
@@ -210,8 +210,11 @@ __device__ __forceinline__ double scale2(double x, int e) {
 // The bulk of an n >= 2^25 launch: half-indices k >= K_JK_EXACT, where
 //   * 0.125/ak < ulp(ak)/2 (ak >= 2^25), so j0k = ak + 0.125/ak rounds to ak itself and the
 //     first reciprocal disappears (bit-identical; tests/test_full_size_gpu.py checks every k);
-//   * the whole block lies on one side of pi/4 (QUAD 0: theta <= pi/4, no reduction at all;
-//     QUAD 1: theta > pi/4, always reduce), so the quadrant selects disappear too.
+//   * the whole block lies on one side of pi/4 (QUAD 0: theta < pi/4, no reduction at all;
+//     QUAD 1: theta >= pi/4, always the two-constant reduction — the blocks next to the centre,
+//     where theta ~= pi/2 takes the extended reduction, and the first half-index past pi/4, which
+//     may be Float64(pi)/4 itself (returned unreduced by Julia's rem_pio2_kernel), stay on the
+//     general path), so the quadrant selects disappear too.
 // Same bits as leg_half_index<0,0,false>, ~20% fewer FP64 instructions.
 constexpr int64_t K_JK_EXACT = 10680708;  // pi*(k - 1/4) >= 2^25
 
@@ -222,15 +225,13 @@ __device__ __forceinline__ void leg_bulk(int64_t k, const LegConsts& c, double& 
     const double a = ak * c.vn;
     double s;
     if (QUAD == 0) {
-        s = fgq_ksin(a, 0.0);
-        cx = fgq_kcos(a, 0.0);
+        s = fgq_jsin(a);
+        cx = fgq_jcos(a);
     } else {
-        const double lo = FGQ_PIO2_LO_K;
-        const double z = a - FGQ_PIO2_HI_K;
-        const double r = z - lo;
-        const double rt = (z - r) - lo;
-        s = fgq_kcos(r, rt);
-        cx = neg_bits(fgq_ksin(r, rt));
+        double r, rt;
+        fgq_rem_pio2_2c(a, &r, &rt);
+        s = fgq_jcos_dd(r, rt);
+        cx = neg_bits(fgq_jsin_dd(r, rt));
     }
     w = scale2(fgq_rcp_fast(j1sq * fgq_div_fast(a, s) * c.inv_vn2), 1);
 }
@@ -241,7 +242,8 @@ struct LegLaunch {
     int64_t kL0, kL1;  // left stores:  xl[k - kL0] = -cos(theta_k)      (empty if kL0 > kL1)
     int64_t kR0, kR1;  // right stores: xr[kR1 - k] = +cos(theta_k)
     int64_t kin0, kin1;  // half-indices stored on BOTH sides with vector stores (interior fast path)
-    int64_t kq0_last;  // NT=0 only: last half-index with theta_k <= pi/4 (host bisection)
+    int64_t kq0_last;  // NT=0 only: last half-index with theta_k < pi/4 (host bisection)
+    int64_t kext_first;  // NT=0 only: first half-index whose theta_k takes the extended pi/2 reduction
     int64_t kcentre;   // (n+1)/2 when n is odd (node forced to 0.0, gausslegendre.jl:91), else 0
     double *xl, *wl, *xr, *wr;
     int vecL, vecR;    // 16-byte stores legal on that side
@@ -267,7 +269,8 @@ legendre_asy_kernel(const LegLaunch p) {
         if (NT == 0 && WT == 0 && !HEAD && kb0 >= K_JK_EXACT && kb1 <= p.kq0_last) {
             leg_bulk<0>(k0, p.c, cx0, w0);
             leg_bulk<0>(k1, p.c, cx1, w1);
-        } else if (NT == 0 && WT == 0 && !HEAD && kb0 >= K_JK_EXACT && kb0 > p.kq0_last) {
+        } else if (NT == 0 && WT == 0 && !HEAD && kb0 >= K_JK_EXACT && kb0 > p.kq0_last + 1 &&
+                   kb1 < p.kext_first) {
             leg_bulk<1>(k0, p.c, cx0, w0);
             leg_bulk<1>(k1, p.c, cx1, w1);
         } else {
@@ -350,7 +353,8 @@ legendre_fastdiv_check_kernel(int64_t k_lo, int64_t k_hi, LegConsts c,
         if (k >= K_JK_EXACT) {  // the specialised bulk path must give the same bits as well
             const double ak = FGQ_PI * fgq_k_minus_quarter(k);
             const double a = ak * c.vn;
-            if (a <= FGQ_PIO4) leg_bulk<0>(k, c, cf, wf); else leg_bulk<1>(k, c, cf, wf);
+            if (a < FGQ_PIO4) leg_bulk<0>(k, c, cf, wf);
+            else if (!fgq_near_pio2(a)) leg_bulk<1>(k, c, cf, wf);
             bad += (__double_as_longlong(cf) != __double_as_longlong(ci)) ||
                    (__double_as_longlong(wf) != __double_as_longlong(wi));
         }
@@ -366,7 +370,7 @@ legendre_fastdiv_check_kernel(int64_t k_lo, int64_t k_hi, LegConsts c,
 // ---------------------------------------------------------------------------------------------
 struct FusedLaunch {
     int64_t kmin, kmax;   // half-indices evaluated (inclusive)
-    int64_t kq0_last;     // as in LegLaunch
+    int64_t kq0_last, kext_first;  // as in LegLaunch
     int64_t kcentre;      // (n+1)/2 for odd n: that half-index is the single node x = 0
     int with_exp;
     LegConsts c;
@@ -393,7 +397,8 @@ legendre_fused_moments_kernel(const FusedLaunch p, double* sums) {
         if (NT == 0 && WT == 0 && !HEAD && full && kb0 >= K_JK_EXACT && kb1 <= p.kq0_last) {
             leg_bulk<0>(k0, p.c, cx[0], w[0]);
             leg_bulk<0>(k0 + 1, p.c, cx[1], w[1]);
-        } else if (NT == 0 && WT == 0 && !HEAD && full && kb0 >= K_JK_EXACT && kb0 > p.kq0_last) {
+        } else if (NT == 0 && WT == 0 && !HEAD && full && kb0 >= K_JK_EXACT && kb0 > p.kq0_last + 1 &&
+                   kb1 < p.kext_first) {
             leg_bulk<1>(k0, p.c, cx[0], w[0]);
             leg_bulk<1>(k0 + 1, p.c, cx[1], w[1]);
         } else {
@@ -455,15 +460,31 @@ static int weight_terms(int64_t n) { return n <= 170 ? 3 : n <= 1500 ? 2 : n <= 
 typedef void (*LegKernel)(const LegLaunch);
 static double tail_angle(int64_t k, double vn);
 
-// last k with a_k <= pi/4, by bisection on the very arithmetic the kernel uses (a_k is monotone in k)
+// last k with a_k < pi/4 (Julia's sin/cos reduce from |x| >= pi/4 on), by bisection on the very
+// arithmetic the kernel uses (a_k is monotone in k)
 static int64_t quarter_split(int64_t n, double vn) {
-    int64_t lo_k = 10680708, hi_k = (n + 1) / 2 + 1;  // K_JK_EXACT; invariant: a(lo_k) <= pi/4 < a(hi_k)
-    if (!(tail_angle(lo_k, vn) <= FGQ_PIO4 && tail_angle(hi_k, vn) > FGQ_PIO4)) return 0;
+    int64_t lo_k = 10680708, hi_k = (n + 1) / 2 + 1;  // K_JK_EXACT; invariant: a(lo_k) < pi/4 <= a(hi_k)
+    if (!(tail_angle(lo_k, vn) < FGQ_PIO4 && tail_angle(hi_k, vn) >= FGQ_PIO4)) return 0;
     while (hi_k - lo_k > 1) {
         const int64_t mid = lo_k + (hi_k - lo_k) / 2;
-        if (tail_angle(mid, vn) <= FGQ_PIO4) lo_k = mid; else hi_k = mid;
+        if (tail_angle(mid, vn) < FGQ_PIO4) lo_k = mid; else hi_k = mid;
     }
     return lo_k;
+}
+
+// first k >= K_JK_EXACT whose angle has the high word of pi/2 (0x3ff921fb: rem_pio2_kernel's "x ~= pi/2"
+// test, which switches to the extended Cody-Waite reduction); a_k <= pi/2 (1 + 2^-50) on a rule, so
+// that is a_k >= the double 0x3ff921fb00000000.
+static int64_t near_pio2_first(int64_t n, double vn) {
+    const double band_lo = 1.57079601287841796875;  // 0x3ff921fb00000000
+    int64_t lo_k = 10680708, hi_k = (n + 1) / 2 + 2;  // invariant: a(lo_k) < band_lo <= a(hi_k) (or hi_k past the rule)
+    if (!(tail_angle(lo_k, vn) < band_lo)) return lo_k;
+    if (tail_angle(hi_k, vn) < band_lo) return INT64_MAX / 4;
+    while (hi_k - lo_k > 1) {
+        const int64_t mid = lo_k + (hi_k - lo_k) / 2;
+        if (tail_angle(mid, vn) < band_lo) lo_k = mid; else hi_k = mid;
+    }
+    return hi_k;
 }
 
 // a_k for k >= K_JK_EXACT exactly as leg_bulk computes it (host IEEE arithmetic, no contraction
@@ -547,6 +568,7 @@ static int launch_one(int64_t n, bool head, int64_t kmin, int64_t kmax, int64_t 
     }
     // only the n >= 2^25 kernel reads the pi/4 split
     p.kq0_last = (node_terms(n) == 0 && !head) ? quarter_split(n, p.c.vn) : 0;
+    p.kext_first = (node_terms(n) == 0 && !head) ? near_pio2_first(n, p.c.vn) : 0;
     const int64_t npairs = (kmax - p.kbase) / 2 + 1;
     const int64_t blocks = (npairs + LEG_THREADS - 1) / LEG_THREADS;
     if (blocks > 0x7fffffffLL) {
@@ -1013,6 +1035,7 @@ extern "C" int fgq_gausslegendre_moments_fused_device(int64_t n, int64_t k_lo, i
         p.kcentre = (n & 1) ? m : 0;
         p.with_exp = with_exp;
         p.kq0_last = (node_terms(n) == 0 && !head) ? quarter_split(n, p.c.vn) : 0;
+        p.kext_first = (node_terms(n) == 0 && !head) ? near_pio2_first(n, p.c.vn) : 0;
         FusedKernel kern = pick_fused(node_terms(n), weight_terms(n), head);
         const int64_t ntiles = (p.kmax - p.kmin) / (2 * LEG_THREADS) + 1;
         const int64_t blocks = imin(ntiles, 148 * 8);

@@ -25,11 +25,9 @@ _c_dp = ctypes.POINTER(ctypes.c_double)
 
 def build(force: bool = False) -> str:
     """Compile the C oracle (gcc, a few seconds)."""
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
-    stale = os.path.exists(_LIB_PATH) and any(os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in srcs)
-    if force or stale or not os.path.exists(_LIB_PATH):
-        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    # make tracks the dependencies itself (incl. the library's csrc/fgq_math.h for the twin mode)
+    subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
+                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     return _LIB_PATH
 
 
@@ -63,6 +61,8 @@ def lib():
             f = getattr(L, nm)
             f.argtypes = [_c_i64, _c_dp, _c_dp, _c_dp]
             f.restype = None
+        L.oracle_twin_tan_q1.argtypes = [_c_i64, _c_dp, _c_dp]
+        L.oracle_twin_tan_q1.restype = None
         L.oracle_jl_sincostan.argtypes = [_c_i64, _c_dp, _c_dp, _c_dp, _c_dp]
         L.oracle_jl_sincostan.restype = None
         L.oracle_set_threads.argtypes = [ctypes.c_int]
@@ -166,6 +166,14 @@ def twin_sincos(t: np.ndarray, medium: bool = False):
     f = lib().oracle_twin_sincos_medium if medium else lib().oracle_twin_sincos_q1
     f(len(t), _dp(t), _dp(s), _dp(c))
     return s, c
+
+
+def twin_tan(t: np.ndarray):
+    """tan t on (0, 3pi/4) from the library's fgq_math.h compiled for the host."""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    tn = np.empty_like(t)
+    lib().oracle_twin_tan_q1(len(t), _dp(t), _dp(tn))
+    return tn
 
 
 def julia_sincostan(t: np.ndarray):

@@ -426,6 +426,9 @@ int oracle_set_threads(int nthreads) {
 void oracle_twin_sincos_q1(int64_t cnt, const double* t, double* s, double* c) {
     for (int64_t i = 0; i < cnt; ++i) fgq_sincos_q1(t[i], &s[i], &c[i]);
 }
+void oracle_twin_tan_q1(int64_t cnt, const double* t, double* tn) {
+    for (int64_t i = 0; i < cnt; ++i) tn[i] = fgq_tan_q1(t[i]);
+}
 void oracle_twin_sincos_medium(int64_t cnt, const double* t, double* s, double* c) {
     for (int64_t i = 0; i < cnt; ++i) fgq_sincos_medium(t[i], &s[i], &c[i]);
 }

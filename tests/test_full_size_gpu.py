@@ -45,15 +45,18 @@ def test_legendre_1e9(fgq, oracle_mod, n, mode):
         ws = left_w[k0 - 1:k1].cpu().numpy()
         xt, wt = oracle_mod.legendre_asy_half(n, k0, k1, twin=True)
         assert np.array_equal(xs, xt) and np.array_equal(ws, wt)
+        xj, wj = oracle_mod.legendre_asy_half(n, k0, k1, twin="julia")
+        assert np.array_equal(xs, xj) and np.array_equal(ws, wj)
         xo, wo = oracle_mod.legendre_asy_half(n, k0, k1)
         assert oracle_mod.ulp_diff(xs, xo).max() <= 2
-        assert oracle_mod.ulp_diff(ws, wo).max() <= 4
 
 
 def test_legendre_1e5_readme_example(fgq, oracle_mod):
     """BASELINE config C1 = the README example (README.md:24-30): dot(w, x.^2) ~ 2/3."""
     x, w = fgq.gausslegendre(100000)
     assert abs(np.dot(w, x * x) - 2 / 3) < 5e-16
+    xj, wj = oracle_mod.gausslegendre(100000, twin="julia")
+    assert np.array_equal(x, xj) and np.array_equal(w, wj)
     xo, wo = oracle_mod.gausslegendre(100000)
     assert oracle_mod.ulp_diff(x, xo).max() <= 2 and oracle_mod.ulp_diff(w, wo).max() <= 4
 
@@ -64,6 +67,8 @@ def test_batch_1e6_rules(fgq, oracle_mod):
     off, x, w = fgq.gausslegendre_batch(n_i)
     _, xt, wt = oracle_mod.gausslegendre_batch(n_i, twin=True)
     assert np.array_equal(x, xt) and np.array_equal(w, wt)
+    _, xj, wj = oracle_mod.gausslegendre_batch(n_i, twin="julia")
+    assert np.array_equal(x, xj) and np.array_equal(w, wj)
     # every rule integrates 1 and x^2 exactly: segment sums
     sw = np.add.reduceat(w, off[:-1])
     sx2 = np.add.reduceat(w * x * x, off[:-1])
@@ -94,30 +99,41 @@ def test_fused_moments(fgq, n):
     assert np.abs(parts - s).max() < 1e-13
 
 
-def test_legendre_1e9_every_index_against_the_oracle(fgq, oracle_mod):
+@pytest.mark.parametrize("n", [10 ** 9, 10 ** 9 + 1])
+def test_legendre_1e9_every_index_against_the_oracle(fgq, oracle_mod, n):
     """at n = 1e9 compare EVERY index, not a sample.  The GPU rule is pulled back in
-    chunks of 2.5e7 half-indices and compared with the C oracle: bit-for-bit against the twin mode;
-    against the libm and julia modes nodes <= 1-2 ulp, weights <= 4 ulp except a ~1e-6 fraction at 5
-    (profiles/r01_parity_legendre_1e9.md holds the full histogram)."""
+    chunks of 2.5e7 half-indices and compared with the C oracle.  Bar: 2 ulp nodes / 4 ulp weights
+    against the reference's Float64 output; met with 0 ulp — every node and weight equals the
+    julia-mode oracle (the reference's algorithm with Julia Base's sin/cos/tan restated) and the twin
+    mode bit for bit.  Against glibc (an unrelated libm) the nodes stay within 1-2 ulp."""
     import torch
-    n = 10 ** 9
     oracle_mod.set_threads(0)
     sh = fgq.gausslegendre_device(n, mode="pair")
     torch.cuda.synchronize()
     (_, _, xl, wl), _ = sh.segments
-    m = n // 2
+    m = (n + 1) // 2
     CH = 25_000_000
     over4 = 0
+    worst_x = worst_w = 0.0
     for k0 in range(1, m + 1, CH):
         k1 = min(k0 + CH - 1, m)
         gx = (-xl[k0 - 1:k1]).cpu().numpy()
         gw = wl[k0 - 1:k1].cpu().numpy()
+        xj, wj = oracle_mod.legendre_asy_half(n, k0, k1, twin="julia")
+        if n % 2 and k1 == m:
+            xj[-1] = 0.0          # the centre node is forced to 0.0 (gausslegendre.jl:91)
+            gx[-1] = abs(gx[-1])  # -0.0 from the negated pull-back
+        ux = oracle_mod.ulp_diff(gx, xj)
+        uw = oracle_mod.ulp_diff(gw, wj)
+        worst_x, worst_w = max(worst_x, ux.max()), max(worst_w, uw.max())
+        over4 += int(np.count_nonzero(uw > 4))
+        assert np.array_equal(gx, xj) and np.array_equal(gw, wj), f"julia-mode mismatch in half-indices {k0}..{k1}"
         xt, wt = oracle_mod.legendre_asy_half(n, k0, k1, twin=True)
+        if n % 2 and k1 == m:
+            xt[-1] = 0.0
         assert np.array_equal(gx, xt) and np.array_equal(gw, wt), f"twin mismatch in half-indices {k0}..{k1}"
-        for md in ("libm", "julia"):   # glibc; the restated Julia Base sin/cos (oracle/julia_libm.h)
-            xo, wo = oracle_mod.legendre_asy_half(n, k0, k1, twin=md)
-            assert oracle_mod.ulp_diff(gx, xo).max() <= 2
-            uw = oracle_mod.ulp_diff(gw, wo)
-            assert uw.max() <= 5
-            over4 += int(np.count_nonzero(uw > 4))
-    assert over4 <= 8e-6 * m
+        xo, _ = oracle_mod.legendre_asy_half(n, k0, k1)
+        if n % 2 and k1 == m:
+            xo[-1] = 0.0
+        assert oracle_mod.ulp_diff(gx, xo).max() <= 2
+    assert worst_x <= 2 and worst_w <= 4 and over4 == 0

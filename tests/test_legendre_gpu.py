@@ -1,9 +1,17 @@
 """GPU parity tests for the Gauss-Legendre path, through the C ABI (ctypes) of libfgq_cuda.so.
 
-Bar (BASELINE.json north_star): nodes within 2 ulp, weights within 4 ulp of the oracle's Float64
-results; theta bit-exact; zero entries exactly zero.  Two oracle modes are used:
-  libm  — glibc sin/cos/tan: the independent stand-in for Julia's libm (tolerance test);
-  twin  — the library's own fgq_math.h compiled for the host: bit-for-bit expectation.
+Bar (BASELINE.json north_star): nodes within 2 ulp, weights within 4 ulp of the reference's
+Float64 results; theta bit-exact; zero entries exactly zero.  Oracle modes:
+  julia — the C restatement of the path with Julia Base's sin/cos/tan restated operation by
+          operation (oracle/julia_libm.h): the functions the reference really calls.  The kernels
+          follow the same association, so the expectation is BIT-FOR-BIT (0 ulp <= 2 / 4 ulp);
+  twin  — the library's own fgq_math.h compiled for the host: bit-for-bit as well (and equal to
+          the julia mode: tests/test_oracle_legendre.py::test_twin_equals_julia_mode);
+  libm  — glibc sin/cos/tan, an unrelated < 1 ulp libm: sanity band for the nodes only.  Two
+          different correct libms put a 1-ulp difference of sin(a) through the four roundings of
+          w = 2/(J1^2 (a/sin a) W), so glibc and Julia weights differ by up to 5 ulp from EACH
+          OTHER (tests/test_oracle_legendre.py::test_glibc_vs_julia_band); that is a property of
+          the two oracles, not of the kernel, and is not the parity bar.
 """
 import json
 import math
@@ -58,6 +66,8 @@ def test_small_rules_bit_exact_vs_twin(fgq, oracle_mod, n):
     x, w = fgq.gausslegendre(n)
     xt, wt = oracle_mod.gausslegendre(n, twin=True)
     assert np.array_equal(x, xt) and np.array_equal(w, wt)
+    xj, wj = oracle_mod.gausslegendre(n, twin="julia")
+    assert np.array_equal(x, xj) and np.array_equal(w, wj)
     xo, wo = oracle_mod.gausslegendre(n)
     assert _ulps(oracle_mod, x, xo) <= X_ULP
 
@@ -72,20 +82,14 @@ def test_asy_parity(fgq, oracle_mod, n):
     xt, wt = oracle_mod.gausslegendre(n, twin=True)
     assert np.array_equal(x, xt), "nodes must match the twin oracle bit-for-bit"
     assert np.array_equal(w, wt), "weights must match the twin oracle bit-for-bit"
+    # the reference's own elementary functions (restated Julia Base libm): every bit
+    xj, wj = oracle_mod.gausslegendre(n, twin="julia")
+    assert np.array_equal(x, xj), "nodes must match the julia-mode oracle bit-for-bit"
+    assert np.array_equal(w, wj), "weights must match the julia-mode oracle bit-for-bit"
+    assert _ulps(oracle_mod, x, xj) <= X_ULP and _ulps(oracle_mod, w, wj) <= W_ULP
+    # an unrelated libm (glibc): nodes within the bar as well
     xo, wo = oracle_mod.gausslegendre(n)
     assert _ulps(oracle_mod, x, xo) <= X_ULP
-    # Weights: w = 2/(J1^2 * (a/sin a) * W) carries a 1-ulp difference between two <1-ulp sines
-    # through four roundings.  Against glibc that stays <= 4 ulp except for ~1e-7 of the weights,
-    # which land on 5 (first seen at n = 2^25-1); see DESIGN.md "what 4 ulp can mean".
-    uw = oracle_mod.ulp_diff(w, wo)
-    assert uw.max() <= W_ULP + 1
-    assert np.count_nonzero(uw > W_ULP) <= max(1, int(2e-7 * n))
-    # the same band against the restated Julia Base libm (oracle/julia_libm.h)
-    xj, wj = oracle_mod.gausslegendre(n, twin="julia")
-    assert _ulps(oracle_mod, x, xj) <= X_ULP
-    uw = oracle_mod.ulp_diff(w, wj)
-    assert uw.max() <= W_ULP + 1
-    assert np.count_nonzero(uw > W_ULP) <= max(1, int(2e-7 * n))
     if n % 2:
         assert x[n // 2] == 0.0
     assert np.all(np.diff(x) >= 0)
@@ -106,11 +110,10 @@ def test_theta_bit_exact(fgq, oracle_mod, n):
         torch.cuda.synchronize()
         got = th.cpu().numpy()
         assert np.array_equal(got, oracle_mod.legendre_theta(n, k_lo, k_hi - 1, twin=True))
+        # cot = inv(tan) with Julia Base's tan (gausslegendre.jl:100): every theta, every bit
+        assert np.array_equal(got, oracle_mod.legendre_theta(n, k_lo, k_hi - 1, twin="julia"))
+        # an unrelated libm (glibc tan): within one ulp of theta
         ref = oracle_mod.legendre_theta(n, k_lo, k_hi - 1)
-        # libm cot vs the library's cos/sin: a differing last bit of cot can flip the rounding of
-        # theta only where the correction is a sizeable fraction of ulp(theta): the first few k
-        bad = np.nonzero(got != ref)[0]
-        assert len(bad) <= 3 and (len(bad) == 0 or (bad + k_lo).max() <= 8), bad
         assert np.abs(got - ref).max() <= np.spacing(ref).max()
 
 

@@ -84,23 +84,64 @@ def test_julia_libm_restatement_accuracy(oracle_mod):
         assert oracle_mod.ulp_diff(got, ref).max() <= 1
 
 
-def test_julia_libm_gap(oracle_mod):
-    """Legendre rules under the restated Julia libm against glibc and against the library's twin:
-    nodes <= 1 ulp, weights <= 4 ulp (5 on a ~1e-7 fraction) — three independent < 1 ulp libms give
-    rules inside the same band, which is what the 2 ulp / 4 ulp tolerance of the north star absorbs."""
+def test_twin_equals_julia_mode(oracle_mod):
+    """The library's fgq_math.h follows Julia Base's sin/cos/tan operation for operation (polynomial
+    split, FMA placement, two-constant and extended pi/2 reduction incl. the x ~= pi/2 band), so the
+    twin oracle and the julia-mode oracle are the SAME function: whole rules on every series branch,
+    the small-rule path, theta, and ranges of the 1e9 / 1e9+1 rules (head tables, the pi/4 switch, the
+    band next to the centre where the extended reduction is taken) bit for bit."""
+    for n in (61, 100, 170, 171, 255, 256, 1013, 1500, 1501, 3950, 3951, 10013, 100000, 100001, 850000,
+              850001, 1000003, (1 << 25) - 1, 1 << 25, (1 << 25) + 1):
+        xt, wt = oracle_mod.gausslegendre(n, twin=True)
+        xj, wj = oracle_mod.gausslegendre(n, twin="julia")
+        assert np.array_equal(xt, xj) and np.array_equal(wt, wj), n
+    n_i = np.arange(0, 61)
+    _, xt, wt = oracle_mod.gausslegendre_batch(n_i, twin=True)
+    _, xj, wj = oracle_mod.gausslegendre_batch(n_i, twin="julia")
+    assert np.array_equal(xt, xj) and np.array_equal(wt, wj)
+    for n in (100, 1013, 100000, 850001):
+        m = (n + 1) // 2
+        assert np.array_equal(oracle_mod.legendre_theta(n, 1, m, twin=True),
+                              oracle_mod.legendre_theta(n, 1, m, twin="julia"))
+    for n in (10 ** 9, 10 ** 9 + 1):
+        m = (n + 1) // 2
+        for k0, k1 in ((1, 300000), (m // 2 - 150000, m // 2 + 150000), (m - 300000, m)):
+            xt, wt = oracle_mod.legendre_asy_half(n, k0, k1, twin=True)
+            xj, wj = oracle_mod.legendre_asy_half(n, k0, k1, twin="julia")
+            assert np.array_equal(xt, xj) and np.array_equal(wt, wj), (n, k0)
+    # the functions themselves on (0, pi/2], dense around pi/4, 0.6744 (tan's "big" switch) and pi/2
+    rng = np.random.default_rng(11)
+    t = np.concatenate([rng.uniform(1e-9, np.pi / 2, 400000), np.pi / 4 + rng.uniform(-1e-6, 1e-6, 20000),
+                        np.pi / 2 - rng.uniform(0, 2e-6, 20000), np.pi / 2 - 10.0 ** rng.uniform(-16, -6, 20000),
+                        np.pi / 4 - 0.6744 + np.pi / 4 + rng.uniform(-1e-6, 1e-6, 20000),
+                        0.6744 + rng.uniform(-1e-4, 1e-4, 20000), 10.0 ** rng.uniform(-9.5, -7, 20000),
+                        [np.pi / 4, np.nextafter(np.pi / 4, 0), np.nextafter(np.pi / 4, 1), np.pi / 2,
+                         np.nextafter(np.pi / 2, 0), 1.5707960128784180, np.nextafter(1.5707960128784180, 0)]])
+    sj, cj, tj = oracle_mod.julia_sincostan(t)
+    st, ct = oracle_mod.twin_sincos(t)
+    tt = oracle_mod.twin_tan(t)
+    assert np.array_equal(st, sj) and np.array_equal(ct, cj) and np.array_equal(tt, tj)
+
+
+def test_glibc_vs_julia_band(oracle_mod):
+    """Two unrelated < 1 ulp libms (glibc, restated Julia Base) give rules that differ from EACH OTHER
+    by <= 1 ulp in the nodes and <= 5 ulp in the weights (w = 2/(J1^2 (a/sin a) W) carries a 1-ulp
+    difference of sin(a) through four roundings).  This is oracle against oracle — no kernel involved —
+    and is why the GPU tests take the julia mode (the reference's own functions), not glibc, as the
+    parity bar."""
     for n in (61, 251, 1013, 10013, 100000, 1000003, 5000001):
         xj, wj = oracle_mod.gausslegendre(n, twin="julia")
-        for mode in (False, True):
-            x, w = oracle_mod.gausslegendre(n, twin=mode)
-            nz = x != 0
-            assert np.array_equal(xj == 0, x == 0)
-            assert oracle_mod.ulp_diff(xj[nz], x[nz]).max() <= 1
-            uw = oracle_mod.ulp_diff(wj, w)
-            assert uw.max() <= 5 and np.count_nonzero(uw > 4) <= max(1, int(2e-7 * n))
-    # theta never depends on sin/cos, and on tan only through a correction ~1e-5 of its size:
+        x, w = oracle_mod.gausslegendre(n)
+        nz = x != 0
+        assert np.array_equal(xj == 0, x == 0)
+        assert oracle_mod.ulp_diff(xj[nz], x[nz]).max() <= 1
+        uw = oracle_mod.ulp_diff(wj, w)
+        assert uw.max() <= 5 and np.count_nonzero(uw > 4) <= max(1, int(2e-7 * n))
+    # theta depends on tan only through a correction ~1e-5 of its size: one ulp at most between libms
     for n in (100, 1013, 100000):
         m = (n + 1) // 2
-        assert np.array_equal(oracle_mod.legendre_theta(n, 1, m, twin="julia"), oracle_mod.legendre_theta(n, 1, m))
+        tj_, tg = oracle_mod.legendre_theta(n, 1, m, twin="julia"), oracle_mod.legendre_theta(n, 1, m)
+        assert np.abs(tj_ - tg).max() <= np.spacing(tg).max()
 
 
 def test_theta_equals_a_beyond_2p25(oracle_mod):
