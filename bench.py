@@ -25,8 +25,62 @@ sys.path.insert(0, ROOT)
 METRIC = "gausslegendre_gnodes_per_s"
 UNIT = "Gnodes/s"
 N_DEFAULT = 10 ** 9
-CPU_SAMPLE_N = 5 * 10 ** 8     # bounded CPU sample: a full gausslegendre(5e8), same branch as 1e9 (~8 s on one core)
+CPU_SAMPLE_N = 5 * 10 ** 8     # bounded single-thread CPU sample: a full gausslegendre(5e8), same branch as 1e9 (~8 s)
+CPU_FULL_N_MIN_FREE_GB = 40    # the oracle at n = 1e9 holds x, w (16 GB) + two half-range temporaries (8 GB)
 PUBLISHED_JULIA_GNODES = 0.0428  # docs/src/benchmark.md:21-22 (n = 1e9+1, hardware unstated)
+NVLINK_GBS_PER_DIR = 900.0     # NVLink 5 per GPU and direction (B200_PROFILING.md)
+
+
+def make_config(n: int) -> dict:
+    """The workload both arms (--impl b200 / reference) are timed on: BASELINE.json configs[1]."""
+    return {"workload": f"gausslegendre(n={n}) Float64 nodes+weights, Bogaert asymptotic path (BASELINE.json configs[1])",
+            "n": n,
+            "l2": "each step writes 16*n bytes (>> 126 MB L2) and reads nothing; no flush needed"}
+
+
+def free_ram_gb() -> float:
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+def ncu_traffic(n: int, world: int, mode: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the tail kernel, per launch, read from the committed
+    `ncu --set full` raw page of the same command (profiles/): never a number measured under this run."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r02_legendre_1e9_ncu_raw.csv")
+    if not (n == 10 ** 9 and world == 1 and mode == "pair" and os.path.exists(path)):
+        return None, "no committed ncu capture for this configuration"
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        kcol = hdr.index("Kernel Name")
+        rcol, wcol = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        units = rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        best = None
+        for r in rows[2:]:
+            if "legendre_asy_kernel" in r[kcol]:
+                tot = float(r[rcol].replace(",", "")) * scale.get(units[rcol], 1.0) + \
+                      float(r[wcol].replace(",", "")) * scale.get(units[wcol], 1.0)
+                best = tot if best is None else max(best, tot)   # the tail launch is the big one
+        return best, "profiles/r02_legendre_1e9_ncu_raw.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+    except Exception as e:  # noqa: BLE001
+        return None, f"unreadable ncu capture: {e!r}"
+
+
+def fp64_counts():
+    """Per-config executed FP64 instruction counts (ncu smsp__sass_thread_inst_executed_op_d{add,mul,fma}_pred_on,
+    summed over the launches of one call), committed as profiles/r02_fp64_counts.json by tools/r2_fp64_counts.py."""
+    path = os.path.join(ROOT, "profiles", "r02_fp64_counts.json")
+    try:
+        return json.load(open(path))
+    except Exception:  # noqa: BLE001
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -111,32 +165,38 @@ def cpu_oracle_rate(n_sample: int, threads: int, reps: int = 1):
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle port (Julia is not installed on the box, so the reference itself cannot
-    run), all host threads, each step one full gausslegendre(CPU_SAMPLE_N)."""
+    """CPU arm: the oracle port (Julia is not installed on the box, so the reference itself cannot run), all host
+    threads.  Each step is one full gausslegendre(n) at the metric's own n = 1e9 when the box has the memory for
+    it, otherwise the stated bounded sample (same branch: 1-term nodes, 0-term weights)."""
     if rank != 0:
         return
     import oracle
     oracle.build()
     cores = os.cpu_count() or 1
-    for _ in range(args.warmup):
-        cpu_oracle_rate(args.cpu_n, 0)
+    free = free_ram_gb()
+    n_step = args.n if (args.cpu_n is None and free >= CPU_FULL_N_MIN_FREE_GB) else (args.cpu_n or CPU_SAMPLE_N)
+    n_step = min(n_step, args.n)
+    warm = min(args.warmup, 3)   # OpenMP pool + first-touch page faults; a step takes seconds
+    for _ in range(warm):
+        cpu_oracle_rate(n_step, 0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, used, _ = cpu_oracle_rate(args.cpu_n, 0)
+        _, used, _ = cpu_oracle_rate(n_step, 0)
     dt = time.perf_counter() - t0
-    value = args.cpu_n * args.steps / dt / 1e9
-    rate1, _, _ = cpu_oracle_rate(args.cpu_n, 1)
-    sample = (f"each step = full oracle gausslegendre(n={args.cpu_n}) on the host "
-              f"(same branch as n=1e9: 1-term nodes, 0-term weights), OpenMP over {used} threads")
+    value = n_step * args.steps / dt / 1e9
+    rate1, _, _ = cpu_oracle_rate(min(CPU_SAMPLE_N, n_step), 1)
+    sample = (f"each step = full oracle gausslegendre(n={n_step}) on the host"
+              + ("" if n_step == args.n else f" (bounded sample of n={args.n}: same branch, 1-term nodes / 0-term weights; "
+                                             f"{free:.0f} GB free < {CPU_FULL_N_MIN_FREE_GB} GB needed for the full n)")
+              + f", OpenMP over {used} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "steps": args.steps, "warmup": warm, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (none read: nodes are generated from their index)",
-        "config": {"workload": f"gausslegendre(n={args.n}) Bogaert asymptotic path", "n": args.n,
-                   "cpu_sample_n": args.cpu_n},
+        "config": make_config(args.n),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
-                         "single_thread_value": rate1, "host_cores": cores},
+                         "sample_n": n_step, "single_thread_value": rate1, "host_cores": cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "published_reference": {"value": PUBLISHED_JULIA_GNODES, "unit": UNIT,
                                 "what": "Julia @btime gausslegendre(1000000001), docs/src/benchmark.md:21-22, hardware unstated"},
@@ -308,6 +368,239 @@ def time_other_configs(fgq_b200, cpu: bool):
     return out
 
 
+def time_e2e(args, fgq_b200, rank, world, barrier, max_over_ranks):
+    """The metric through the host-returning C-ABI call, host buffers, copies inside the timed region.
+    world == 1: the drop-in call gausslegendre(n) itself, into (a) pinned, pre-faulted, reused buffers — the headline
+    `value` —, (b) pre-faulted pageable buffers, (c) a FRESH untouched allocation every step (what
+    `Vector{Float64}(undef, n)` in julia/FGQCuda.jl is); beside them the host's own store-bandwidth roofline.
+    world > 1: each rank fetches its mirror-pair shard into pinned buffers."""
+    import ctypes
+    import numpy as np
+    import torch
+    n = args.n
+    L = fgq_b200.lib()
+    hw = None
+    if world == 1 and args.e2e_mode == "pair":
+        hx = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        hw = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        out = (hx.numpy(), hw.numpy())
+        call = lambda: fgq_b200.gausslegendre(n, out=out)  # noqa: E731
+    elif args.e2e_mode == "pair":
+        k_lo, k_hi = fgq_b200.half_index_partition(n, world)[rank]
+        bufs = [torch.empty(k_hi - k_lo, dtype=torch.float64, pin_memory=True) for _ in range(4)]
+        out4 = tuple(b.numpy() for b in bufs)
+        call = lambda: fgq_b200.gausslegendre_host_pair(n, rank, world, out=out4)  # noqa: E731
+    else:
+        # both segments of the rank's mirror-pair shard by DMA (16 B/node over PCIe, no host threads)
+        k_lo, k_hi = fgq_b200.half_index_partition(n, world)[rank]
+        segs = [(k_lo - 1, min(k_hi - 1, (n + 1) // 2)), (n - min(k_hi - 1, n // 2), n - k_lo + 1)]
+        outs = [tuple(torch.empty(b - a, dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)) for a, b in segs]
+
+        def call():
+            for (a, b), o in zip(segs, outs):
+                fgq_b200.gausslegendre(n, index_range=(a, b), out=o)
+
+    def timed(fn, steps, fresh=None):
+        per = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            t1 = time.perf_counter()
+            fn()
+            per.append(time.perf_counter() - t1)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0), per
+
+    for _ in range(2):  # warm-up (scratch allocation, host worker threads)
+        call()
+    barrier()
+    st_p, st_d, st_l, st_s = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+    L.fgq_debug_drain_stats(ctypes.byref(st_p), ctypes.byref(st_d), ctypes.byref(st_l), ctypes.byref(st_s))
+    cd_b, cd_v = ctypes.c_int64(0), ctypes.c_int64(0)
+    L.fgq_debug_codec_stats(ctypes.byref(cd_b), ctypes.byref(cd_v))  # reset
+    dt, per_call = timed(call, args.e2e_steps)
+    L.fgq_debug_drain_stats(ctypes.byref(st_p), ctypes.byref(st_d), ctypes.byref(st_l), ctypes.byref(st_s))
+    L.fgq_debug_codec_stats(ctypes.byref(cd_b), ctypes.byref(cd_v))
+    coded = torch.tensor([float(cd_b.value), float(cd_v.value)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(coded)
+    coded_bytes, coded_values = float(coded[0].item()), float(coded[1].item())
+    # bytes that really crossed PCIe per step: the coded streams when the transport coding is active
+    # (FGQ_HOST_CODEC, default on), otherwise the plain left half
+    d2h = int(coded_bytes / args.e2e_steps) if coded_values > 0 else 8 * (n + n % 2)
+    e2e = {"value": n * args.e2e_steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 0,
+           "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+           "destination": "pinned host buffers, pre-faulted, reused every step",
+           "transport": ({"coding": "second differences of the bit patterns, lossless (csrc/delta_codec.h)",
+                          "bytes_per_value": coded_bytes / coded_values} if coded_values > 0 else
+                         {"coding": "none"}),
+           "call_s_min": min(per_call), "call_s_median": float(np.median(per_call)),
+           "what": "host-returning C-ABI call: kernel + device-side packing + PCIe D2H of the coded left half of each "
+                   "shard, chunk-pipelined; host threads unpack it into the left half and write the mirrored half "
+                   "(+-x symmetry)",
+           "mode": args.e2e_mode,
+           "drain_rank0": {"pieces": st_p.value, "mirror_by_dma": st_d.value, "landed_before_pickup": st_l.value,
+                           "last_dma_share": st_s.value / 1000.0},
+           "check_sum_w_minus_2": float(np.float64(hw.sum().item()) - 2.0) if hw is not None else None}
+    if world == 1 and args.e2e_mode == "pair":
+        # the host's own roofline: every result byte is written once by a host thread (non-temporal stores)
+        g = ctypes.c_double(0.0)
+        if L.fgq_measure_host_store_peak(out[0].ctypes.data, n, 0, ctypes.byref(g)) == 0 and g.value > 0:
+            ach = 16.0 * n / min(per_call) / 1e9
+            e2e["host_roofline"] = {"bound": "host memory stores", "achieved_gbs": ach, "peak_gbs": g.value,
+                                    "frac": ach / g.value, "algorithmic_bytes_per_node": 16,
+                                    "peak_source": "fgq_measure_host_store_peak: the library's host threads streaming "
+                                                   "non-temporal stores into the same pinned buffer",
+                                    "host_threads": int(os.environ.get("FGQ_HOST_THREADS", 0)) or min(16, os.cpu_count() or 16)}
+        del hx, hw, out
+        k = max(1, min(args.e2e_steps, 10))
+        px, pw = np.zeros(n), np.zeros(n)        # pageable, pre-faulted
+        fgq_b200.gausslegendre(n, out=(px, pw))
+        dtp, per_p = timed(lambda: fgq_b200.gausslegendre(n, out=(px, pw)), k)
+        e2e["e2e_pageable"] = {"value": n * k / dtp / 1e9, "unit": UNIT, "steps": k, "call_s_min": min(per_p),
+                               "destination": "pageable numpy arrays, pre-faulted, reused"}
+        del px, pw
+        k = max(1, min(args.e2e_steps, 5))
+        dtf, per_f = timed(lambda: fgq_b200.gausslegendre(n), k)   # np.empty inside: untouched pages every step
+        e2e["e2e_fresh"] = {"value": n * k / dtf / 1e9, "unit": UNIT, "steps": k, "call_s_min": min(per_f),
+                            "destination": "a fresh untouched allocation per step (np.empty = Vector{Float64}(undef, n)): "
+                                           "first-touch page faults inside the timed region"}
+    return e2e
+
+
+def attach_rooflines(other, counts, dfma_tf, hbm_gbs):
+    """Every other_configs entry gets its own roofline: executed FP64 work per node from the committed ncu
+    instruction counts (profiles/r02_fp64_counts.json) against the measured DFMA peak, and 16 B per node of
+    algorithmic store traffic against the measured HBM peak."""
+    if not other:
+        return
+    for key, ent in other.items():
+        ms = ent.get("device_ms") or ent.get("stream_ms_incl_host_planning")
+        nodes = ent.get("nodes") or {"C1_gausslegendre_1e5": 1e5, "fused_moments_gausslegendre_1e9": 1e9,
+                                     "C2_odd_gausslegendre_1e9p1": 1e9 + 1, "C3_gaussjacobi_1e7": 1e7,
+                                     "C4_gausshermite_1e6": 1e6, "C4_gausslaguerre_1e6": 1e6,
+                                     "reduced_gausshermite_1e6": ent.get("entries")}.get(key)
+        if not ms or not nodes:
+            continue
+        c = counts.get(key, {})
+        r = {"bytes_per_node": 0 if key.startswith("fused") else 16,
+             "achieved_gbs": (0 if key.startswith("fused") else 16.0) * nodes / (ms * 1e-3) / 1e9}
+        r["frac_of_hbm"] = r["achieved_gbs"] / hbm_gbs
+        if "flops_per_node" in c:
+            tf = c["flops_per_node"] * nodes / (ms * 1e-3) / 1e12
+            r.update({"flops_per_node": c["flops_per_node"], "flops_source": c.get("source"),
+                      "achieved_tflops": tf, "frac_of_dfma_peak": tf / dfma_tf if dfma_tf else None})
+        r["bound"] = "hbm" if r["frac_of_hbm"] >= (r.get("frac_of_dfma_peak") or 0) else "fp64"
+        ent["roofline"] = r
+
+
+def run_capi(args):
+    """ONE process, --gpus devices, nothing but `ccall`-able symbols of libfgq_cuda.so (ctypes here): fgq_init,
+    fgq_gausslegendre_device_sharded, fgq_timer_*, fgq_allgather, fgq_gausslegendre_device_replicated,
+    fgq_gausslegendre_host_multi.  Same metric, same kernels, same partition as the torchrun arm."""
+    import ctypes
+    import numpy as np
+    import torch
+    import fgq_b200
+    m = fgq_b200.multi
+    n = args.n
+    nd = m.init(ndev=args.gpus)
+    rule = m.gausslegendre_sharded(n)            # allocates, fills, reduces sum w / sum w x^2
+    sums = rule.sums
+    for _ in range(max(args.warmup, 3)):
+        m.gausslegendre_sharded(n, out=rule, sums=False)
+    m.synchronize()
+    samplers = [ClockSampler(d) for d in range(nd)]
+    for sp in samplers:
+        sp.start()
+    launches0 = fgq_b200.launch_count()
+    m.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.gausslegendre_sharded(n, out=rule, sums=False)
+    ms, per_dev = m.timer_stop()
+    wall = time.perf_counter() - t0
+    launches = fgq_b200.launch_count() - launches0
+    clk = [sp.stop() for sp in samplers]
+    clocks = {"sm_mhz": min(c["sm_mhz"] for c in clk if c["sm_mhz"]) if any(c["sm_mhz"] for c in clk) else None,
+              "sm_max_mhz": clk[0]["sm_max_mhz"], "reasons": sorted(set(r for c in clk for r in c["reasons"])),
+              "samples": sum(c["samples"] for c in clk), "per_device_sm_mhz": [c["sm_mhz"] for c in clk]}
+    value = n * args.steps / (ms * 1e-3) / 1e9
+    allgather = None
+    if nd > 1 and not args.no_allgather:
+        inbound = 16.0 * ((n + 1) // 2) * (nd - 1) / nd
+        allgather = {"inbound_bytes_per_gpu": inbound}
+        rep = None
+        for transport in ("push", "ce", "nccl"):
+            os.environ["FGQ_ALLGATHER"] = transport
+            try:
+                rep = m.allgather(rule, out=rep)   # warm-up / allocation
+                m.synchronize()
+                m.timer_start()
+                for _ in range(3):
+                    m.allgather(rule, out=rep)
+                t_ms, _ = m.timer_stop()
+                t_ms /= 3
+                allgather[transport] = {"ms": t_ms, "inbound_gbs_per_gpu": inbound / (t_ms * 1e-3) / 1e9,
+                                        "frac_of_nvlink_900": inbound / (t_ms * 1e-3) / 1e9 / NVLINK_GBS_PER_DIR}
+            except Exception as e:  # noqa: BLE001
+                allgather[transport] = {"error": repr(e)}
+        os.environ.pop("FGQ_ALLGATHER", None)
+        if rep is not None:
+            xs, ws = rep.tensors(nd - 1)
+            allgather["replica_sum_w_minus_2"] = float(ws.sum().item() - 2.0)
+            allgather["replica_symmetric"] = bool(torch.equal(xs[: n // 2], -xs[n - n // 2:].flip(0)))
+            m.gausslegendre_replicated(n, out=rep)
+            m.synchronize()
+            m.timer_start()
+            for _ in range(3):
+                m.gausslegendre_replicated(n, out=rep)
+            t_ms, _ = m.timer_stop()
+            allgather["replicate_by_generation_ms"] = t_ms / 3
+            allgather["what"] = ("left segments shipped (push: one kernel per device storing into every peer replica "
+                                 "over NVLink; ce: cudaMemcpyPeerAsync; nccl: grouped send/recv), right halves mirrored locally")
+            rep.free()
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        hw = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        out = (hx.numpy(), hw.numpy())
+        for _ in range(2):
+            m.gausslegendre_host_multi(n, out=out)
+        cd_b, cd_v = ctypes.c_int64(0), ctypes.c_int64(0)
+        fgq_b200.lib().fgq_debug_codec_stats(ctypes.byref(cd_b), ctypes.byref(cd_v))
+        per = []
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            t1 = time.perf_counter()
+            m.gausslegendre_host_multi(n, out=out)
+            per.append(time.perf_counter() - t1)
+        dt = time.perf_counter() - t0
+        fgq_b200.lib().fgq_debug_codec_stats(ctypes.byref(cd_b), ctypes.byref(cd_v))
+        g = ctypes.c_double(0.0)
+        fgq_b200.lib().fgq_measure_host_store_peak(out[0].ctypes.data, n, 0, ctypes.byref(g))
+        e2e = {"value": n * args.e2e_steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": int(cd_b.value / args.e2e_steps) if cd_v.value else 8 * (n + n % 2),
+               "steps": args.e2e_steps, "call_s_min": min(per), "call_s_median": float(np.median(per)),
+               "what": "fgq_gausslegendre_host_multi: every device generates, packs and ships its half-index range over its "
+                       "own PCIe link; the host's threads are shared out between the devices",
+               "destination": "pinned host buffers, pre-faulted, reused every step",
+               "check_sum_w_minus_2": float(np.float64(hw.sum().item()) - 2.0),
+               "host_roofline": {"achieved_gbs": 16.0 * n / min(per) / 1e9, "peak_gbs": g.value,
+                                 "frac": (16.0 * n / min(per) / 1e9) / g.value if g.value else None}}
+    cfg = make_config(n)
+    detail = {"shard_mode": "pair", "driver": "capi: one process, multi-GPU C ABI (include/fgq.h)"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nd, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (none read: nodes are generated from their index)",
+            "config": cfg, "config_detail": detail, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "device_ms_per_device": [v / args.steps for v in per_dev], "host_wall_ms_per_step": wall / args.steps * 1e3,
+            "allgather": allgather,
+            "checks": {"sum_w_minus_2": sums[0] - 2.0, "sum_wx2_minus_2_3": sums[1] - 2.0 / 3.0}}
+    print(json.dumps(line), flush=True)
+    rule.free()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -316,8 +609,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--mode", default="pair", choices=["pair", "contiguous"])
-    ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-n", type=int, default=None,
+                    help="nodes per reference-arm step (default: n itself when the box has >= 40 GB free, else 5e8)")
+    ap.add_argument("--driver", default="torch", choices=["torch", "capi"],
+                    help="torch: one process per GPU (torchrun); capi: ONE process drives --gpus devices through the "
+                         "multi-GPU C ABI (fgq_init / fgq_gausslegendre_device_sharded / fgq_allgather)")
+    ap.add_argument("--no-allgather", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=None, help="default: --steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-mode", choices=["pair", "dma"], default="pair",
@@ -331,6 +629,11 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.e2e_steps is None:
+        args.e2e_steps = args.steps
+    if args.driver == "capi":
+        run_capi(args)
         return
 
     import numpy as np
@@ -352,6 +655,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     n = args.n
     L = fgq_b200.lib()
@@ -376,88 +685,69 @@ def main():
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     clocks = sampler.stop()
-
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = max_over_ranks(total_ms)
     value = n * args.steps / (total_ms_max * 1e-3) / 1e9
 
-    # invariant check of the last step's output: sum w = 2, sum w x^2 = 2/3 (all-reduced)
+    # invariant check of the last step's output: sum w = 2, sum w x^2 = 2/3 (all-reduced: 2 doubles over NCCL)
     sums = fgq_b200.rule_moments_device(shard)
     if world > 1:
         dist.all_reduce(sums)
     sums = sums.cpu().numpy()
 
-    # ---- end-to-end through the host-returning C-ABI call: device generation + D2H into pinned
-    # host buffers, every step (h2d = 0: the only input is the integer n).
+    # ---- optional collective, reported separately (north star: "NCCL over NVLink is used only for an optional
+    # allgather into a replicated array"): one all_gather_into_tensor per array of the LEFT segments + a local
+    # mirror kernel; beside it the same replicated result by generation on every rank (no transfer at all).
+    allgather = None
+    if world > 1 and not args.no_allgather:
+        from fgq_b200 import distributed as fd
+        xr = torch.empty(n, dtype=torch.float64, device="cuda")
+        wr = torch.empty(n, dtype=torch.float64, device="cuda")
+        st = {}
+        fd.allgather_rule(shard, out=(xr, wr), stats=st)   # warm-up (NCCL channel set-up)
+        barrier()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fd.allgather_rule(shard, out=(xr, wr))
+        e1.record()
+        barrier()
+        ag_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+        # checksum of the replica against the sharded rule: same sum w, sum w x^2 (to rounding), symmetric, ordered
+        full = fgq_b200.LegendreShard(n, 0, 1, "contiguous", [(0, n, xr, wr)])
+        rs = fgq_b200.rule_moments_device(full).cpu().numpy()
+        k_lo, k_hi = fgq_b200.half_index_partition(n, world)[rank]
+        own_ok = bool(torch.equal(xr[k_lo - 1:k_hi - 1], shard.segments[0][2])) and \
+            bool(torch.equal(wr[n - (k_hi - 1):n - (k_lo - 1)].flip(0)[:shard.segments[1][3].numel()],
+                             shard.segments[1][3].flip(0)))
+        inbound = 16.0 * ((n + 1) // 2) * (world - 1) / world   # bytes arriving at each GPU: left halves of the peers
+        # the alternative: every rank generates the whole rule itself
+        e0.record()
+        for _ in range(reps):
+            m_all = (n + 1) // 2
+            fgq_b200._lib.check(L.fgq_gausslegendre_device_pair(n, 1, m_all + 1, xr.data_ptr(), wr.data_ptr(),
+                                                                xr.data_ptr() + 8 * (n - m_all), wr.data_ptr() + 8 * (n - m_all),
+                                                                torch.cuda.current_stream().cuda_stream))
+        e1.record()
+        barrier()
+        regen_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+        allgather = {"ms": ag_ms, "collectives_per_call": st.get("collectives"),
+                     "inbound_bytes_per_gpu": inbound, "inbound_gbs_per_gpu": inbound / (ag_ms * 1e-3) / 1e9,
+                     "frac_of_nvlink_900": inbound / (ag_ms * 1e-3) / 1e9 / NVLINK_GBS_PER_DIR,
+                     "what": "all_gather_into_tensor (NCCL) of the left segments, x and w, + local +-x mirror kernel; "
+                             "the replica ends up complete on every rank",
+                     "replica_sum_w_minus_2": float(rs[0] - 2.0), "replica_sum_wx2_minus_2_3": float(rs[1] - 2.0 / 3.0),
+                     "replica_matches_own_shard": own_ok,
+                     "replicate_by_generation_ms": regen_ms,
+                     "note": "generating the whole rule on every rank is cheaper than gathering it"}
+        del xr, wr, full
+        torch.cuda.empty_cache()
+
+    # ---- end-to-end through the host-returning C-ABI call: device generation + D2H into HOST buffers every step
+    # (h2d = 0: the only input is the integer n).
     e2e = None
     if not args.no_e2e:
-        # world == 1: the drop-in call gausslegendre(n) itself (pinned result buffers); world > 1: each rank
-        # fetches its mirror-pair shard.  Either way only the left half of a shard crosses PCIe.
-        if world == 1 and args.e2e_mode == "pair":
-            hx = torch.empty(n, dtype=torch.float64, pin_memory=True)
-            hw = torch.empty(n, dtype=torch.float64, pin_memory=True)
-            out = (hx.numpy(), hw.numpy())
-            call = lambda: fgq_b200.gausslegendre(n, out=out)  # noqa: E731
-        elif args.e2e_mode == "pair":
-            k_lo, k_hi = fgq_b200.half_index_partition(n, world)[rank]
-            bufs = [torch.empty(k_hi - k_lo, dtype=torch.float64, pin_memory=True) for _ in range(4)]
-            out4 = tuple(b.numpy() for b in bufs)
-            hw = None
-            call = lambda: fgq_b200.gausslegendre_host_pair(n, rank, world, out=out4)  # noqa: E731
-        else:
-            # both segments of the rank's mirror-pair shard by DMA (16 B/node over PCIe, no host threads)
-            k_lo, k_hi = fgq_b200.half_index_partition(n, world)[rank]
-            segs = [(k_lo - 1, min(k_hi - 1, (n + 1) // 2)), (n - min(k_hi - 1, n // 2), n - k_lo + 1)]
-            outs = [tuple(torch.empty(b - a, dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)) for a, b in segs]
-            hw = None
-
-            def call():
-                for (a, b), o in zip(segs, outs):
-                    fgq_b200.gausslegendre(n, index_range=(a, b), out=o)
-        for _ in range(2):  # warm-up (scratch allocation, host worker threads)
-            call()
-        barrier()
-        import ctypes
-        st_p, st_d, st_l, st_s = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
-        fgq_b200.lib().fgq_debug_drain_stats(ctypes.byref(st_p), ctypes.byref(st_d), ctypes.byref(st_l), ctypes.byref(st_s))
-        cd_b, cd_v = ctypes.c_int64(0), ctypes.c_int64(0)
-        fgq_b200.lib().fgq_debug_codec_stats(ctypes.byref(cd_b), ctypes.byref(cd_v))  # reset
-        per_call = []
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            t1 = time.perf_counter()
-            call()
-            per_call.append(time.perf_counter() - t1)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        fgq_b200.lib().fgq_debug_drain_stats(ctypes.byref(st_p), ctypes.byref(st_d), ctypes.byref(st_l), ctypes.byref(st_s))
-        fgq_b200.lib().fgq_debug_codec_stats(ctypes.byref(cd_b), ctypes.byref(cd_v))
-        coded = torch.tensor([float(cd_b.value), float(cd_v.value)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(coded)
-        coded_bytes, coded_values = float(coded[0].item()), float(coded[1].item())
-        # bytes that really crossed PCIe per step: the coded streams when the transport coding is active
-        # (FGQ_HOST_CODEC, default on), otherwise the plain left half
-        d2h = int(coded_bytes / args.e2e_steps) if coded_values > 0 else 8 * (n + n % 2)
-        e2e = {"value": n * args.e2e_steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 0,
-               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-               "transport": ({"coding": "second differences of the bit patterns, lossless (csrc/delta_codec.h)",
-                              "bytes_per_value": coded_bytes / coded_values} if coded_values > 0 else
-                             {"coding": "none"}),
-               "call_s_min": min(per_call), "call_s_median": float(np.median(per_call)),
-               "what": "host-returning C-ABI call into pinned host buffers: kernel + device-side packing + PCIe D2H of the "
-                       "coded left half of each shard, chunk-pipelined; host threads unpack it into the left half and write "
-                       "the mirrored half (+-x symmetry)",
-               "mode": args.e2e_mode,
-               "drain_rank0": {"pieces": st_p.value, "mirror_by_dma": st_d.value, "landed_before_pickup": st_l.value,
-                               "last_dma_share": st_s.value / 1000.0},
-               "check_sum_w_minus_2": float(np.float64(hw.sum().item()) - 2.0) if hw is not None else None}
+        e2e = time_e2e(args, fgq_b200, rank, world, barrier, max_over_ranks)
 
     if rank == 0:
         peaks, peaks_src = measured_peaks()
@@ -487,29 +777,35 @@ def main():
             tail_nodes = shard.count
         achieved = 16.0 * tail_nodes / (kern_ms * 1e-3) / 1e9
         dfma_tf, store_gbs = fgq_b200.measure_peaks()
+        traffic, traffic_src = ncu_traffic(n, world, args.mode)
+        counts = fp64_counts()
+        c2 = counts.get("C2_gausslegendre_1e9", {})
+        flops_node = c2.get("flops_per_node", 2 * 109 / 2.0)   # executed FP64 instr/node x (1 + fma share); fallback: SASS count
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the committed ncu --set full
-            # capture (profiles/r01_legendre_1e9_ncu.md): 15.943408 GB + 0.5 MB for the n = 1e9, 1-GPU launch
-            "traffic": 15.943935e9 if (n == 10 ** 9 and world == 1 and args.mode == "pair") else None,
+            "traffic": traffic, "traffic_source": traffic_src,
             "kernel": "legendre_asy_kernel<NT=0,WT=0,HEAD=false>", "kernel_ms": kern_ms,
             "algorithmic_bytes_per_node": 16, "nodes_per_launch": tail_nodes,
             "peak_source": peaks_src,
             "store_only_peak_gbs": store_gbs, "frac_of_store_peak": achieved / store_gbs if store_gbs else None,
-            "fp64": {"algorithmic_flops_per_node": 22, "achieved_tflops": 22.0 * tail_nodes / (kern_ms * 1e-3) / 1e12,
+            "fp64": {"algorithmic_flops_per_node": 22, "executed_flops_per_node": flops_node,
+                     "executed_source": c2.get("source", "static SASS count of the two bulk paths (100 / 118 FP64 instructions per 4 nodes)"),
+                     "achieved_tflops_algorithmic": 22.0 * tail_nodes / (kern_ms * 1e-3) / 1e12,
+                     "achieved_tflops_executed": flops_node * tail_nodes / (kern_ms * 1e-3) / 1e12,
                      "dfma_peak_tflops": dfma_tf,
-                     "frac": (22.0 * tail_nodes / (kern_ms * 1e-3) / 1e12) / dfma_tf if dfma_tf else None},
+                     "frac_executed": (flops_node * tail_nodes / (kern_ms * 1e-3) / 1e12) / dfma_tf if dfma_tf else None},
         }
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()
-            r_all, used, t_all = cpu_oracle_rate(args.cpu_n, 0)
-            r_one, _, t_one = cpu_oracle_rate(args.cpu_n, 1)
+            cn = args.cpu_n or CPU_SAMPLE_N
+            r_all, used, t_all = cpu_oracle_rate(cn, 0)
+            r_one, _, t_one = cpu_oracle_rate(cn, 1)
             cpu_baseline = {
                 "value": r_one, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"full oracle gausslegendre(n={args.cpu_n}) (same branch as n=1e9), one thread like the reference; {t_one:.2f} s",
+                "sample": f"full oracle gausslegendre(n={cn}) (same branch as n=1e9), one thread like the reference; {t_one:.2f} s",
                 "all_cores_value": r_all, "all_cores": used,
                 "published_julia": {"value": PUBLISHED_JULIA_GNODES, "what": "docs/src/benchmark.md:21-22, hardware unstated"},
             }
@@ -518,17 +814,18 @@ def main():
             del shard
             torch.cuda.empty_cache()
             other = time_other_configs(fgq_b200, cpu=not args.no_cpu_baseline)
+            attach_rooflines(other, counts, dfma_tf, peaks["hbm_gbs"])
+        cfg = make_config(n)   # identical to the reference arm's
+        detail = {"shard_mode": args.mode, "driver": "torch.distributed, one process per GPU",
+                  "sharding": f"{args.mode}-sharded over {world} GPU(s), device-resident, no collective on the path"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (none read: nodes are generated from their index)",
-            "config": {"workload": f"gausslegendre(n={n}) Bogaert asymptotic path, device-resident, "
-                                   f"{args.mode}-sharded over {world} GPU(s)",
-                       "n": n, "shard_mode": args.mode,
-                       "l2": "each step writes 16*n/N bytes (>> 126 MB L2) and reads nothing; no flush needed"},
+            "config": cfg, "config_detail": detail,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "allgather": allgather,
             "checks": {"sum_w_minus_2": float(sums[0] - 2.0), "sum_wx2_minus_2_3": float(sums[1] - 2.0 / 3.0)},
             "step_ms_median": statistics.median(step_ms), "step_ms_min": min(step_ms),
             "other_configs": other,

@@ -5,6 +5,7 @@ path (reference src/FastGaussQuadrature.jl:7-19), over the C ABI of ``libfgq_cud
 (``include/fgq.h``).  Import it as ``import fgq_b200`` (see ``fgq_b200.py`` at the repo root).
 """
 from ._lib import DomainError, FGQError, NotImplementedOnDevice, build, lib  # noqa: F401
+from . import multi  # noqa: F401  (single-process multi-GPU face of the C ABI)
 from .api import (  # noqa: F401
     approx_besselroots,
     besselroots,

@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfgq_cuda.so")
+# FGQ_LIB_PATH: developer aid for timing an alternative build of the same library (tools/time_tail.py)
+LIB_PATH = os.environ.get("FGQ_LIB_PATH") or os.path.join(_HERE, "libfgq_cuda.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 FGQ_OK, FGQ_EDOMAIN, FGQ_ENOTIMPL, FGQ_EINVAL, FGQ_ECUDA = 0, 1, 2, 3, 100
@@ -20,6 +21,15 @@ _dp = ctypes.POINTER(ctypes.c_double)
 _vp = ctypes.c_void_p
 _i32p = ctypes.POINTER(ctypes.c_int32)
 _i64p = ctypes.POINTER(ctypes.c_int64)
+
+class FgqShard(ctypes.Structure):
+    """``fgq_shard`` of include/fgq.h."""
+    _fields_ = [("device", ctypes.c_int32), ("owner", ctypes.c_int32), ("lo", ctypes.c_int64), ("hi", ctypes.c_int64),
+                ("x", ctypes.c_void_p), ("w", ctypes.c_void_p)]
+
+
+_shp = ctypes.POINTER(FgqShard)
+_vpp = ctypes.POINTER(ctypes.c_void_p)
 
 # name -> (restype, argtypes); must list every symbol include/fgq.h declares
 SIGNATURES = {
@@ -74,6 +84,7 @@ SIGNATURES = {
     "fgq_gausslegendre_moments_fused_device": (ctypes.c_int, [_i64, _i64, _i64, ctypes.c_int, _vp, _vp]),
     "fgq_measure_dfma_peak": (ctypes.c_int, [_dp]),
     "fgq_measure_store_peak": (ctypes.c_int, [_i64, _dp]),
+    "fgq_measure_host_store_peak": (ctypes.c_int, [_vp, _i64, ctypes.c_int, _dp]),
     "fgq_debug_legendre_theta_device": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp]),
     "fgq_debug_fastdiv_check": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp]),
     "fgq_debug_codec_stats": (ctypes.c_int, [_i64p, _i64p]),
@@ -81,6 +92,22 @@ SIGNATURES = {
     "fgq_debug_jacobi_skip_angles": (ctypes.c_int, [_i64, ctypes.c_double, ctypes.c_double, _dp, _dp]),
     "fgq_debug_codec_unpack_host": (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, ctypes.c_int, ctypes.c_int]),
     "fgq_debug_drain_stats": (ctypes.c_int, [_i64p, _i64p, _i64p, ctypes.POINTER(ctypes.c_int)]),
+    # multi-GPU, one process
+    "fgq_init": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "fgq_finalize": (ctypes.c_int, []),
+    "fgq_num_devices": (ctypes.c_int, []),
+    "fgq_shard_count": (ctypes.c_int, [_i64]),
+    "fgq_gausslegendre_device_sharded": (ctypes.c_int, [_i64, _shp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), _dp]),
+    "fgq_free_shards": (ctypes.c_int, [_shp, ctypes.c_int]),
+    "fgq_synchronize": (ctypes.c_int, []),
+    "fgq_timer_start": (ctypes.c_int, []),
+    "fgq_timer_stop": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    "fgq_allgather": (ctypes.c_int, [_shp, ctypes.c_int, _i64, _vpp, _vpp]),
+    "fgq_gausslegendre_mirror_device": (ctypes.c_int, [_i64, _vp, _vp, _vp]),
+    "fgq_gausslegendre_device_replicated": (ctypes.c_int, [_i64, _vpp, _vpp]),
+    "fgq_free_replicas": (ctypes.c_int, [_vpp, _vpp]),
+    "fgq_gausslegendre_host_multi": (ctypes.c_int, [_i64, _vp, _vp]),
+    "fgq_debug_half_index_range": (ctypes.c_int, [_i64, ctypes.c_int, ctypes.c_int, _i64p, _i64p]),
 }
 
 _lib = None

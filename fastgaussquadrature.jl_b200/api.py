@@ -37,6 +37,28 @@ def _host_pair(n: int, pinned: bool):
     return np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
 
 
+def _check_out(x, w, cnt: int) -> None:
+    """Caller-supplied result buffers: the C side writes `cnt` CONTIGUOUS doubles through the base pointer."""
+    for a in (x, w):
+        if not isinstance(a, np.ndarray) or a.shape != (cnt,) or a.dtype != np.float64:
+            raise ValueError("out must be two float64 arrays of the requested length")
+        if not a.flags.c_contiguous or not a.flags.writeable:
+            raise ValueError("out arrays must be C-contiguous and writeable (a strided view would be overrun)")
+
+
+def _check_offsets(n_i: np.ndarray, offsets: np.ndarray) -> None:
+    """CSR layout of a batch: len(n_i) + 1 non-decreasing offsets, rule r inside [offsets[r], offsets[r+1]), so
+    that offsets[-1] (the size of x and w) bounds everything the C side writes."""
+    if offsets.ndim != 1 or len(offsets) != len(n_i) + 1:
+        raise ValueError(f"offsets must have len(n_i) + 1 = {len(n_i) + 1} entries, got {offsets.shape}")
+    if len(n_i) == 0:
+        return
+    if offsets[0] < 0 or np.any(np.diff(offsets) < 0):
+        raise ValueError("offsets must be non-negative and non-decreasing")
+    if np.any(offsets[:-1] + np.maximum(n_i, 0) > offsets[1:]):
+        raise ValueError("offsets[r] + n_i[r] must not exceed offsets[r+1]")
+
+
 def launch_count() -> int:
     return int(lib().fgq_launch_count())
 
@@ -63,8 +85,7 @@ def gausslegendre(n, *, pinned: bool = False, out: Optional[Tuple[np.ndarray, np
     cnt = hi - lo
     if out is not None:
         x, w = out
-        if x.shape != (cnt,) or w.shape != (cnt,) or x.dtype != np.float64 or w.dtype != np.float64:
-            raise ValueError("out must be two float64 arrays of the requested length")
+        _check_out(x, w, cnt)
     else:
         x, w = _host_pair(cnt, pinned)
     if cnt == 0:
@@ -90,6 +111,8 @@ def gausslegendre_host_pair(n, rank: int = 0, world: int = 1, out=None, pinned: 
         xr, wr = _host_pair(cnt, pinned)
     else:
         xl, wl, xr, wr = out
+        _check_out(xl, wl, cnt)
+        _check_out(xr, wr, cnt)
     if cnt:
         check(lib().fgq_gausslegendre_host_pair(n, k_lo, k_hi, _ptr(xl), _ptr(wl), _ptr(xr), _ptr(wr)))
     return [(k_lo - 1, k_hi - 1, xl, wl), (n - k_hi + 1 + skip, n - k_lo + 1, xr[skip:], wr[skip:])], (xl, wl, xr, wr)
@@ -106,8 +129,9 @@ def gausslegendre_batch(n_i, offsets=None):
         raise ValueError("n_i must be one-dimensional")
     if offsets is None:
         offsets = np.zeros(len(n_i) + 1, dtype=np.int64)
-        np.cumsum(n_i, out=offsets[1:])
+        np.cumsum(np.maximum(n_i, 0), out=offsets[1:])
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    _check_offsets(n_i, offsets)
     total = int(offsets[-1]) if len(offsets) else 0
     x = np.empty(total, dtype=np.float64)
     w = np.empty(total, dtype=np.float64)
@@ -124,6 +148,7 @@ def _batch_layout(n_i, offsets):
         offsets = np.zeros(len(n_i) + 1, dtype=np.int64)
         np.cumsum(np.maximum(n_i, 0), out=offsets[1:])
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    _check_offsets(n_i, offsets)
     total = int(offsets[-1]) if len(offsets) else 0
     return n_i, offsets, np.empty(total, dtype=np.float64), np.empty(total, dtype=np.float64)
 

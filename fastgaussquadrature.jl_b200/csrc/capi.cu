@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -25,7 +26,7 @@ namespace fgq {
 static thread_local char t_err[512] = "";
 static thread_local int t_warn = 0;
 static std::atomic<int64_t> g_launches{0};
-static std::mutex g_host_mutex;
+static std::mutex g_host_mutex[16];  // host-returning calls serialise PER DEVICE (fgq_gausslegendre_host_multi runs one per device)
 static std::mutex g_res_mutex;  // lazily created per-device streams / events / scratch
 
 void set_error(const char* fmt, ...) {
@@ -41,8 +42,21 @@ void clear_status() {
 void add_warning(int bits) { t_warn |= bits; }
 void count_launch(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-HostPathLock::HostPathLock() { g_host_mutex.lock(); }
-HostPathLock::~HostPathLock() { g_host_mutex.unlock(); }
+static int host_dev_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        dev = 0;
+    }
+    return (dev >= 0 && dev < 16) ? dev : 0;
+}
+HostPathLock::HostPathLock() : slot(host_dev_slot()) { g_host_mutex[slot].lock(); }
+HostPathLock::~HostPathLock() { g_host_mutex[slot].unlock(); }
+
+// Host threads a host-returning call may use; 0 = the pool's default.  fgq_gausslegendre_host_multi sets it on the
+// per-device threads it starts so that the devices share the host's cores instead of each claiming all of them.
+static thread_local int t_host_thread_budget = 0;
+void set_host_thread_budget(int threads) { t_host_thread_budget = threads; }
 
 constexpr int MAX_DEV = 16, MAX_SLOT = 8;
 static void* g_scratch[MAX_DEV][MAX_SLOT];
@@ -76,20 +90,23 @@ int scratch_device(size_t bytes, int slot, void** out) {
     return FGQ_OK;
 }
 
-static void* g_pinned[3];
-static size_t g_pinned_bytes[3];
-// library-owned pinned staging (grow-only), for destinations that are ordinary pageable memory
+static void* g_pinned[MAX_DEV][3];
+static size_t g_pinned_bytes[MAX_DEV][3];
+// library-owned pinned staging (grow-only, per device: the caller holds that device's HostPathLock), for
+// destinations that are ordinary pageable memory and for the coded streams
 static int scratch_pinned(size_t bytes, int slot, void** out) {
-    if (g_pinned_bytes[slot] < bytes) {
-        if (g_pinned[slot]) {
-            FGQ_CUDA_TRY(cudaFreeHost(g_pinned[slot]));
-            g_pinned[slot] = nullptr;
-            g_pinned_bytes[slot] = 0;
+    int dev;
+    FGQ_TRY(cur_dev(&dev));
+    if (g_pinned_bytes[dev][slot] < bytes) {
+        if (g_pinned[dev][slot]) {
+            FGQ_CUDA_TRY(cudaFreeHost(g_pinned[dev][slot]));
+            g_pinned[dev][slot] = nullptr;
+            g_pinned_bytes[dev][slot] = 0;
         }
-        FGQ_CUDA_TRY(cudaHostAlloc(&g_pinned[slot], bytes, cudaHostAllocDefault));
-        g_pinned_bytes[slot] = bytes;
+        FGQ_CUDA_TRY(cudaHostAlloc(&g_pinned[dev][slot], bytes, cudaHostAllocPortable));
+        g_pinned_bytes[dev][slot] = bytes;
     }
-    *out = g_pinned[slot];
+    *out = g_pinned[dev][slot];
     return FGQ_OK;
 }
 
@@ -276,11 +293,18 @@ static void mirror_copy(const double* src, double* dst, int64_t cnt, int64_t a, 
 // outlive the synchronisation objects they wait on during static destruction.
 class WorkerPool {
   public:
-    static WorkerPool& get() {
-        static WorkerPool* pool = new WorkerPool();
-        return *pool;
+    static WorkerPool& get() {  // one pool per device slot: calls on different devices run concurrently
+        static WorkerPool* pools[16] = {};
+        static std::mutex mu;
+        const int slot = host_dev_slot();
+        std::lock_guard<std::mutex> lk(mu);
+        if (!pools[slot]) pools[slot] = new WorkerPool();
+        return *pools[slot];
     }
-    int max_threads() const { return (int)threads_; }
+    int max_threads() const {
+        if (t_host_thread_budget > 0) return t_host_thread_budget < 64 ? t_host_thread_budget : 64;
+        return (int)threads_;
+    }
     // runs job(t) for t in [0, T): t = 0 on the calling thread, the others on pool threads; returns when
     // all of them have finished
     void run(int T, const std::function<void(int)>& job) {
@@ -422,7 +446,8 @@ int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const Piec
     // share); a piece the thread had to wait for means PCIe is behind (lower it).
     // The share carries over from call to call (the caller holds HostPathLock): the feeder runs up to RING
     // pieces ahead of the host threads, so a short drain is over before its own observations can act.
-    static double s_dma_share = 0.0;
+    static double s_dma_share_dev[16] = {};
+    double& s_dma_share = s_dma_share_dev[host_dev_slot()];
     double dma_share = s_dma_share, dma_acc = 0.0;
     bool adapt = true;
     if (const char* e = getenv("FGQ_HOST_MIRROR_DMA_SHARE")) {  // tests / tuning: a fixed share in [0, 1]
@@ -1132,6 +1157,54 @@ extern "C" int fgq_debug_drain_stats(int64_t* pieces, int64_t* dma_pieces, int64
     if (dma_pieces) *dma_pieces = g_drain_dma.exchange(0);
     if (landed) *landed = g_drain_landed.exchange(0);
     if (share_milli) *share_milli = g_drain_share_milli.load();
+    return FGQ_OK;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void fill_stream_avx2(double* p, int64_t len, double value) {
+    int64_t i = 0;
+    while (i < len && ((uintptr_t)(p + i) & 31) != 0) p[i++] = value;
+    const __m256d v = _mm256_set1_pd(value);
+    for (; i + 4 <= len; i += 4) _mm256_stream_pd(p + i, v);
+    for (; i < len; ++i) p[i] = value;
+    _mm_sfence();
+}
+#endif
+
+// Host-memory roofline of the host-returning calls: every result byte is written exactly once by a host thread
+// (decoder output / mirror image) with non-temporal stores.  This measures that pattern alone — `threads` pool
+// threads streaming constants into buf[0 .. count) — so that e2e can be stated as a fraction of what the host's
+// memory system accepts (bench.py).  Needs no device.
+extern "C" int fgq_measure_host_store_peak(double* buf, int64_t count, int threads, double* gbs) {
+    clear_status();
+    if (!buf || !gbs || count < (1 << 16)) {
+        set_error("invalid host store measurement request");
+        return FGQ_EINVAL;
+    }
+    WorkerPool& pool = WorkerPool::get();
+    int T = threads > 0 ? threads : pool.max_threads();
+    if (T > 64) T = 64;
+    set_host_thread_budget(T);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        const auto t0 = std::chrono::steady_clock::now();
+        pool.run(T, [&](int t) {
+            const int64_t a = (count * t / T) & ~(int64_t)3, b = t + 1 == T ? count : (count * (t + 1) / T) & ~(int64_t)3;
+#if defined(__x86_64__)
+            static const bool have_avx2 = __builtin_cpu_supports("avx2");
+            if (have_avx2) {
+                fill_stream_avx2(buf + a, b - a, 1.0 + rep);
+                return;
+            }
+#endif
+            for (int64_t i = a; i < b; ++i) buf[i] = 1.0 + rep;
+        });
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const double g = (double)count * 8.0 / dt / 1e9;
+        if (rep > 0 && g > best) best = g;
+    }
+    set_host_thread_budget(0);
+    *gbs = best;
     return FGQ_OK;
 }
 

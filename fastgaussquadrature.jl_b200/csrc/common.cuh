@@ -53,11 +53,13 @@ __device__ __forceinline__ void st_stream2(double* p, double a, double b) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Library-owned device scratch + pinned staging for the *_host entry points.
-// Guarded by a process-wide mutex (host entry points serialise).
-struct HostPathLock {
+// Guarded by a per-device mutex (host entry points serialise per device).
+struct HostPathLock {   // per current device
     HostPathLock();
     ~HostPathLock();
+    int slot;
 };
+void set_host_thread_budget(int threads);  // thread-local cap on the host threads of this thread's *_host calls (0 = default)
 int scratch_device(size_t bytes, int slot, void** out);   // grow-only, per (device, slot)
 int scratch_stream(int which, cudaStream_t* out);          // two library streams
 int scratch_event(int which, cudaEvent_t* out);

@@ -251,10 +251,13 @@ struct LegLaunch {
 };
 
 constexpr int LEG_THREADS = 256;
+#ifndef FGQ_LEG_MIN_BLOCKS
+#define FGQ_LEG_MIN_BLOCKS 1   // resident blocks per SM the compiler must allow for (register cap); tuning aid
+#endif
 
 
 template <int NT, int WT, bool HEAD>
-__global__ void __launch_bounds__(LEG_THREADS)
+__global__ void __launch_bounds__(LEG_THREADS, FGQ_LEG_MIN_BLOCKS)
 legendre_asy_kernel(const LegLaunch p) {
     const int64_t t = (int64_t)blockIdx.x * LEG_THREADS + threadIdx.x;
     const int64_t k0 = p.kbase + 2 * t;

@@ -236,6 +236,73 @@ int fgq_gausslaguerre_batch_device(int64_t nrules, const int32_t* n_i, const dou
 int fgq_gausslaguerre_batch_host(int64_t nrules, const int32_t* n_i, const double* alpha_i, const int64_t* offsets,
                                  double* x, double* w);
 
+/* ---- multi-GPU, one process ------------------------------------------- */
+
+/* A piece of a rule resident on one device: output indices [lo, hi) of the n-point rule live at
+ * x[0 .. hi-lo), w[0 .. hi-lo) in the memory of CUDA device `device`.  The buffers are owned by the
+ * library until fgq_free_shards.  This is the "sharded device buffers" handle of the device-resident
+ * variant of gausslegendre(n) (src/gausslegendre.jl:22-69 returns two host Vectors; the replacement keeps
+ * the result where it was generated). */
+typedef struct fgq_shard {
+    int32_t device;  /* CUDA device ordinal */
+    int32_t owner;   /* 1: x is the base of an allocation (released by fgq_free_shards); 0: a view into one */
+    int64_t lo, hi;  /* output indices [lo, hi), 0-based */
+    double* x;       /* device pointers on `device` */
+    double* w;
+} fgq_shard;
+
+/* Selects the devices (NULL / ndev <= 0: all visible ones, or the first ndev when only ndev > 0 is given),
+ * creates one stream per device and enables peer access between them.  Optional: every call below
+ * initialises with all visible devices on first use.  Idempotent for the same list. */
+int fgq_init(const int* device_ids, int ndev);
+int fgq_finalize(void);
+int fgq_num_devices(void);
+/* number of fgq_shard entries fgq_gausslegendre_device_sharded writes for this n (2 per device: the left
+ * segment and its mirror image; 1 for n <= 60) */
+int fgq_shard_count(int64_t n);
+
+/* Device-resident gausslegendre(n) over all initialised devices: device d generates the half-index range of
+ * rank d — output indices [k_lo-1, k_hi-1) and their mirror image [n-k_hi+1, n-k_lo+1), each half-index
+ * evaluated once — into its own HBM.  No collective: every node is a function of (n, index).
+ *   shards[2d], shards[2d+1]  left / right segment of device d, ascending in the output index.
+ *   Zero-initialised descriptors are allocated by the call; descriptors filled by a previous call for the same
+ *   n are reused (no allocation: steady-state calls only enqueue two launches per device).
+ *   sums != NULL: sums[0] = sum w, sums[1] = sum w x^2 over the whole rule (per-device reductions added on the
+ *   host in device order); the call then returns after the result is complete.  sums == NULL: the call only
+ *   enqueues on the per-device streams; fgq_synchronize / fgq_timer_stop wait.
+ * n < 0 -> FGQ_EDOMAIN (gausslegendre.jl:26). */
+int fgq_gausslegendre_device_sharded(int64_t n, fgq_shard* shards, int max_shards, int* nshards, double* sums);
+int fgq_free_shards(fgq_shard* shards, int nshards);
+int fgq_synchronize(void);
+/* Device-side timing of everything enqueued between the two calls: one event pair per device on the library's
+ * per-device streams; *ms_max = the slowest device, ms_per_device[fgq_num_devices()] optional. */
+int fgq_timer_start(void);
+int fgq_timer_stop(float* ms_max, float* ms_per_device);
+
+/* Optional replicated copy of the whole rule on every device (north star: "NCCL over NVLink is used only for
+ * an optional allgather into a replicated array"): x_repl[d], w_repl[d] (d < fgq_num_devices()) are device
+ * pointers on device d holding all n entries; NULL entries are allocated by the call (fgq_free_replicas).
+ * Stream-ordered after the generation; fgq_synchronize waits.  Transport (environment FGQ_ALLGATHER):
+ *   push (default)  one kernel per device: reads its shard once and stores it into every replica through the
+ *                   peer mappings (NVLink / NVSwitch);
+ *   ce              copy engines (cudaMemcpyPeerAsync), one stream per destination;
+ *   nccl            grouped ncclSend / ncclRecv straight into place (libnccl.so.2, dlopen'ed). */
+int fgq_allgather(const fgq_shard* shards, int nshards, int64_t n, double** x_repl, double** w_repl);
+/* Mirror-pair shards travel as their left segments only (half the NVLink bytes): once a replica's left half is in
+ * place its owner writes x[n-1-i] = -x[i], w[n-1-i] = w[i] (gausslegendre.jl:83-90 mirrors the same way) with
+ * this kernel; FGQ_ALLGATHER_HALF=0 ships both segments instead.  Also callable on its own: fills output indices
+ * [n - n/2, n) of x_dev, w_dev (n entries each, current device) from [0, n/2). */
+int fgq_gausslegendre_mirror_device(int64_t n, double* x_dev, double* w_dev, void* stream);
+/* The same replicated result without any transfer: every device generates the whole rule itself (generation at
+ * ~7 TB/s of local HBM stores is cheaper than moving 14 of 16 GB into every GPU over NVLink). */
+int fgq_gausslegendre_device_replicated(int64_t n, double** x_repl, double** w_repl);
+int fgq_free_replicas(double** x_repl, double** w_repl);
+
+/* Host-returning gausslegendre(n) that drains through ALL initialised devices at once: device d generates,
+ * packs and ships the half-index range of rank d over its own PCIe link; the host threads (shared out between
+ * the devices) unpack into x, w and write the mirror images.  Same result as fgq_gausslegendre_host, bit for bit. */
+int fgq_gausslegendre_host_multi(int64_t n, double* x, double* w);
+
 /* ---- consumers / checks ------------------------------------------------------------------ */
 
 /* sums_dev[0] += sum w_i, sums_dev[1] += sum w_i x_i^2 over count entries (device buffers;
@@ -258,6 +325,11 @@ int fgq_gausslegendre_moments_fused_device(int64_t n, int64_t k_lo, int64_t k_hi
 int fgq_measure_dfma_peak(double* tflops);
 /* Store-only streaming bandwidth (16-byte st.global.cs over `bytes` of scratch), GB/s. */
 int fgq_measure_store_peak(int64_t bytes, double* gbs);
+
+/* Host-memory store bandwidth, GB/s: `threads` host threads (0 = the library's default) streaming non-temporal
+ * stores into buf[0 .. count) — the pattern with which the host-returning calls write their result.  The e2e
+ * figures of bench.py are stated against it.  Needs no device. */
+int fgq_measure_host_store_peak(double* buf, int64_t count, int threads, double* gbs);
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
 
@@ -289,6 +361,8 @@ int fgq_debug_jacobi_skip_angles(int64_t n, double a, double b, double* t_right,
  * fused != 0 selects the register-to-destination variant (FGQ_CODEC_FUSED=1 in the product; off by default). */
 int fgq_debug_codec_unpack_host(const double* in, int64_t cnt, double* left, double* right, int64_t mirror_cnt,
                                 int negate, int fused);
+/* The half-index range [k_lo, k_hi) that device / rank `rank` of `world` owns in the sharded calls (host-only). */
+int fgq_debug_half_index_range(int64_t n, int world, int rank, int64_t* k_lo, int64_t* k_hi);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t fgq_launch_count(void);
 

@@ -254,6 +254,153 @@ def asy1(n, a, b, nbdy, info=None):
     return np.concatenate([-x_left, x_right]), np.concatenate([w_left, w_right])
 
 
+# ---- the same interior solve evaluated in node chunks (full-size parity at n = 1e7) ----------------
+#
+# feval_asy1 builds ~10 dense 20 x N arrays (8 GB per call at N = 5e6, as the reference does).  Every node is
+# independent EXCEPT for two global, data-dependent decisions: the series truncation index (the first m > 11
+# whose interior inf-norm is below eps/100, :309) and the Newton stopping rule (:209-218).  The chunked form
+# reproduces both exactly with two passes per evaluation: pass 1 collects the per-term interior norms over all
+# chunks (the norm of term m does not depend on where the sum is cut), pass 2 evaluates every chunk with the
+# truncation index fixed.  tests/test_oracle_jacobi.py checks it against asy1 itself.
+
+def _feval_asy1_chunk(n, a, b, t, interior, used=None):
+    """One chunk of feval_asy1.  used=None: returns the 20 interior inf-norms |dS1 + dS2| of this chunk
+    (0 where the chunk has no interior node); otherwise (vals, ders) with the series cut at `used` terms."""
+    M = 20
+    N = len(t)
+    mm = np.arange(1, M + 1, dtype=np.float64)
+    A = ((2 * n + a + b) + mm)[:, None] * t[None, :] / 2 - (a + 1 / 2) * PI / 2
+    cosA = np.cos(A)
+    sinA = np.sin(A)
+    sinT_ = np.sin(t)
+    cosT_ = np.cos(t)
+    cosA2 = cosA * cosT_[None, :] + sinA * sinT_[None, :]
+    sinA2 = sinA * cosT_[None, :] - cosA * sinT_[None, :]
+    del A
+    csc = (1.0 / np.sin(t / 2)) / 2
+    sinT = np.concatenate([np.ones((N, 1)), np.cumprod(np.repeat(csc[:, None], M - 1, axis=1), axis=1)], axis=1)
+    secT = (1.0 / np.cos(t / 2)) / 2
+    PHI, PHI2 = _phi_tables(n, a, b, M)
+    S = np.zeros(N)
+    S2 = np.zeros(N)
+    norms = np.zeros(M)
+    for m in range(1, M + 1):
+        if used is not None and m - 1 == used:
+            break
+        lo = np.arange(0, m, 2)
+        le = np.arange(1, m, 2)
+        dS1 = (sinT[:, lo] @ PHI[lo, m - 1]) * cosA[m - 1, :]
+        dS12 = (sinT[:, lo] @ PHI2[lo, m - 1]) * cosA2[m - 1, :]
+        if len(le):
+            dS2 = (sinT[:, le] @ PHI[le, m - 1]) * sinA[m - 1, :]
+            dS22 = (sinT[:, le] @ PHI2[le, m - 1]) * sinA2[m - 1, :]
+        else:
+            dS2 = np.zeros(N)
+            dS22 = np.zeros(N)
+        if used is None:
+            if interior.any():
+                norms[m - 1] = np.max(np.abs(dS1[interior] + dS2[interior]))
+        else:
+            S += dS1
+            S += dS2
+            S2 += dS12
+            S2 += dS22
+        sinT[:, :m] *= secT[:, None]
+    if used is None:
+        return norms
+    C, C2 = feval_asy1_constants(n, a, b)
+    vals = C * S
+    ders = (n * ((a - b) - (2 * n + a + b) * cosT_) * vals + (2 * (n + a) * (n + b) * C2) * S2) / (2 * n + a + b) / sinT_
+    denom = 1.0 / (np.sin(np.abs(t) / 2) ** (a + 0.5) * np.cos(t / 2) ** (b + 0.5))
+    return vals * denom, ders * denom
+
+
+def _feval_asy1_chunked(n, a, b, t, i0, i1, chunk, info=None):
+    """feval_asy1 over all of t, interior = indices [i0, i1), in chunks."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    N = len(t)
+    starts = list(range(0, N, chunk))
+
+    def norm_job(c0):
+        c1 = min(c0 + chunk, N)
+        interior = np.zeros(c1 - c0, dtype=bool)
+        interior[max(i0 - c0, 0):max(min(i1, c1) - c0, 0)] = True
+        return _feval_asy1_chunk(n, a, b, t[c0:c1], interior)
+
+    # chunks are independent (numpy releases the GIL inside its loops): spread them over the host cores
+    pool = ThreadPoolExecutor(max_workers=min(len(starts), os.cpu_count() or 1))
+    norms = np.zeros(20)
+    for r in pool.map(norm_job, starts):
+        norms = np.maximum(norms, r)
+    used = 20
+    for m in range(1, 21):
+        if m - 1 > 10 and norms[m - 1] < EPS / 100:
+            used = m - 1
+            break
+    if info is not None:
+        info.setdefault("terms", []).append(used)
+    vals = np.empty(N)
+    ders = np.empty(N)
+
+    def eval_job(c0):
+        c1 = min(c0 + chunk, N)
+        vals[c0:c1], ders[c0:c1] = _feval_asy1_chunk(n, a, b, t[c0:c1], None, used)
+
+    list(pool.map(eval_job, starts))
+    pool.shutdown()
+    return vals, ders
+
+
+def asy1_chunked(n, a, b, nbdy, chunk=250_000, info=None):
+    """asy1 (:196-247) with every feval_asy1 evaluated in node chunks: same global decisions, bounded memory."""
+    j = np.arange(n, 0, -1, dtype=np.float64)
+    K = PI * (2 * j + a - 0.5) / (2 * n + a + b + 1)
+    tt = K + (1 / (2 * n + a + b + 1) ** 2) * ((0.25 - a ** 2) * (1.0 / np.tan(K / 2)) - (0.25 - b ** 2) * np.tan(K / 2))
+    del j, K
+
+    def solve(a, b, t, i0, i1):
+        sweeps = 0
+        for _ in range(10):
+            vals, ders = _feval_asy1_chunked(n, a, b, t, i0, i1, chunk, info)
+            dt = vals / ders
+            t = t + dt
+            sweeps += 1
+            if np.max(np.abs(dt[i0:i1])) < np.sqrt(EPS) / 100:
+                break
+        vals, ders = _feval_asy1_chunked(n, a, b, t, i0, i1, chunk, info)
+        t = t + vals / ders
+        return np.cos(t), 1.0 / ders ** 2, sweeps
+
+    t = tt[tt <= PI / 2]
+    mint = t[len(t) - nbdy]
+    first = int(np.argmax(t < mint)) if np.any(t < mint) else None
+    x_right, w_right, sweeps_r = solve(a, b, t, 0, max(first, 1))
+    t = PI - tt[: n - len(x_right)]
+    mint = t[nbdy - 1]
+    first = int(np.argmax(t > mint))
+    x_left, w_left, sweeps_l = solve(b, a, t, max(first, 0), len(t))
+    if info is not None:
+        info["sweeps"] = (sweeps_r, sweeps_l)
+        info["n_right"] = len(x_right)
+    return np.concatenate([-x_left, x_right]), np.concatenate([w_left, w_right])
+
+
+def jacobi_asy_chunked(n, a, b, chunk=250_000, info=None):
+    """jacobi_asy (:170-194) on top of asy1_chunked."""
+    nbdy = 10
+    x, w = asy1_chunked(n, a, b, nbdy, chunk, info)
+    xb, wb = asy2(n, a, b, nbdy)
+    x[n - nbdy:] = xb
+    w[n - nbdy:] = wb
+    if a != b:
+        xb, wb = asy2(n, b, a, nbdy)
+    x[:nbdy] = -xb[::-1]
+    w[:nbdy] = wb[::-1]
+    w = w * weights_constant(n, a, b)
+    return x, w
+
+
 # ---- boundary: gaussjacobi.jl:363-667 ------------------------------------------------------------
 
 def nck_mat(n):

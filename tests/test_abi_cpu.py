@@ -141,3 +141,53 @@ def test_batch_descriptions_are_validated_before_any_device_work(fgq_cpu):
     b = L.fgq_gausshermite_reduced_bound(1_000_000)
     assert 24_000 < b < 25_000 and b % 2 == 0
     assert L.fgq_gausshermite_reduced_bound(1_000_001) % 2 == 1  # odd rules keep their centre node
+
+
+def test_c_partition_equals_python_partition(fgq_cpu):
+    """The half-index partition of the single-process multi-GPU calls (multi.cu) is the one the
+    one-process-per-GPU mirror uses (api.half_index_partition): same shards either way."""
+    import ctypes
+    L = fgq_cpu.lib()
+    for n in (61, 100, 101, 26383, 1000003, 10 ** 9, 10 ** 9 + 1, 2 ** 40 + 7):
+        for world in (1, 2, 3, 4, 7, 8, 16):
+            hp = fgq_cpu.half_index_partition(n, world)
+            for r in range(world):
+                lo, hi = ctypes.c_int64(0), ctypes.c_int64(0)
+                assert L.fgq_debug_half_index_range(n, world, r, ctypes.byref(lo), ctypes.byref(hi)) == 0
+                assert (lo.value, hi.value) == hp[r], (n, world, r)
+    assert L.fgq_debug_half_index_range(100, 4, 4, None, None) == 3
+
+
+def test_multi_gpu_calls_fail_loudly_without_a_device(fgq_cpu):
+    if fgq_cpu.lib().fgq_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(fgq_cpu.FGQError):
+        fgq_cpu.multi.init()
+    with pytest.raises(fgq_cpu.FGQError):
+        fgq_cpu.multi.gausslegendre_sharded(1000)
+    with pytest.raises(fgq_cpu.FGQError):
+        fgq_cpu.multi.gausslegendre_host_multi(1000)
+    with pytest.raises(fgq_cpu.DomainError):
+        fgq_cpu.multi.gausslegendre_sharded(-1)
+    assert fgq_cpu.multi.num_devices() == 0
+
+
+def test_out_buffers_and_offsets_are_validated(fgq_cpu):
+    """a strided `out` view or an inconsistent CSR description must be refused before the C side
+    writes through the base pointer."""
+    big = np.zeros(20)
+    with pytest.raises(ValueError):
+        fgq_cpu.gausslegendre(10, out=(big[::2], np.zeros(10)))
+    ro = np.zeros(10)
+    ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        fgq_cpu.gausslegendre(10, out=(np.zeros(10), ro))
+    i64 = np.int64
+    with pytest.raises(ValueError):
+        fgq_cpu.gausslegendre_batch([5, 6], offsets=np.array([0, 5], dtype=i64))          # len(n_i) entries only
+    with pytest.raises(ValueError):
+        fgq_cpu.gausslegendre_batch([5, 6], offsets=np.array([0, 5, 8], dtype=i64))       # last rule overruns the total
+    with pytest.raises(ValueError):
+        fgq_cpu.gaussjacobi_batch([5, 6], 0.1, 0.2, offsets=np.array([0, 9, 5], dtype=i64))  # decreasing
+    with pytest.raises(ValueError):
+        fgq_cpu.gausshermite_batch([5, 6], offsets=np.array([3, 4, 11], dtype=i64))       # overlap

@@ -137,3 +137,27 @@ def test_legendre_1e9_every_index_against_the_oracle(fgq, oracle_mod, n):
             xo[-1] = 0.0
         assert oracle_mod.ulp_diff(gx, xo).max() <= 2
     assert worst_x <= 2 and worst_w <= 4 and over4 == 0
+
+
+@pytest.mark.parametrize("dest", ["pinned", "pageable"])
+@pytest.mark.parametrize("n", [10 ** 9, 10 ** 9 + 1])
+def test_host_returning_rule_at_full_size_equals_the_device_rule(fgq, n, dest):
+    """The host-returning drop-in call at the headline size — kernel, device-side transport coding, PCIe, host
+    decode + mirror — against the device-resident rule, EVERY entry, bit for bit (the device rule itself is
+    compared with the oracle at every index above).  Pinned and pageable (fresh, untouched) destinations."""
+    import torch
+    sh = fgq.gausslegendre_device(n, mode="contiguous")
+    torch.cuda.synchronize()
+    (_, _, xd, wd), = sh.segments
+    if dest == "pinned":
+        out = tuple(torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for _ in range(2))
+        x, w = fgq.gausslegendre(n, out=out)
+    else:
+        x, w = fgq.gausslegendre(n)
+    CH = 50_000_000
+    for lo in range(0, n, CH):
+        hi = min(lo + CH, n)
+        assert np.array_equal(x[lo:hi], xd[lo:hi].cpu().numpy()), f"nodes differ in [{lo}, {hi})"
+        assert np.array_equal(w[lo:hi], wd[lo:hi].cpu().numpy()), f"weights differ in [{lo}, {hi})"
+    if n % 2:
+        assert x[n // 2] == 0.0 and not np.signbit(x[n // 2])

@@ -212,6 +212,34 @@ def test_config_c3_full_size(fgq):
     assert float(x[0]) > -1 and float(x[-1]) < 1
 
 
+def test_config_c3_every_node_against_the_oracle(fgq):
+    """BASELINE config C3 at FULL size: all 1e7 nodes and weights of gaussjacobi(1e7, 0.3, -0.7) against the oracle,
+    evaluated in node chunks (oracle.jacobi_oracle.jacobi_asy_chunked: the reference's interior solve with its two
+    global decisions — series truncation index, Newton stopping rule — reproduced exactly over the chunks;
+    bit-identical to the dense form, tests/test_oracle_jacobi.py).  Same bounds as the smaller cases: nodes within
+    4 ulp(1), weights within 2e-13 relative, same sweep counts and truncation indices."""
+    import torch
+    n, a, b = 10 ** 7, 0.3, -0.7
+    info = {}
+    xo, wo = jo.jacobi_asy_chunked(n, a, b, chunk=250_000, info=info)
+    x, w, ws = fgq.gaussjacobi_device(n, a, b)
+    torch.cuda.synchronize()
+    x = x.cpu().numpy()
+    w = w.cpu().numpy()
+    sw = (ctypes.c_int * 2)()
+    tm = (ctypes.c_int * 2)()
+    fgq._lib.check(fgq.lib().fgq_gaussjacobi_stats(ws.data_ptr(), sw, tm))
+    ex = np.abs(x - xo) / EPS
+    rw = np.abs(w - wo) / np.abs(wo)
+    print(f"C3 full size: node err max {ex.max():.2f} ulp(1), mean {ex.mean():.3f}; weight rel err max {rw.max():.2e}; "
+          f"sweeps gpu {tuple(sw)} oracle {info['sweeps']}; terms gpu {tuple(tm)} oracle {info['terms']}")
+    assert tuple(sw) == tuple(info["sweeps"])
+    assert tm[0] == info["terms"][info["sweeps"][0]] and tm[1] == info["terms"][-1]
+    assert ex.max() <= 4, f"nodes differ by {ex.max()} ulp(1)"
+    assert rw.max() <= 2e-13, f"weights differ by {rw.max()} relatively"
+    assert np.all(np.diff(x) > 0)
+
+
 @pytest.mark.parametrize("n,a,b", [(2, 6.0, 0.3), (6, 5.0, 5.0), (7, 6.5, 6.5), (20, 11.0, 0.0), (100, 19.0, 21.0), (257, 5.0, -0.5), (1000, 7.5, 12.0), (4000, 5.5, 0.0)])
 def test_golub_welsch_region(fgq, n, a, b):
     """max(a,b) >= 5 (gaussjacobi.jl:50-51, 570-599): the reference's dense eigen-solve against the

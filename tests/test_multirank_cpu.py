@@ -58,9 +58,10 @@ def _worker(rank, world, port, n, mode, out_dir):
 
 
 @pytest.mark.parametrize("mode", ["pair", "contiguous"])
-@pytest.mark.parametrize("n", [1000, 100001])
-def test_two_rank_sharding_and_collectives(tmp_path, n, mode):
-    world = 2
+@pytest.mark.parametrize("n,world", [(1000, 2), (100001, 2), (100003, 3)])
+def test_multi_rank_sharding_and_collectives(tmp_path, n, world, mode):
+    """world 2: regular partitions (one in-place all-gather per array); world 3 with an odd n: unequal shards
+    (padded all-gather); pair mode ships left segments only and mirrors locally."""
     mp.spawn(_worker, args=(world, _free_port(), n, mode, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / f"rank{r}.ok").read() == "1"

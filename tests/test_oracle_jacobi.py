@@ -69,3 +69,15 @@ def test_large_n_continues_past_the_reference_bounds_error():
     x, w = jo.gaussjacobi(6 * 10 ** 6, 0.3, -0.7)
     assert abs(w.sum() - 2 ** 0.6 * beta(1.3, 0.3)) < 1e-13
     assert np.all(np.diff(x) > 0)
+
+
+def test_chunked_interior_solve_equals_the_dense_one():
+    """jacobi_asy_chunked (used for the full-size C3 comparison on the GPU box) is the same function as
+    jacobi_asy: identical bits, sweep counts and truncation indices, whatever the chunk size."""
+    from oracle import jacobi_oracle as jo
+    for n, a, b, chunk in ((2000, 0.3, -0.7, 777), (10013, 0.9, -0.1, 1000), (10000, 0.1, 0.2, 4096), (60000, 0.3, -0.7, 25000)):
+        i1, i2 = {}, {}
+        x, w = jo.jacobi_asy(n, a, b, i1)
+        xc, wc = jo.jacobi_asy_chunked(n, a, b, chunk=chunk, info=i2)
+        assert np.array_equal(x, xc) and np.array_equal(w, wc), (n, a, b)
+        assert i1 == i2
