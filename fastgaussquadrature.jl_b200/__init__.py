@@ -32,6 +32,8 @@ from .api import (  # noqa: F401
     gausslegendre_device,
     gausslegendre_host_pair,
     gausslegendre_moments_fused,
+    gausslegendre_integrate,
+    rule_integrate,
     half_index_partition,
     index_partition,
     LegendreShard,

@@ -82,6 +82,8 @@ SIGNATURES = {
     "fgq_gausslaguerre_batch_host": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "fgq_rule_moments_device": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "fgq_gausslegendre_moments_fused_device": (ctypes.c_int, [_i64, _i64, _i64, ctypes.c_int, _vp, _vp]),
+    "fgq_gausslegendre_integrate_device": (ctypes.c_int, [_i64, _i64, _i64, ctypes.c_char_p, _vp, _vp]),
+    "fgq_rule_integrate_device": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_char_p, _vp, _vp]),
     "fgq_measure_dfma_peak": (ctypes.c_int, [_dp]),
     "fgq_measure_store_peak": (ctypes.c_int, [_i64, _dp]),
     "fgq_measure_host_store_peak": (ctypes.c_int, [_vp, _i64, ctypes.c_int, _dp]),

@@ -547,6 +547,51 @@ def gausslegendre_moments_fused(n, rank: int = 0, world: int = 1, with_exp: bool
     return sums
 
 
+def _check_integrand(f: str) -> bytes:
+    """Syntax screening of a user integrand by the library (no device work), then the no-CPU-fallback rule."""
+    if not isinstance(f, str):
+        raise TypeError("the integrand must be a string: an expression in x")
+    dummy = (ctypes.c_double * 2)()
+    check(lib().fgq_rule_integrate_device(None, None, 0, f.encode(), dummy, None))
+    if lib().fgq_device_count() == 0:
+        raise _lib.FGQError("user integrands need a CUDA device (no CPU fallback)")
+    return f.encode()
+
+
+def gausslegendre_integrate(n, f: str, rank: int = 0, world: int = 1, stream=None):
+    """``dot(w, f.(x))`` over ``gausslegendre(n)`` (n > 60) for a USER integrand, generated and reduced in one
+    kernel — x and w are never stored (README.md:27-30 is exactly this reduction).
+
+    ``f`` is an expression in ``x`` in CUDA C++ syntax, e.g. ``"exp(x) * cos(3 * x)"`` or ``"1 / (1 + 25 * x * x)"``;
+    it is compiled once per (expression, series branch) with NVRTC together with the library's own node-generation
+    source and cached.  Returns a 2-element CUDA tensor ``[sum w f(x), sum w]`` for this rank's half-index shard;
+    all-reduce it across ranks."""
+    import torch
+    n = _as_int(n)
+    fb = _check_integrand(f)
+    if n <= 60:
+        raise ValueError(f"fused integration needs the asymptotic path (n > 60), got n={n}; use rule_integrate on a stored rule")
+    sums = torch.zeros(2, dtype=torch.float64, device="cuda")
+    k_lo, k_hi = half_index_partition(n, world)[rank]
+    check(lib().fgq_gausslegendre_integrate_device(n, k_lo, k_hi, fb, sums.data_ptr(), _stream_ptr(stream)))
+    return sums
+
+
+def rule_integrate(x, w, f: str, stream=None):
+    """``dot(w, f.(x))`` over a STORED rule (torch CUDA tensors of any family: Jacobi, Hermite, Laguerre, ...) for a
+    user integrand ``f`` (expression in ``x``, as in :func:`gausslegendre_integrate`).  Returns
+    ``[sum w f(x), sum w]`` as a CUDA tensor."""
+    import torch
+    if x.numel() != w.numel() or x.dtype != torch.float64 or w.dtype != torch.float64 or not x.is_cuda or not w.is_cuda:
+        raise ValueError("x and w must be float64 CUDA tensors of equal length")
+    fb = _check_integrand(f)
+    x, w = x.contiguous(), w.contiguous()
+    sums = torch.zeros(2, dtype=torch.float64, device=x.device)
+    check(lib().fgq_rule_integrate_device(x.data_ptr(), w.data_ptr(), x.numel(), fb, sums.data_ptr(),
+                                          _stream_ptr(stream)))
+    return sums
+
+
 def measure_peaks(store_bytes: int = 4 << 30):
     """Roofline denominators on the current device: (FP64 TFLOP/s from the DFMA microbenchmark,
     store-only HBM GB/s)."""

@@ -577,7 +577,8 @@ static int laguerre_check(int64_t n, double alpha) {
     return FGQ_OK;
 }
 
-static LaguerreParams laguerre_params(int64_t n, double alpha) {
+// for_rule: the parameters of gausslaguerre_asy (false: of a plain approx_besselroots(nu, .) call)
+static LaguerreParams laguerre_params(int64_t n, double alpha, bool for_rule = true) {
     LaguerreParams p;
     p.n = n;
     p.alpha = alpha;
@@ -588,6 +589,12 @@ static LaguerreParams laguerre_params(int64_t n, double alpha) {
     // approx_besselroots(alpha, k_bessel): only the first 20 (alpha = 0) / 6 entries are not McMahon
     p.head_count = alpha == 0.0 ? 20 : ((-1 <= alpha && alpha <= 5) ? 6 : 0);
     if (p.head_count) approx_besselroots(alpha, p.head_count, p.jak_head);
+    if (for_rule) {
+        // gausslaguerre_asy takes jak_vector[k] only for k < k_bessel = max(ceil(sqrt(n)), 7) and McMahon(alpha, k)
+        // from k_bessel on (gausslaguerre.jl:131,144): for alpha = 0 and n < 441 that cuts into the 20 tabulated zeros
+        const int64_t k_bessel = std::max<int64_t>((int64_t)ceil(sqrt((double)n)), 7);
+        if (p.head_count > k_bessel - 1) p.head_count = (int)(k_bessel - 1);
+    }
     const double mu = 4 * alpha * alpha;
     p.mu_m1 = mu - 1;
     p.mc[0] = 1.0 / 8;
@@ -717,7 +724,10 @@ extern "C" int fgq_gausslaguerre_host(int64_t n, double alpha, int reduced, doub
     LaguerreState h;
     FGQ_CUDA_TRY(cudaMemcpyAsync(&h, ws, sizeof(h), cudaMemcpyDeviceToHost, st));
     FGQ_CUDA_TRY(cudaStreamSynchronize(st));
-    const int64_t cnt = reduced ? (int64_t)h.n_out : n;
+    // `reduced` exists only inside gausslaguerre_asy (gausslaguerre.jl:88-95, 163-169): the closed-form, Golub-Welsch
+    // and recurrence branches (n < 128 or alpha >= 5) always return all n entries, underflowed weights included
+    const bool asy_branch = n >= 128 && alpha < 5;
+    const int64_t cnt = (reduced && asy_branch) ? (int64_t)h.n_out : n;
     FGQ_TRY(drain_to_host(x, w, xd, wd, cnt, st));
     if (n_out) *n_out = cnt;
     add_warning(warn0 | (int)h.warn);
@@ -847,7 +857,7 @@ extern "C" int fgq_approx_besselroots_device(double nu, int64_t n, double* x_dev
     // laguerre_params plans exactly the nu-only data this needs: the table / Piessens head and McMahon's
     // coefficients (its n-dependent fields are not read by the kernel)
     const bool zero_all = !(nu >= -1.0);
-    const LaguerreParams p = laguerre_params(1, zero_all ? 0.0 : nu);
+    const LaguerreParams p = laguerre_params(1, zero_all ? 0.0 : nu, false);
     besselroots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(p, zero_all ? 1 : 0, n, x_dev);
     FGQ_LAUNCH_CHECK();
     return FGQ_OK;

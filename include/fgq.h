@@ -319,6 +319,20 @@ int fgq_rule_moments_device(const double* x_dev, const double* w_dev, int64_t co
 int fgq_gausslegendre_moments_fused_device(int64_t n, int64_t k_lo, int64_t k_hi, int with_exp,
                                            double* sums_dev, void* stream);
 
+/* The same reduction for a USER integrand: `expr` is f as an expression in x in CUDA C++ syntax ("exp(x) * cos(3 * x)",
+ * "1 / (1 + 25 * x * x)", "pow(fabs(x), 2.5)" ...).  It is compiled once per (expression, series branch) at run time
+ * (NVRTC, sm_100a, --fmad=false) together with the library's node-generation source, cached, and launched:
+ *   fgq_gausslegendre_integrate_device  generate-and-reduce over half-indices [k_lo, k_hi) of the n-point rule and
+ *                                       their mirror images (n > 60): nodes and weights are never stored;
+ *   fgq_rule_integrate_device           dot(w, f.(x)) over a stored rule of any family (count entries, device buffers).
+ * sums_dev[0] += sum w f(x), sums_dev[1] += sum w (2 doubles, zeroed by the caller; all-reduce across ranks).
+ * This is dot(w, f.(x)) of README.md:27-30.  A malformed expression -> FGQ_EINVAL with the compiler's diagnostic in
+ * fgq_last_error(); no NVRTC on the box -> FGQ_ENOTIMPL. */
+int fgq_gausslegendre_integrate_device(int64_t n, int64_t k_lo, int64_t k_hi, const char* expr, double* sums_dev,
+                                       void* stream);
+int fgq_rule_integrate_device(const double* x_dev, const double* w_dev, int64_t count, const char* expr,
+                              double* sums_dev, void* stream);
+
 /* ---- roofline denominators (measured on the current device) ------------------------------ */
 
 /* DFMA issue-rate microbenchmark: independent FMA chains on every SM.  *tflops = 2*FMA/s/1e12. */

@@ -171,6 +171,95 @@ function gausslaguerre(n::Integer, α::Real = 0.0; reduced = false)
     return x, w
 end
 
+# ---- type-first methods of the reference (Float64 only: there is no CPU fallback and no generic-T kernel) ----
+# gausshermite(::Type{T}, n; normalize) src/gausshermite.jl:28; gausslaguerre(::Type{T}, n) src/gausslaguerre.jl:1;
+# gaussradau(::Type{T}, n) src/gaussradau.jl:31; gausslobatto(::Type{T}, n) src/gausslobatto.jl:31;
+# gausschebyshev{t,u,v,w}(::Type{T}, n) src/gausschebyshev.jl:22,51,80,109
+_only_f64(::Type{Float64}) = nothing
+_only_f64(::Type{T}) where {T} = error("libfgq_cuda serves Float64 only (requested $T); use FastGaussQuadrature's generic method")
+gausshermite(::Type{T}, n::Integer; normalize = false) where {T<:AbstractFloat} = (_only_f64(T); gausshermite(n; normalize = normalize))
+gausslaguerre(::Type{T}, n::Integer) where {T<:AbstractFloat} = (_only_f64(T); gausslaguerre(n))
+gaussradau(::Type{T}, n::Integer) where {T<:AbstractFloat} = (_only_f64(T); gaussradau(n))
+gausslobatto(::Type{T}, n::Integer) where {T<:AbstractFloat} = (_only_f64(T); gausslobatto(n))
+gausschebyshevt(::Type{T}, n::Integer) where {T<:AbstractFloat} = (_only_f64(T); gausschebyshevt(n))
+gausschebyshevu(::Type{T}, n::Integer) where {T<:AbstractFloat} = (_only_f64(T); gausschebyshevu(n))
+gausschebyshevv(::Type{T}, n::Integer) where {T<:AbstractFloat} = (_only_f64(T); gausschebyshevv(n))
+gausschebyshevw(::Type{T}, n::Integer) where {T<:AbstractFloat} = (_only_f64(T); gausschebyshevw(n))
+
+# ---- multi-GPU from ONE Julia process (include/fgq.h "multi-GPU, one process") ---------------------------------
+# `fgq_shard` of include/fgq.h; x, w are device pointers on `device` (wrap them with CUDA.jl's unsafe_wrap to use them)
+struct FGQShard
+    device::Int32
+    owner::Int32
+    lo::Int64
+    hi::Int64
+    x::Ptr{Float64}
+    w::Ptr{Float64}
+end
+FGQShard() = FGQShard(0, 0, 0, 0, C_NULL, C_NULL)
+
+# fgq_init: devices = nothing -> all visible devices
+function init(devices::Union{Nothing,Vector{Int32}} = nothing)
+    rc = devices === nothing ?
+        ccall((:fgq_init, libfgq), Cint, (Ptr{Cint}, Cint), C_NULL, 0) :
+        ccall((:fgq_init, libfgq), Cint, (Ptr{Cint}, Cint), devices, length(devices))
+    check(rc, devices)
+    return Int(ccall((:fgq_num_devices, libfgq), Cint, ()))
+end
+finalize() = check(ccall((:fgq_finalize, libfgq), Cint, ()), nothing)
+synchronize() = check(ccall((:fgq_synchronize, libfgq), Cint, ()), nothing)
+
+# Device-resident gausslegendre(n) over every initialised GPU: returns (shards, (sum w, sum w x^2)).  Pass the
+# shards of a previous call to refill them without allocation; free them with free_shards!.
+function gausslegendre_sharded(n::Integer, shards::Vector{FGQShard} = FGQShard[]; sums::Bool = true)
+    n < 0 && throw(DomainError(n, "Input n must be a non-negative integer"))
+    cap = Int(ccall((:fgq_shard_count, libfgq), Cint, (Int64,), n))
+    isempty(shards) && (shards = [FGQShard() for _ in 1:max(cap, 1)])
+    cnt = Ref{Cint}(0); s = zeros(Float64, 2)
+    GC.@preserve shards s check(ccall((:fgq_gausslegendre_device_sharded, libfgq), Cint,
+        (Int64, Ptr{FGQShard}, Cint, Ref{Cint}, Ptr{Float64}), n, shards, length(shards), cnt, sums ? pointer(s) : C_NULL), n)
+    resize!(shards, cnt[])
+    return shards, (s[1], s[2])
+end
+free_shards!(shards::Vector{FGQShard}) =
+    (GC.@preserve shards check(ccall((:fgq_free_shards, libfgq), Cint, (Ptr{FGQShard}, Cint), shards, length(shards)), nothing); empty!(shards))
+
+# Optional replicated copy on every device: vectors of device pointers (one per device), n entries each
+function allgather(shards::Vector{FGQShard}, n::Integer)
+    nd = Int(ccall((:fgq_num_devices, libfgq), Cint, ()))
+    xr = fill(Ptr{Float64}(C_NULL), nd); wr = fill(Ptr{Float64}(C_NULL), nd)
+    GC.@preserve shards xr wr check(ccall((:fgq_allgather, libfgq), Cint,
+        (Ptr{FGQShard}, Cint, Int64, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}), shards, length(shards), n, xr, wr), n)
+    return xr, wr
+end
+function gausslegendre_replicated(n::Integer)
+    nd = Int(ccall((:fgq_num_devices, libfgq), Cint, ()))
+    xr = fill(Ptr{Float64}(C_NULL), nd); wr = fill(Ptr{Float64}(C_NULL), nd)
+    GC.@preserve xr wr check(ccall((:fgq_gausslegendre_device_replicated, libfgq), Cint,
+        (Int64, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}), n, xr, wr), n)
+    return xr, wr
+end
+free_replicas!(xr::Vector{Ptr{Float64}}, wr::Vector{Ptr{Float64}}) =
+    GC.@preserve xr wr check(ccall((:fgq_free_replicas, libfgq), Cint, (Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}), xr, wr), nothing)
+
+# Host-returning gausslegendre(n) drained through all GPUs at once (same result as gausslegendre(n), bit for bit)
+function gausslegendre_multi(n::Integer)
+    n < 0 && throw(DomainError(n, "Input n must be a non-negative integer"))
+    x = Vector{Float64}(undef, n); w = Vector{Float64}(undef, n)
+    n == 0 && return x, w
+    GC.@preserve x w check(ccall((:fgq_gausslegendre_host_multi, libfgq), Cint,
+        (Int64, Ptr{Float64}, Ptr{Float64}), n, x, w), n)
+    return x, w
+end
+
+# Device-side timing of what was enqueued between the two calls (slowest device, milliseconds)
+timer_start() = check(ccall((:fgq_timer_start, libfgq), Cint, ()), nothing)
+function timer_stop()
+    ms = Ref{Cfloat}(0)
+    check(ccall((:fgq_timer_stop, libfgq), Cint, (Ref{Cfloat}, Ptr{Cfloat}), ms, C_NULL), nothing)
+    return ms[]
+end
+
 # Device-resident shard (with CUDA.jl): x_dev, w_dev are CuVector{Float64} of length hi-lo;
 # asynchronous on `stream`; output indices are 0-based here, [lo, hi).
 function gausslegendre_device!(x_dev, w_dev, n::Integer, lo::Integer, hi::Integer, stream::Ptr{Cvoid} = C_NULL)

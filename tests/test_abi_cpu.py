@@ -1,6 +1,7 @@
 """CPU tests of the boundary: the C-ABI library loads, exports every symbol include/fgq.h
 declares, the Python mirror binds all of them, argument checks that need no GPU behave like the
 reference, and there is no silent CPU fallback."""
+import ctypes
 import os
 import re
 import subprocess
@@ -191,3 +192,17 @@ def test_out_buffers_and_offsets_are_validated(fgq_cpu):
         fgq_cpu.gaussjacobi_batch([5, 6], 0.1, 0.2, offsets=np.array([0, 9, 5], dtype=i64))  # decreasing
     with pytest.raises(ValueError):
         fgq_cpu.gausshermite_batch([5, 6], offsets=np.array([3, 4, 11], dtype=i64))       # overlap
+
+
+def test_user_integrand_expressions_are_checked_without_a_device(fgq_cpu):
+    """The integrand string is validated before any compilation or device work; without a device a well-formed
+    request fails loudly like every other compute entry point."""
+    for bad in ("", "exp(x", "x; x", "x }", "x # y", 'printf("x")'):
+        with pytest.raises(ValueError):
+            fgq_cpu.gausslegendre_integrate(1000, bad)
+    L = fgq_cpu.lib()
+    assert L.fgq_rule_integrate_device(None, None, -1, b"x", None, None) == 3
+    assert L.fgq_rule_integrate_device(None, None, 0, b"exp(x) * cos(3 * x)", (ctypes.c_double * 2)(), None) == 0
+    if L.fgq_device_count() == 0:
+        with pytest.raises(fgq_cpu.FGQError):
+            fgq_cpu.gausslegendre_integrate(1000, "exp(x)")

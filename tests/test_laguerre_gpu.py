@@ -47,7 +47,7 @@ def test_api_edges(fgq):
     assert len(xr) == len(xo)
 
 
-@pytest.mark.parametrize("n,alpha", [(128, 0.0), (251, 0.0), (251, 0.5), (1000, -0.7), (1000, 4.5), (5000, 1.0),
+@pytest.mark.parametrize("n,alpha", [(128, 0.0), (200, 0.0), (251, 0.0), (256, 0.0), (400, 0.0), (251, 0.5), (1000, -0.7), (1000, 4.5), (5000, 1.0),
                                      (350000, 0.0), (350000, 0.44), (1000000, 0.0), (1000001, 2.5)])
 def test_parity_with_oracle(fgq, n, alpha):
     import torch
@@ -86,6 +86,11 @@ def test_parity_with_oracle(fgq, n, alpha):
     assert np.all(np.diff(x) > 0)
     if alpha == 0.0:
         assert abs(w.sum() - 1) < 1e-13 and abs(np.dot(w, x) - 1) < 1e-13
+    # Bessel region (k < k_b): explicit series in the Bessel zero — the reference takes the tabulated / Piessens zero
+    # only for k < k_bessel = max(ceil(sqrt(n)), 7) and McMahon's expansion from k_bessel on (gausslaguerre.jl:131,144;
+    # for alpha = 0 and n < 441 that is inside the 20 tabulated zeros, which differ from McMahon by an ulp): bit for bit
+    nb = info["k_b"] - 1
+    assert np.array_equal(x[:nb], xo[:nb]), "Bessel-region nodes must equal the oracle's bit for bit"
 
 
 @pytest.mark.parametrize("alpha", [0.0, 0.5, -0.7, 2.5, 6.0])
@@ -111,6 +116,11 @@ def test_small_rules_parity(fgq, alpha):
         # extrapolated initial guesses make Newton find one root twice: sum w = 820 instead of 720, reproduced)
         if abs(wo.sum() - gamma(alpha + 1)) < 1e-12 * gamma(alpha + 1):
             assert abs(w.sum() - gamma(alpha + 1)) < 2e-12 * gamma(alpha + 1)
+    # `reduced` only exists inside gausslaguerre_asy (gausslaguerre.jl:88-95): the small-n / alpha >= 5 branches
+    # return all n entries whatever the flag says
     xr, wr = fgq.gausslaguerre(100, alpha, reduced=True)
     xo, wo = lo.gausslaguerre(100, alpha, reduced=True)
-    assert len(xr) == len(xo)
+    assert len(xr) == len(xo) == 100
+    if alpha >= 5:
+        xr, wr = fgq.gausslaguerre(2000, alpha, reduced=True)
+        assert len(xr) == 2000 and wr[-1] == 0.0

@@ -26,7 +26,9 @@ def test_sharded_rule_equals_the_single_call(fgq, multi, n):
     x, w = rule.to_host()
     assert np.array_equal(x, x1) and np.array_equal(w, w1)
     if n:
-        assert abs(rule.sums[0] - 2.0) < 1e-12 and abs(rule.sums[1] - 2.0 / 3.0) < 1e-12
+        assert abs(rule.sums[0] - 2.0) < 1e-12
+    if n >= 2:   # a one-point rule integrates x^2 to 0
+        assert abs(rule.sums[1] - 2.0 / 3.0) < 1e-12
     # shards tile [0, n) exactly once, two per device for the asymptotic path
     segs = rule.segments()
     assert len(segs) == (0 if n == 0 else 1 if n <= 60 else 2 * multi.num_devices())

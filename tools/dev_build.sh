@@ -7,6 +7,7 @@ make -C $R/fastgaussquadrature.jl_b200/csrc -j8 OUT=/tmp/fgqbuild/libfgq_cuda.so
 rc=$?
 grep -v "^/usr/local/cuda/bin/nvcc\|^make" /tmp/fgqbuild/make.log | tail -20
 if [ $rc -ne 0 ]; then echo "BUILD FAILED"; exit 1; fi
+if [ "$1" = "noswap" ]; then echo "built (not swapped in: /tmp/fgqbuild/libfgq_cuda.so)"; exit 0; fi
 cp /tmp/fgqbuild/libfgq_cuda.so $R/fastgaussquadrature.jl_b200/libfgq_cuda.so.new
 mv $R/fastgaussquadrature.jl_b200/libfgq_cuda.so.new $R/fastgaussquadrature.jl_b200/libfgq_cuda.so
 echo built
