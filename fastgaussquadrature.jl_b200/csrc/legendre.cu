@@ -31,6 +31,13 @@ struct LegLaunch {
     int64_t kcentre;   // (n+1)/2 when n is odd (node forced to 0.0, gausslegendre.jl:91), else 0
     double *xl, *wl, *xr, *wr;
     int vecL, vecR;    // 16-byte stores legal on that side
+    // Block-uniform bulk ranges of an NT = 0 tail launch with both sides 16-byte aligned (host-planned): every
+    // half-index of blocks [bq0_lo, bq0_hi) has theta < pi/4, of blocks [bq1_lo, bq1_hi) pi/4 < theta below the
+    // band next to pi/2; all of them are interior (stored on both sides, no centre) and have k >= K_JK_EXACT.
+    // Pair t = blockIdx.x * LEG_THREADS + threadIdx.x of the launch lives at xl2[t], wl2[t], xr2[-t], wr2[-t].
+    unsigned bq0_lo, bq0_hi, bq1_lo, bq1_hi;
+    double2 *xl2, *wl2, *xr2, *wr2;
+    int64_t v_base;    // 4 kbase - 1: pair t holds half-indices with 4k - 1 = v_base + 8t and v_base + 8t + 4
     LegConsts c;
 };
 
@@ -40,9 +47,34 @@ constexpr int LEG_THREADS = 256;
 #endif
 
 
+// One block of a bulk range: no index clamping, no per-element predicates, 32-bit pair index, four address
+// computations (one multiply-add each) and four 16-byte streaming stores per thread.
+template <int QUAD>
+__device__ __forceinline__ void leg_bulk_block(const LegLaunch& p) {
+    const unsigned t = blockIdx.x * LEG_THREADS + threadIdx.x;
+    const int64_t v0 = p.v_base + 8 * (int64_t)t;
+    double cx0, w0, cx1, w1;
+    leg_bulk_v<QUAD>(__ll2double_rn(v0), p.c, cx0, w0);
+    leg_bulk_v<QUAD>(__ll2double_rn(v0 + 4), p.c, cx1, w1);
+    __stcs(p.xl2 + t, make_double2(neg_bits(cx0), neg_bits(cx1)));
+    __stcs(p.wl2 + t, make_double2(w0, w1));
+    __stcs(p.xr2 - t, make_double2(cx1, cx0));
+    __stcs(p.wr2 - t, make_double2(w1, w0));
+}
+
 template <int NT, int WT, bool HEAD>
 __global__ void __launch_bounds__(LEG_THREADS, FGQ_LEG_MIN_BLOCKS)
 legendre_asy_kernel(const LegLaunch p) {
+    if (NT == 0 && WT == 0 && !HEAD) {
+        if (blockIdx.x - p.bq0_lo < p.bq0_hi - p.bq0_lo) {
+            leg_bulk_block<0>(p);
+            return;
+        }
+        if (blockIdx.x - p.bq1_lo < p.bq1_hi - p.bq1_lo) {
+            leg_bulk_block<1>(p);
+            return;
+        }
+    }
     const int64_t t = (int64_t)blockIdx.x * LEG_THREADS + threadIdx.x;
     const int64_t k0 = p.kbase + 2 * t;
     const int64_t k1 = k0 + 1;
@@ -53,10 +85,11 @@ legendre_asy_kernel(const LegLaunch p) {
     const int64_t kb1 = kb0 + 2 * LEG_THREADS - 1;
     if (kb0 >= p.kin0 && kb1 <= p.kin1) {
         double cx0, w0, cx1, w1;
-        if (NT == 0 && WT == 0 && !HEAD && kb0 >= K_JK_EXACT && kb1 <= p.kq0_last) {
+        if (NT == 0 && WT == 0 && !HEAD && !p.vecR && kb0 >= K_JK_EXACT && kb1 <= p.kq0_last) {
+            // (odd n: the right pair is shifted by one element, so these blocks cannot take leg_bulk_block)
             leg_bulk<0>(k0, p.c, cx0, w0);
             leg_bulk<0>(k1, p.c, cx1, w1);
-        } else if (NT == 0 && WT == 0 && !HEAD && kb0 >= K_JK_EXACT && kb0 > p.kq0_last + 1 &&
+        } else if (NT == 0 && WT == 0 && !HEAD && !p.vecR && kb0 >= K_JK_EXACT && kb0 > p.kq0_last + 1 &&
                    kb1 < p.kext_first) {
             leg_bulk<1>(k0, p.c, cx0, w0);
             leg_bulk<1>(k1, p.c, cx1, w1);
@@ -372,6 +405,28 @@ static int launch_one(int64_t n, bool head, int64_t kmin, int64_t kmax, int64_t 
     p.kext_first = (node_terms(n) == 0 && !head) ? near_pio2_first(n, p.c.vn) : 0;
     const int64_t npairs = (kmax - p.kbase) / 2 + 1;
     const int64_t blocks = (npairs + LEG_THREADS - 1) / LEG_THREADS;
+    // bulk block ranges (see LegLaunch): block b covers half-indices kbase + 512 b .. kbase + 512 b + 511
+    p.bq0_lo = p.bq0_hi = p.bq1_lo = p.bq1_hi = 0;
+    p.xl2 = p.wl2 = p.xr2 = p.wr2 = nullptr;
+    p.v_base = 4 * p.kbase - 1;
+    if (node_terms(n) == 0 && weight_terms(n) == 0 && !head && p.vecL && p.vecR && blocks * LEG_THREADS < (1LL << 32)) {
+        const int64_t B = 2 * LEG_THREADS;
+        auto ceil_div = [](int64_t a, int64_t b) { return a <= 0 ? 0 : (a + b - 1) / b; };
+        auto floor_div = [](int64_t a, int64_t b) { return a < 0 ? 0 : a / b; };
+        const int64_t first = ceil_div(imax(p.kin0, K_JK_EXACT) - p.kbase, B);   // kb0 >= max(kin0, K_JK_EXACT)
+        const int64_t last = floor_div(p.kin1 + 1 - p.kbase, B);                  // kb1 <= kin1 (exclusive bound)
+        const int64_t q0_hi = imin(last, floor_div(p.kq0_last + 1 - p.kbase, B));               // kb1 <= kq0_last
+        const int64_t q1_lo = imax(first, ceil_div(p.kq0_last + 2 - p.kbase, B));               // kb0 > kq0_last + 1
+        const int64_t q1_hi = imin(last, floor_div(p.kext_first - p.kbase, B));                 // kb1 < kext_first
+        if (q0_hi > first) { p.bq0_lo = (unsigned)first; p.bq0_hi = (unsigned)q0_hi; }
+        if (q1_hi > q1_lo) { p.bq1_lo = (unsigned)q1_lo; p.bq1_hi = (unsigned)q1_hi; }
+        // element k of the left side lives at xl + (k - kL0); pair t starts at k = kbase + 2t
+        p.xl2 = reinterpret_cast<double2*>(xl + (p.kbase - kL0));
+        p.wl2 = reinterpret_cast<double2*>(wl + (p.kbase - kL0));
+        // right side: elements k1 = kbase + 2t + 1, k0 at xr + (kR1 - k1), + 1
+        p.xr2 = reinterpret_cast<double2*>(xr + (kR1 - p.kbase - 1));
+        p.wr2 = reinterpret_cast<double2*>(wr + (kR1 - p.kbase - 1));
+    }
     if (blocks > 0x7fffffffLL) {
         set_error("legendre launch too large (%lld blocks)", (long long)blocks);
         return FGQ_EINVAL;

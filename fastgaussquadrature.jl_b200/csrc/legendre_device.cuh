@@ -25,6 +25,7 @@ static __constant__ double c_j1sq[10] = {
 
 struct LegConsts {
     double vn, vn2, vn4, vn6, inv_vn2;
+    double vn_q, inv_vn2_x4;  // vn / 4, 4 / vn^2 (exact scalings, see leg_bulk)
 };
 
 #if !defined(__CUDACC_RTC__)   // host side of the launches
@@ -35,6 +36,8 @@ static LegConsts make_consts(int64_t n) {
     c.vn4 = c.vn2 * c.vn2;
     c.vn6 = c.vn4 * c.vn2;
     c.inv_vn2 = 1.0 / c.vn2;
+    c.vn_q = 0.25 * c.vn;
+    c.inv_vn2_x4 = 4.0 * c.inv_vn2;
     return c;
 }
 #endif
@@ -211,11 +214,17 @@ __device__ __forceinline__ double scale2(double x, int e) {
 // Same bits as leg_half_index<0,0,false>, ~20% fewer FP64 instructions.
 constexpr int64_t K_JK_EXACT = 10680708;  // pi*(k - 1/4) >= 2^25
 
+// All power-of-two factors of the formulas are folded into constants: scaling by 2^e commutes with rounding (no
+// intermediate leaves the normal range), so with v = 4k - 1 (an exact double)
+//   4 ak   = RN(pi v)                       a = RN(ak vn)          = RN(RN(pi v) (vn/4))
+//   4 X    = RN(pi RN(pi v))                J1^2 = 2 RN(1/X)       = 8 RN(1/(4X))
+//   w = RN(2 / RN(RN(J1^2 q) V)),  q = RN(a/s), V = 1/vn^2        = RN(1 / RN(RN(RN(1/(4X)) q) (4V)))
+// bit for bit, without any exponent adjustments.
 template <int QUAD>
-__device__ __forceinline__ void leg_bulk(int64_t k, const LegConsts& c, double& cx, double& w) {
-    const double ak = FGQ_PI_K * fgq_k_minus_quarter(k);
-    const double j1sq = scale2(fgq_rcp_fast(FGQ_PI_K * ak), 1);
-    const double a = ak * c.vn;
+__device__ __forceinline__ void leg_bulk_v(double v, const LegConsts& c, double& cx, double& w) {
+    const double pv = FGQ_PI_K * v;
+    const double t4 = fgq_rcp_fast(FGQ_PI_K * pv);
+    const double a = pv * c.vn_q;
     double s;
     if (QUAD == 0) {
         s = fgq_jsin(a);
@@ -226,7 +235,12 @@ __device__ __forceinline__ void leg_bulk(int64_t k, const LegConsts& c, double& 
         s = fgq_jcos_dd(r, rt);
         cx = neg_bits(fgq_jsin_dd(r, rt));
     }
-    w = scale2(fgq_rcp_fast(j1sq * fgq_div_fast(a, s) * c.inv_vn2), 1);
+    w = fgq_rcp_fast(t4 * fgq_div_fast(a, s) * c.inv_vn2_x4);
+}
+
+template <int QUAD>
+__device__ __forceinline__ void leg_bulk(int64_t k, const LegConsts& c, double& cx, double& w) {
+    leg_bulk_v<QUAD>(__ll2double_rn(4 * k - 1), c, cx, w);
 }
 
 }  // namespace fgq

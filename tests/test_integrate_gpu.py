@@ -27,12 +27,13 @@ def test_fused_user_integrand_against_oracle_dot(fgq, oracle_mod, n, expr, f, ex
     ref = _oracle_dot(xo, wo, f)
     scale = _oracle_dot(xo, wo, lambda x: np.abs(f(x)))
     assert abs(s[0] - ref) <= 4e-15 * scale + 1e-300, (s[0], ref)
-    assert abs(s[1] - 2.0) < 1e-13
+    # sum w of the rule itself (the reference's n > 850000 branch drops the W1 term: sum w = 2 + O(1e-13) there)
+    assert abs(s[1] - float(np.sum(wo.astype(np.longdouble)))) < 1e-13
     if exact is not None and n >= 251:
         assert abs(s[0] - exact) < 1e-12 * max(1.0, abs(exact)) or "fabs" in expr  # |x|^2.5 converges algebraically
     # any rank split gives the same sum
     parts = sum(fgq.gausslegendre_integrate(n, expr, rank=r, world=3) for r in range(3)).cpu().numpy()
-    assert abs(parts[0] - s[0]) <= 4e-15 * scale and abs(parts[1] - 2.0) < 1e-13
+    assert abs(parts[0] - s[0]) <= 4e-15 * scale and abs(parts[1] - s[1]) < 1e-13
 
 
 @pytest.mark.parametrize("n", [1 << 25, 10 ** 9, 10 ** 9 + 1])
