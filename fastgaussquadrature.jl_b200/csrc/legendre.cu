@@ -35,7 +35,11 @@ struct LegLaunch {
     // half-index of blocks [bq0_lo, bq0_hi) has theta < pi/4, of blocks [bq1_lo, bq1_hi) pi/4 < theta below the
     // band next to pi/2; all of them are interior (stored on both sides, no centre) and have k >= K_JK_EXACT.
     // Pair t = blockIdx.x * LEG_THREADS + threadIdx.x of the launch lives at xl2[t], wl2[t], xr2[-t], wr2[-t].
+    // Odd n: the mirrored pair of a thread straddles a 16-byte boundary; shiftR = 1 selects the variant that stores the
+    // aligned pair (k0, k0 - 1) instead, the second element coming from the previous lane (one shuffle), with 8-byte
+    // stores at the two ends of each warp; xr2 / wr2 then address the pair (k0, k0 - 1) of pair t at [-t].
     unsigned bq0_lo, bq0_hi, bq1_lo, bq1_hi;
+    int shiftR;
     double2 *xl2, *wl2, *xr2, *wr2;
     int64_t v_base;    // 4 kbase - 1: pair t holds half-indices with 4k - 1 = v_base + 8t and v_base + 8t + 4
     LegConsts c;
@@ -58,8 +62,27 @@ __device__ __forceinline__ void leg_bulk_block(const LegLaunch& p) {
     leg_bulk_v<QUAD>(__ll2double_rn(v0 + 4), p.c, cx1, w1);
     __stcs(p.xl2 + t, make_double2(neg_bits(cx0), neg_bits(cx1)));
     __stcs(p.wl2 + t, make_double2(w0, w1));
-    __stcs(p.xr2 - t, make_double2(cx1, cx0));
-    __stcs(p.wr2 - t, make_double2(w1, w0));
+    if (!p.shiftR) {
+        __stcs(p.xr2 - t, make_double2(cx1, cx0));
+        __stcs(p.wr2 - t, make_double2(w1, w0));
+    } else {
+        const double pc1 = __shfl_up_sync(0xffffffffu, cx1, 1);
+        const double pw1 = __shfl_up_sync(0xffffffffu, w1, 1);
+        const int lane = threadIdx.x & 31;
+        double* xr = reinterpret_cast<double*>(p.xr2 - t);   // element k0; k0 - 1 follows, k1 precedes
+        double* wr = reinterpret_cast<double*>(p.wr2 - t);
+        if (lane > 0) {
+            __stcs(p.xr2 - t, make_double2(cx0, pc1));
+            __stcs(p.wr2 - t, make_double2(w0, pw1));
+        } else {
+            st_stream(xr, cx0);
+            st_stream(wr, w0);
+        }
+        if (lane == 31) {
+            st_stream(xr - 1, cx1);
+            st_stream(wr - 1, w1);
+        }
+    }
 }
 
 template <int NT, int WT, bool HEAD>
@@ -85,18 +108,8 @@ legendre_asy_kernel(const LegLaunch p) {
     const int64_t kb1 = kb0 + 2 * LEG_THREADS - 1;
     if (kb0 >= p.kin0 && kb1 <= p.kin1) {
         double cx0, w0, cx1, w1;
-        if (NT == 0 && WT == 0 && !HEAD && !p.vecR && kb0 >= K_JK_EXACT && kb1 <= p.kq0_last) {
-            // (odd n: the right pair is shifted by one element, so these blocks cannot take leg_bulk_block)
-            leg_bulk<0>(k0, p.c, cx0, w0);
-            leg_bulk<0>(k1, p.c, cx1, w1);
-        } else if (NT == 0 && WT == 0 && !HEAD && !p.vecR && kb0 >= K_JK_EXACT && kb0 > p.kq0_last + 1 &&
-                   kb1 < p.kext_first) {
-            leg_bulk<1>(k0, p.c, cx0, w0);
-            leg_bulk<1>(k1, p.c, cx1, w1);
-        } else {
-            leg_half_index<NT, WT, HEAD>(k0, p.c, cx0, w0);
-            leg_half_index<NT, WT, HEAD>(k1, p.c, cx1, w1);
-        }
+        leg_half_index<NT, WT, HEAD>(k0, p.c, cx0, w0);
+        leg_half_index<NT, WT, HEAD>(k1, p.c, cx1, w1);
         st_stream2(p.xl + (k0 - p.kL0), neg_bits(cx0), neg_bits(cx1));
         st_stream2(p.wl + (k0 - p.kL0), w0, w1);
         if (p.vecR) {
@@ -409,7 +422,9 @@ static int launch_one(int64_t n, bool head, int64_t kmin, int64_t kmax, int64_t 
     p.bq0_lo = p.bq0_hi = p.bq1_lo = p.bq1_hi = 0;
     p.xl2 = p.wl2 = p.xr2 = p.wr2 = nullptr;
     p.v_base = 4 * p.kbase - 1;
-    if (node_terms(n) == 0 && weight_terms(n) == 0 && !head && p.vecL && p.vecR && blocks * LEG_THREADS < (1LL << 32)) {
+    p.shiftR = 0;
+    if (node_terms(n) == 0 && weight_terms(n) == 0 && !head && p.vecL && (p.vecR || vecR_shifted) &&
+        blocks * LEG_THREADS < (1LL << 32)) {
         const int64_t B = 2 * LEG_THREADS;
         auto ceil_div = [](int64_t a, int64_t b) { return a <= 0 ? 0 : (a + b - 1) / b; };
         auto floor_div = [](int64_t a, int64_t b) { return a < 0 ? 0 : a / b; };
@@ -423,9 +438,10 @@ static int launch_one(int64_t n, bool head, int64_t kmin, int64_t kmax, int64_t 
         // element k of the left side lives at xl + (k - kL0); pair t starts at k = kbase + 2t
         p.xl2 = reinterpret_cast<double2*>(xl + (p.kbase - kL0));
         p.wl2 = reinterpret_cast<double2*>(wl + (p.kbase - kL0));
-        // right side: elements k1 = kbase + 2t + 1, k0 at xr + (kR1 - k1), + 1
-        p.xr2 = reinterpret_cast<double2*>(xr + (kR1 - p.kbase - 1));
-        p.wr2 = reinterpret_cast<double2*>(wr + (kR1 - p.kbase - 1));
+        // right side: elements k1 = kbase + 2t + 1, k0 at xr + (kR1 - k1), + 1; shifted: k0, k0 - 1 at xr + (kR1 - k0), + 1
+        p.shiftR = p.vecR ? 0 : 1;
+        p.xr2 = reinterpret_cast<double2*>(xr + (kR1 - p.kbase - 1 + p.shiftR));
+        p.wr2 = reinterpret_cast<double2*>(wr + (kR1 - p.kbase - 1 + p.shiftR));
     }
     if (blocks > 0x7fffffffLL) {
         set_error("legendre launch too large (%lld blocks)", (long long)blocks);
