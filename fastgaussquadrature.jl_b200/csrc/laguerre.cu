@@ -528,6 +528,161 @@ laguerre_small_batch_kernel(int64_t nrules, const LaguerreBatchRule* __restrict_
     laguerre_small_rule(r, r.q, warn_word, x + r.off, w + r.off);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The batched recurrence rule, table-driven (replaces one-thread-per-rule calls of laguerre_small_rule for n >= 15).
+//
+// gausslaguerre_rec is a strictly sequential chain per rule (each Newton start is extrapolated from the seven
+// previous nodes; each Newton step is an n-step recurrence), ~5.5 n^2 recurrence steps, so the parallelism is across
+// rules: one lane per rule.  What made the first version slow (25 ms per 1e5 rules, FP64 pipe 32 %) is that every
+// recurrence step recomputed its abscissa-independent coefficients — two square roots and three of its five divisions.
+// Here a lane tabulates c1_k = sqrt(k (alpha + k)), c2_k = sqrt((k-1+alpha)(k-1)/k/(k+alpha)) and the correctly
+// rounded 1/c1_k of ITS rule once (same IEEE expressions as evalLaguerreRec, gausslaguerre.jl:631-637) in shared
+// memory, laid out [k][lane] (conflict-free), and a step becomes 16 FP64 operations: the two remaining quotients
+// are the last three operations of the IEEE division's fast path against the tabulated reciprocal (same bits; an
+// operand outside the safe range takes the IEEE operator).  Lanes run a small state machine so that every trip of
+// the warp-wide loop is one polynomial evaluation for every lane (no lane waits for another lane's Newton loop).
+// The batch is cut into buckets of similar n (rules arrive sorted by n): shared memory per warp is 768 B x n_max of
+// the bucket, so short rules get many resident warps and long ones as many as fit.
+// ---------------------------------------------------------------------------------------------
+struct LagTab {
+    double* c1;   // [k][lane], k = 1..nmax
+    double* c2;
+    double* r1;
+};
+
+// (pn, pnd) of evalLaguerreRec(deg, alpha, x) for this lane from its tables; lanes with act == false idle.
+__device__ __forceinline__ void lag_eval_tab(const LagTab& t, int lane, int deg, double alpha, double pn0, double x, bool act,
+                                             int deg_warp, double& pn_out, double& pnd_out) {
+    double pnprev = 0.0, pn = pn0, pndprev = 0.0, pnd = 0.0;
+    for (int k = 1; k <= deg_warp; ++k) {
+        if (act && k <= deg) {
+            const double dk = (double)k;
+            const double c1 = t.c1[k * 32 + lane], c2 = t.c2[k * 32 + lane], r1 = t.r1[k * 32 + lane];
+            const double u = x - 2 * dk - alpha + 1;
+            // u / c1: |u| <= ~4n + alpha, c1 in [~0.3, ~200]: always inside the safe range of the fast path
+            double q = u * r1;
+            q = fma(r1, fma(-c1, q, u), q);
+            const double pnold = pn;
+            pn = q * pnold - c2 * pnprev;
+            pnprev = pnold;
+            const double pndold = pnd;
+            const double v = pnold + u * pndold;
+            double qv;
+            const unsigned ev = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;   // biased exponent of v
+            if (ev > 0x0a0u && ev < 0x750u) {       // ~1e-260 < |v| < ~1e255: fast path == IEEE quotient
+                qv = v * r1;
+                qv = fma(r1, fma(-c1, qv, v), qv);
+            } else {
+                qv = v / c1;
+            }
+            pnd = qv - c2 * pndprev;
+            pndprev = pndold;
+        }
+    }
+    pn_out = pn;
+    pnd_out = pnd;
+}
+
+__global__ void __launch_bounds__(32)
+laguerre_rec_batch_kernel(int64_t first, int64_t count, int nmax, const LaguerreBatchRule* __restrict__ rules,
+                          unsigned int* warn_word, double* __restrict__ x, double* __restrict__ w) {
+    extern __shared__ double s_tab[];
+    const int lane = threadIdx.x;
+    const int64_t i = first + (int64_t)blockIdx.x * 32 + lane;
+    const bool have = i < first + count;
+    LaguerreBatchRule r;
+    if (have) r = rules[i];
+    const int n = have ? (int)r.n : 0;
+    double* xr = x + (have ? r.off : 0);
+    double* wr = w + (have ? r.off : 0);
+    if (have && n > 0 && n < 15) {   // closed forms / Golub-Welsch: no recurrence rule, no tables
+        laguerre_small_rule(r, r.q, warn_word, xr, wr);
+    }
+    const bool rec = have && n >= 15;
+    LagTab t{s_tab, s_tab + (size_t)(nmax + 1) * 32, s_tab + 2 * (size_t)(nmax + 1) * 32};
+    const double al = r.alpha;
+    if (rec) {
+        for (int k = 1; k <= n; ++k) {
+            const double dk = (double)k;
+            const double c1 = sqrt(dk * (al + dk));
+            t.c1[k * 32 + lane] = c1;
+            t.c2[k * 32 + lane] = sqrt((dk - 1 + al) * (dk - 1) / dk / (dk + al));
+            t.r1[k * 32 + lane] = 1.0 / c1;
+        }
+    }
+    __syncwarp();
+    const int n_warp = __reduce_max_sync(0xffffffffu, rec ? n : 0);
+    if (n_warp == 0) return;
+    // gausslaguerre_rec (:582-618) + gl_rec_newton (:547-579) as a per-lane state machine
+    const double eps = 2.220446049250313e-16;
+    const double nu = 4 * (double)n + 2 * al + 2;
+    int k = 1;                       // node being solved (1-based)
+    int phase = rec ? 0 : 3;         // 0 = Newton evaluation pending, 1 = weight evaluation pending, 3 = finished
+    bool no_underflow = true;
+    unsigned int warn = 0;
+    double step = 0, xk = 0, xk_prev = 0, pn_prev = 0, pn_deriv = 0;
+    int iter = 0;
+    double h1 = 0, h2 = 0, h3 = 0, h4 = 0, h5 = 0, h6 = 0, h7 = 0;   // the seven previous nodes, h1 = x[k-1]
+    auto start_node = [&]() {        // initial guess and the entry test of the Newton loop
+        double x0;
+        if (k <= 7) {
+            x0 = r.q.jak_pre[k - 1] * r.q.jak_pre[k - 1] / nu;
+        } else {
+            x0 = 7 * h1 - 21 * h2 + 35 * h3 - 35 * h4 + 21 * h5 - 7 * h6 + h7;
+        }
+        step = x0; xk = x0; xk_prev = x0; pn_prev = 1.7976931348623157e308; pn_deriv = 0.0; iter = 0;
+    };
+    // after the Newton loop: the warning test, then either a weight evaluation or the end of the node
+    auto finish_node = [&](double wk) {
+        if (no_underflow && fabs(wk) < 10 * 2.2250738585072014e-308) no_underflow = false;
+        xr[k - 1] = xk;
+        wr[k - 1] = wk;
+        h7 = h6; h6 = h5; h5 = h4; h4 = h3; h3 = h2; h2 = h1; h1 = xk;
+        k += 1;
+        if (k > n) { phase = 3; return; }
+        start_node();
+        phase = 0;
+    };
+    auto after_newton = [&]() {
+        if (xk < 0 || xk > r.xmax || iter == 20) warn |= (unsigned int)FGQ_WARN_NEWTON_MAXITER;
+        if (no_underflow) phase = 1; else finish_node(0.0);
+    };
+    // phase 0 requires the loop test to hold; settle states that need no evaluation
+    auto settle = [&]() {
+        while (phase == 0 && !(fabs(step) > 40 * eps * xk && iter < 20)) after_newton();
+    };
+    if (rec) {
+        start_node();
+        settle();
+    }
+    while (__any_sync(0xffffffffu, phase != 3)) {
+        const bool act = phase != 3;
+        const int deg = phase == 1 ? n - 1 : n;
+        double pn, pnd;
+        lag_eval_tab(t, lane, deg, al, r.pn0, xk, act, n_warp, pn, pnd);
+        if (act) {
+            if (phase == 0) {
+                iter += 1;
+                pn_deriv = pnd;
+                if (fabs(pn) >= fabs(pn_prev) * (1 - 50 * eps)) {
+                    xk = xk_prev;
+                    after_newton();
+                } else {
+                    step = pn / pn_deriv;
+                    xk_prev = xk;
+                    xk -= step;
+                    pn_prev = pn;
+                }
+                settle();
+            } else {
+                finish_node(r.wnorm / pn / pn_deriv);
+                settle();
+            }
+        }
+    }
+    if (warn) atomicOr(warn_word, warn);
+}
+
 // reduced rule (:163-169 ...): the rule ends before the first weight below 10 floatmin
 __global__ void laguerre_reduced_kernel(int64_t n, const double* w, LaguerreState* st) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -736,6 +891,7 @@ extern "C" int fgq_gausslaguerre_host(int64_t n, double alpha, int reduced, doub
 
 // ---- batched small rules: n < 128 ----
 constexpr int LAGUERRE_BATCH_MAX_N = 127;
+constexpr int MAX_ATTR_DEV = 16;
 
 extern "C" int64_t fgq_gausslaguerre_batch_workspace_bytes(int64_t nrules) {
     if (nrules < 0) return 0;
@@ -807,10 +963,42 @@ extern "C" int fgq_gausslaguerre_batch_device(int64_t nrules, const int32_t* n_i
     FGQ_LAUNCH_CHECK();
     FGQ_CUDA_TRY(cudaMemcpyAsync(ws + 256, rules.data(), rules.size() * sizeof(LaguerreBatchRule),
                                  cudaMemcpyHostToDevice, st));
-    const int64_t blocks = (nrules + LAG_BATCH_THREADS - 1) / LAG_BATCH_THREADS;
-    laguerre_small_batch_kernel<<<(unsigned)blocks, LAG_BATCH_THREADS, 0, st>>>(
-        nrules, (const LaguerreBatchRule*)(ws + 256), &((LaguerreState*)ws)->warn, x_dev, w_dev);
-    FGQ_LAUNCH_CHECK();
+    // Buckets of similar n over the sorted rules (longest first): shared memory per warp follows the bucket's n_max.
+    // FGQ_LAGUERRE_BATCH=thread selects the first version (one thread per rule, coefficients recomputed per step).
+    static const bool per_thread = []() {
+        const char* e = getenv("FGQ_LAGUERRE_BATCH");
+        return e && strcmp(e, "thread") == 0;
+    }();
+    const LaguerreBatchRule* drules = (const LaguerreBatchRule*)(ws + 256);
+    unsigned int* warn_word = &((LaguerreState*)ws)->warn;
+    if (per_thread) {
+        const int64_t blocks = (nrules + LAG_BATCH_THREADS - 1) / LAG_BATCH_THREADS;
+        laguerre_small_batch_kernel<<<(unsigned)blocks, LAG_BATCH_THREADS, 0, st>>>(nrules, drules, warn_word, x_dev, w_dev);
+        FGQ_LAUNCH_CHECK();
+        return FGQ_OK;
+    }
+    static bool attr_set[MAX_ATTR_DEV] = {};
+    int dev = 0;
+    FGQ_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < MAX_ATTR_DEV && !attr_set[dev]) {
+        FGQ_CUDA_TRY(cudaFuncSetAttribute(laguerre_rec_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          768 * (LAGUERRE_BATCH_MAX_N + 1)));
+        attr_set[dev] = true;
+    }
+    int64_t j = 0;
+    while (j < nrules) {
+        const int n_top = (int)rules[(size_t)j].n;                 // largest n of this bucket
+        const int n_floor = n_top <= 16 ? 0 : ((n_top - 1) / 16) * 16;  // the bucket takes n in (n_floor, n_top]
+        int64_t e = j;
+        while (e < nrules && rules[(size_t)e].n > n_floor) ++e;
+        if (n_top > 0) {
+            const int64_t cnt = e - j;
+            const size_t smem = n_top >= 15 ? (size_t)768 * (size_t)(n_top + 1) : 0;
+            laguerre_rec_batch_kernel<<<(unsigned)((cnt + 31) / 32), 32, smem, st>>>(j, cnt, n_top, drules, warn_word, x_dev, w_dev);
+            FGQ_LAUNCH_CHECK();
+        }
+        j = e;
+    }
     return FGQ_OK;
 }
 
