@@ -139,6 +139,46 @@ int scratch_event(int which, cudaEvent_t* out) {
     return FGQ_OK;
 }
 
+static std::vector<cudaEvent_t> g_event_pool[MAX_DEV];
+static std::vector<cudaStream_t> g_stream_pool[MAX_DEV];
+
+int ScopedEvents::acquire(int count) {
+    if (count < 0 || count > 64) return FGQ_EINVAL;
+    FGQ_TRY(cur_dev(&dev));
+    std::lock_guard<std::mutex> guard(g_res_mutex);
+    while (n < count) {
+        if (!g_event_pool[dev].empty()) {
+            ev[n] = g_event_pool[dev].back();
+            g_event_pool[dev].pop_back();
+        } else {
+            FGQ_CUDA_TRY(cudaEventCreateWithFlags(&ev[n], cudaEventDisableTiming));
+        }
+        ++n;
+    }
+    return FGQ_OK;
+}
+ScopedEvents::~ScopedEvents() {
+    if (n == 0 || dev < 0) return;
+    std::lock_guard<std::mutex> guard(g_res_mutex);
+    for (int i = 0; i < n; ++i) g_event_pool[dev].push_back(ev[i]);
+}
+int ScopedStream::acquire() {
+    FGQ_TRY(cur_dev(&dev));
+    std::lock_guard<std::mutex> guard(g_res_mutex);
+    if (!g_stream_pool[dev].empty()) {
+        st = g_stream_pool[dev].back();
+        g_stream_pool[dev].pop_back();
+        return FGQ_OK;
+    }
+    FGQ_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    return FGQ_OK;
+}
+ScopedStream::~ScopedStream() {
+    if (!st || dev < 0) return;
+    std::lock_guard<std::mutex> guard(g_res_mutex);
+    g_stream_pool[dev].push_back(st);
+}
+
 // sum w, sum w x^2: block-level tree + one atomicAdd pair per block
 __global__ void __launch_bounds__(256)
 rule_moments_kernel(const double* __restrict__ x, const double* __restrict__ w, int64_t count,
@@ -425,9 +465,9 @@ int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const Piec
     if (T > pieces) T = (int)pieces;
     int dev;
     FGQ_CUDA_TRY(cudaGetDevice(&dev));
-    cudaEvent_t ev[MAX_RING];
-    if (threaded)
-        for (int i = 0; i < RING; ++i) FGQ_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    ScopedEvents evs;
+    if (threaded) FGQ_TRY(evs.acquire(RING));
+    cudaEvent_t* ev = evs.ev;
     std::mutex mu;
     std::condition_variable cv;
     int64_t published = 0;            // pieces whose copies and event have been enqueued
@@ -557,8 +597,6 @@ int drain_to_host(double* x, double* w, int64_t cnt, cudaStream_t st, const Piec
     cudaError_t e2 = cudaStreamSynchronize(st);
     g_drain_share_milli = (int)(dma_share * 1000);
     if (adapt && dma_mirror_ok) s_dma_share = dma_share;
-    if (threaded)
-        for (int i = 0; i < RING; ++i) cudaEventDestroy(ev[i]);
     if (rc != FGQ_OK) return rc;
     FGQ_CUDA_TRY(err);
     FGQ_CUDA_TRY(e2);
@@ -807,12 +845,11 @@ static int codec_pair_pipeline(int64_t n, int64_t k_lo, int64_t cnt, double* xl,
     cudaStream_t s_compute, s_copy;
     FGQ_TRY(scratch_stream(0, &s_compute));
     FGQ_TRY(scratch_stream(1, &s_copy));
-    cudaEvent_t packed[2], sent[2], landed[2];  // per device slot: packed / all payload copied; per staging slot: landed
-    for (int i = 0; i < 2; ++i) {
-        FGQ_CUDA_TRY(cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming));
-        FGQ_CUDA_TRY(cudaEventCreateWithFlags(&sent[i], cudaEventDisableTiming));
-        FGQ_CUDA_TRY(cudaEventCreateWithFlags(&landed[i], cudaEventDisableTiming));
-    }
+    ScopedEvents evs;   // per device slot: packed / all payload copied; per staging slot: landed
+    FGQ_TRY(evs.acquire(6));
+    cudaEvent_t* packed = evs.ev;
+    cudaEvent_t* sent = evs.ev + 2;
+    cudaEvent_t* landed = evs.ev + 4;
     WorkerPool& pool = WorkerPool::get();
     const int T = pool.max_threads() > 1 ? pool.max_threads() : 1;
     int dev;
@@ -1006,11 +1043,6 @@ static int codec_pair_pipeline(int64_t n, int64_t k_lo, int64_t cnt, double* xl,
     });
     cudaError_t e1 = cudaStreamSynchronize(s_compute);
     cudaError_t e2 = cudaStreamSynchronize(s_copy);
-    for (int i = 0; i < 2; ++i) {
-        cudaEventDestroy(packed[i]);
-        cudaEventDestroy(sent[i]);
-        cudaEventDestroy(landed[i]);
-    }
     if (rc != FGQ_OK) {
         set_error("internal: transport coding failed");
         return rc;

@@ -64,6 +64,29 @@ int scratch_device(size_t bytes, int slot, void** out);   // grow-only, per (dev
 int scratch_stream(int which, cudaStream_t* out);          // two library streams
 int scratch_event(int which, cudaEvent_t* out);
 
+// Events / side streams for the duration of one call, taken from a per-device pool and handed back by the
+// destructor on EVERY return path (the objects are reused, never destroyed: an event or stream may still be
+// referenced by work the call enqueued).  Replaces per-call cudaEventCreate / Destroy pairs that leaked on early
+// returns, and the library-wide side stream that concurrent device-API callers (or a graph capture) had to share.
+struct ScopedEvents {
+    ScopedEvents() {}
+    ~ScopedEvents();
+    int acquire(int count);          // timing disabled; ev[0 .. count)
+    cudaEvent_t ev[64];
+    int n = 0, dev = -1;
+    ScopedEvents(const ScopedEvents&) = delete;
+    ScopedEvents& operator=(const ScopedEvents&) = delete;
+};
+struct ScopedStream {
+    ScopedStream() {}
+    ~ScopedStream();
+    int acquire();                   // a non-blocking stream nobody else holds right now
+    cudaStream_t st = nullptr;
+    int dev = -1;
+    ScopedStream(const ScopedStream&) = delete;
+    ScopedStream& operator=(const ScopedStream&) = delete;
+};
+
 // D2H of a finished result, ordered after `st`; blocks until the data is in place.  Pageable destinations
 // go through a pinned ring drained by host threads (capi.cu).  Caller holds HostPathLock.
 struct MirrorSpec {      // optional +-x mirroring done by the same host threads (Legendre pair shards)

@@ -51,6 +51,9 @@ struct JacobiLaunch {
 };
 
 constexpr int JAC_THREADS = 128;
+#ifndef JAC_ROTATE
+#define JAC_ROTATE 1   // 0: every term's phase through its own medium-range sincos (round 1)
+#endif
 constexpr double JAC_SKIP_TMAX = 1.5718;  // pi/2 + 1e-3: the bound behind tskip assumes 1/(2 cos(t/2)) <= 0.7079
 constexpr int JAC_NORM_STAGE1 = 4;  // truncation candidates (terms 12, 13, ...) examined by the first norm stage
 constexpr int64_t JAC_GRID = 148 * 5;  // persistent grid: 5 blocks of 128 threads fit one SM at 96 registers
@@ -69,8 +72,10 @@ __device__ __forceinline__ void feval_asy1_node(const JacobiHalfPlan& P, double 
     const double a = P.a, b = P.b;
     double sinT_, cosT_;
     sincos(t, &sinT_, &cosT_);
-    const double csc = (1.0 / sin(t / 2)) / 2;
-    const double sec = (1.0 / cos(t / 2)) / 2;
+    double sinH, cosH;
+    sincos(t / 2, &sinH, &cosH);
+    const double csc = (1.0 / sinH) / 2;
+    const double sec = (1.0 / cosH) / 2;
     double pw[JAC_M];  // sinT[:, j] of the reference (:271), rescaled by secT after every term (:316)
     pw[0] = 1.0;
 #pragma unroll
@@ -78,13 +83,24 @@ __device__ __forceinline__ void feval_asy1_node(const JacobiHalfPlan& P, double 
     const double c0 = 2 * nn + a + b;
     const double shift = (a + 0.5) * PI / 2;
     double S = 0.0, S2 = 0.0;
+    double sA = 0.0, cA = 1.0;
 #pragma unroll
     for (int m = 1; m <= M_LAST; ++m) {
         if (m >= M_FIRST) {
             if (!NORM && m == mbreak) break;
-            const double A = (c0 + m) * t / 2 - shift;
-            double sA, cA;
-            fgq_sincos_medium(A, &sA, &cA);
+            if (NORM || m == 1 || !JAC_ROTATE) {
+                const double A = (c0 + m) * t / 2 - shift;
+                fgq_sincos_medium(A, &sA, &cA);
+            } else {
+                // A_m = A_{m-1} + t/2: one plane rotation by t/2 instead of a 1e7-radian sincos per term.  The
+                // rotation is more accurate than the reference's own phase (whose rounding, ulp(A)/2 ~ 1e-9 rad at
+                // n = 1e7, this does not reproduce), and terms m >= 2 are smaller than the first by (n t)^-(m-1),
+                // n t >= ~10 pi on the interior set: the node moves by < 1e-16 / n.  The truncation norms (NORM
+                // modes) keep the reference's phases, so the truncation index is unchanged.
+                const double c2 = cA * cosH - sA * sinH;
+                sA = sA * cosH + cA * sinH;
+                cA = c2;
+            }
             double d1 = 0.0, d2 = 0.0, d12 = 0.0, d22 = 0.0;
 #pragma unroll
             for (int l = 0; l < m; l += 2) {
@@ -721,11 +737,12 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
     // a == b the reference reuses the right-end result; the same solve gives the same numbers).  Two
     // single-block kernels, independent of the interior: forked onto a side stream and joined at the end
     // (event dependencies only, so the call stays stream-ordered and graph-capturable).
-    cudaStream_t side;
-    FGQ_TRY(scratch_stream(1, &side));
-    cudaEvent_t ev_fork, ev_join;
-    FGQ_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    FGQ_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    ScopedStream side_holder;   // a side stream and two events of this call's own (returned on every exit path)
+    FGQ_TRY(side_holder.acquire());
+    cudaStream_t side = side_holder.st;
+    ScopedEvents evs;
+    FGQ_TRY(evs.acquire(2));
+    cudaEvent_t ev_fork = evs.ev[0], ev_join = evs.ev[1];
     FGQ_CUDA_TRY(cudaEventRecord(ev_fork, st));
     FGQ_CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
     for (int sd = 0; sd < 2; ++sd) {
@@ -772,8 +789,6 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
         }
     }
     FGQ_CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0));
-    cudaEventDestroy(ev_fork);
-    cudaEventDestroy(ev_join);
     return FGQ_OK;
 }
 

@@ -898,6 +898,43 @@ extern "C" int64_t fgq_gausslaguerre_batch_workspace_bytes(int64_t nrules) {
     return 256 + nrules * (int64_t)sizeof(LaguerreBatchRule);
 }
 
+// Buckets of the batch kernel over rules sorted by n (descending): a bucket holds the rules with n in
+// (16 floor((n_top - 1)/16), n_top] (everything up to 16 in the last one); rules with n <= 0 sort last and get none.
+struct LagBucket {
+    int64_t first, count;
+    int n_top;
+};
+static std::vector<LagBucket> laguerre_batch_buckets(const std::vector<int>& sorted_n) {
+    std::vector<LagBucket> out;
+    const int64_t nr = (int64_t)sorted_n.size();
+    int64_t j = 0;
+    while (j < nr) {
+        const int n_top = sorted_n[(size_t)j];
+        if (n_top <= 0) break;
+        const int n_floor = n_top <= 16 ? 0 : ((n_top - 1) / 16) * 16;
+        int64_t e = j;
+        while (e < nr && sorted_n[(size_t)e] > n_floor) ++e;
+        out.push_back(LagBucket{j, e - j, n_top});
+        j = e;
+    }
+    return out;
+}
+
+// test hook (host only): the buckets for an UNSORTED list of rule sizes; returns their number
+extern "C" int fgq_debug_laguerre_batch_buckets(int64_t nrules, const int32_t* n_i, int64_t* first, int64_t* count,
+                                                int32_t* n_top, int max_buckets) {
+    std::vector<int> v;
+    for (int64_t i = 0; i < nrules; ++i) v.push_back(n_i[i]);
+    std::sort(v.begin(), v.end(), [](int a, int b) { return a > b; });
+    const std::vector<LagBucket> b = laguerre_batch_buckets(v);
+    for (size_t i = 0; i < b.size() && (int)i < max_buckets; ++i) {
+        first[i] = b[i].first;
+        count[i] = b[i].count;
+        n_top[i] = b[i].n_top;
+    }
+    return (int)b.size();
+}
+
 static int laguerre_batch_plan(int64_t nrules, const int32_t* n_i, const double* alpha_i, const int64_t* offsets,
                                std::vector<LaguerreBatchRule>* rules, int64_t* total, int* warn) {
     FGQ_TRY(small_batch_rules(nrules, n_i, offsets, LAGUERRE_BATCH_MAX_N, "gausslaguerre", nullptr, total));
@@ -985,19 +1022,13 @@ extern "C" int fgq_gausslaguerre_batch_device(int64_t nrules, const int32_t* n_i
                                           768 * (LAGUERRE_BATCH_MAX_N + 1)));
         attr_set[dev] = true;
     }
-    int64_t j = 0;
-    while (j < nrules) {
-        const int n_top = (int)rules[(size_t)j].n;                 // largest n of this bucket
-        const int n_floor = n_top <= 16 ? 0 : ((n_top - 1) / 16) * 16;  // the bucket takes n in (n_floor, n_top]
-        int64_t e = j;
-        while (e < nrules && rules[(size_t)e].n > n_floor) ++e;
-        if (n_top > 0) {
-            const int64_t cnt = e - j;
-            const size_t smem = n_top >= 15 ? (size_t)768 * (size_t)(n_top + 1) : 0;
-            laguerre_rec_batch_kernel<<<(unsigned)((cnt + 31) / 32), 32, smem, st>>>(j, cnt, n_top, drules, warn_word, x_dev, w_dev);
-            FGQ_LAUNCH_CHECK();
-        }
-        j = e;
+    std::vector<int> sorted_n((size_t)nrules);
+    for (int64_t q = 0; q < nrules; ++q) sorted_n[(size_t)q] = (int)rules[(size_t)q].n;
+    for (const LagBucket& bk : laguerre_batch_buckets(sorted_n)) {
+        const size_t smem = bk.n_top >= 15 ? (size_t)768 * (size_t)(bk.n_top + 1) : 0;
+        laguerre_rec_batch_kernel<<<(unsigned)((bk.count + 31) / 32), 32, smem, st>>>(bk.first, bk.count, bk.n_top, drules,
+                                                                                     warn_word, x_dev, w_dev);
+        FGQ_LAUNCH_CHECK();
     }
     return FGQ_OK;
 }

@@ -377,6 +377,10 @@ int fgq_debug_codec_unpack_host(const double* in, int64_t cnt, double* left, dou
                                 int negate, int fused);
 /* The half-index range [k_lo, k_hi) that device / rank `rank` of `world` owns in the sharded calls (host-only). */
 int fgq_debug_half_index_range(int64_t n, int world, int rank, int64_t* k_lo, int64_t* k_hi);
+/* Launch buckets of fgq_gausslaguerre_batch_* for a list of rule sizes (host only; tests): rules sorted by n,
+ * longest first, are cut into groups of similar n; returns the number of buckets (first/count index the sorted list). */
+int fgq_debug_laguerre_batch_buckets(int64_t nrules, const int32_t* n_i, int64_t* first, int64_t* count,
+                                     int32_t* n_top, int max_buckets);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t fgq_launch_count(void);
 

@@ -206,3 +206,27 @@ def test_user_integrand_expressions_are_checked_without_a_device(fgq_cpu):
     if L.fgq_device_count() == 0:
         with pytest.raises(fgq_cpu.FGQError):
             fgq_cpu.gausslegendre_integrate(1000, "exp(x)")
+
+
+def test_laguerre_batch_buckets_cover_every_rule_once(fgq_cpu):
+    """Host planning of the bucketed Laguerre batch launches: terminates for any size list (empty rules included),
+    every rule with n > 0 lands in exactly one bucket, a bucket spans at most 16 sizes."""
+    L = fgq_cpu.lib()
+    rng = np.random.default_rng(3)
+    for n_i in (np.arange(0, 128), np.zeros(5, dtype=int), np.array([], dtype=int), rng.integers(0, 128, 10000),
+                np.array([127, 127, 1, 0, 0, 16, 17]), np.array([0]), np.array([15])):
+        n_i = np.ascontiguousarray(n_i, dtype=np.int32)
+        first = np.zeros(16, dtype=np.int64)
+        count = np.zeros(16, dtype=np.int64)
+        top = np.zeros(16, dtype=np.int32)
+        nb = L.fgq_debug_laguerre_batch_buckets(len(n_i), n_i.ctypes.data, first.ctypes.data, count.ctypes.data,
+                                                top.ctypes.data, 16)
+        srt = np.sort(n_i)[::-1]
+        assert 0 <= nb <= 8
+        assert count[:nb].sum() == np.count_nonzero(n_i > 0)
+        pos = 0
+        for b in range(nb):
+            assert first[b] == pos and count[b] > 0 and top[b] == srt[pos]
+            seg = srt[pos:pos + count[b]]
+            assert seg.min() > (0 if top[b] <= 16 else ((top[b] - 1) // 16) * 16) and seg.max() == top[b]
+            pos += count[b]
