@@ -22,6 +22,7 @@
 #include "airy.cuh"
 #include "bessel.cuh"
 #include "common.cuh"
+#include "fgq_math.h"
 #include "gw.cuh"
 #include "jacobi_plan.h"
 
@@ -537,50 +538,60 @@ laguerre_small_batch_kernel(int64_t nrules, const LaguerreBatchRule* __restrict_
 // recurrence step recomputed its abscissa-independent coefficients — two square roots and three of its five divisions.
 // Here a lane tabulates c1_k = sqrt(k (alpha + k)), c2_k = sqrt((k-1+alpha)(k-1)/k/(k+alpha)) and the correctly
 // rounded 1/c1_k of ITS rule once (same IEEE expressions as evalLaguerreRec, gausslaguerre.jl:631-637) in shared
-// memory, laid out [k][lane] (conflict-free), and a step becomes 16 FP64 operations: the two remaining quotients
-// are the last three operations of the IEEE division's fast path against the tabulated reciprocal (same bits; an
-// operand outside the safe range takes the IEEE operator).  Lanes run a small state machine so that every trip of
+// memory, laid out [k][lane] (conflict-free), and a step becomes ~21 FP64 operations: the two remaining quotients
+// are the last three operations of the IEEE division's fast path against the correctly rounded reciprocal (same
+// bits; an evaluation that leaves the safe range is repeated with the IEEE operators).  Lanes run a small state machine so that every trip of
 // the warp-wide loop is one polynomial evaluation for every lane (no lane waits for another lane's Newton loop).
-// The batch is cut into buckets of similar n (rules arrive sorted by n): shared memory per warp is 768 B x n_max of
+// The batch is cut into buckets of similar n (rules arrive sorted by n): shared memory per warp is 512 B x n_max of
 // the bucket, so short rules get many resident warps and long ones as many as fit.
 // ---------------------------------------------------------------------------------------------
 struct LagTab {
     double* c1;   // [k][lane], k = 1..nmax
     double* c2;
-    double* r1;
 };
 
-// (pn, pnd) of evalLaguerreRec(deg, alpha, x) for this lane from its tables; lanes with act == false idle.
-__device__ __forceinline__ void lag_eval_tab(const LagTab& t, int lane, int deg, double alpha, double pn0, double x, bool act,
-                                             int deg_warp, double& pn_out, double& pnd_out) {
+// (pn, pnd) of evalLaguerreRec(deg, alpha, x) for this lane from its tables; straight-line per step (no branches in
+// the dependent chain): a lane whose rule is shorter than the warp's longest keeps its state by selects.
+// SAFE = false: the two quotients by c1 are the last three operations of the IEEE division's fast path against the
+// correctly rounded 1/c1 (same bits as u / c1, v / c1 while v stays inside ~[1e-260, 1e255]); the exponent range of
+// v is tracked on the integer pipe and reported through `out_of_range`, in which case the caller repeats the
+// evaluation with SAFE = true (IEEE operators).
+template <bool SAFE>
+__device__ __forceinline__ void lag_eval_tab(const LagTab& t, int lane, int deg, double alpha, double pn0, double x,
+                                             int deg_warp, double& pn_out, double& pnd_out, bool& out_of_range) {
     double pnprev = 0.0, pn = pn0, pndprev = 0.0, pnd = 0.0;
+    unsigned bad = 0;
+#pragma unroll 4
     for (int k = 1; k <= deg_warp; ++k) {
-        if (act && k <= deg) {
-            const double dk = (double)k;
-            const double c1 = t.c1[k * 32 + lane], c2 = t.c2[k * 32 + lane], r1 = t.r1[k * 32 + lane];
-            const double u = x - 2 * dk - alpha + 1;
-            // u / c1: |u| <= ~4n + alpha, c1 in [~0.3, ~200]: always inside the safe range of the fast path
-            double q = u * r1;
+        const double dk = (double)k;
+        const double c1 = t.c1[k * 32 + lane], c2 = t.c2[k * 32 + lane];
+        const double u = x - 2 * dk - alpha + 1;
+        const double pnold = pn, pndold = pnd;
+        const double v = pnold + u * pndold;
+        double q, qv;
+        if (SAFE) {
+            q = u / c1;
+            qv = v / c1;
+        } else {
+            const double r1 = fgq_rcp_fast(c1);   // == 1.0 / c1 (c1 in [~0.3, ~200])
+            q = u * r1;
             q = fma(r1, fma(-c1, q, u), q);
-            const double pnold = pn;
-            pn = q * pnold - c2 * pnprev;
-            pnprev = pnold;
-            const double pndold = pnd;
-            const double v = pnold + u * pndold;
-            double qv;
-            const unsigned ev = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;   // biased exponent of v
-            if (ev > 0x0a0u && ev < 0x750u) {       // ~1e-260 < |v| < ~1e255: fast path == IEEE quotient
-                qv = v * r1;
-                qv = fma(r1, fma(-c1, qv, v), qv);
-            } else {
-                qv = v / c1;
-            }
-            pnd = qv - c2 * pndprev;
-            pndprev = pndold;
+            qv = v * r1;
+            qv = fma(r1, fma(-c1, qv, v), qv);
+            const unsigned ev = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+            bad |= (ev - 0x0a1u > 0x74fu - 0x0a1u) && (k <= deg) ? 1u : 0u;
         }
+        const double pn_new = q * pnold - c2 * pnprev;
+        const double pnd_new = qv - c2 * pndprev;
+        const bool live = k <= deg;
+        pnprev = live ? pnold : pnprev;
+        pn = live ? pn_new : pn;
+        pndprev = live ? pndold : pndprev;
+        pnd = live ? pnd_new : pnd;
     }
     pn_out = pn;
     pnd_out = pnd;
+    out_of_range = bad != 0;
 }
 
 __global__ void __launch_bounds__(32)
@@ -599,16 +610,13 @@ laguerre_rec_batch_kernel(int64_t first, int64_t count, int nmax, const Laguerre
         laguerre_small_rule(r, r.q, warn_word, xr, wr);
     }
     const bool rec = have && n >= 15;
-    LagTab t{s_tab, s_tab + (size_t)(nmax + 1) * 32, s_tab + 2 * (size_t)(nmax + 1) * 32};
+    LagTab t{s_tab, s_tab + (size_t)(nmax + 1) * 32};
     const double al = r.alpha;
-    if (rec) {
-        for (int k = 1; k <= n; ++k) {
-            const double dk = (double)k;
-            const double c1 = sqrt(dk * (al + dk));
-            t.c1[k * 32 + lane] = c1;
-            t.c2[k * 32 + lane] = sqrt((dk - 1 + al) * (dk - 1) / dk / (dk + al));
-            t.r1[k * 32 + lane] = 1.0 / c1;
-        }
+    for (int k = 1; k <= nmax; ++k) {   // (entries beyond a lane's own n are read but never used: keep them finite)
+        const double dk = (double)k;
+        const bool mine = rec && k <= n;
+        t.c1[k * 32 + lane] = mine ? sqrt(dk * (al + dk)) : 1.0;
+        t.c2[k * 32 + lane] = mine ? sqrt((dk - 1 + al) * (dk - 1) / dk / (dk + al)) : 0.0;
     }
     __syncwarp();
     const int n_warp = __reduce_max_sync(0xffffffffu, rec ? n : 0);
@@ -659,7 +667,17 @@ laguerre_rec_batch_kernel(int64_t first, int64_t count, int nmax, const Laguerre
         const bool act = phase != 3;
         const int deg = phase == 1 ? n - 1 : n;
         double pn, pnd;
-        lag_eval_tab(t, lane, deg, al, r.pn0, xk, act, n_warp, pn, pnd);
+        bool oor;
+        lag_eval_tab<false>(t, lane, act ? deg : 0, al, r.pn0, xk, n_warp, pn, pnd, oor);
+        if (__any_sync(0xffffffffu, act && oor)) {   // a value outside the fast quotient's range: IEEE operators
+            double pn_s, pnd_s;
+            bool dummy;
+            lag_eval_tab<true>(t, lane, act ? deg : 0, al, r.pn0, xk, n_warp, pn_s, pnd_s, dummy);
+            if (oor) {
+                pn = pn_s;
+                pnd = pnd_s;
+            }
+        }
         if (act) {
             if (phase == 0) {
                 iter += 1;
@@ -1019,13 +1037,13 @@ extern "C" int fgq_gausslaguerre_batch_device(int64_t nrules, const int32_t* n_i
     FGQ_CUDA_TRY(cudaGetDevice(&dev));
     if (dev >= 0 && dev < MAX_ATTR_DEV && !attr_set[dev]) {
         FGQ_CUDA_TRY(cudaFuncSetAttribute(laguerre_rec_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          768 * (LAGUERRE_BATCH_MAX_N + 1)));
+                                          512 * (LAGUERRE_BATCH_MAX_N + 1)));
         attr_set[dev] = true;
     }
     std::vector<int> sorted_n((size_t)nrules);
     for (int64_t q = 0; q < nrules; ++q) sorted_n[(size_t)q] = (int)rules[(size_t)q].n;
     for (const LagBucket& bk : laguerre_batch_buckets(sorted_n)) {
-        const size_t smem = bk.n_top >= 15 ? (size_t)768 * (size_t)(bk.n_top + 1) : 0;
+        const size_t smem = bk.n_top >= 15 ? (size_t)512 * (size_t)(bk.n_top + 1) : 0;
         laguerre_rec_batch_kernel<<<(unsigned)((bk.count + 31) / 32), 32, smem, st>>>(bk.first, bk.count, bk.n_top, drules,
                                                                                      warn_word, x_dev, w_dev);
         FGQ_LAUNCH_CHECK();
