@@ -557,6 +557,21 @@ def run_capi(args):
                 m.gausslegendre_replicated(n, out=rep)
             t_ms, _ = m.timer_stop()
             allgather["replicate_by_generation_ms"] = t_ms / 3
+            torch.cuda.set_device(0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                fgq_b200._lib.check(fgq_b200.lib().fgq_gausslegendre_mirror_device(n, rep.x[0], rep.w[0],
+                                                                                   torch.cuda.current_stream().cuda_stream))
+            e1.record()
+            torch.cuda.synchronize()
+            allgather["mirror_ms"] = e0.elapsed_time(e1) / 3
+            for tr in ("push", "ce", "nccl"):
+                if "ms" in allgather.get(tr, {}):
+                    tm = allgather[tr]["ms"] - allgather["mirror_ms"]
+                    allgather[tr]["transfer_ms"] = tm
+                    allgather[tr]["transfer_gbs_per_gpu"] = inbound / (tm * 1e-3) / 1e9
             allgather["what"] = ("left segments shipped (push: one kernel per device storing into every peer replica "
                                  "over NVLink; ce: cudaMemcpyPeerAsync; nccl: grouped send/recv), right halves mirrored locally")
             rep.free()
@@ -731,7 +746,16 @@ def main():
         e1.record()
         barrier()
         regen_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
-        allgather = {"ms": ag_ms, "collectives_per_call": st.get("collectives"),
+        e0.record()
+        for _ in range(reps):   # the local +-x mirror alone (part of `ms`)
+            fgq_b200._lib.check(L.fgq_gausslegendre_mirror_device(n, xr.data_ptr(), wr.data_ptr(),
+                                                                  torch.cuda.current_stream().cuda_stream))
+        e1.record()
+        barrier()
+        mirror_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+        allgather = {"ms": ag_ms, "mirror_ms": mirror_ms, "transfer_ms": ag_ms - mirror_ms,
+                     "transfer_gbs_per_gpu": inbound / ((ag_ms - mirror_ms) * 1e-3) / 1e9,
+                     "collectives_per_call": st.get("collectives"),
                      "inbound_bytes_per_gpu": inbound, "inbound_gbs_per_gpu": inbound / (ag_ms * 1e-3) / 1e9,
                      "frac_of_nvlink_900": inbound / (ag_ms * 1e-3) / 1e9 / NVLINK_GBS_PER_DIR,
                      "what": "all_gather_into_tensor (NCCL) of the left segments, x and w, + local +-x mirror kernel; "

@@ -84,11 +84,15 @@ __device__ __forceinline__ void feval_asy1_node(const JacobiHalfPlan& P, double 
     const double shift = (a + 0.5) * PI / 2;
     double S = 0.0, S2 = 0.0;
     double sA = 0.0, cA = 1.0;
+    // Next to the ends (n t up to a few hundred) the first two terms of S2 nearly cancel (to 1 part in ~400 at
+    // n t = 40), so the weight there is sensitive to the 1e-14 rad by which an exactly advanced phase differs from the
+    // reference's individually rounded A_m: those nodes (a few hundred per end, whatever n) keep the reference's phases.
+    const bool rotate = JAC_ROTATE && c0 * t >= 8192.0;
 #pragma unroll
     for (int m = 1; m <= M_LAST; ++m) {
         if (m >= M_FIRST) {
             if (!NORM && m == mbreak) break;
-            if (NORM || m == 1 || !JAC_ROTATE) {
+            if (NORM || m == 1 || !rotate) {
                 const double A = (c0 + m) * t / 2 - shift;
                 fgq_sincos_medium(A, &sA, &cA);
             } else {

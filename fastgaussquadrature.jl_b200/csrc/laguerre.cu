@@ -612,7 +612,8 @@ laguerre_rec_batch_kernel(int64_t first, int64_t count, int nmax, const Laguerre
     const bool rec = have && n >= 15;
     LagTab t{s_tab, s_tab + (size_t)(nmax + 1) * 32};
     const double al = r.alpha;
-    for (int k = 1; k <= nmax; ++k) {   // (entries beyond a lane's own n are read but never used: keep them finite)
+    // (a bucket of closed-form / Golub-Welsch rules only, nmax < 15, is launched without shared memory)
+    for (int k = 1; nmax >= 15 && k <= nmax; ++k) {   // entries beyond a lane's own n are read but never used: keep them finite
         const double dk = (double)k;
         const bool mine = rec && k <= n;
         t.c1[k * 32 + lane] = mine ? sqrt(dk * (al + dk)) : 1.0;
