@@ -1043,11 +1043,33 @@ extern "C" int fgq_gausslaguerre_batch_device(int64_t nrules, const int32_t* n_i
     }
     std::vector<int> sorted_n((size_t)nrules);
     for (int64_t q = 0; q < nrules; ++q) sorted_n[(size_t)q] = (int)rules[(size_t)q].n;
-    for (const LagBucket& bk : laguerre_batch_buckets(sorted_n)) {
+    const std::vector<LagBucket> buckets = laguerre_batch_buckets(sorted_n);
+    // The long-n buckets run at a few warps per SM (their tables fill the shared memory) and every bucket ends in a
+    // partially filled wave: the buckets are spread over the caller's stream and three side streams (forked and
+    // joined with events: still stream-ordered for the caller, graph-capturable) so that they fill each other's gaps.
+    constexpr int NSIDE = 3;
+    ScopedStream side[NSIDE];
+    ScopedEvents evs;
+    const bool fork = buckets.size() > 1;
+    if (fork) {
+        for (int q = 0; q < NSIDE; ++q) FGQ_TRY(side[q].acquire());
+        FGQ_TRY(evs.acquire(1 + NSIDE));
+        FGQ_CUDA_TRY(cudaEventRecord(evs.ev[0], st));
+        for (int q = 0; q < NSIDE; ++q) FGQ_CUDA_TRY(cudaStreamWaitEvent(side[q].st, evs.ev[0], 0));
+    }
+    for (size_t bi = 0; bi < buckets.size(); ++bi) {
+        const LagBucket& bk = buckets[bi];
         const size_t smem = bk.n_top >= 15 ? (size_t)512 * (size_t)(bk.n_top + 1) : 0;
-        laguerre_rec_batch_kernel<<<(unsigned)((bk.count + 31) / 32), 32, smem, st>>>(bk.first, bk.count, bk.n_top, drules,
-                                                                                     warn_word, x_dev, w_dev);
+        cudaStream_t s_b = (fork && bi % (NSIDE + 1) != 0) ? side[bi % (NSIDE + 1) - 1].st : st;
+        laguerre_rec_batch_kernel<<<(unsigned)((bk.count + 31) / 32), 32, smem, s_b>>>(bk.first, bk.count, bk.n_top, drules,
+                                                                                      warn_word, x_dev, w_dev);
         FGQ_LAUNCH_CHECK();
+    }
+    if (fork) {
+        for (int q = 0; q < NSIDE; ++q) {
+            FGQ_CUDA_TRY(cudaEventRecord(evs.ev[1 + q], side[q].st));
+            FGQ_CUDA_TRY(cudaStreamWaitEvent(st, evs.ev[1 + q], 0));
+        }
     }
     return FGQ_OK;
 }
