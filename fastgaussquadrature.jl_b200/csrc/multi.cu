@@ -25,6 +25,8 @@
 // device, a few microseconds each; the GPUs run concurrently because nothing synchronises between the enqueues).
 #include <dlfcn.h>
 
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -42,8 +44,54 @@ struct DevCtx {
     double* sums = nullptr;         // 2 doubles of device scratch for the moments
 };
 
+// One enqueue thread per device (created by fgq_init, parked on a condition variable): a steady-state sharded call
+// hands each of them its device's two launches, so the devices are fed at the same moment instead of one after the
+// other from the calling thread (8 devices x 2 launches of ~5 us would skew the last device's start by ~70 us).
+// Deliberately leaked at process exit, like the host-path worker pool.
+struct EnqueueWorker {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, done = false;
+    int rc = FGQ_OK;
+    std::string err;
+    int dev = -1;
+    void loop() {
+        cudaSetDevice(dev);
+        for (;;) {
+            std::function<int()> j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return has_job; });
+                j = job;
+                has_job = false;
+            }
+            const int r = j();
+            std::string e = r != FGQ_OK ? std::string(fgq_last_error()) : std::string();
+            std::lock_guard<std::mutex> lk(mu);
+            rc = r;
+            err = e;
+            done = true;
+            cv.notify_all();
+        }
+    }
+    void submit(std::function<int()> j) {
+        std::lock_guard<std::mutex> lk(mu);
+        job = std::move(j);
+        has_job = true;
+        done = false;
+        cv.notify_all();
+    }
+    int wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return done; });
+        return rc;
+    }
+};
+
 static std::mutex g_multi_mu;
 static std::vector<DevCtx> g_ctx;
+static std::vector<EnqueueWorker*> g_workers;   // parallel to g_ctx
 static bool g_peer_ok = false;
 
 struct DeviceGuard {
@@ -297,6 +345,13 @@ static int fgq::init_locked(const int* device_ids, int ndev) {
     }
     g_peer_ok = peer;
     g_ctx.swap(ctx);
+    g_workers.clear();
+    for (auto& c : g_ctx) {
+        EnqueueWorker* wk = new EnqueueWorker();
+        wk->dev = c.dev;
+        std::thread([wk]() { wk->loop(); }).detach();
+        g_workers.push_back(wk);
+    }
     return FGQ_OK;
 }
 
@@ -460,9 +515,31 @@ extern "C" int fgq_gausslegendre_device_sharded(int64_t n, fgq_shard* shards, in
                           "(zero-initialise them before the first call)", (long long)n);
                 return FGQ_EINVAL;
             }
-            if (L.cnt > 0)
-                FGQ_TRY(fgq_gausslegendre_device_pair(n, L.k_lo, L.k_hi, sl.x, sl.w, sr.x - L.skip, sr.w - L.skip, c.st));
         }
+        // every descriptor is valid: hand each device its launches (nothing above this line has been submitted, so an
+        // early return cannot leave a worker with a job nobody waits for)
+        for (int r = 0; r < world; ++r) {
+            const ShardLayout L = shard_layout(n, world, r);
+            const fgq_shard& sl = shards[2 * r];
+            const fgq_shard& sr = shards[2 * r + 1];
+            if (L.cnt > 0) {
+                double *xl = sl.x, *wl = sl.w, *xr = sr.x - L.skip, *wr = sr.w - L.skip;
+                cudaStream_t stq = g_ctx[r].st;
+                const int64_t klo = L.k_lo, khi = L.k_hi;
+                g_workers[r]->submit([=]() { return fgq_gausslegendre_device_pair(n, klo, khi, xl, wl, xr, wr, stq); });
+            } else {
+                g_workers[r]->submit([]() { return (int)FGQ_OK; });
+            }
+        }
+        int rc_all = FGQ_OK;
+        for (int r = 0; r < world; ++r) {
+            const int rc = g_workers[r]->wait();
+            if (rc != FGQ_OK && rc_all == FGQ_OK) {
+                rc_all = rc;
+                set_error("device %d: %s", g_ctx[r].dev, g_workers[r]->err.c_str());
+            }
+        }
+        if (rc_all != FGQ_OK) return rc_all;
     }
     if (!sums) return FGQ_OK;  // stream-ordered: fgq_synchronize() / fgq_timer_stop() wait for the result
     // sum w, sum w x^2 per device, added on the host in device order (deterministic)
