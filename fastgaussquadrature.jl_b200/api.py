@@ -431,10 +431,13 @@ def gausshermite(n, *, normalize: bool = False):
 
 
 def gausshermite_reduced(n, *, normalize: bool = False):
-    """Truncated Gauss-Hermite rule: ``(first, x, w)``, the centre block ``first : first+len(x)`` (0-based) of
-    ``gausshermite(n)`` holding every weight >= 10 floatmin; all omitted weights are 0.0 in the full rule
-    (exp(-x^2) underflows, gausshermite.jl:30).  Only that block is computed (2.4 % of the nodes at n = 1e6);
-    the analogue of ``gausslaguerre(n; reduced=true)`` (gausslaguerre.jl:163-169)."""
+    """Truncated Gauss-Hermite rule: ``(first, x, w)`` covering positions ``first : first+len(x)`` (0-based) of
+    ``gausshermite(n)`` — every weight >= 10 floatmin; all omitted weights are 0.0 in the full rule (exp(-x^2)
+    underflows, gausshermite.jl:30).  Only that block is computed (2.4 % of the nodes at n = 1e6), with the same
+    kernels, Newton stopping rule and normalisation sum taken over the block: the entries agree with the full rule
+    to the Newton tolerance (a few ulp of sqrt(2n+1); the global stopping rule sees fewer nodes and may stop one
+    sweep apart) and are bit-identical only when nothing is truncated (n <= 200).  The analogue of
+    ``gausslaguerre(n; reduced=true)`` (gausslaguerre.jl:163-169)."""
     import ctypes
     n = _as_int(n)
     if n < 0:

@@ -72,8 +72,9 @@ function gausslaguerre_batch(ns::Vector{Int32}, α::Vector{Float64})
     return offsets, x, w
 end
 
-# Truncated Gauss-Hermite rule: (first, x, w) with x, w = entries first+1 : first+length(x) (1-based) of
-# gausshermite(n); every omitted weight is 0.0 in the full rule
+# Truncated Gauss-Hermite rule: (first, x, w) with x, w covering positions first+1 : first+length(x) (1-based) of
+# gausshermite(n); every omitted weight is 0.0 in the full rule.  The entries agree with the full rule to the Newton
+# tolerance (the stopping rule is taken over the computed block), bit for bit only when nothing is truncated.
 function gausshermite_reduced(n::Integer; normalize::Bool=false)
     n < 0 && throw(DomainError(n, "Input n must be a non-negative integer"))
     bound = ccall((:fgq_gausshermite_reduced_bound, libfgq), Int64, (Int64,), n)
