@@ -230,3 +230,13 @@ def test_laguerre_batch_buckets_cover_every_rule_once(fgq_cpu):
             seg = srt[pos:pos + count[b]]
             assert seg.min() > (0 if top[b] <= 16 else ((top[b] - 1) // 16) * 16) and seg.max() == top[b]
             pos += count[b]
+
+
+def test_host_store_peak_needs_no_device(fgq_cpu):
+    """The host-memory roofline of the host-returning calls is measured by host threads only."""
+    L = fgq_cpu.lib()
+    buf = np.zeros(1 << 20)
+    g = ctypes.c_double(0.0)
+    assert L.fgq_measure_host_store_peak(buf.ctypes.data, len(buf), 2, ctypes.byref(g)) == 0
+    assert g.value > 0.1 and np.all(buf == buf[0]) and buf[0] >= 1.0
+    assert L.fgq_measure_host_store_peak(None, len(buf), 2, ctypes.byref(g)) == 3

@@ -99,3 +99,28 @@ def test_timer(fgq, multi):
     ms, per = multi.timer_stop()
     assert 0 < ms < 1000 and len(per) == multi.num_devices() and max(per) == ms
     rule.free()
+
+
+def test_explicit_device_list_and_reinit(fgq, multi):
+    """fgq_init with an explicit list: idempotent for the same list, refused for a different one until fgq_finalize,
+    out-of-range and duplicate ordinals are argument errors; after a re-init the sharded rule is the same rule."""
+    nd = multi.num_devices()
+    assert multi.init(list(range(nd))) == nd                      # same list: nothing to do
+    with pytest.raises(ValueError):
+        multi.init([nd + 3])
+    with pytest.raises(ValueError):
+        multi.init([0, 0])
+    if nd > 1:
+        with pytest.raises(ValueError):
+            multi.init([0])                                       # different list while initialised
+    multi.synchronize()
+    multi.finalize()
+    assert multi.num_devices() == 0
+    assert multi.init([0]) == 1                                   # one device only
+    rule = multi.gausslegendre_sharded(100001)
+    x1, w1 = fgq.gausslegendre(100001)
+    x, w = rule.to_host()
+    assert np.array_equal(x, x1) and np.array_equal(w, w1) and len(rule.segments()) == 2
+    rule.free()
+    multi.finalize()
+    assert multi.init() == nd                                     # back to all devices for the fixture's teardown
