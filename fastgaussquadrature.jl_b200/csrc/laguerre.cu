@@ -601,7 +601,7 @@ laguerre_rec_batch_kernel(int64_t first, int64_t count, int nmax, const Laguerre
     const int lane = threadIdx.x;
     const int64_t i = first + (int64_t)blockIdx.x * 32 + lane;
     const bool have = i < first + count;
-    LaguerreBatchRule r;
+    LaguerreBatchRule r = {};
     if (have) r = rules[i];
     const int n = have ? (int)r.n : 0;
     double* xr = x + (have ? r.off : 0);

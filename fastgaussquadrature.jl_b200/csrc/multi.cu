@@ -683,8 +683,21 @@ extern "C" int fgq_allgather(const fgq_shard* shards, int nshards, int64_t n, do
     }
     shards = list.data();
     nshards = (int)list.size();
-    // the replicas must not be written before whatever produced the shards has finished on every device: the
-    // producing streams are the library's own per-device streams, and every transport below runs on them
+    // The shards are produced on the library's per-device streams, and every transport below runs on them, so a
+    // source's own data is ordered.  But a transport WRITES into the other devices' replicas: it must not overtake
+    // what those devices still have queued on them (the mirror kernel of a previous all-gather, a previous
+    // generation into the same replica): every stream first waits for every other stream's current tail.
+    if (world > 1) {
+        for (auto& c : g_ctx) {
+            FGQ_CUDA_TRY(cudaSetDevice(c.dev));
+            FGQ_CUDA_TRY(cudaEventRecord(c.done, c.st));
+        }
+        for (auto& c : g_ctx) {
+            FGQ_CUDA_TRY(cudaSetDevice(c.dev));
+            for (auto& o : g_ctx)
+                if (o.dev != c.dev) FGQ_CUDA_TRY(cudaStreamWaitEvent(c.st, o.done, 0));
+        }
+    }
     if (mode == "push") {
         for (int i = 0; i < nshards; ++i) {
             const fgq_shard& s = shards[i];
