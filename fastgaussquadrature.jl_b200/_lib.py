@@ -98,6 +98,7 @@ SIGNATURES = {
     "fgq_init": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "fgq_finalize": (ctypes.c_int, []),
     "fgq_num_devices": (ctypes.c_int, []),
+    "fgq_device_ordinal": (ctypes.c_int, [ctypes.c_int]),
     "fgq_shard_count": (ctypes.c_int, [_i64]),
     "fgq_gausslegendre_device_sharded": (ctypes.c_int, [_i64, _shp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), _dp]),
     "fgq_free_shards": (ctypes.c_int, [_shp, ctypes.c_int]),

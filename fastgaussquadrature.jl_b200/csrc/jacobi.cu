@@ -181,6 +181,11 @@ template <int MODE>
 __global__ void __launch_bounds__(JAC_THREADS, 5)
 jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, double* theta, double* x, double* w) {
     constexpr bool NORM = MODE != 0;
+    // Programmatic dependent launch: the pass kernels are enqueued as a fixed sequence of 66 launches of which most
+    // return at once; with the stream-serialisation attribute the launch of kernel j+1 is processed while kernel j
+    // still runs.  Nothing of the predecessor's output is read before the wait (full completion + visibility).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     const int h = p.half;
     const int phase = *((volatile int*)&st->phase[h]);
     if (phase == 2) return;
@@ -265,6 +270,26 @@ jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, doub
             __threadfence();
         }
     }
+}
+
+// kernel<<<grid, block, 0, st>>>(args...) with programmatic stream serialisation allowed (FGQ_JACOBI_PDL=0: plain launch)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    static const bool pdl = []() {
+        const char* e = getenv("FGQ_JACOBI_PDL");
+        return !(e && atoi(e) == 0);
+    }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 struct JacobiPatch {
@@ -784,12 +809,12 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
             L[h].sweep = s;
             const int64_t tiles = (L[h].count + JAC_THREADS - 1) / JAC_THREADS;
             const unsigned blocks = (unsigned)(tiles < JAC_GRID ? tiles : JAC_GRID);
-            jacobi_pass_kernel<1><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
-            FGQ_LAUNCH_CHECK();
-            jacobi_pass_kernel<2><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
-            FGQ_LAUNCH_CHECK();
-            jacobi_pass_kernel<0><<<blocks, JAC_THREADS, 0, st>>>(L[h], state, theta, x_dev, w_dev);
-            FGQ_LAUNCH_CHECK();
+            FGQ_CUDA_TRY(launch_pdl(jacobi_pass_kernel<1>, blocks, JAC_THREADS, st, L[h], state, theta, x_dev, w_dev));
+            count_launch();
+            FGQ_CUDA_TRY(launch_pdl(jacobi_pass_kernel<2>, blocks, JAC_THREADS, st, L[h], state, theta, x_dev, w_dev));
+            count_launch();
+            FGQ_CUDA_TRY(launch_pdl(jacobi_pass_kernel<0>, blocks, JAC_THREADS, st, L[h], state, theta, x_dev, w_dev));
+            count_launch();
         }
     }
     FGQ_CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0));

@@ -366,6 +366,11 @@ extern "C" int fgq_num_devices(void) {
     return (int)g_ctx.size();
 }
 
+extern "C" int fgq_device_ordinal(int index) {
+    std::lock_guard<std::mutex> guard(g_multi_mu);
+    return (index >= 0 && index < (int)g_ctx.size()) ? g_ctx[(size_t)index].dev : -1;
+}
+
 extern "C" int fgq_finalize(void) {
     clear_status();
     std::lock_guard<std::mutex> guard(g_multi_mu);

@@ -136,7 +136,7 @@ class Replicas:
         self.ndev = nd
 
     def tensors(self, d: int):
-        dev = d  # replicas are listed in fgq_init order; with the default list, ordinal == position
+        dev = int(lib().fgq_device_ordinal(d))   # replicas are listed in fgq_init order
         return _as_tensor(self.x[d] or 0, self.n, dev), _as_tensor(self.w[d] or 0, self.n, dev)
 
     def free(self) -> None:

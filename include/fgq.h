@@ -257,6 +257,8 @@ typedef struct fgq_shard {
 int fgq_init(const int* device_ids, int ndev);
 int fgq_finalize(void);
 int fgq_num_devices(void);
+/* CUDA ordinal of the index-th initialised device (the order of x_repl / w_repl and of the shard pairs); -1 if out of range */
+int fgq_device_ordinal(int index);
 /* number of fgq_shard entries fgq_gausslegendre_device_sharded writes for this n (2 per device: the left
  * segment and its mirror image; 1 for n <= 60) */
 int fgq_shard_count(int64_t n);

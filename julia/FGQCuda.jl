@@ -208,6 +208,7 @@ function init(devices::Union{Nothing,Vector{Int32}} = nothing)
     return Int(ccall((:fgq_num_devices, libfgq), Cint, ()))
 end
 finalize() = check(ccall((:fgq_finalize, libfgq), Cint, ()), nothing)
+device_ordinal(i::Integer) = Int(ccall((:fgq_device_ordinal, libfgq), Cint, (Cint,), i))   # 0-based position -> CUDA ordinal
 synchronize() = check(ccall((:fgq_synchronize, libfgq), Cint, ()), nothing)
 
 # Device-resident gausslegendre(n) over every initialised GPU: returns (shards, (sum w, sum w x^2)).  Pass the
