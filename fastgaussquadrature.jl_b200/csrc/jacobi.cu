@@ -804,18 +804,40 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
     L[0].idx_lo = n_left;         L[0].idx_hi = n - (JAC_NBDY - 1);   // all but the last 9 (:206)
     L[1].first = 0;               L[1].count = n_left;
     L[1].idx_lo = JAC_NBDY;       L[1].idx_hi = n_left;              // all but the first 10 (:228)
+    // The two halves are independent chains (their own phase flags, norms, tickets, theta ranges and outputs): the
+    // left half's 33 launches go to a second side stream, forked after the initial guesses and joined at the end, so
+    // that the launch gaps and the converged-and-return launches of one chain are hidden behind the other's work
+    // (FGQ_JACOBI_TWO_STREAMS=0: one stream, as in round 1).
+    static const bool two_streams = []() {
+        const char* e = getenv("FGQ_JACOBI_TWO_STREAMS");
+        return !(e && atoi(e) == 0);
+    }();
+    ScopedStream left_holder;
+    ScopedEvents evs2;
+    cudaStream_t chain[2] = {st, st};
+    if (two_streams) {
+        FGQ_TRY(left_holder.acquire());
+        FGQ_TRY(evs2.acquire(2));
+        chain[1] = left_holder.st;
+        FGQ_CUDA_TRY(cudaEventRecord(evs2.ev[0], st));              // after jacobi_init_kernel
+        FGQ_CUDA_TRY(cudaStreamWaitEvent(chain[1], evs2.ev[0], 0));
+    }
     for (int s = 0; s < 11; ++s) {
         for (int h = 0; h < 2; ++h) {
             L[h].sweep = s;
             const int64_t tiles = (L[h].count + JAC_THREADS - 1) / JAC_THREADS;
             const unsigned blocks = (unsigned)(tiles < JAC_GRID ? tiles : JAC_GRID);
-            FGQ_CUDA_TRY(launch_pdl(jacobi_pass_kernel<1>, blocks, JAC_THREADS, st, L[h], state, theta, x_dev, w_dev));
+            FGQ_CUDA_TRY(launch_pdl(jacobi_pass_kernel<1>, blocks, JAC_THREADS, chain[h], L[h], state, theta, x_dev, w_dev));
             count_launch();
-            FGQ_CUDA_TRY(launch_pdl(jacobi_pass_kernel<2>, blocks, JAC_THREADS, st, L[h], state, theta, x_dev, w_dev));
+            FGQ_CUDA_TRY(launch_pdl(jacobi_pass_kernel<2>, blocks, JAC_THREADS, chain[h], L[h], state, theta, x_dev, w_dev));
             count_launch();
-            FGQ_CUDA_TRY(launch_pdl(jacobi_pass_kernel<0>, blocks, JAC_THREADS, st, L[h], state, theta, x_dev, w_dev));
+            FGQ_CUDA_TRY(launch_pdl(jacobi_pass_kernel<0>, blocks, JAC_THREADS, chain[h], L[h], state, theta, x_dev, w_dev));
             count_launch();
         }
+    }
+    if (two_streams) {
+        FGQ_CUDA_TRY(cudaEventRecord(evs2.ev[1], chain[1]));
+        FGQ_CUDA_TRY(cudaStreamWaitEvent(st, evs2.ev[1], 0));
     }
     FGQ_CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0));
     return FGQ_OK;
