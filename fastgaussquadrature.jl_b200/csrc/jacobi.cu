@@ -70,24 +70,34 @@ __device__ __forceinline__ void feval_asy1_node(const JacobiHalfPlan& P, double 
     constexpr int M_LAST = MODE == 1 ? 11 + JAC_NORM_STAGE1 : JAC_M;
     const double PI = 3.141592653589793;
     const double a = P.a, b = P.b;
-    double sinT_, cosT_;
-    sincos(t, &sinT_, &cosT_);
     double sinH, cosH;
     sincos(t / 2, &sinH, &cosH);
+    const double c0 = 2 * nn + a + b;
+    // Away from the ends (see `rotate` below) sin t, cos t follow from the half-angle pair (4 operations instead of a
+    // second sincos) and the two pow calls of the normalisation become one exp of two logs: a few ulp in quantities
+    // that enter the node only through vals / ders and the weight at the 1e-15 level.  Next to the ends, where the
+    // derivative sum cancels, the reference's own operations are kept.
+    const bool lean = JAC_ROTATE && !NORM && c0 * t >= 8192.0;
+    double sinT_, cosT_;
+    if (lean) {
+        sinT_ = 2 * sinH * cosH;
+        cosT_ = (cosH - sinH) * (cosH + sinH);
+    } else {
+        sincos(t, &sinT_, &cosT_);
+    }
     const double csc = (1.0 / sinH) / 2;
     const double sec = (1.0 / cosH) / 2;
     double pw[JAC_M];  // sinT[:, j] of the reference (:271), rescaled by secT after every term (:316)
     pw[0] = 1.0;
 #pragma unroll
     for (int j = 1; j < JAC_M; ++j) pw[j] = pw[j - 1] * csc;
-    const double c0 = 2 * nn + a + b;
     const double shift = (a + 0.5) * PI / 2;
     double S = 0.0, S2 = 0.0;
     double sA = 0.0, cA = 1.0;
     // Next to the ends (n t up to a few hundred) the first two terms of S2 nearly cancel (to 1 part in ~400 at
     // n t = 40), so the weight there is sensitive to the 1e-14 rad by which an exactly advanced phase differs from the
     // reference's individually rounded A_m: those nodes (a few hundred per end, whatever n) keep the reference's phases.
-    const bool rotate = JAC_ROTATE && c0 * t >= 8192.0;
+    const bool rotate = lean;
 #pragma unroll
     for (int m = 1; m <= M_LAST; ++m) {
         if (m >= M_FIRST) {
@@ -140,7 +150,8 @@ __device__ __forceinline__ void feval_asy1_node(const JacobiHalfPlan& P, double 
     if (NORM) return;
     vals = P.C * S;
     ders = (nn * ((a - b) - c0 * cosT_) * vals + (2 * (nn + a) * (nn + b) * P.C2) * S2) / c0 / sinT_;
-    const double denom = 1.0 / (pow(sin(fabs(t) / 2), a + 0.5) * pow(cos(t / 2), b + 0.5));
+    const double denom = lean ? exp(-((a + 0.5) * log(sinH) + (b + 0.5) * log(cosH)))
+                              : 1.0 / (pow(sin(fabs(t) / 2), a + 0.5) * pow(cos(t / 2), b + 0.5));
     vals *= denom;
     ders *= denom;
 }
