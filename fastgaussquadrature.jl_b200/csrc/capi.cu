@@ -141,6 +141,7 @@ int scratch_event(int which, cudaEvent_t* out) {
 
 static std::vector<cudaEvent_t> g_event_pool[MAX_DEV];
 static std::vector<cudaStream_t> g_stream_pool[MAX_DEV];
+static std::vector<cudaStream_t> g_stream_pool_hp[MAX_DEV];  // created at the greatest stream priority
 
 int ScopedEvents::acquire(int count) {
     if (count < 0 || count > 64) return FGQ_EINVAL;
@@ -162,21 +163,29 @@ ScopedEvents::~ScopedEvents() {
     std::lock_guard<std::mutex> guard(g_res_mutex);
     for (int i = 0; i < n; ++i) g_event_pool[dev].push_back(ev[i]);
 }
-int ScopedStream::acquire() {
+int ScopedStream::acquire(bool high_priority) {
     FGQ_TRY(cur_dev(&dev));
+    high = high_priority;
     std::lock_guard<std::mutex> guard(g_res_mutex);
-    if (!g_stream_pool[dev].empty()) {
-        st = g_stream_pool[dev].back();
-        g_stream_pool[dev].pop_back();
+    std::vector<cudaStream_t>& pool = high ? g_stream_pool_hp[dev] : g_stream_pool[dev];
+    if (!pool.empty()) {
+        st = pool.back();
+        pool.pop_back();
         return FGQ_OK;
     }
-    FGQ_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (high) {
+        int least = 0, greatest = 0;
+        FGQ_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        FGQ_CUDA_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest));
+    } else {
+        FGQ_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    }
     return FGQ_OK;
 }
 ScopedStream::~ScopedStream() {
     if (!st || dev < 0) return;
     std::lock_guard<std::mutex> guard(g_res_mutex);
-    g_stream_pool[dev].push_back(st);
+    (high ? g_stream_pool_hp[dev] : g_stream_pool[dev]).push_back(st);
 }
 
 // sum w, sum w x^2: block-level tree + one atomicAdd pair per block

@@ -80,9 +80,12 @@ struct ScopedEvents {
 struct ScopedStream {
     ScopedStream() {}
     ~ScopedStream();
-    int acquire();                   // a non-blocking stream nobody else holds right now
+    // a non-blocking stream nobody else holds right now; high_priority: its blocks are scheduled ahead of those of
+    // default-priority streams (a latency-bound chain beside a throughput kernel)
+    int acquire(bool high_priority = false);
     cudaStream_t st = nullptr;
     int dev = -1;
+    bool high = false;
     ScopedStream(const ScopedStream&) = delete;
     ScopedStream& operator=(const ScopedStream&) = delete;
 };

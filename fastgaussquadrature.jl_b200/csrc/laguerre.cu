@@ -17,6 +17,8 @@
 #include <math.h>
 
 #include <algorithm>
+#include <cooperative_groups.h>
+
 #include <vector>
 
 #include "airy.cuh"
@@ -25,6 +27,8 @@
 #include "fgq_math.h"
 #include "gw.cuh"
 #include "jacobi_plan.h"
+
+namespace cg = cooperative_groups;
 
 namespace fgq {
 
@@ -50,6 +54,14 @@ struct LaguerreState {
     unsigned long long n_out; // reduced rule: number of nodes before the first underflowed weight
     unsigned int n_flagged;
     unsigned int warn;
+    unsigned int n_flagged_b; // large rules: candidates flagged by the bulk-only launch (their own list)
+    unsigned int fallback;    // large rules: the Bessel hand-over was not inside the search window
+};
+
+// large rules: the expansion a window / Airy-candidate node did NOT get into x, w (see laguerre_edge_eval_kernel)
+struct __align__(32) LagSide {
+    double x, w, delta;
+    unsigned long long warn;
 };
 
 // Julia's max/min propagate NaN (CUDA's fmax/fmin drop it)
@@ -301,6 +313,8 @@ __global__ void laguerre_state_init_kernel(LaguerreState* st, int64_t n) {
     st->n_out = (unsigned long long)n;
     st->n_flagged = 0;
     st->warn = 0;
+    st->n_flagged_b = 0;
+    st->fallback = 0;
 }
 
 // first k where delta_bulk < delta_bessel (:138-151), searched over k in [k_first, k_last] with a grid
@@ -335,16 +349,9 @@ laguerre_handover_airy_kernel(const LaguerreParams p, LaguerreState* st) {
     if (da < du) atomicMin(&st->k_a, (unsigned long long)k);
 }
 
-// One thread per node: the region walk of gausslaguerre_asy (:138-253) with the hand-over indices known.
-__global__ void __launch_bounds__(LAG_THREADS)
-laguerre_nodes_kernel(const LaguerreParams p, LaguerreState* st, double* x, double* w, double* delta_out,
-                      unsigned int* flagged) {
-    const int64_t k = 1 + (int64_t)blockIdx.x * LAG_THREADS + threadIdx.x;
-    if (k > p.n) return;
-    const int64_t kb = (int64_t)st->k_b;  // n + 1 when the Bessel expansion never loses
-    const int64_t ka = (int64_t)st->k_a;  // n + 1 when the bulk expansion never loses
-    unsigned int warn = 0;
-    double xk, wk, delta;
+// The region walk of gausslaguerre_asy (:138-253) for node k with the hand-over indices known.
+__device__ __forceinline__ void laguerre_node_walk(const LaguerreParams& p, int64_t k, int64_t kb, int64_t ka, double& xk,
+                                                   double& wk, double& delta, unsigned int& warn) {
     if (k <= kb) {
         // loop A: both expansions are evaluated; Bessel is used except at k_b itself
         double xb, wb, db, xu, wu, du;
@@ -368,6 +375,19 @@ laguerre_nodes_kernel(const LaguerreParams p, LaguerreState* st, double* x, doub
     } else {
         laguerre_airy(p, k, xk, wk, delta);  // loop D
     }
+}
+
+// One thread per node.
+__global__ void __launch_bounds__(LAG_THREADS)
+laguerre_nodes_kernel(const LaguerreParams p, LaguerreState* st, double* x, double* w, double* delta_out,
+                      unsigned int* flagged) {
+    const int64_t k = 1 + (int64_t)blockIdx.x * LAG_THREADS + threadIdx.x;
+    if (k > p.n) return;
+    const int64_t kb = (int64_t)st->k_b;  // n + 1 when the Bessel expansion never loses
+    const int64_t ka = (int64_t)st->k_a;  // n + 1 when the bulk expansion never loses
+    unsigned int warn = 0;
+    double xk, wk, delta;
+    laguerre_node_walk(p, k, kb, ka, xk, wk, delta, warn);
     x[k - 1] = xk;
     w[k - 1] = wk;
     delta_out[k - 1] = delta;
@@ -422,24 +442,271 @@ __device__ void gl_rec_newton_dev(const P& p, double x0, bool computeweight, dou
     }
 }
 
+// evalLaguerreRec with a WARP per evaluation (every lane holds the same x and returns the same values).  One thread
+// spends ~500 cycles per recurrence step, nearly all of it on the two square roots and four quotients of the step's
+// coefficients, which do not depend on the running values: here lane j forms the coefficients of step k0 + j, and the
+// 32 steps are then advanced (by every lane alike) with broadcasts — what remains in the dependent chain is two
+// products and a difference for p_n, and a product, a sum, the quotient by sqrt(k (alpha + k)) and a difference for
+// p_n'.  Operation for operation the expressions of eval_laguerre_rec, so the same bits.
+__device__ void eval_laguerre_rec_warp(int64_t n, double alpha, double pn0, double x, double& pn_out, double& pnd_out) {
+    const int lane = threadIdx.x & 31;
+    double pnprev = 0.0, pn = pn0, pndprev = 0.0, pnd = 0.0;
+    bool dead = false;
+    for (int64_t k0 = 1; k0 <= n && !dead; k0 += 32) {
+        const double dk = (double)(k0 + lane);
+        const double c = x - 2 * dk - alpha + 1;
+        const double sq = sqrt(dk * (alpha + dk));
+        const double a = c / sq;
+        const double b = sqrt((dk - 1 + alpha) * (dk - 1) / dk / (dk + alpha));
+        const int m = n - k0 + 1 < 32 ? (int)(n - k0 + 1) : 32;
+        for (int j = 0; j < m; ++j) {
+            const double aj = __shfl_sync(0xffffffffu, a, j), bj = __shfl_sync(0xffffffffu, b, j);
+            const double cj = __shfl_sync(0xffffffffu, c, j), sj = __shfl_sync(0xffffffffu, sq, j);
+            const double pnold = pn;
+            pn = aj * pnold - bj * pnprev;
+            pnprev = pnold;
+            const double pndold = pnd;
+            pnd = (pnold + cj * pndold) / sj - bj * pndprev;
+            pndprev = pndold;
+            if (pn != pn && pnprev != pnprev && pnd != pnd && pndprev != pndprev) {
+                dead = true;
+                break;
+            }
+        }
+    }
+    pn_out = pn;
+    pnd_out = pnd;
+}
+
+// gl_rec_newton (:547-579) on eval_laguerre_rec_warp: called by whole warps with lane-uniform arguments
+template <class P>
+__device__ void gl_rec_newton_warp(const P& p, double x0, double& xk_out, double& wk_out, unsigned int* warn) {
+    const double eps = 2.220446049250313e-16;
+    double step = x0, xk = x0, xk_prev = x0, pn_prev = 1.7976931348623157e308, pn_deriv = 0.0;
+    int iter = 0;
+    while (fabs(step) > 40 * eps * xk && iter < 20) {
+        iter += 1;
+        double pn;
+        eval_laguerre_rec_warp(p.n, p.alpha, p.pn0, xk, pn, pn_deriv);
+        if (fabs(pn) >= fabs(pn_prev) * (1 - 50 * eps)) {
+            xk = xk_prev;
+            break;
+        }
+        step = pn / pn_deriv;
+        xk_prev = xk;
+        xk -= step;
+        pn_prev = pn;
+    }
+    if (xk < 0 || xk > p.xmax || iter == 20) *warn |= (unsigned int)FGQ_WARN_NEWTON_MAXITER;
+    xk_out = xk;
+    double pn_min1, dummy;
+    eval_laguerre_rec_warp(p.n - 1, p.alpha, p.pn0, xk, pn_min1, dummy);
+    wk_out = p.wnorm / pn_min1 / pn_deriv;
+}
+
 // the recompute hook (:153-162 etc.): gl_rec_newton for every flagged node, accepted only if it stays
-// within 100 delta of the asymptotic value
-__global__ void laguerre_recompute_kernel(const LaguerreParams p, LaguerreState* st, double* x, double* w,
-                                          const double* delta_in, const unsigned int* flagged) {
-    const unsigned int cnt = st->n_flagged;
-    for (unsigned int f = blockIdx.x * blockDim.x + threadIdx.x; f < cnt; f += gridDim.x * blockDim.x) {
+// within 100 delta of the asymptotic value.  One warp per flagged node; first / stride count threads of whole warps.
+__device__ __forceinline__ void laguerre_recompute_list(const LaguerreParams& p, LaguerreState* st, double* x, double* w,
+                                                        const double* delta_in, const unsigned int* flagged,
+                                                        unsigned int cnt, unsigned int first, unsigned int stride) {
+    for (unsigned int f = first >> 5; f < cnt; f += stride >> 5) {
         const unsigned int i = flagged[f];
         const double x0 = x[i];
         const double delta = delta_in[i];
         unsigned int warn = 0;
         double xk, wk;
-        gl_rec_newton_dev(p, x0, true, xk, wk, &warn);
-        if (warn) atomicOr(&st->warn, warn);
-        if (fabs(xk - x0) < 100 * delta) {
-            x[i] = xk;
-            w[i] = wk;
+        gl_rec_newton_warp(p, x0, xk, wk, &warn);
+        if ((threadIdx.x & 31) == 0) {
+            if (warn) atomicOr(&st->warn, warn);
+            if (fabs(xk - x0) < 100 * delta) {
+                x[i] = xk;
+                w[i] = wk;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// (the list of a large rule is void once the fall-back has been raised)
+__global__ void laguerre_recompute_kernel(const LaguerreParams p, LaguerreState* st, double* x, double* w,
+                                          const double* delta_in, const unsigned int* flagged) {
+    if (st->fallback) return;
+    laguerre_recompute_list(p, st, x, w, delta_in, flagged, st->n_flagged, blockIdx.x * blockDim.x + threadIdx.x,
+                            gridDim.x * blockDim.x);
+}
+
+// ---- large rules: the hand-over searches beside the bulk nodes ----
+// Whatever the two searches return, the nodes between the Bessel search window (a few sqrt(n)) and k_airy = 0.9 n
+// are bulk nodes (loop B) — 90 % of the rule — so they do not have to wait for the searches.  Three launches replace
+// search, search, nodes:
+//   edge_eval    (high-priority side stream) window nodes k <= W: Bessel into x, w and bulk into `side`, k_b by
+//                atomicMin; Airy candidates k >= k_airy: bulk into x, w and Airy into `side`, k_a by atomicMin — what
+//                the two search launches computed and threw away
+//   edge_select  (same stream) picks per edge node what the region walk takes, with k_b, k_a known; its flagged list
+//                is recomputed on that stream at once
+//   bulk_nodes   (the caller's stream, concurrently) nodes W < k < k_airy, their own flagged list
+// and laguerre_finish_kernel closes the rule.  If the window did not hold k_b (never seen; FGQ_LAGUERRE_WINDOW forces
+// it in the tests), edge_select raises `fallback`, the dependent launches return, and the finish kernel redoes the
+// rule the sequential way.
+__global__ void __launch_bounds__(LAG_THREADS)
+laguerre_edge_eval_kernel(const LaguerreParams p, LaguerreState* st, int64_t window, unsigned window_blocks,
+                          double* x, double* w, double* delta_out, LagSide* side) {
+    if (blockIdx.x < window_blocks) {
+        const int64_t k = 1 + (int64_t)blockIdx.x * LAG_THREADS + threadIdx.x;
+        if (k > window) return;
+        unsigned int warn = 0;
+        double xb, wb, db, xu, wu, du;
+        laguerre_bessel(p, laguerre_jak(p, k), xb, wb, db);
+        laguerre_bulk(p, k, xu, wu, du, &warn);
+        if (du < db) atomicMin(&st->k_b, (unsigned long long)k);
+        x[k - 1] = xb;
+        w[k - 1] = wb;
+        delta_out[k - 1] = jl_min(db, du);
+        LagSide s;
+        s.x = xu; s.w = wu; s.delta = du; s.warn = warn;
+        side[k - 1] = s;
+    } else {
+        const int64_t j = (int64_t)(blockIdx.x - window_blocks) * LAG_THREADS + threadIdx.x;
+        const int64_t k = p.k_airy + j;  // k_airy > window >= 1 on this path
+        if (k > p.n) return;
+        unsigned int warn = 0;
+        double xu, wu, du, xa, wa, da;
+        laguerre_bulk(p, k, xu, wu, du, &warn);
+        laguerre_airy(p, k, xa, wa, da);
+        if (da < du) atomicMin(&st->k_a, (unsigned long long)k);
+        x[k - 1] = xu;
+        w[k - 1] = wu;
+        delta_out[k - 1] = jl_min(da, du);
+        LagSide s;
+        s.x = xa; s.w = wa; s.delta = da; s.warn = warn;
+        side[window + j] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+laguerre_edge_select_kernel(const LaguerreParams p, LaguerreState* st, int64_t window, double* x, double* w,
+                            double* delta_out, const LagSide* side, unsigned int* flagged) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t kb = (int64_t)st->k_b, ka = (int64_t)st->k_a;
+    if (kb > window) {  // the sentinel n + 1: not inside the window
+        if (i == 0) st->fallback = 1;
+        return;
+    }
+    const int64_t k = i < window ? i + 1 : p.k_airy + (i - window);
+    if (k > p.n) return;
+    const LagSide s = side[i];
+    unsigned int warn = (unsigned int)s.warn;
+    double delta = delta_out[k - 1];
+    if (i < window) {
+        // k < k_b: Bessel stays (loop A); k_b itself: bulk, delta = the minimum; beyond: loop B
+        if (k >= kb) {
+            x[k - 1] = s.x;
+            w[k - 1] = s.w;
+            if (k > kb) delta_out[k - 1] = delta = s.delta;
+        }
+    } else {
+        // k < k_a: bulk stays (loop C); k_a itself: Airy, delta = the minimum; beyond: loop D, which never
+        // evaluates the bulk expansion (so its Newton warning does not count)
+        if (k >= ka) {
+            x[k - 1] = s.x;
+            w[k - 1] = s.w;
+            if (k > ka) {
+                delta_out[k - 1] = delta = s.delta;
+                warn = 0;
+            }
         }
     }
+    if (delta > 1.0e-13) flagged[atomicAdd(&st->n_flagged, 1u)] = (unsigned int)(k - 1);
+    if (warn) atomicOr(&st->warn, warn);
+}
+
+__global__ void __launch_bounds__(LAG_THREADS)
+laguerre_bulk_nodes_kernel(const LaguerreParams p, LaguerreState* st, int64_t k_first, int64_t k_last, double* x,
+                           double* w, double* delta_out, unsigned int* flagged_b) {
+    const int64_t k = k_first + (int64_t)blockIdx.x * LAG_THREADS + threadIdx.x;
+    if (k > k_last) return;
+    unsigned int warn = 0;
+    double xk, wk, delta;
+    laguerre_bulk(p, k, xk, wk, delta, &warn);
+    x[k - 1] = xk;
+    w[k - 1] = wk;
+    delta_out[k - 1] = delta;
+    if (delta > 1.0e-13) flagged_b[atomicAdd(&st->n_flagged_b, 1u)] = (unsigned int)(k - 1);
+    if (warn) atomicOr(&st->warn, warn);
+}
+
+// Last launch of a large rule (cooperative, one co-resident grid), three steps in one:
+//   * only after edge_select raised `fallback`: the sequential form of the rule, with grid barriers where the
+//     separate launches of the small-n path are;
+//   * the recompute hook for the bulk-only launch's flagged list (normally empty);
+//   * the reduced length (:163-169 ...): first index whose weight is below 10 floatmin.  Grid-stride from the low
+//     end with a poll of the running minimum: ~98 % of the weights of a large rule underflow, so only the first
+//     pass over the grid reads anything.
+__global__ void __launch_bounds__(LAG_THREADS)
+laguerre_finish_kernel(const LaguerreParams p, LaguerreState* st, int64_t window, double* x, double* w,
+                       double* delta_out, unsigned int* flagged, const unsigned int* flagged_b) {
+    cg::grid_group grid = cg::this_grid();
+    const int64_t tid = (int64_t)blockIdx.x * LAG_THREADS + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * LAG_THREADS;
+    if (st->fallback) {  // written by an earlier launch: the same for every thread
+        if (tid == 0) {
+            st->k_a = (unsigned long long)(p.n + 1);  // the speculative Airy search assumed k_b < k_airy
+            st->n_flagged = 0;
+            st->n_flagged_b = 0;
+            st->warn = 0;
+        }
+        grid.sync();
+        for (int64_t k = window + 1 + tid; k <= p.n; k += stride) {
+            if ((unsigned long long)k >= *((volatile unsigned long long*)&st->k_b)) break;
+            double xb, wb, db, xu, wu, du;
+            laguerre_bessel(p, laguerre_jak(p, k), xb, wb, db);
+            laguerre_bulk(p, k, xu, wu, du, nullptr);
+            if (du < db) atomicMin(&st->k_b, (unsigned long long)k);
+        }
+        grid.sync();
+        const int64_t kb = (int64_t)st->k_b;
+        {
+            const int64_t start = kb + 1 > p.k_airy ? kb + 1 : p.k_airy;
+            for (int64_t k = start + tid; k <= p.n; k += stride) {
+                double xu, wu, du, xa, wa, da;
+                laguerre_bulk(p, k, xu, wu, du, nullptr);
+                laguerre_airy(p, k, xa, wa, da);
+                if (da < du) atomicMin(&st->k_a, (unsigned long long)k);
+            }
+        }
+        grid.sync();
+        const int64_t ka = (int64_t)st->k_a;
+        for (int64_t k = 1 + tid; k <= p.n; k += stride) {
+            unsigned int warn = 0;
+            double xk, wk, delta;
+            laguerre_node_walk(p, k, kb, ka, xk, wk, delta, warn);
+            x[k - 1] = xk;
+            w[k - 1] = wk;
+            delta_out[k - 1] = delta;
+            if (delta > 1.0e-13) flagged[atomicAdd(&st->n_flagged, 1u)] = (unsigned int)(k - 1);
+            if (warn) atomicOr(&st->warn, warn);
+        }
+        grid.sync();
+        laguerre_recompute_list(p, st, x, w, delta_out, flagged, st->n_flagged, (unsigned int)tid, (unsigned int)stride);
+        grid.sync();
+    } else if (st->n_flagged_b) {  // written by the bulk-only launch: the same for every thread
+        laguerre_recompute_list(p, st, x, w, delta_out, flagged_b, st->n_flagged_b, (unsigned int)tid, (unsigned int)stride);
+        grid.sync();
+    }
+    unsigned long long cand = ~0ull;
+    for (int64_t i = tid; i < p.n; i += stride) {
+        if ((unsigned long long)i >= *((volatile unsigned long long*)&st->n_out)) break;
+        if (fabs(w[i]) < 10 * 2.2250738585072014e-308) {
+            cand = (unsigned long long)i;
+            break;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, cand, o);
+        cand = other < cand ? other : cand;
+    }
+    if ((threadIdx.x & 31) == 0 && cand < *((volatile unsigned long long*)&st->n_out)) atomicMin(&st->n_out, cand);
 }
 
 // Small rules, one thread (the work is inherently sequential and tiny):
@@ -728,6 +995,7 @@ __global__ void laguerre_reduced_kernel(int64_t n, const double* w, LaguerreStat
 
 using namespace fgq;
 
+constexpr int MAX_ATTR_DEV_LAG = 16;
 constexpr int64_t LAG_REC_MAX = 4096;  // sequential recurrence rule: one thread, O(n^2) dependent steps
 
 static int laguerre_check(int64_t n, double alpha) {
@@ -796,9 +1064,38 @@ static LaguerreParams laguerre_params(int64_t n, double alpha, bool for_rule = t
     return p;
 }
 
+// Large rules (n >= LAG_FAST_MIN): the Bessel hand-over is searched in a window of a few sqrt(n) (it sits at
+// ~1.8 sqrt(n)); the window ends below k_airy = floor(0.9 n) for every such n.
+constexpr int64_t LAG_FAST_MIN = 8192;
+
+static int64_t laguerre_window(int64_t n) {
+    int64_t window = 8 * (int64_t)ceil(sqrt((double)n));
+    if (window < 1024) window = 1024;
+    if (window > n) window = n;
+    return window;
+}
+
+// FGQ_LAGUERRE_FAST=0: the sequential launch chain for every n (regression checks)
+static bool laguerre_use_fast() {
+    static const bool on = []() {
+        const char* e = getenv("FGQ_LAGUERRE_FAST");
+        if (e && atoi(e) == 0) return false;
+        int dev = 0, coop = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) return false;
+        return coop != 0;
+    }();
+    return on;
+}
+
 extern "C" int64_t fgq_gausslaguerre_workspace_bytes(int64_t n) {
     if (n < 0) return 0;
-    return 256 + 8 * n + 4 * n + 64;
+    int64_t bytes = 256 + 8 * n + 4 * n + 64;
+    if (n >= LAG_FAST_MIN) {
+        const int64_t k_airy = (int64_t)floor(0.9 * (double)n);
+        bytes += 32 + (int64_t)sizeof(LagSide) * (laguerre_window(n) + (n - k_airy + 1));
+    }
+    return bytes;
 }
 
 extern "C" int fgq_gausslaguerre_device(int64_t n, double alpha, double* x_dev, double* w_dev,
@@ -832,10 +1129,63 @@ extern "C" int fgq_gausslaguerre_device(int64_t n, double alpha, double* x_dev, 
         return FGQ_OK;
     }
     const unsigned blocks = (unsigned)((n + LAG_THREADS - 1) / LAG_THREADS);
+    int64_t window = laguerre_window(n);
+    if (n >= LAG_FAST_MIN && laguerre_use_fast()) {
+        // FGQ_LAGUERRE_WINDOW=<count>: a smaller search window (the tests use it to reach the fall-back)
+        static const int64_t window_env = []() {
+            const char* e = getenv("FGQ_LAGUERRE_WINDOW");
+            return e ? (int64_t)atoll(e) : (int64_t)0;
+        }();
+        if (window_env > 0 && window_env < window) window = window_env;
+        const int64_t cand = n - p.k_airy + 1;
+        LagSide* side = (LagSide*)(((uintptr_t)(flagged + n) + 31) & ~(uintptr_t)31);
+        unsigned int* flagged_b = flagged + (window + cand);
+        ScopedStream edge_holder;
+        ScopedEvents evs;
+        FGQ_TRY(edge_holder.acquire(true));
+        FGQ_TRY(evs.acquire(2));
+        cudaStream_t edge = edge_holder.st;
+        FGQ_CUDA_TRY(cudaEventRecord(evs.ev[0], st));  // after the state reset
+        FGQ_CUDA_TRY(cudaStreamWaitEvent(edge, evs.ev[0], 0));
+        const unsigned window_blocks = (unsigned)((window + LAG_THREADS - 1) / LAG_THREADS);
+        const unsigned cand_blocks = (unsigned)((cand + LAG_THREADS - 1) / LAG_THREADS);
+        laguerre_edge_eval_kernel<<<window_blocks + cand_blocks, LAG_THREADS, 0, edge>>>(p, state, window, window_blocks,
+                                                                                      x_dev, w_dev, delta, side);
+        FGQ_LAUNCH_CHECK();
+        const int64_t nb = p.k_airy - 1 - window;  // bulk-only nodes window < k < k_airy
+        laguerre_bulk_nodes_kernel<<<(unsigned)((nb + LAG_THREADS - 1) / LAG_THREADS), LAG_THREADS, 0, st>>>(
+            p, state, window + 1, p.k_airy - 1, x_dev, w_dev, delta, flagged_b);
+        FGQ_LAUNCH_CHECK();
+        laguerre_edge_select_kernel<<<(unsigned)((window + cand + 255) / 256), 256, 0, edge>>>(p, state, window, x_dev, w_dev,
+                                                                                            delta, side, flagged);
+        FGQ_LAUNCH_CHECK();
+        laguerre_recompute_kernel<<<64, 64, 0, edge>>>(p, state, x_dev, w_dev, delta, flagged);
+        FGQ_LAUNCH_CHECK();
+        FGQ_CUDA_TRY(cudaEventRecord(evs.ev[1], edge));
+        FGQ_CUDA_TRY(cudaStreamWaitEvent(st, evs.ev[1], 0));
+        {
+            static int grid_cache[MAX_ATTR_DEV_LAG] = {0};
+            int dev = 0;
+            FGQ_CUDA_TRY(cudaGetDevice(&dev));
+            int grid = dev < MAX_ATTR_DEV_LAG ? grid_cache[dev] : 0;
+            if (grid == 0) {
+                int per_sm = 0, sms = 0;
+                FGQ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, laguerre_finish_kernel, LAG_THREADS, 0));
+                FGQ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                grid = per_sm * sms;
+                if (grid < 1) grid = 1;
+                if (dev < MAX_ATTR_DEV_LAG) grid_cache[dev] = grid;
+            }
+            const LaguerreParams* pp = &p;
+            void* args[] = {(void*)pp, (void*)&state, (void*)&window, (void*)&x_dev, (void*)&w_dev, (void*)&delta,
+                            (void*)&flagged, (void*)&flagged_b};
+            FGQ_CUDA_TRY(cudaLaunchCooperativeKernel((void*)laguerre_finish_kernel, dim3((unsigned)grid),
+                                                     dim3(LAG_THREADS), args, 0, st));
+            count_launch();
+        }
+        return FGQ_OK;
+    }
     {
-        int64_t window = 8 * (int64_t)ceil(sqrt((double)n));
-        if (window < 1024) window = 1024;
-        if (window > n) window = n;
         laguerre_handover_bessel_kernel<<<(unsigned)((window + LAG_THREADS - 1) / LAG_THREADS), LAG_THREADS, 0, st>>>(
             p, state, 1, window);
         FGQ_LAUNCH_CHECK();
@@ -868,7 +1218,7 @@ extern "C" int fgq_gausslaguerre_stats(const void* workspace_dev, int64_t* k_b, 
     FGQ_CUDA_TRY(cudaMemcpy(&h, workspace_dev, sizeof(h), cudaMemcpyDeviceToHost));
     if (k_b) *k_b = (int64_t)h.k_b;
     if (k_a) *k_a = (int64_t)h.k_a;
-    if (n_flagged) *n_flagged = (int64_t)h.n_flagged;
+    if (n_flagged) *n_flagged = (int64_t)h.n_flagged + (int64_t)h.n_flagged_b;
     if (n_reduced) *n_reduced = (int64_t)h.n_out;
     if (h.warn) add_warning((int)h.warn);
     return FGQ_OK;
