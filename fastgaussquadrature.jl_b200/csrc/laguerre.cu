@@ -1064,14 +1064,17 @@ static LaguerreParams laguerre_params(int64_t n, double alpha, bool for_rule = t
     return p;
 }
 
-// Large rules (n >= LAG_FAST_MIN): the Bessel hand-over is searched in a window of a few sqrt(n) (it sits at
-// ~1.8 sqrt(n)); the window ends below k_airy = floor(0.9 n) for every such n.
-constexpr int64_t LAG_FAST_MIN = 8192;
+// The asymptotic rule (n >= 128): the Bessel hand-over is searched in a window of a few sqrt(n) (it sits at
+// ~1.8 sqrt(n)) that ends below k_airy = floor(0.9 n); for small n the window is everything below k_airy and there
+// are no bulk-only nodes.
+constexpr int64_t LAG_FAST_MIN = 128;
 
 static int64_t laguerre_window(int64_t n) {
     int64_t window = 8 * (int64_t)ceil(sqrt((double)n));
     if (window < 1024) window = 1024;
-    if (window > n) window = n;
+    const int64_t k_airy = (int64_t)floor(0.9 * (double)n);
+    if (window > k_airy - 1) window = k_airy - 1;
+    if (window < 1) window = 1;
     return window;
 }
 
@@ -1153,9 +1156,11 @@ extern "C" int fgq_gausslaguerre_device(int64_t n, double alpha, double* x_dev, 
                                                                                       x_dev, w_dev, delta, side);
         FGQ_LAUNCH_CHECK();
         const int64_t nb = p.k_airy - 1 - window;  // bulk-only nodes window < k < k_airy
-        laguerre_bulk_nodes_kernel<<<(unsigned)((nb + LAG_THREADS - 1) / LAG_THREADS), LAG_THREADS, 0, st>>>(
-            p, state, window + 1, p.k_airy - 1, x_dev, w_dev, delta, flagged_b);
-        FGQ_LAUNCH_CHECK();
+        if (nb > 0) {
+            laguerre_bulk_nodes_kernel<<<(unsigned)((nb + LAG_THREADS - 1) / LAG_THREADS), LAG_THREADS, 0, st>>>(
+                p, state, window + 1, p.k_airy - 1, x_dev, w_dev, delta, flagged_b);
+            FGQ_LAUNCH_CHECK();
+        }
         laguerre_edge_select_kernel<<<(unsigned)((window + cand + 255) / 256), 256, 0, edge>>>(p, state, window, x_dev, w_dev,
                                                                                             delta, side, flagged);
         FGQ_LAUNCH_CHECK();

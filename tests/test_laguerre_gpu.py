@@ -128,7 +128,7 @@ def test_small_rules_parity(fgq, alpha):
 
 
 def test_large_rule_launch_forms_agree():
-    """n >= 8192 runs the hand-over searches beside the bulk nodes (laguerre_edge_eval / edge_select / bulk_nodes /
+    """The asymptotic rule runs the hand-over searches beside the bulk nodes (laguerre_edge_eval / edge_select / bulk_nodes /
     finish).  Its results, hand-over indices, flagged counts and reduced lengths must equal, bit for bit (digest), the
     sequential launch chain (FGQ_LAGUERRE_FAST=0) and its own fall-back, reached by shrinking the Bessel search window
     below k_b (FGQ_LAGUERRE_WINDOW=64).  The switches are read once per process, hence the subprocesses."""
@@ -142,6 +142,6 @@ def test_large_rule_launch_forms_agree():
         r = subprocess.run([sys.executable, tool], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout)
-    assert outs[0].count("digest") == 7
+    assert outs[0].count("digest") == 12
     assert outs[0] == outs[1], "large-rule path != sequential chain"
     assert outs[2] == outs[1], "fall-back != sequential chain"

@@ -13,7 +13,7 @@ import fgq_b200  # noqa: E402
 
 L = fgq_b200.lib()
 mode = f"FAST={os.environ.get('FGQ_LAGUERRE_FAST', '1')} WINDOW={os.environ.get('FGQ_LAGUERRE_WINDOW', '-')}"
-for n, alpha in ((8192, 0.0), (10 ** 4, 0.5), (10 ** 5, 0.0), (350000, 0.44), (10 ** 6, 0.0), (10 ** 6 + 1, 2.5), (10 ** 7, -0.5)):
+for n, alpha in ((128, 0.0), (200, 0.0), (1000, -0.7), (1000, 4.5), (5000, 1.0), (8192, 0.0), (10 ** 4, 0.5), (10 ** 5, 0.0), (350000, 0.44), (10 ** 6, 0.0), (10 ** 6 + 1, 2.5), (10 ** 7, -0.5)):
     x = torch.empty(n, dtype=torch.float64, device="cuda")
     w = torch.empty(n, dtype=torch.float64, device="cuda")
     ws = torch.empty(int(L.fgq_gausslaguerre_workspace_bytes(n)) + 16, dtype=torch.uint8, device="cuda")
