@@ -410,8 +410,10 @@ __device__ __forceinline__ void jacobi_inner_rec(int n, double xj, double a, dou
 __device__ __forceinline__ void jacobi_rec_block(const JacobiRecParams& p, double* x, double* w) {
     const double PI = 3.141592653589793;
     const int tid = threadIdx.x;
-    const int h = tid >> 6;          // 0: HalfRec(n, alpha, beta, 1); 1: HalfRec(n, beta, alpha, 0)
-    const int i0 = tid & 63;
+    // Blocks of 128 threads (two warps per half: any n <= 100) or of 64 (one warp per half: n <= 64, batch launches)
+    const int hshift = blockDim.x == 128 ? 6 : 5;
+    const int h = tid >> hshift;     // 0: HalfRec(n, alpha, beta, 1); 1: HalfRec(n, beta, alpha, 0)
+    const int i0 = tid & ((1 << hshift) - 1);
     const int n = p.n;
     const int m1 = (n + 1) / 2, m2 = n / 2;
     const int m = h == 0 ? m1 : m2;
@@ -456,7 +458,8 @@ __device__ __forceinline__ void jacobi_rec_block(const JacobiRecParams& p, doubl
         if ((tid & 31) == 0) s_dx2[tid >> 5] = mx;
         __syncthreads();
         if (tid < 2 && !s_done[tid]) {
-            const double m0 = s_dx2[2 * tid], m1v = s_dx2[2 * tid + 1];
+            // the half's one or two warp maxima (all >= 0)
+            const double m0 = hshift == 6 ? s_dx2[2 * tid] : s_dx2[tid], m1v = hshift == 6 ? s_dx2[2 * tid + 1] : 0.0;
             const double mm = m1v > m0 ? m1v : m0;
             if (!(mm > 2.220446049250313e-16 / 1.0e6)) s_done[tid] = 1;
         }
@@ -481,9 +484,11 @@ __device__ __forceinline__ void jacobi_rec_block(const JacobiRecParams& p, doubl
         s_scale = p.c / sum_w;
     }
     __syncthreads();
-    if (tid < n && tid >= p.lo && tid < p.hi) {
-        x[tid - p.lo] = xs[tid];
-        w[tid - p.lo] = wsum[tid] * s_scale;
+    for (int i = tid; i < n; i += (int)blockDim.x) {
+        if (i >= p.lo && i < p.hi) {
+            x[i - p.lo] = xs[i];
+            w[i - p.lo] = wsum[i] * s_scale;
+        }
     }
 }
 
@@ -495,6 +500,8 @@ __global__ void __launch_bounds__(128) jacobi_rec_kernel(const JacobiRecParams p
 // launch, so a batch is bit-identical to the concatenation of single calls.  kind 1: the one-node rule
 // (gaussjacobi.jl:42-43; node in `alpha`, weight in `c`); kind 2: jacobi_rec (:61-155); kind 0: nothing
 // to do here (empty, or served by the Legendre / Chebyshev / Golub-Welsch routes from the host loop).
+// The host sorts the batch into two classes, n > 64 (blocks of 128 threads, two warps per half) and n <= 64
+// (blocks of 64, one warp per half), so that a resident block has no warp without nodes.
 struct JacobiBatchRule {
     int32_t n;
     int32_t kind;
@@ -967,11 +974,26 @@ extern "C" int fgq_gaussjacobi_batch_device(int64_t nrules, const int32_t* n_i, 
     }
     cudaStream_t st = as_stream(stream);
     char* ws = (char*)workspace_dev;
-    FGQ_CUDA_TRY(cudaMemcpyAsync(ws + JACOBI_BATCH_GW_BYTES, rules.data(), rules.size() * sizeof(JacobiBatchRule),
-                                 cudaMemcpyHostToDevice, st));
-    jacobi_small_batch_kernel<<<(unsigned)nrules, 128, 0, st>>>((const JacobiBatchRule*)(ws + JACOBI_BATCH_GW_BYTES),
-                                                                x_dev, w_dev);
-    FGQ_LAUNCH_CHECK();
+    // rules with work for the batch kernel, wide class (n > 64) first; each carries its own output offset
+    std::vector<JacobiBatchRule> sorted;
+    sorted.reserve(rules.size());
+    for (const JacobiBatchRule& r : rules)
+        if (r.kind != 0 && r.n > 64) sorted.push_back(r);
+    const size_t n_wide = sorted.size();
+    for (const JacobiBatchRule& r : rules)
+        if (r.kind != 0 && r.n <= 64) sorted.push_back(r);
+    if (!sorted.empty())
+        FGQ_CUDA_TRY(cudaMemcpyAsync(ws + JACOBI_BATCH_GW_BYTES, sorted.data(), sorted.size() * sizeof(JacobiBatchRule),
+                                     cudaMemcpyHostToDevice, st));
+    const JacobiBatchRule* drules = (const JacobiBatchRule*)(ws + JACOBI_BATCH_GW_BYTES);
+    if (n_wide) {
+        jacobi_small_batch_kernel<<<(unsigned)n_wide, 128, 0, st>>>(drules, x_dev, w_dev);
+        FGQ_LAUNCH_CHECK();
+    }
+    if (sorted.size() > n_wide) {
+        jacobi_small_batch_kernel<<<(unsigned)(sorted.size() - n_wide), 64, 0, st>>>(drules + n_wide, x_dev, w_dev);
+        FGQ_LAUNCH_CHECK();
+    }
     for (int64_t i : others) {
         const JacobiBatchRule& r = rules[(size_t)i];
         FGQ_TRY(fgq_gaussjacobi_device(r.n, r.alpha, r.beta, 0, r.n, x_dev + r.off, w_dev + r.off, ws, stream));
