@@ -8,6 +8,7 @@ from ._lib import DomainError, FGQError, NotImplementedOnDevice, build, lib  # n
 from . import multi  # noqa: F401  (single-process multi-GPU face of the C ABI)
 from .api import (  # noqa: F401
     approx_besselroots,
+    empty_pinned,
     besselroots,
     gausschebyshev,
     gausschebyshevt,

@@ -38,6 +38,8 @@ SIGNATURES = {
     "fgq_warnings": (ctypes.c_int, []),
     "fgq_device_count": (ctypes.c_int, []),
     "fgq_launch_count": (_i64, []),
+    "fgq_host_alloc": (ctypes.c_int, [_i64, _vp]),
+    "fgq_host_free": (ctypes.c_int, [_vp]),
     "fgq_gausslegendre_host": (ctypes.c_int, [_i64, _vp, _vp]),
     "fgq_gausslegendre_host_slice": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp]),
     "fgq_gausslegendre_host_pair": (ctypes.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -27,13 +27,41 @@ def _as_int(n) -> int:
     return int(n)
 
 
+class _PinnedBlock:
+    """Owner of one fgq_host_alloc block (released when the last array viewing it is collected)."""
+
+    def __init__(self, nbytes: int):
+        p = ctypes.c_void_p()
+        check(lib().fgq_host_alloc(nbytes, ctypes.byref(p)))
+        self.ptr, self.nbytes = p.value, nbytes
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            try:
+                lib().fgq_host_free(self.ptr)
+            except Exception:
+                pass
+            self.ptr = None
+
+
+def empty_pinned(n: int) -> np.ndarray:
+    """A length-n float64 array in page-locked memory from the library (``fgq_host_alloc``): a destination the
+    ``*_host`` calls fill by DMA, without staging and without first-touch page faults.  Reuse it across calls."""
+    n = int(n)
+    if n < 0:
+        raise ValueError("n must be non-negative")
+    if n == 0:
+        return np.empty(0, dtype=np.float64)
+    block = _PinnedBlock(8 * n)
+    buf = (ctypes.c_double * n).from_address(block.ptr)
+    buf._fgq_owner = block            # the ctypes array is the ndarray's base: keeps the block alive
+    return np.frombuffer(buf, dtype=np.float64, count=n)
+
+
 def _host_pair(n: int, pinned: bool):
-    """Two length-n float64 host arrays; pinned (page-locked) ones come from torch."""
+    """Two length-n float64 host arrays; pinned (page-locked) ones come from fgq_host_alloc."""
     if pinned:
-        import torch
-        tx = torch.empty(n, dtype=torch.float64, pin_memory=True)
-        tw = torch.empty(n, dtype=torch.float64, pin_memory=True)
-        return tx.numpy(), tw.numpy()
+        return empty_pinned(n), empty_pinned(n)
     return np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
 
 

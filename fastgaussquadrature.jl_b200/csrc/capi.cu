@@ -240,6 +240,25 @@ extern "C" int fgq_device_count(void) {
     return n;
 }
 
+extern "C" int fgq_host_alloc(int64_t bytes, void** out) {
+    clear_status();
+    if (!out || bytes < 0) {
+        set_error("fgq_host_alloc: invalid arguments");
+        return FGQ_EINVAL;
+    }
+    *out = nullptr;
+    if (bytes == 0) return FGQ_OK;
+    FGQ_CUDA_TRY(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+    return FGQ_OK;
+}
+
+extern "C" int fgq_host_free(void* p) {
+    clear_status();
+    if (!p) return FGQ_OK;
+    FGQ_CUDA_TRY(cudaFreeHost(p));
+    return FGQ_OK;
+}
+
 extern "C" int fgq_rule_moments_device(const double* x_dev, const double* w_dev, int64_t count,
                                        double* sums_dev, void* stream) {
     clear_status();

@@ -49,6 +49,14 @@ int fgq_warnings(void);
 /* number of visible CUDA devices (0 => every compute entry point fails with FGQ_ECUDA) */
 int fgq_device_count(void);
 
+/* Page-locked host memory for the destinations of the *_host calls.  The reference returns freshly allocated
+ * arrays (`Vector{Float64}(undef, n)`, src/gausslegendre.jl:244-248): at n = 1e9 the first touch of such a 16 GB
+ * result costs ~0.3 s of page faults, three times the whole transfer.  A client that reuses its result vectors
+ * (or wraps these: `unsafe_wrap(Vector{Float64}, ptr, n)`) gets the DMA straight into place instead.  The memory
+ * is usable from every device; fgq_host_free(NULL) is a no-op. */
+int fgq_host_alloc(int64_t bytes, void** out);
+int fgq_host_free(void* p);
+
 /* ---- Gauss-Legendre: gausslegendre(n) — src/gausslegendre.jl:22-69 ---------------------- */
 
 /* x[0..n), w[0..n) on the host.  n < 0 -> FGQ_EDOMAIN (gausslegendre.jl:26). */

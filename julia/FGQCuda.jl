@@ -22,6 +22,27 @@ function check(rc::Cint, arg)
     error("libfgq_cuda: rc=$rc: $msg")                  # CUDA failure; there is no CPU fallback
 end
 
+# Page-locked result vectors (fgq_host_alloc): `x = pinned_vector(n)` is an ordinary Vector{Float64} whose memory
+# the *_host calls fill by DMA, without staging and without the first-touch page faults of `Vector{Float64}(undef, n)`
+# (0.3 s per 16 GB).  Meant to be reused: `gausslegendre!(x, w)`.
+function pinned_vector(n::Integer)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:fgq_host_alloc, libfgq), Cint, (Int64, Ptr{Ptr{Cvoid}}), 8 * n, p), n)
+    v = unsafe_wrap(Vector{Float64}, Ptr{Float64}(p[]), n; own = false)
+    n > 0 && finalizer(_ -> ccall((:fgq_host_free, libfgq), Cint, (Ptr{Cvoid},), p[]), v)
+    return v
+end
+
+# in-place form: x, w are caller-owned (e.g. pinned_vector) and of the rule's length
+function gausslegendre!(x::Vector{Float64}, w::Vector{Float64})
+    n = length(x)
+    length(w) == n || throw(ArgumentError("x and w must have the same length"))
+    n == 0 && return x, w
+    GC.@preserve x w check(ccall((:fgq_gausslegendre_host, libfgq), Cint,
+        (Int64, Ptr{Float64}, Ptr{Float64}), n, x, w), n)
+    return x, w
+end
+
 # gausslegendre(n) — src/gausslegendre.jl:22-69
 function gausslegendre(n::Integer)
     n < 0 && throw(DomainError(n, "Input n must be a non-negative integer"))

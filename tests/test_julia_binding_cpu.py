@@ -12,7 +12,7 @@ JL2C = {
     "Ptr{Float64}": {"double*"}, "Ptr{Int32}": {"int32_t*"}, "Ptr{Int64}": {"int64_t*"}, "Ptr{Cint}": {"int*"},
     "Ptr{Cfloat}": {"float*"}, "Ref{Int64}": {"int64_t*"}, "Ref{Cint}": {"int*"}, "Ref{Cfloat}": {"float*"},
     "Ptr{Cvoid}": {"void*", "double*"}, "Ptr{FGQShard}": {"fgq_shard*"}, "Ptr{Ptr{Float64}}": {"double**"},
-    "Cstring": {"char*"},
+    "Cstring": {"char*"}, "Ptr{Ptr{Cvoid}}": {"void**"},
 }
 RET = {"Cint": "int", "Int64": "int64_t", "Cstring": "char*", "Cvoid": "void"}
 

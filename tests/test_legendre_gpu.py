@@ -192,6 +192,32 @@ def test_host_pipeline_multi_chunk(fgq, oracle_mod):
     assert np.array_equal(x, xt) and np.array_equal(w, wt)
 
 
+def test_library_pinned_destinations(fgq):
+    """fgq_host_alloc / fgq_host_free: the library's page-locked destinations (what `pinned=True` and the Julia
+    wrapper's `pinned_vector` hand out) are recognised as pinned by the runtime, reusable across calls via `out=`,
+    and released with their last view."""
+    import gc
+    import torch
+    n = (1 << 21) + 5
+    x, w = fgq.empty_pinned(n), fgq.empty_pinned(n)
+    assert x.dtype == np.float64 and x.shape == (n,) and x.flags.c_contiguous and x.flags.writeable
+    assert torch.from_numpy(x).is_pinned() and torch.from_numpy(w).is_pinned()
+    x[:] = 7.0
+    fgq.gausslegendre(n, out=(x, w))
+    xr, wr = fgq.gausslegendre(n)
+    assert np.array_equal(x, xr) and np.array_equal(w, wr)
+    fgq.gausslegendre(n, out=(x, w))     # reuse
+    assert np.array_equal(x, xr)
+    view = x[10:20]
+    del x
+    gc.collect()
+    assert view[0] == xr[10]              # the block lives as long as a view does
+    assert fgq.empty_pinned(0).shape == (0,)
+    L = fgq.lib()
+    assert L.fgq_host_free(None) == 0
+    assert L.fgq_host_alloc(-1, None) == 3
+
+
 def test_batch_small_rules(fgq, oracle_mod):
     """BASELINE config C5 (reduced count here; the full 1e6-rule batch is in test_full_size)."""
     rng = np.random.default_rng(0)
