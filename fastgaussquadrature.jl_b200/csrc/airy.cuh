@@ -30,10 +30,13 @@ __device__ __forceinline__ void airy_neg(double z, double& ai, double& aip) {
         a[0] = c_airy_anchor[i][0];
         a[1] = c_airy_anchor[i][1];
         a[2] = c * a[0] * 0.5;
-#pragma unroll
-        for (int j = 1; j + 2 <= J; ++j) a[j + 2] = fma(c, a[j], a[j - 1]) / ((j + 2.0) * (j + 1.0));
+        // Rolled on purpose: unrolled, the 37 coefficients live in 74 registers and set the register count (hence the
+        // occupancy) of every kernel that inlines this function, for a branch that a few dozen nodes per rule take;
+        // rolled, a[] is thread-local memory.  Same operations in the same order.
+#pragma unroll 1
+        for (int j = 1; j + 2 <= J; ++j) a[j + 2] = fma(c, a[j], a[j - 1]) / ((double)(j + 2) * (double)(j + 1));
         double val = 0.0, der = 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int j = J; j >= 0; --j) {
             der = fma(der, h, val);
             val = fma(val, h, a[j]);

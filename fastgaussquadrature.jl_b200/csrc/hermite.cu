@@ -47,6 +47,10 @@ struct HermiteState {   // lives at the start of the workspace
     double norm_part[HERMITE_SUM_BLOCKS];  // per-block partial sums, added in block order by the last block
 };
 static_assert(sizeof(HermiteState) <= 1024, "state must fit the workspace header");
+// workspace: [0, 1024) HermiteState; [1024, HERM_WS_HEADER) two arrays of per-block |dtheta| maxima of the fused
+// kernel (alternating between sweeps); then theta, xh, wh
+constexpr int HERM_FUSED_MAX_GRID = 1024;
+constexpr int64_t HERM_WS_HEADER = 1024 + 2 * 8 * HERM_FUSED_MAX_GRID;
 
 struct HermiteParams {
     int64_t n;
@@ -101,7 +105,7 @@ __device__ double hermite_guess(const HermiteParams& p, int64_t i) {
         const double t = 3.0 * PI / 8.0 * (double)(4 * j - 1);
         const double it2 = 1.0 / (t * t);
         const double it4 = it2 * it2, it6 = it4 * it2, it8 = it4 * it4, it10 = it8 * it2;
-        r = -(pow(t, 2.0 / 3.0) * (1.0 + 5.0 / 48.0 * it2 - 5.0 / 36.0 * it4 + (77125.0 / 82944.0) * it6 -
+        r = -(cbrt(t * t) * (1.0 + 5.0 / 48.0 * it2 - 5.0 / 36.0 * it4 + (77125.0 / 82944.0) * it6 -
                                    108056875.0 / 6967296.0 * it8 + 162375596875.0 / 334430208.0 * it10));
     }
     const double r2 = r * r, r3 = r2 * r, r4 = r2 * r2, r5 = r4 * r;
@@ -149,8 +153,11 @@ __device__ __forceinline__ void hermpoly_asy_airy(const HermiteParams& p, double
                                                   double cosT, double& val, double& dval) {
     const double sin2T = 2.0 * cosT * sinT;
     const double eta = 0.5 * th - 0.25 * sin2T;
-    const double chi = -pow(3.0 * eta / 2.0, 2.0 / 3.0);
-    const double phi = pow(-chi / (sinT * sinT), 0.25);
+    // (3 eta / 2)^(2/3) and (.)^(1/4) (gausshermite.jl:176-177) as cbrt of the square and sqrt of sqrt: within 1.2 and
+    // 0.75 ulp of the exact powers (CUDA's pow: 2 ulp) at a fifth of pow's ~250 instructions each
+    const double y32 = 3.0 * eta / 2.0;
+    const double chi = -cbrt(y32 * y32);
+    const double phi = sqrt(sqrt(-chi / (sinT * sinT)));
     const double SQPI = 1.7724538509055159;  // sqrt(pi)
     double C = 2.0 * SQPI * p.musq16 * phi;
     double Airy0, Airy1;
@@ -463,19 +470,18 @@ hermite_fold_kernel(HermiteParams p, int normalize, const HermiteState* st, cons
 // compares the two).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(HERM_THREADS, 4)
-hermite_fused_kernel(HermiteParams p, int normalize, HermiteState* st, double* theta, double* xh, double* wh,
-                     int64_t lo, int64_t hi, double* x, double* w) {
+hermite_fused_kernel(HermiteParams p, int normalize, HermiteState* st, unsigned long long* block_max, double* theta,
+                     double* xh, double* wh, int64_t lo, int64_t hi, double* x, double* w) {
     cg::grid_group grid = cg::this_grid();
     const int64_t gid = (int64_t)blockIdx.x * HERM_THREADS + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * HERM_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (gid == 0) hermite_state_reset(st);
-    for (int64_t t = gid; t < p.nact; t += stride) theta[t] = hermite_theta0(p, t);
-    grid.sync();  // the reset is visible before anybody reduces into the state
+    if (gid == 0) hermite_state_reset(st);  // nothing below reduces into it: only the last writer of each field counts
     __shared__ unsigned long long sh_bits[HERM_THREADS / 32];
     for (int sweep = 0; sweep < 20; ++sweep) {
         unsigned long long bits = 0ull;
         for (int64_t t = gid; t < p.nact; t += stride) {
+            if (sweep == 0) theta[t] = hermite_theta0(p, t);  // the initial guess feeds its own node's first step
             const unsigned long long b = hermite_sweep_node(p, t, theta, xh, wh);
             bits = b > bits ? b : bits;
         }
@@ -486,14 +492,35 @@ hermite_fused_kernel(HermiteParams p, int normalize, HermiteState* st, double* t
         }
         if (lane == 0) sh_bits[wid] = bits;
         __syncthreads();
+        // The reference's stopping rule (:79) needs max |dtheta| over the whole rule: every block publishes its
+        // maximum in its own slot (no atomics, hence no reset and no barrier before the first sweep), and after
+        // the grid barrier every block reduces the slots itself.  Two slot arrays alternate: a block can only
+        // overwrite the array of sweep s in sweep s + 2, after everybody has passed the barrier of sweep s + 1.
+        unsigned long long* slots = block_max + (sweep & 1) * HERM_FUSED_MAX_GRID;
         if (tid == 0) {
             for (int i = 1; i < HERM_THREADS / 32; ++i) bits = sh_bits[i] > bits ? sh_bits[i] : bits;
-            atomicMax(&st->maxdt_bits[sweep], bits);
+            slots[blockIdx.x] = bits;
         }
         grid.sync();
-        const double mx = __longlong_as_double((long long)*((volatile unsigned long long*)&st->maxdt_bits[sweep]));
+        unsigned long long mb = 0ull;
+        for (unsigned i = tid; i < gridDim.x; i += HERM_THREADS) {
+            const unsigned long long v = ((volatile unsigned long long*)slots)[i];
+            mb = v > mb ? v : mb;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_down_sync(0xffffffffu, mb, o);
+            mb = other > mb ? other : mb;
+        }
+        __syncthreads();  // sh_bits of this sweep has been read by thread 0
+        if (lane == 0) sh_bits[wid] = mb;
+        __syncthreads();
+        mb = sh_bits[0];
+        for (int i = 1; i < HERM_THREADS / 32; ++i) mb = sh_bits[i] > mb ? sh_bits[i] : mb;
+        __syncthreads();
+        const double mx = __longlong_as_double((long long)mb);
         if (gid == 0) st->sweeps = sweep + 1;
-        if (mx < p.tol) break;  // the reference's stopping rule (:79); the same value everywhere
+        if (mx < p.tol) break;  // the same value everywhere
     }
     // normalisation sum: real block b plays virtual block b of hermite_normsum_kernel (512 threads = 16 warps;
     // each of the 4 real warps takes 4 of them)
@@ -658,7 +685,7 @@ static HermiteParams hermite_params(int64_t n) {
 extern "C" int64_t fgq_gausshermite_workspace_bytes(int64_t n) {
     if (n < 0) return 0;
     const int64_t nh = (n >> 1) + 1;
-    return 1024 + 3 * 8 * nh;
+    return HERM_WS_HEADER + 3 * 8 * nh;
 }
 
 // FGQ_HERMITE_FUSED=0: the multi-launch form (regression checks); default: one cooperative launch
@@ -680,7 +707,8 @@ static int hermite_device_impl(int64_t n, int normalize, int64_t lo, int64_t hi,
     HermiteParams p = hermite_params(n);
     p.nact = nact;
     HermiteState* state = (HermiteState*)workspace_dev;
-    double* theta = (double*)((char*)workspace_dev + 1024);
+    double* theta = (double*)((char*)workspace_dev + HERM_WS_HEADER);
+    unsigned long long* block_max = (unsigned long long*)((char*)workspace_dev + 1024);
     double* xh = theta + p.nh;
     double* wh = xh + p.nh;
     const unsigned b128 = (unsigned)((p.nact + HERM_THREADS - 1) / HERM_THREADS);
@@ -692,8 +720,9 @@ static int hermite_device_impl(int64_t n, int normalize, int64_t lo, int64_t hi,
         int64_t grid = (int64_t)per_sm * sms;
         if (grid > b128) grid = b128;
         if (grid < 1) grid = 1;
-        void* args[] = {(void*)&p, (void*)&normalize, (void*)&state, (void*)&theta, (void*)&xh, (void*)&wh,
-                        (void*)&lo, (void*)&hi, (void*)&x_dev, (void*)&w_dev};
+        if (grid > HERM_FUSED_MAX_GRID) grid = HERM_FUSED_MAX_GRID;
+        void* args[] = {(void*)&p, (void*)&normalize, (void*)&state, (void*)&block_max, (void*)&theta, (void*)&xh,
+                        (void*)&wh, (void*)&lo, (void*)&hi, (void*)&x_dev, (void*)&w_dev};
         FGQ_CUDA_TRY(cudaLaunchCooperativeKernel((void*)hermite_fused_kernel, dim3((unsigned)grid), dim3(HERM_THREADS),
                                                  args, 0, st));
         count_launch();
