@@ -1,0 +1,3 @@
+set -x
+timeout 300 python tools/jacobi_time.py
+timeout 900 python -m pytest tests/test_jacobi_gpu.py tests/test_fuzz_gpu.py -m gpu -q -s --timeout=600 2>&1 | grep -i "C3 full\|passed\|failed\|error" | tail -8
