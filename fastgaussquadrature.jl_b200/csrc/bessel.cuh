@@ -18,23 +18,23 @@ namespace fgq {
 struct ddv {
     double hi, lo;
 };
-__device__ __forceinline__ ddv dd_two_sum(double a, double b) {
+__host__ __device__ __forceinline__ ddv dd_two_sum(double a, double b) {
     const double s = a + b, bb = s - a;
     return {s, (a - (s - bb)) + (b - bb)};
 }
-__device__ __forceinline__ ddv dd_two_prod(double a, double b) {
+__host__ __device__ __forceinline__ ddv dd_two_prod(double a, double b) {
     const double p = a * b;
     return {p, fma(a, b, -p)};
 }
-__device__ __forceinline__ ddv dd_add(ddv a, ddv b) {
+__host__ __device__ __forceinline__ ddv dd_add(ddv a, ddv b) {
     const ddv s = dd_two_sum(a.hi, b.hi);
     return dd_two_sum(s.hi, s.lo + a.lo + b.lo);
 }
-__device__ __forceinline__ ddv dd_mul(ddv a, ddv b) {
+__host__ __device__ __forceinline__ ddv dd_mul(ddv a, ddv b) {
     const ddv p = dd_two_prod(a.hi, b.hi);
     return dd_two_sum(p.hi, p.lo + (a.hi * b.lo + a.lo * b.hi));
 }
-__device__ __forceinline__ ddv dd_div(ddv a, ddv b) {
+__host__ __device__ __forceinline__ ddv dd_div(ddv a, ddv b) {
     const double q1 = a.hi / b.hi;
     ddv r = dd_add(a, dd_mul({-q1, 0.0}, b));
     const double q2 = r.hi / b.hi;
@@ -62,9 +62,45 @@ __device__ inline double besselj_series_dd(const BesselOrder& o, double x) {
     return o.sign * (pow(0.5 * x, nu) * o.rgamma) * sum.hi;
 }
 
-__device__ inline double besselj_dev(const BesselOrder& o, double x) {
+// The same series with the reciprocals 1 / ((k+1)(nu+k+1)) of its term ratios tabulated (they depend on the order
+// only: BESSEL_INV_DEN entries planned on the host with these very double-double routines, besselj_inv_den_table).
+// The three dependent divisions of dd_div leave the term recurrence, whose dependent chain is then two double-double
+// products: ~7x shorter, and this chain is the latency of the first Bessel-region nodes of a Laguerre rule.
+constexpr int BESSEL_INV_DEN = 96;
+
+__host__ __device__ inline ddv besselj_term_den(double nu, int k) {
+    return dd_mul({(double)(k + 1), 0.0}, dd_two_sum(nu, (double)(k + 1)));
+}
+
+inline void besselj_inv_den_table(double nu, ddv* inv_den) {
+    for (int k = 0; k < BESSEL_INV_DEN; ++k) inv_den[k] = dd_div({1.0, 0.0}, besselj_term_den(nu, k));
+}
+
+__device__ inline double besselj_series_dd_tab(const BesselOrder& o, double x, const ddv* __restrict__ inv_den) {
     const double nu = o.nu;
-    if (x < 25.0) return besselj_series_dd(o, x);
+    if (x == 0.0) return nu == 0.0 ? 1.0 : 0.0;
+    const ddv q = dd_mul(dd_two_prod(x, x), {0.25, 0.0});
+    ddv term = {1.0, 0.0}, sum = {1.0, 0.0};
+    double maxterm = 1.0;
+    for (int k = 0; k < 400; ++k) {
+        if (k < BESSEL_INV_DEN) {
+            term = dd_mul(dd_mul(term, q), inv_den[k]);
+        } else {
+            term = dd_div(dd_mul(term, q), besselj_term_den(nu, k));
+        }
+        term.hi = -term.hi;
+        term.lo = -term.lo;
+        sum = dd_add(sum, term);
+        maxterm = fmax(maxterm, fabs(term.hi));
+        if (fabs(term.hi) < 1e-36 * maxterm && (double)k > 0.5 * x) break;
+    }
+    return o.sign * (pow(0.5 * x, nu) * o.rgamma) * sum.hi;
+}
+
+// inv_den: besselj_inv_den_table of the order, or null (plain series)
+__device__ inline double besselj_dev(const BesselOrder& o, double x, const ddv* __restrict__ inv_den = nullptr) {
+    const double nu = o.nu;
+    if (x < 25.0) return inv_den ? besselj_series_dd_tab(o, x, inv_den) : besselj_series_dd(o, x);
     const double mu = 4.0 * nu * nu;
     const double i8x = 1.0 / (8.0 * x);
     double a = 1.0, P = 1.0, Q = 0.0, prev = 1.0;

@@ -43,6 +43,7 @@ struct LaguerreParams {
     double mc[7];        // McMahon coefficients a1..a13 for this alpha (besselroots.jl:79-111)
     double mu_m1;        // 4 alpha^2 - 1
     BesselOrder jorder;  // order alpha - 1
+    ddv jinv_den[BESSEL_INV_DEN];  // besselj_inv_den_table(jorder.nu): term ratios of the ascending series
     double pn0;          // 1/sqrt(gamma(alpha+1))           (evalLaguerreRec :628)
     double wnorm;        // (n^2 + alpha n)^(-1/2)           (gl_rec_newton :575)
     double xmax;         // 4n + 2 alpha + 2
@@ -263,7 +264,7 @@ __device__ void laguerre_bessel(const LaguerreParams& p, double jak, double& xk,
     const double xfactor = jak * jak * d;
     xk = xfactor * (1 + xk);
     xdelta *= xfactor;
-    const double J = besselj_dev(p.jorder, jak);
+    const double J = besselj_dev(p.jorder, jak, p.jinv_den);
     double wfactor = 4 * d * exp(-xk) / (J * J);
     if (!p.alpha0) wfactor = 4 * d * pow(xk, al) * exp(-xk) / (J * J);
     wk = wfactor * (1 + wk);
@@ -1059,6 +1060,7 @@ static LaguerreParams laguerre_params(int64_t n, double alpha, bool for_rule = t
     const double c = (nu / 2 + 0.25) * 3.141592653589793;
     p.jorder.cosc = cos(c);
     p.jorder.sinc = sin(c);
+    besselj_inv_den_table(nu, p.jinv_den);
     p.pn0 = 1 / sqrt(tgamma(alpha + 1));
     p.wnorm = pow((double)n * (double)n + alpha * (double)n, -0.5);
     return p;
