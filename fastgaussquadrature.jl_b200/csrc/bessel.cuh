@@ -76,7 +76,10 @@ inline void besselj_inv_den_table(double nu, ddv* inv_den) {
     for (int k = 0; k < BESSEL_INV_DEN; ++k) inv_den[k] = dd_div({1.0, 0.0}, besselj_term_den(nu, k));
 }
 
-__device__ inline double besselj_series_dd_tab(const BesselOrder& o, double x, const ddv* __restrict__ inv_den) {
+// stride: distance between consecutive k of this order's reciprocals (1: a table of its own; 64: the interleaved
+// per-order tables of the Jacobi boundary block, conflict-free across the lanes of a warp)
+__device__ inline double besselj_series_dd_tab(const BesselOrder& o, double x, const ddv* __restrict__ inv_den,
+                                               int stride = 1) {
     const double nu = o.nu;
     if (x == 0.0) return nu == 0.0 ? 1.0 : 0.0;
     const ddv q = dd_mul(dd_two_prod(x, x), {0.25, 0.0});
@@ -84,7 +87,7 @@ __device__ inline double besselj_series_dd_tab(const BesselOrder& o, double x, c
     double maxterm = 1.0;
     for (int k = 0; k < 400; ++k) {
         if (k < BESSEL_INV_DEN) {
-            term = dd_mul(dd_mul(term, q), inv_den[k]);
+            term = dd_mul(dd_mul(term, q), inv_den[k * stride]);
         } else {
             term = dd_div(dd_mul(term, q), besselj_term_den(nu, k));
         }

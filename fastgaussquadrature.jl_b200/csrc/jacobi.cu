@@ -781,8 +781,8 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
     }
     const double wc = jacobi_weights_constant(n, a, b);
     // Boundary nodes (:182-190): asy2 with (a, b) at the right end, with (b, a) mirrored at the left end (for
-    // a == b the reference reuses the right-end result; the same solve gives the same numbers).  Two
-    // single-block kernels, independent of the interior: forked onto a side stream and joined at the end
+    // a == b the reference reuses the right-end result; the same solve gives the same numbers).  One
+    // launch of two blocks (one per end), independent of the interior: forked onto a side stream and joined at the end
     // (event dependencies only, so the call stays stream-ordered and graph-capturable).
     ScopedStream side_holder;   // a side stream and two events of this call's own (returned on every exit path)
     FGQ_TRY(side_holder.acquire());
@@ -792,14 +792,20 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
     cudaEvent_t ev_fork = evs.ev[0], ev_join = evs.ev[1];
     FGQ_CUDA_TRY(cudaEventRecord(ev_fork, st));
     FGQ_CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
-    for (int sd = 0; sd < 2; ++sd) {
-        JacobiBoundaryPlan bp;
-        jacobi_boundary_plan(n, sd == 0 ? a : b, sd == 0 ? b : a, &bp);
-        bp.wc = wc;
-        bp.side = sd;
-        bp.lo = lo;
-        bp.hi = hi;
-        jacobi_boundary_kernel<<<1, JB_THREADS, 0, side>>>(bp, x_dev, w_dev);
+    {
+        JacobiBoundaryPlans plans;
+        for (int sd = 0; sd < 2; ++sd) {
+            JacobiBoundaryPlan& bp = plans.end[sd];
+            jacobi_boundary_plan(n, sd == 0 ? a : b, sd == 0 ? b : a, &bp);
+            bp.wc = wc;
+            bp.side = sd;
+            bp.lo = lo;
+            bp.hi = hi;
+        }
+        static const cudaError_t smem_attr = cudaFuncSetAttribute(
+            jacobi_boundary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JB_TABLE_BYTES);
+        FGQ_CUDA_TRY(smem_attr);
+        jacobi_boundary_kernel<<<2, JB_THREADS, JB_TABLE_BYTES, side>>>(plans, x_dev, w_dev);  // one block per end
         FGQ_LAUNCH_CHECK();
     }
     FGQ_CUDA_TRY(cudaEventRecord(ev_join, side));

@@ -207,7 +207,24 @@ constexpr int JB_THREADS = 640;
 
 // asy2 (:363-398) for one end; writes the 10 nodes/weights straight into the rule.
 // side 0: right end (x -> +1), global indices n-10..n-1 ascending; side 1: left end, mirrored.
-__global__ void __launch_bounds__(JB_THREADS) jacobi_boundary_kernel(const JacobiBoundaryPlan P, double* x, double* w) {
+// One block per end (blockIdx.x selects the plan): the two ends are independent and run side by side.  Dynamic shared
+// memory: the reciprocals 1 / ((k+1)(nu+k+1)) of the Bessel series' term ratios for the 62 orders, interleaved
+// [k][order] (JB_TABLE_BYTES), filled by the block itself before the first sweep — every sweep then runs 640
+// series whose dependent chain is two double-double products per term instead of a double-double quotient.
+struct JacobiBoundaryPlans {
+    JacobiBoundaryPlan end[2];
+};
+constexpr size_t JB_TABLE_BYTES = (size_t)BESSEL_INV_DEN * 64 * sizeof(ddv);
+
+__global__ void __launch_bounds__(JB_THREADS)
+jacobi_boundary_kernel(const __grid_constant__ JacobiBoundaryPlans plans, double* x, double* w) {
+    const JacobiBoundaryPlan& P = plans.end[blockIdx.x];
+    extern __shared__ __align__(16) unsigned char jb_dyn_smem[];
+    ddv* inv_den = reinterpret_cast<ddv*>(jb_dyn_smem);  // [BESSEL_INV_DEN][64]
+    for (int e = threadIdx.x; e < BESSEL_INV_DEN * 64; e += JB_THREADS) {
+        const int k = e >> 6, oo = e & 63;
+        if (oo <= 61) inv_den[e] = dd_div({1.0, 0.0}, besselj_term_den(P.ord[oo].nu, k));
+    }
     __shared__ double t[JAC_NBDY], vals[JAC_NBDY], ders[JAC_NBDY];
     __shared__ double Bjk[JAC_NBDY][64];
     __shared__ HigherTerms H;
@@ -239,8 +256,8 @@ __global__ void __launch_bounds__(JB_THREADS) jacobi_boundary_kernel(const Jacob
         {
             const int nu = o - 30;
             const int need = kmax > 1 ? kmax : 1;
-            if (o <= 60 && nu >= -need && nu <= need) Bjk[p][o] = besselj_series_dd(P.ord[o], P.rho * t[p]);
-            if (o == 62) Bjk[p][62] = besselj_series_dd(P.ord[31], P.rho2 * t[p]);
+            if (o <= 60 && nu >= -need && nu <= need) Bjk[p][o] = besselj_series_dd_tab(P.ord[o], P.rho * t[p], inv_den + o, 64);
+            if (o == 62) Bjk[p][62] = besselj_series_dd_tab(P.ord[31], P.rho2 * t[p], inv_den + 31, 64);
         }
         __syncthreads();
         if (tid < JAC_NBDY) {
