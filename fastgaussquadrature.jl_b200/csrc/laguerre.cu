@@ -17,6 +17,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <memory>
 #include <cooperative_groups.h>
 
 #include <vector>
@@ -1311,8 +1312,29 @@ extern "C" int fgq_debug_laguerre_batch_buckets(int64_t nrules, const int32_t* n
     return (int)b.size();
 }
 
+// the per-rule constants (3 tgamma, pow, the Bessel-zero guesses): the same expressions as laguerre_params /
+// fgq_gausslaguerre_device
+static LaguerreBatchRule laguerre_batch_rule(int64_t n, double alpha, int64_t off) {
+    LaguerreBatchRule r;
+    r.n = n;
+    r.off = off;
+    r.alpha = alpha;
+    r.pn0 = 1 / sqrt(tgamma(alpha + 1));
+    r.wnorm = pow((double)n * (double)n + alpha * (double)n, -0.5);
+    r.xmax = 4 * (double)n + 2 * alpha + 2;
+    r.q.g1 = tgamma(1 + alpha);
+    r.q.g2 = tgamma(alpha + 2);
+    for (int k = 0; k < 7; ++k) r.q.jak_pre[k] = 0.0;
+    if (n >= 15) approx_besselroots(alpha, 7, r.q.jak_pre);
+    return r;
+}
+
+// Validates the batch and fixes the launch order.  order (may be null): order[s] = index of the rule processed at
+// position s.  rules (may be null): filled with the constants of every rule at its position, on host threads for a
+// large batch — unless `defer_constants`, where only the vector is sized (the caller plans with an OrderedPlanner).
 static int laguerre_batch_plan(int64_t nrules, const int32_t* n_i, const double* alpha_i, const int64_t* offsets,
-                               std::vector<LaguerreBatchRule>* rules, int64_t* total, int* warn) {
+                               std::vector<LaguerreBatchRule>* rules, int64_t* total, int* warn,
+                               std::vector<int64_t>* order = nullptr, bool defer_constants = false) {
     FGQ_TRY(small_batch_rules(nrules, n_i, offsets, LAGUERRE_BATCH_MAX_N, "gausslaguerre", nullptr, total));
     if (nrules > 0 && !alpha_i) {
         set_error("invalid batch description");
@@ -1333,25 +1355,14 @@ static int laguerre_batch_plan(int64_t nrules, const int32_t* n_i, const double*
     for (int64_t i = 0; i < nrules; ++i) start[LAGUERRE_BATCH_MAX_N - n_i[i] + 1]++;
     for (int k = 0; k <= LAGUERRE_BATCH_MAX_N; ++k) start[k + 1] += start[k];
     for (int64_t i = 0; i < nrules; ++i) slot[(size_t)i] = start[LAGUERRE_BATCH_MAX_N - n_i[i]]++;
-    // per-rule constants (3 tgamma, pow, the Bessel-zero guesses), on host threads for a large batch
+    if (order) {
+        order->resize((size_t)nrules);
+        for (int64_t i = 0; i < nrules; ++i) (*order)[(size_t)slot[(size_t)i]] = i;
+    }
+    if (defer_constants) return FGQ_OK;
     host_parallel_for(nrules, [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
-            const int64_t n = n_i[i];
-            const double alpha = alpha_i[i];
-            LaguerreBatchRule r;
-            r.n = n;
-            r.off = offsets[i];
-            r.alpha = alpha;
-            // the same expressions as laguerre_params / fgq_gausslaguerre_device
-            r.pn0 = 1 / sqrt(tgamma(alpha + 1));
-            r.wnorm = pow((double)n * (double)n + alpha * (double)n, -0.5);
-            r.xmax = 4 * (double)n + 2 * alpha + 2;
-            r.q.g1 = tgamma(1 + alpha);
-            r.q.g2 = tgamma(alpha + 2);
-            for (int k = 0; k < 7; ++k) r.q.jak_pre[k] = 0.0;
-            if (n >= 15) approx_besselroots(alpha, 7, r.q.jak_pre);
-            (*rules)[(size_t)slot[(size_t)i]] = r;
-        }
+        for (int64_t i = lo; i < hi; ++i)
+            (*rules)[(size_t)slot[(size_t)i]] = laguerre_batch_rule(n_i[i], alpha_i[i], offsets[i]);
     });
     return FGQ_OK;
 }
@@ -1361,9 +1372,16 @@ extern "C" int fgq_gausslaguerre_batch_device(int64_t nrules, const int32_t* n_i
                                               void* workspace_dev, void* stream) {
     clear_status();
     std::vector<LaguerreBatchRule> rules;
+    std::vector<int64_t> order;
     int64_t total = 0;
     int warn = 0;
-    FGQ_TRY(laguerre_batch_plan(nrules, n_i, alpha_i, offsets, &rules, &total, &warn));
+    // FGQ_LAGUERRE_BATCH=thread selects the first version (one thread per rule, coefficients recomputed per step).
+    static const bool per_thread = []() {
+        const char* e = getenv("FGQ_LAGUERRE_BATCH");
+        return e && strcmp(e, "thread") == 0;
+    }();
+    const bool pipelined = !per_thread && nrules >= 16384;  // plan beside the kernels (OrderedPlanner)
+    FGQ_TRY(laguerre_batch_plan(nrules, n_i, alpha_i, offsets, &rules, &total, &warn, pipelined ? &order : nullptr, pipelined));
     if (warn) add_warning(warn);
     if (nrules == 0 || total == 0) return FGQ_OK;
     if (!x_dev || !w_dev || !workspace_dev) {
@@ -1374,16 +1392,10 @@ extern "C" int fgq_gausslaguerre_batch_device(int64_t nrules, const int32_t* n_i
     char* ws = (char*)workspace_dev;
     laguerre_state_init_kernel<<<1, 1, 0, st>>>((LaguerreState*)ws, 0);
     FGQ_LAUNCH_CHECK();
-    FGQ_CUDA_TRY(cudaMemcpyAsync(ws + 256, rules.data(), rules.size() * sizeof(LaguerreBatchRule),
-                                 cudaMemcpyHostToDevice, st));
-    // Buckets of similar n over the sorted rules (longest first): shared memory per warp follows the bucket's n_max.
-    // FGQ_LAGUERRE_BATCH=thread selects the first version (one thread per rule, coefficients recomputed per step).
-    static const bool per_thread = []() {
-        const char* e = getenv("FGQ_LAGUERRE_BATCH");
-        return e && strcmp(e, "thread") == 0;
-    }();
-    const LaguerreBatchRule* drules = (const LaguerreBatchRule*)(ws + 256);
+    LaguerreBatchRule* drules = (LaguerreBatchRule*)(ws + 256);
     unsigned int* warn_word = &((LaguerreState*)ws)->warn;
+    if (!pipelined)
+        FGQ_CUDA_TRY(cudaMemcpyAsync(drules, rules.data(), rules.size() * sizeof(LaguerreBatchRule), cudaMemcpyHostToDevice, st));
     if (per_thread) {
         const int64_t blocks = (nrules + LAG_BATCH_THREADS - 1) / LAG_BATCH_THREADS;
         laguerre_small_batch_kernel<<<(unsigned)blocks, LAG_BATCH_THREADS, 0, st>>>(nrules, drules, warn_word, x_dev, w_dev);
@@ -1398,32 +1410,73 @@ extern "C" int fgq_gausslaguerre_batch_device(int64_t nrules, const int32_t* n_i
                                           512 * (LAGUERRE_BATCH_MAX_N + 1)));
         attr_set[dev] = true;
     }
+    // Buckets of similar n over the sorted rules (longest first): shared memory per warp follows the bucket's n_max.
     std::vector<int> sorted_n((size_t)nrules);
-    for (int64_t q = 0; q < nrules; ++q) sorted_n[(size_t)q] = (int)rules[(size_t)q].n;
+    if (pipelined) {
+        for (int64_t q = 0; q < nrules; ++q) sorted_n[(size_t)q] = (int)n_i[order[(size_t)q]];
+    } else {
+        for (int64_t q = 0; q < nrules; ++q) sorted_n[(size_t)q] = (int)rules[(size_t)q].n;
+    }
     const std::vector<LagBucket> buckets = laguerre_batch_buckets(sorted_n);
     // The long-n buckets run at a few warps per SM (their tables fill the shared memory) and every bucket ends in a
-    // partially filled wave: the buckets are spread over the caller's stream and three side streams (forked and
-    // joined with events: still stream-ordered for the caller, graph-capturable) so that they fill each other's gaps.
-    constexpr int NSIDE = 3;
+    // partially filled wave: the buckets are spread over several streams (forked and joined with events: still
+    // stream-ordered for the caller, graph-capturable) so that they fill each other's gaps.  Pipelined form: the
+    // caller's stream carries only the uploads, bucket by bucket as the planner delivers them, and every bucket
+    // runs on a side stream behind the event of its own upload — an upload never queues behind a kernel.
+    constexpr int NSIDE = 4;
     ScopedStream side[NSIDE];
-    ScopedEvents evs;
-    const bool fork = buckets.size() > 1;
+    ScopedEvents evs, ev_up;
+    const bool fork = pipelined || buckets.size() > 1;
+    const int nside = pipelined ? NSIDE : NSIDE - 1;
     if (fork) {
-        for (int q = 0; q < NSIDE; ++q) FGQ_TRY(side[q].acquire());
-        FGQ_TRY(evs.acquire(1 + NSIDE));
+        for (int q = 0; q < nside; ++q) FGQ_TRY(side[q].acquire());
+        FGQ_TRY(evs.acquire(1 + nside));
         FGQ_CUDA_TRY(cudaEventRecord(evs.ev[0], st));
-        for (int q = 0; q < NSIDE; ++q) FGQ_CUDA_TRY(cudaStreamWaitEvent(side[q].st, evs.ev[0], 0));
+        for (int q = 0; q < nside; ++q) FGQ_CUDA_TRY(cudaStreamWaitEvent(side[q].st, evs.ev[0], 0));
     }
-    for (size_t bi = 0; bi < buckets.size(); ++bi) {
-        const LagBucket& bk = buckets[bi];
-        const size_t smem = bk.n_top >= 15 ? (size_t)512 * (size_t)(bk.n_top + 1) : 0;
-        cudaStream_t s_b = (fork && bi % (NSIDE + 1) != 0) ? side[bi % (NSIDE + 1) - 1].st : st;
-        laguerre_rec_batch_kernel<<<(unsigned)((bk.count + 31) / 32), 32, smem, s_b>>>(bk.first, bk.count, bk.n_top, drules,
-                                                                                      warn_word, x_dev, w_dev);
-        FGQ_LAUNCH_CHECK();
+    if (buckets.size() > 60) {
+        set_error("internal: too many buckets");
+        return FGQ_EINVAL;
+    }
+    {
+        // declared after the streams and events: joined (destructor) before they are handed back
+        std::unique_ptr<OrderedPlanner> planner;
+        if (pipelined) {
+            FGQ_TRY(ev_up.acquire((int)buckets.size()));
+            const int64_t* ord = order.data();
+            LaguerreBatchRule* out = rules.data();
+            planner.reset(new OrderedPlanner(nrules, [=](int64_t lo, int64_t hi) {
+                for (int64_t s = lo; s < hi; ++s) {
+                    const int64_t i = ord[s];
+                    out[s] = laguerre_batch_rule(n_i[i], alpha_i[i], offsets[i]);
+                }
+            }));
+        }
+        int64_t uploaded = 0;
+        for (size_t bi = 0; bi < buckets.size(); ++bi) {
+            const LagBucket& bk = buckets[bi];
+            const size_t smem = bk.n_top >= 15 ? (size_t)512 * (size_t)(bk.n_top + 1) : 0;
+            cudaStream_t s_b;
+            if (pipelined) {
+                // the last bucket also takes the rules without nodes that sort behind it (never read by a kernel)
+                const int64_t up_hi = bi + 1 == buckets.size() ? nrules : bk.first + bk.count;
+                planner->wait(up_hi);
+                FGQ_CUDA_TRY(cudaMemcpyAsync(drules + uploaded, rules.data() + uploaded,
+                                             (size_t)(up_hi - uploaded) * sizeof(LaguerreBatchRule), cudaMemcpyHostToDevice, st));
+                uploaded = up_hi;
+                FGQ_CUDA_TRY(cudaEventRecord(ev_up.ev[bi], st));
+                s_b = side[bi % NSIDE].st;
+                FGQ_CUDA_TRY(cudaStreamWaitEvent(s_b, ev_up.ev[bi], 0));
+            } else {
+                s_b = (fork && bi % NSIDE != 0) ? side[bi % NSIDE - 1].st : st;
+            }
+            laguerre_rec_batch_kernel<<<(unsigned)((bk.count + 31) / 32), 32, smem, s_b>>>(bk.first, bk.count, bk.n_top, drules,
+                                                                                          warn_word, x_dev, w_dev);
+            FGQ_LAUNCH_CHECK();
+        }
     }
     if (fork) {
-        for (int q = 0; q < NSIDE; ++q) {
+        for (int q = 0; q < nside; ++q) {
             FGQ_CUDA_TRY(cudaEventRecord(evs.ev[1 + q], side[q].st));
             FGQ_CUDA_TRY(cudaStreamWaitEvent(st, evs.ev[1 + q], 0));
         }
