@@ -112,6 +112,7 @@ SIGNATURES = {
     "fgq_gausslegendre_device_replicated": (ctypes.c_int, [_i64, _vpp, _vpp]),
     "fgq_free_replicas": (ctypes.c_int, [_vpp, _vpp]),
     "fgq_gausslegendre_host_multi": (ctypes.c_int, [_i64, _vp, _vp]),
+    "fgq_debug_ordered_planner": (_i64, [_i64, _i64]),
     "fgq_debug_laguerre_batch_buckets": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, ctypes.c_int]),
     "fgq_debug_half_index_range": (ctypes.c_int, [_i64, ctypes.c_int, ctypes.c_int, _i64p, _i64p]),
 }

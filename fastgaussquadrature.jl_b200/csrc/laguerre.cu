@@ -1297,6 +1297,29 @@ static std::vector<LagBucket> laguerre_batch_buckets(const std::vector<int>& sor
     return out;
 }
 
+// test hook (host only): OrderedPlanner's contract
+extern "C" int64_t fgq_debug_ordered_planner(int64_t n, int64_t wait_step) {
+    if (n <= 0 || wait_step <= 0) return -1;
+    std::vector<std::atomic<int>> hits((size_t)n);
+    for (auto& h : hits) h.store(0, std::memory_order_relaxed);
+    int64_t bad = 0;
+    {
+        std::atomic<int>* hp = hits.data();
+        OrderedPlanner planner(n, [hp](int64_t lo, int64_t hi) {
+            for (int64_t s = lo; s < hi; ++s) hp[s].fetch_add(1, std::memory_order_relaxed);
+        });
+        for (int64_t hi = wait_step; hi < n + wait_step; hi += wait_step) {
+            const int64_t bound = hi < n ? hi : n;
+            planner.wait(bound);
+            for (int64_t s = bound - wait_step < 0 ? 0 : bound - wait_step; s < bound; ++s)
+                if (hits[(size_t)s].load(std::memory_order_relaxed) != 1) ++bad;
+        }
+    }
+    for (int64_t s = 0; s < n; ++s)
+        if (hits[(size_t)s].load(std::memory_order_relaxed) != 1) ++bad;
+    return bad;
+}
+
 // test hook (host only): the buckets for an UNSORTED list of rule sizes; returns their number
 extern "C" int fgq_debug_laguerre_batch_buckets(int64_t nrules, const int32_t* n_i, int64_t* first, int64_t* count,
                                                 int32_t* n_top, int max_buckets) {

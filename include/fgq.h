@@ -391,6 +391,10 @@ int fgq_debug_half_index_range(int64_t n, int world, int rank, int64_t* k_lo, in
  * longest first, are cut into groups of similar n; returns the number of buckets (first/count index the sorted list). */
 int fgq_debug_laguerre_batch_buckets(int64_t nrules, const int32_t* n_i, int64_t* first, int64_t* count,
                                      int32_t* n_top, int max_buckets);
+/* The in-order background planner of the batch calls (host only; tests): n positions are processed on the library's
+ * host threads while the caller waits for growing prefixes (wait_step positions at a time).  Returns the number of
+ * violations — a position below a waited-for bound not yet processed, or a position not processed exactly once. */
+int64_t fgq_debug_ordered_planner(int64_t n, int64_t wait_step);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t fgq_launch_count(void);
 

@@ -232,6 +232,16 @@ def test_laguerre_batch_buckets_cover_every_rule_once(fgq_cpu):
             pos += count[b]
 
 
+def test_ordered_planner_delivers_prefixes(fgq_cpu):
+    """The background planner of the batch calls (OrderedPlanner): once wait(hi) returns every position below hi has
+    been processed, and in the end every position exactly once — for sizes around its block size and wait steps that
+    do not divide them."""
+    L = fgq_cpu.lib()
+    for n, step in ((1, 1), (1023, 100), (1024, 1024), (1025, 7), (100_000, 12_500), (250_001, 33_333)):
+        assert L.fgq_debug_ordered_planner(n, step) == 0, (n, step)
+    assert L.fgq_debug_ordered_planner(0, 1) == -1
+
+
 def test_host_store_peak_needs_no_device(fgq_cpu):
     """The host-memory roofline of the host-returning calls is measured by host threads only."""
     L = fgq_cpu.lib()
