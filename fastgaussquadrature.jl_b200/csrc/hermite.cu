@@ -12,7 +12,8 @@
 // (||dtheta||_inf < sqrt(eps)/10 over all nodes, :79) is kept without a host round trip: each sweep
 // kernel reduces its max into the workspace, the last block to finish sets a `done` flag, and the
 // remaining (pre-enqueued) sweep launches exit immediately.  Then a reduction for the global
-// normalisation sum (:62) and a fold/scale kernel that also applies exp(-x^2) (:30).
+// normalisation sum (:62) and a fold/scale kernel that also applies exp(-x^2) (:30).  That is the multi-launch
+// form (FGQ_HERMITE_FUSED=0); by default the whole rule is ONE cooperative launch, hermite_fused_kernel below.
 #include <cooperative_groups.h>
 
 #include "airy.cuh"

@@ -13,7 +13,10 @@
 // and on the region it falls in, so here the two hand-over indices are found by "first index
 // where" reductions (atomicMin) over candidate ranges, then one thread per node evaluates the
 // region(s) it needs.  Nodes whose error estimate exceeds 1e-13 are appended to a list and redone
-// by Newton on the O(n) recurrence, one thread per flagged node (about 35 nodes at n = 1e6).
+// by Newton on the O(n) recurrence, one WARP per flagged node (about 35 nodes at n = 1e6).
+// Launch structure of the asymptotic rule: the searches evaluate the expansions the edge nodes need anyway and run
+// on a high-priority side stream beside the bulk-only nodes (90 % of the rule, independent of the searches); see
+// laguerre_edge_eval_kernel.  FGQ_LAGUERRE_FAST=0 selects the sequential chain search, search, nodes.
 #include <math.h>
 
 #include <algorithm>
