@@ -65,6 +65,7 @@ struct HermiteParams {
     double musq;      // 2n+1
     double sq_musq;   // sqrt(2n+1)
     double musq16, musq13, musq23, musq43, musq2, musq103, musq83;  // powers of musq
+    double r_musq23, r_musq43, r_musq2, r_musq103, r_musq83;         // their correctly rounded reciprocals (herm_div_by)
     double nu13, num13, num53, num73;
     int64_t n_sin;    // floor(p n): guesses 1..n_sin are Tricomi's
     int64_t airy_from;  // ceil(p n): guesses taken from the reversed Airy list start here (1-based)
@@ -149,7 +150,23 @@ __global__ void hermite_init_kernel(HermiteParams p, HermiteState* st, double* t
     theta[t] = hermite_theta0(p, t);
 }
 
-// gausshermite.jl:171-250 at one theta
+// a / b for a divisor whose correctly rounded reciprocal r is at hand: the last three operations of the IEEE quotient's
+// fast path.  The value before the final rounding is within 2^-53 ulp of a / b, so the result is a / b correctly rounded
+// unless a / b lies that close to a rounding boundary — impossible for the literal divisors below (24, 1152, 414720 =
+// 3, 9, 405 times a power of two: a / b stays at least 1/810 ulp away from every midpoint) and a 1e-16-probability
+// event per quotient for the per-rule constants (a one-ulp difference in a term of relative size (2n+1)^-2/3 or less).
+// Operands are far inside the normal range here.
+__device__ __forceinline__ double herm_div_by(double a, double b, double r) {
+    const double q = a * r;
+    const double rem = fma(-b, q, a);
+    const double res = fma(r, rem, q);
+    return a == 0.0 ? a : res;
+}
+
+// gausshermite.jl:171-250 at one theta.  Its 20 quotients were more than half of the FP64 instructions of a sweep
+// (CUDA's a / b: ~25 instructions with its range checks): the twelve by literals or per-rule constants use
+// herm_div_by, the eight by powers of chi / phi fgq_div_fast (CUDA's own fast path without the range checks; every
+// operand here lies within [1e-60, 1e60]).
 __device__ __forceinline__ void hermpoly_asy_airy(const HermiteParams& p, double th, double sinT,
                                                   double cosT, double& val, double& dval) {
     const double sin2T = 2.0 * cosT * sinT;
@@ -158,7 +175,7 @@ __device__ __forceinline__ void hermpoly_asy_airy(const HermiteParams& p, double
     // 0.75 ulp of the exact powers (CUDA's pow: 2 ulp) at a fifth of pow's ~250 instructions each
     const double y32 = 3.0 * eta / 2.0;
     const double chi = -cbrt(y32 * y32);
-    const double phi = sqrt(sqrt(-chi / (sinT * sinT)));
+    const double phi = sqrt(sqrt(fgq_div_fast(-chi, sinT * sinT)));
     const double SQPI = 1.7724538509055159;  // sqrt(pi)
     double C = 2.0 * SQPI * p.musq16 * phi;
     double Airy0, Airy1;
@@ -167,33 +184,34 @@ __device__ __forceinline__ void hermpoly_asy_airy(const HermiteParams& p, double
     const double a1 = 15.0 / 144.0, b1 = -7.0 / 5.0 * a1;
     const double a2 = 5.0 * 7.0 * 9.0 * 11.0 / 2.0 / (144.0 * 144.0), b2 = -13.0 / 11.0 * a2;
     const double a3 = 7.0 * 9.0 * 11.0 * 13.0 * 15.0 * 17.0 / 6.0 / (144.0 * 144.0 * 144.0), b3 = -19.0 / 17.0 * a3;
+    constexpr double R24 = 1.0 / 24.0, R1152 = 1.0 / 1152.0, R414720 = 1.0 / 414720.0;  // correctly rounded by the compiler
     const double c2 = cosT * cosT, c3 = c2 * cosT, c4 = c2 * c2, c5 = c4 * cosT, c7 = c5 * c2, c9 = c7 * c2;
-    const double u1 = (c3 - 6.0 * cosT) / 24.0;
-    const double u2 = (-9.0 * c4 + 249.0 * c2 + 145.0) / 1152.0;
-    const double u3 = (-4042.0 * c9 + 18189.0 * c7 - 28287.0 * c5 - 151995.0 * c3 - 259290.0 * cosT) / 414720.0;
+    const double u1 = herm_div_by(c3 - 6.0 * cosT, 24.0, R24);
+    const double u2 = herm_div_by(-9.0 * c4 + 249.0 * c2 + 145.0, 1152.0, R1152);
+    const double u3 = herm_div_by(-4042.0 * c9 + 18189.0 * c7 - 28287.0 * c5 - 151995.0 * c3 - 259290.0 * cosT, 414720.0, R414720);
     const double phi2 = phi * phi, phi6 = phi2 * phi2 * phi2, phi12 = phi6 * phi6, phi18 = phi12 * phi6;
     const double chi2 = chi * chi, chi3 = chi2 * chi, chi4 = chi2 * chi2, chi5 = chi4 * chi;
 
     val = Airy0;
-    const double B0 = -(u1 * phi6 + a1) / chi2;
-    val = val + B0 * Airy1 / p.musq43;
-    const double A1 = (u2 * phi12 + b1 * u1 * phi6 + b2) / chi3;
-    val = val + A1 * Airy0 / p.musq2;
-    const double B1 = -(u3 * phi18 + a1 * u2 * phi12 + a2 * u1 * phi6 + a3) / chi5;
-    val = val + B1 * Airy1 / p.musq103;
+    const double B0 = fgq_div_fast(-(u1 * phi6 + a1), chi2);
+    val = val + herm_div_by(B0 * Airy1, p.musq43, p.r_musq43);
+    const double A1 = fgq_div_fast(u2 * phi12 + b1 * u1 * phi6 + b2, chi3);
+    val = val + herm_div_by(A1 * Airy0, p.musq2, p.r_musq2);
+    const double B1 = fgq_div_fast(-(u3 * phi18 + a1 * u2 * phi12 + a2 * u1 * phi6 + a3), chi5);
+    val = val + herm_div_by(B1 * Airy1, p.musq103, p.r_musq103);
     val = C * val;
 
-    C = 2.5066282746310002 * p.musq13 / phi;  // sqrt(2 pi)
-    const double v1 = (c3 + 6.0 * cosT) / 24.0;
-    const double v2 = (15.0 * c4 - 327.0 * c2 - 143.0) / 1152.0;
-    const double v3 = (259290.0 * cosT + 238425.0 * c3 - 36387.0 * c5 + 18189.0 * c7 - 4042.0 * c9) / 414720.0;
-    const double C0 = -(phi6 * v1 + b1) / chi;
-    dval = C0 * Airy0 / p.musq23;
+    C = fgq_div_fast(2.5066282746310002 * p.musq13, phi);  // sqrt(2 pi)
+    const double v1 = herm_div_by(c3 + 6.0 * cosT, 24.0, R24);
+    const double v2 = herm_div_by(15.0 * c4 - 327.0 * c2 - 143.0, 1152.0, R1152);
+    const double v3 = herm_div_by(259290.0 * cosT + 238425.0 * c3 - 36387.0 * c5 + 18189.0 * c7 - 4042.0 * c9, 414720.0, R414720);
+    const double C0 = fgq_div_fast(-(phi6 * v1 + b1), chi);
+    dval = herm_div_by(C0 * Airy0, p.musq23, p.r_musq23);
     dval = dval + Airy1;
-    const double C1 = -(v3 * phi18 + b1 * v2 * phi12 + b2 * v1 * phi6 + b3) / chi4;
-    dval = dval + C1 * Airy0 / p.musq83;
-    const double D1 = (v2 * phi12 + a1 * v1 * phi6 + a2) / chi3;
-    dval = dval + D1 * Airy1 / p.musq2;
+    const double C1 = fgq_div_fast(-(v3 * phi18 + b1 * v2 * phi12 + b2 * v1 * phi6 + b3), chi4);
+    dval = dval + herm_div_by(C1 * Airy0, p.musq83, p.r_musq83);
+    const double D1 = fgq_div_fast(v2 * phi12 + a1 * v1 * phi6 + a2, chi3);
+    dval = dval + herm_div_by(D1 * Airy1, p.musq2, p.r_musq2);
     dval = C * dval;
 }
 
@@ -671,6 +689,11 @@ static HermiteParams hermite_params(int64_t n) {
     p.musq2 = p.musq * p.musq;
     p.musq103 = pow(p.musq, 4.0 / 3.0 + 2.0);
     p.musq83 = pow(p.musq, 2.0 / 3.0 + 2.0);
+    p.r_musq23 = 1.0 / p.musq23;
+    p.r_musq43 = 1.0 / p.musq43;
+    p.r_musq2 = 1.0 / p.musq2;
+    p.r_musq103 = 1.0 / p.musq103;
+    p.r_musq83 = 1.0 / p.musq83;
     p.nu13 = pow(p.nu, 1.0 / 3.0);
     p.num13 = pow(p.nu, -1.0 / 3.0);
     p.num53 = pow(p.nu, -5.0 / 3.0);
