@@ -150,22 +150,11 @@ __global__ void hermite_init_kernel(HermiteParams p, HermiteState* st, double* t
     theta[t] = hermite_theta0(p, t);
 }
 
-// a / b for a divisor whose correctly rounded reciprocal r is at hand: the last three operations of the IEEE quotient's
-// fast path.  The value before the final rounding is within 2^-53 ulp of a / b, so the result is a / b correctly rounded
-// unless a / b lies that close to a rounding boundary — impossible for the literal divisors below (24, 1152, 414720 =
-// 3, 9, 405 times a power of two: a / b stays at least 1/810 ulp away from every midpoint) and a 1e-16-probability
-// event per quotient for the per-rule constants (a one-ulp difference in a term of relative size (2n+1)^-2/3 or less).
-// Operands are far inside the normal range here.
-__device__ __forceinline__ double herm_div_by(double a, double b, double r) {
-    const double q = a * r;
-    const double rem = fma(-b, q, a);
-    const double res = fma(r, rem, q);
-    return a == 0.0 ? a : res;
-}
-
 // gausshermite.jl:171-250 at one theta.  Its 20 quotients were more than half of the FP64 instructions of a sweep
 // (CUDA's a / b: ~25 instructions with its range checks): the twelve by literals or per-rule constants use
-// herm_div_by, the eight by powers of chi / phi fgq_div_fast (CUDA's own fast path without the range checks; every
+// fgq_div_by_inrange (fgq_math.h; every operand here lies within [1e-60, 1e60]; for the per-rule constants a quotient within 2^-53 ulp of a rounding boundary — a
+// 1e-16-probability event, in a term of relative size (2n+1)^-2/3 or less — would come out one ulp off), the eight
+// by powers of chi / phi fgq_div_fast (CUDA's own fast path without the range checks; every
 // operand here lies within [1e-60, 1e60]).
 __device__ __forceinline__ void hermpoly_asy_airy(const HermiteParams& p, double th, double sinT,
                                                   double cosT, double& val, double& dval) {
@@ -186,32 +175,32 @@ __device__ __forceinline__ void hermpoly_asy_airy(const HermiteParams& p, double
     const double a3 = 7.0 * 9.0 * 11.0 * 13.0 * 15.0 * 17.0 / 6.0 / (144.0 * 144.0 * 144.0), b3 = -19.0 / 17.0 * a3;
     constexpr double R24 = 1.0 / 24.0, R1152 = 1.0 / 1152.0, R414720 = 1.0 / 414720.0;  // correctly rounded by the compiler
     const double c2 = cosT * cosT, c3 = c2 * cosT, c4 = c2 * c2, c5 = c4 * cosT, c7 = c5 * c2, c9 = c7 * c2;
-    const double u1 = herm_div_by(c3 - 6.0 * cosT, 24.0, R24);
-    const double u2 = herm_div_by(-9.0 * c4 + 249.0 * c2 + 145.0, 1152.0, R1152);
-    const double u3 = herm_div_by(-4042.0 * c9 + 18189.0 * c7 - 28287.0 * c5 - 151995.0 * c3 - 259290.0 * cosT, 414720.0, R414720);
+    const double u1 = fgq_div_by_inrange(c3 - 6.0 * cosT, 24.0, R24);
+    const double u2 = fgq_div_by_inrange(-9.0 * c4 + 249.0 * c2 + 145.0, 1152.0, R1152);
+    const double u3 = fgq_div_by_inrange(-4042.0 * c9 + 18189.0 * c7 - 28287.0 * c5 - 151995.0 * c3 - 259290.0 * cosT, 414720.0, R414720);
     const double phi2 = phi * phi, phi6 = phi2 * phi2 * phi2, phi12 = phi6 * phi6, phi18 = phi12 * phi6;
     const double chi2 = chi * chi, chi3 = chi2 * chi, chi4 = chi2 * chi2, chi5 = chi4 * chi;
 
     val = Airy0;
     const double B0 = fgq_div_fast(-(u1 * phi6 + a1), chi2);
-    val = val + herm_div_by(B0 * Airy1, p.musq43, p.r_musq43);
+    val = val + fgq_div_by_inrange(B0 * Airy1, p.musq43, p.r_musq43);
     const double A1 = fgq_div_fast(u2 * phi12 + b1 * u1 * phi6 + b2, chi3);
-    val = val + herm_div_by(A1 * Airy0, p.musq2, p.r_musq2);
+    val = val + fgq_div_by_inrange(A1 * Airy0, p.musq2, p.r_musq2);
     const double B1 = fgq_div_fast(-(u3 * phi18 + a1 * u2 * phi12 + a2 * u1 * phi6 + a3), chi5);
-    val = val + herm_div_by(B1 * Airy1, p.musq103, p.r_musq103);
+    val = val + fgq_div_by_inrange(B1 * Airy1, p.musq103, p.r_musq103);
     val = C * val;
 
     C = fgq_div_fast(2.5066282746310002 * p.musq13, phi);  // sqrt(2 pi)
-    const double v1 = herm_div_by(c3 + 6.0 * cosT, 24.0, R24);
-    const double v2 = herm_div_by(15.0 * c4 - 327.0 * c2 - 143.0, 1152.0, R1152);
-    const double v3 = herm_div_by(259290.0 * cosT + 238425.0 * c3 - 36387.0 * c5 + 18189.0 * c7 - 4042.0 * c9, 414720.0, R414720);
+    const double v1 = fgq_div_by_inrange(c3 + 6.0 * cosT, 24.0, R24);
+    const double v2 = fgq_div_by_inrange(15.0 * c4 - 327.0 * c2 - 143.0, 1152.0, R1152);
+    const double v3 = fgq_div_by_inrange(259290.0 * cosT + 238425.0 * c3 - 36387.0 * c5 + 18189.0 * c7 - 4042.0 * c9, 414720.0, R414720);
     const double C0 = fgq_div_fast(-(phi6 * v1 + b1), chi);
-    dval = herm_div_by(C0 * Airy0, p.musq23, p.r_musq23);
+    dval = fgq_div_by_inrange(C0 * Airy0, p.musq23, p.r_musq23);
     dval = dval + Airy1;
     const double C1 = fgq_div_fast(-(v3 * phi18 + b1 * v2 * phi12 + b2 * v1 * phi6 + b3), chi4);
-    dval = dval + herm_div_by(C1 * Airy0, p.musq83, p.r_musq83);
+    dval = dval + fgq_div_by_inrange(C1 * Airy0, p.musq83, p.r_musq83);
     const double D1 = fgq_div_fast(v2 * phi12 + a1 * v1 * phi6 + a2, chi3);
-    dval = dval + herm_div_by(D1 * Airy1, p.musq2, p.r_musq2);
+    dval = dval + fgq_div_by_inrange(D1 * Airy1, p.musq2, p.r_musq2);
     dval = C * dval;
 }
 

@@ -143,37 +143,37 @@ __device__ void laguerre_bulk(const LaguerreParams& p, int64_t k, double& xk, do
     const double d2 = d * d, d4 = d2 * d2, d6 = d4 * d2;
     double xs[4], ws[3];
     const double tm1 = t - 1;
-    ws[0] = d2 / 6 * (2 * t + 3) / (tm1 * tm1 * tm1);
+    ws[0] = FGQ_DIV_LIT(d2, 6.0) * (2 * t + 3) / (tm1 * tm1 * tm1);
     if (p.alpha0) {
-        { const double c[3] = {-4, -4, 5}; xs[0] = -d / 12 * evalpoly(tinv, c); }
-        { const double c[7] = {224, -336, -16, -576, 2814, -3815, 1600}; xs[1] = d2 * d * _t / 720 * evalpoly(tinv, c); }
+        { const double c[3] = {-4, -4, 5}; xs[0] = FGQ_DIV_LIT(-d, 12.0) * evalpoly(tinv, c); }
+        { const double c[7] = {224, -336, -16, -576, 2814, -3815, 1600}; xs[1] = FGQ_DIV_LIT(d2 * d * _t, 720.0) * evalpoly(tinv, c); }
         { const double c[11] = {-285696, 714240, -516864, -13760, -17680, -1727136, 16131880, -48469876, 66424575, -43122800, 10797500};
-          xs[2] = -d4 * d / 181440 * _t2 * evalpoly(tinv, c); }
+          xs[2] = FGQ_DIV_LIT(-d4 * d, 181440.0) * _t2 * evalpoly(tinv, c); }
         { const double c[15] = {210677760, -737372160, 916264704, -426423552, -10338048, 2863616, -26285280, -3062050944.0,
                                 43651480992.0, -212307298152.0, 518401904799.0, -714465642135.0, 566519158800.0, -241928673000.0, 43222750000.0};
-          xs[3] = d6 * d / 10886400 * _t3 * evalpoly(tinv, c); }
-        { const double c[9] = {0, 0, 112, 32, 1712, -12408, 27517, -24860, 8000}; ws[1] = d4 / 720 * _t2 * evalpoly(tinv, c); }
+          xs[3] = FGQ_DIV_LIT(d6 * d, 10886400.0) * _t3 * evalpoly(tinv, c); }
+        { const double c[9] = {0, 0, 112, 32, 1712, -12408, 27517, -24860, 8000}; ws[1] = FGQ_DIV_LIT(d4, 720.0) * _t2 * evalpoly(tinv, c); }
         { const double c[13] = {0, 0, -71424, 159744, 20640, 28480, 4300160, -50986344, 201908326, -386872990, 393326325, -204917300, 43190000};
-          ws[2] = -d6 * _t3 / 90720 * evalpoly(tinv, c); }
+          ws[2] = FGQ_DIV_LIT(-d6 * _t3, 90720.0) * evalpoly(tinv, c); }
     } else {
         const double a2 = al * al;
         {
             const double c1 = evalpoly2(a2, -4, 12);
             const double c[3] = {c1, -4, 5};
-            xs[0] = -evalpoly(tinv, c) * d / 12;
+            xs[0] = FGQ_DIV_LIT(-evalpoly(tinv, c) * d, 12.0);
         }
         {
             const double q1[3] = {224, -960, 480}, q2[3] = {7, -30, 15};
             const double c1 = evalpoly(a2, q1), c2 = evalpoly(a2, q2);
             const double c[7] = {c1, -48 * c2, -16, -576, 2814, -3815, 1600};
-            xs[1] = d2 * d * _t / 720 * evalpoly(tinv, c);
+            xs[1] = FGQ_DIV_LIT(d2 * d * _t, 720.0) * evalpoly(tinv, c);
         }
         {
             const double q1[4] = {-285696, 1354752, -967680, 193536}, q2[4] = {-31, 147, -105, 21}, q3[4] = {-1346, 6405, -4620, 945};
             const double q4[3] = {43, -126, 63}, q5[3] = {-221, -630, 315};
             const double c1 = evalpoly(a2, q1), c2 = evalpoly(a2, q2), c3 = evalpoly(a2, q3), c4 = evalpoly(a2, q4), c5 = evalpoly(a2, q5);
             const double c[11] = {c1, -23040 * c2, 384 * c3, -320 * c4, 80 * c5, -1727136, 16131880, -48469876, 66424575, -43122800, 10797500};
-            xs[2] = -d4 * d / 181440 * _t2 * evalpoly(tinv, c);
+            xs[2] = FGQ_DIV_LIT(-d4 * d, 181440.0) * _t2 * evalpoly(tinv, c);
         }
         {
             const double q1[5] = {210677760, -1028505600, 812851200, -232243200, 24883200}, q2[5] = {127, -620, 490, -140, 15};
@@ -184,20 +184,20 @@ __device__ void laguerre_bulk(const LaguerreParams& p, int64_t k, double& xk, do
             const double c6 = evalpoly(a2, q6), c7 = evalpoly(a2, q7), c8 = evalpoly(a2, q8), c9 = evalpoly(a2, q9);
             const double c[15] = {c1, -5806080 * c2, 768 * c3, -768 * c4, 16128 * c5, -1792 * c6, 3360 * c7, -192 * c8, 672 * c9,
                                   -212307298152.0, 518401904799.0, -714465642135.0, 566519158800.0, -241928673000.0, 43222750000.0};
-            xs[3] = d6 * d / 10886400 * _t3 * evalpoly(tinv, c);
+            xs[3] = FGQ_DIV_LIT(d6 * d, 10886400.0) * _t3 * evalpoly(tinv, c);
         }
         {
             const double q1[3] = {7, -30, 15};
             const double c1 = evalpoly(a2, q1);
             const double c[9] = {0, 0, 16 * c1, 32, 1712, -12408, 27517, -24860, 8000};
-            ws[1] = d4 * _t2 / 720 * evalpoly(tinv, c);
+            ws[1] = FGQ_DIV_LIT(d4 * _t2, 720.0) * evalpoly(tinv, c);
         }
         {
             const double q1[4] = {-31, 147, -105, 21}, q2[4] = {-416, 1995, -1470, 315}, q3[3] = {43, -126, 63};
             const double q4[3] = {-89, -378, 189}, q5[3] = {53752, -630, 315};
             const double c1 = evalpoly(a2, q1), c2 = evalpoly(a2, q2), c3 = evalpoly(a2, q3), c4 = evalpoly(a2, q4), c5 = evalpoly(a2, q5);
             const double c[13] = {0, 0, 2304 * c1, -384 * c2, 480 * c3, -320 * c4, 80 * c5, -50986344, 201908326, -386872990, 393326325, -204917300, 43190000};
-            ws[2] = -d6 * _t3 / 90720 * evalpoly(tinv, c);
+            ws[2] = FGQ_DIV_LIT(-d6 * _t3, 90720.0) * evalpoly(tinv, c);
         }
     }
     double xdelta, wdelta;
@@ -219,16 +219,16 @@ __device__ void laguerre_bessel(const LaguerreParams& p, double jak, double& xk,
     double xdelta, wdelta;
     if (p.alpha0) {
         double xs[5], ws[5];
-        { const double c[2] = {-2, 1}; xs[0] = d2 * evalpoly(j2, c) / 3; }
-        { const double c[3] = {94, -57, 11}; xs[1] = d4 * evalpoly(j2, c) / 45; }
-        { const double c[4] = {-48308, 28102, -6516, 657}; xs[2] = d4 * d2 * evalpoly(j2, c) / 2835; }
-        { const double c[5] = {12059918, -6605817, 1456807, -172740, 10644}; xs[3] = d8 * evalpoly(j2, c) / 42525; }
-        { const double c[6] = {-11427291076.0, 6028914206.0, -1248722004, 138902061, -9908262, 410649}; xs[4] = d8 * d2 * evalpoly(j2, c) / 1403325; }
-        { const double c[2] = {-1, 1}; ws[0] = 2 * d2 * evalpoly(j2, c) / 3; }
-        { const double c[3] = {94, -114, 33}; ws[1] = d4 * evalpoly(j2, c) / 45; }
-        { const double c[4] = {-12077, 14051, -4887, 657}; ws[2] = 4 * d4 * d2 * evalpoly(j2, c) / 2835; }
-        { const double c[5] = {12059918, -13211634, 4370421, -690960, 53220}; ws[3] = d8 * evalpoly(j2, c) / 42525; }
-        { const double c[6] = {-5713645538.0, 6028914206.0, -1873083006, 277804122, -24770655, 1231947}; ws[4] = 2 * d8 * d2 * evalpoly(j2, c) / 1403325; }
+        { const double c[2] = {-2, 1}; xs[0] = FGQ_DIV_LIT(d2 * evalpoly(j2, c), 3.0); }
+        { const double c[3] = {94, -57, 11}; xs[1] = FGQ_DIV_LIT(d4 * evalpoly(j2, c), 45.0); }
+        { const double c[4] = {-48308, 28102, -6516, 657}; xs[2] = FGQ_DIV_LIT(d4 * d2 * evalpoly(j2, c), 2835.0); }
+        { const double c[5] = {12059918, -6605817, 1456807, -172740, 10644}; xs[3] = FGQ_DIV_LIT(d8 * evalpoly(j2, c), 42525.0); }
+        { const double c[6] = {-11427291076.0, 6028914206.0, -1248722004, 138902061, -9908262, 410649}; xs[4] = FGQ_DIV_LIT(d8 * d2 * evalpoly(j2, c), 1403325.0); }
+        { const double c[2] = {-1, 1}; ws[0] = FGQ_DIV_LIT(2 * d2 * evalpoly(j2, c), 3.0); }
+        { const double c[3] = {94, -114, 33}; ws[1] = FGQ_DIV_LIT(d4 * evalpoly(j2, c), 45.0); }
+        { const double c[4] = {-12077, 14051, -4887, 657}; ws[2] = FGQ_DIV_LIT(4 * d4 * d2 * evalpoly(j2, c), 2835.0); }
+        { const double c[5] = {12059918, -13211634, 4370421, -690960, 53220}; ws[3] = FGQ_DIV_LIT(d8 * evalpoly(j2, c), 42525.0); }
+        { const double c[6] = {-5713645538.0, 6028914206.0, -1873083006, 277804122, -24770655, 1231947}; ws[4] = FGQ_DIV_LIT(2 * d8 * d2 * evalpoly(j2, c), 1403325.0); }
         sum_adaptive(xs, xk, xdelta);
         sum_adaptive(ws, wk, wdelta);
     } else {
@@ -237,30 +237,30 @@ __device__ void laguerre_bessel(const LaguerreParams& p, double jak, double& xk,
         {
             const double c1 = evalpoly2(a2, -2, 2);
             const double cx[2] = {c1, 1}, cw[2] = {c1, 2};
-            xs[0] = d2 * evalpoly(j2, cx) / 3;
-            ws[0] = d2 * evalpoly(j2, cw) / 3;
+            xs[0] = FGQ_DIV_LIT(d2 * evalpoly(j2, cx), 3.0);
+            ws[0] = FGQ_DIV_LIT(d2 * evalpoly(j2, cw), 3.0);
         }
         {
             const double q1[3] = {94, -140, 46};
             const double c1 = evalpoly(a2, q1), c2 = evalpoly2(a2, -19, 11);
             const double cx[3] = {c1, 3 * c2, 11}, cw[3] = {c1, 6 * c2, 33};
-            xs[1] = d4 * evalpoly(j2, cx) / 45;
-            ws[1] = d4 * evalpoly(j2, cw) / 45;
+            xs[1] = FGQ_DIV_LIT(d4 * evalpoly(j2, cx), 45.0);
+            ws[1] = FGQ_DIV_LIT(d4 * evalpoly(j2, cw), 45.0);
         }
         {
             const double q1[4] = {-12077, 19887, -9303, 1493}, q2[3] = {14051, -10750, 2459};
             const double c1 = evalpoly(a2, q1), c2 = evalpoly(a2, q2), c3 = evalpoly2(a2, -181, 73);
             const double cx[4] = {4 * c1, 2 * c2, 36 * c3, 657}, cw[4] = {c1, c2, 27 * c3, 657};
-            xs[2] = d4 * d2 * evalpoly(j2, cx) / 2835;
-            ws[2] = 4 * d4 * d2 * evalpoly(j2, cw) / 2835;
+            xs[2] = FGQ_DIV_LIT(d4 * d2 * evalpoly(j2, cx), 2835.0);
+            ws[2] = FGQ_DIV_LIT(4 * d4 * d2 * evalpoly(j2, cw), 2835.0);
         }
         {
             const double q1[5] = {6029959, -10087180, 5095482, -1146220, 107959}, q2[4] = {-2201939, 1678761, -507801, 63299};
             const double q3[3] = {1456807, -729422, 125671};
             const double c1 = evalpoly(a2, q1), c2 = evalpoly(a2, q2), c3 = evalpoly(a2, q3), c4 = evalpoly2(a2, -2879, 887);
             const double cx[5] = {2 * c1, 3 * c2, c3, 60 * c4, 10644}, cw[5] = {2 * c1, 6 * c2, 3 * c3, 240 * c4, 53220};
-            xs[3] = d8 * evalpoly(j2, cx) / 42525;
-            ws[3] = d8 * evalpoly(j2, cw) / 42525;
+            xs[3] = FGQ_DIV_LIT(d8 * evalpoly(j2, cx), 42525.0);
+            ws[3] = FGQ_DIV_LIT(d8 * evalpoly(j2, cw), 42525.0);
         }
         sum_adaptive(xs, xk, xdelta);
         sum_adaptive(ws, wk, wdelta);
