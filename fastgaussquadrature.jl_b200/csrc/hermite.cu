@@ -151,11 +151,11 @@ __global__ void hermite_init_kernel(HermiteParams p, HermiteState* st, double* t
 }
 
 // gausshermite.jl:171-250 at one theta.  Its 20 quotients were more than half of the FP64 instructions of a sweep
-// (CUDA's a / b: ~25 instructions with its range checks): the twelve by literals or per-rule constants use
-// fgq_div_by_inrange (fgq_math.h; every operand here lies within [1e-60, 1e60]; for the per-rule constants a quotient within 2^-53 ulp of a rounding boundary — a
-// 1e-16-probability event, in a term of relative size (2n+1)^-2/3 or less — would come out one ulp off), the eight
-// by powers of chi / phi fgq_div_fast (CUDA's own fast path without the range checks; every
-// operand here lies within [1e-60, 1e60]).
+// (CUDA's a / b: ~25 instructions with its range checks).  The twelve by literals or per-rule constants use
+// fgq_div_by_inrange (fgq_math.h): exact for the literal divisors; for the per-rule constants a quotient within
+// 2^-53 ulp of a rounding boundary — a 1e-16-probability event, in a term of relative size (2n+1)^-2/3 or less —
+// would come out one ulp off.  The eight by powers of chi / phi use fgq_div_fast (CUDA's own fast path without the
+// range checks).  Every operand here is far inside the normal range.
 __device__ __forceinline__ void hermpoly_asy_airy(const HermiteParams& p, double th, double sinT,
                                                   double cosT, double& val, double& dval) {
     const double sin2T = 2.0 * cosT * sinT;
