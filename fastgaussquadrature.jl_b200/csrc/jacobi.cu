@@ -48,6 +48,7 @@ struct JacobiLaunch {
     int64_t lo, hi;        // output slice
     double tol;
     double tskip;          // norm passes: nodes with theta >= tskip provably stay below the truncation threshold
+    int64_t norm_tile_lo, norm_tile_hi;  // norm passes: the tiles (of this half) that can hold a node with theta < tskip
 };
 
 constexpr int JAC_THREADS = 128;
@@ -212,7 +213,10 @@ jacobi_pass_kernel(const __grid_constant__ JacobiLaunch p, JacobiState* st, doub
         double tmax[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) tmax[q] = 0.0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // theta is monotone along a half and small only at its outer end: the host bounds the tiles that can hold a
+        // node with theta < tskip (twice the angle on the initial guesses, at least 4096 nodes), the others are not
+        // even read (reading all of theta was 34 of a norm pass's 37 us at n = 1e7)
+        for (int64_t tile = p.norm_tile_lo + blockIdx.x; tile < p.norm_tile_hi; tile += gridDim.x) {
             const int64_t r = tile * JAC_THREADS + threadIdx.x;
             const int64_t ig = p.first + r;
             const bool active = r < p.count;
@@ -828,6 +832,38 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
     L[0].idx_lo = n_left;         L[0].idx_hi = n - (JAC_NBDY - 1);   // all but the last 9 (:206)
     L[1].first = 0;               L[1].count = n_left;
     L[1].idx_lo = JAC_NBDY;       L[1].idx_hi = n_left;              // all but the first 10 (:228)
+    // Norm passes: only nodes with theta < tskip are evaluated (see jacobi_norm_skip_angle), and theta = tt(i) (right
+    // half) / pi - tt(i) (left half) is monotone in i, small at the outer end of the half.  Bound the node range
+    // generously on the initial guesses — angle 2 tskip (Newton moves an interior theta by a 1e-6 fraction at most),
+    // never fewer than 4096 nodes — and hand the kernels the tiles that cover it.  A half whose inner end could exceed
+    // JAC_SKIP_TMAX (it cannot: the split is at pi/2) keeps every tile.
+    for (int h = 0; h < 2; ++h) {
+        const int64_t count = L[h].count;
+        const int64_t ntiles = (count + JAC_THREADS - 1) / JAC_THREADS;
+        L[h].norm_tile_lo = 0;
+        L[h].norm_tile_hi = ntiles;
+        const double inner = h == 0 ? jacobi_tt_host(n, a, b, n_left) : 3.141592653589793 - jacobi_tt_host(n, a, b, n_left - 1);
+        if (!(inner < JAC_SKIP_TMAX - 5e-4) || !(L[h].tskip > 0) || count <= 8192) continue;
+        const double bound = 2 * L[h].tskip;
+        // number of nodes, counted from the outer end, whose initial theta is below the bound
+        int64_t lo_c = 0, hi_c = count;  // theta(outer end + lo_c) < bound assumed for lo_c = 0; bisect the first c with theta >= bound
+        auto theta_at = [&](int64_t c) {  // c-th node from the outer end
+            return h == 0 ? jacobi_tt_host(n, a, b, n - 1 - c) : 3.141592653589793 - jacobi_tt_host(n, a, b, c);
+        };
+        if (!(theta_at(count - 1) >= bound)) continue;  // the whole half is below the bound: every tile
+        while (hi_c - lo_c > 1) {
+            const int64_t mid = lo_c + (hi_c - lo_c) / 2;
+            if (theta_at(mid) >= bound) hi_c = mid; else lo_c = mid;
+        }
+        int64_t keep = hi_c + 1;
+        if (keep < 4096) keep = 4096;
+        if (keep >= count) continue;
+        if (h == 0) {
+            L[h].norm_tile_lo = (count - keep) / JAC_THREADS;   // nodes r >= count - keep
+        } else {
+            L[h].norm_tile_hi = (keep + JAC_THREADS - 1) / JAC_THREADS;  // nodes r < keep
+        }
+    }
     // The two halves are independent chains (their own phase flags, norms, tickets, theta ranges and outputs): the
     // left half's 33 launches go to a second side stream, forked after the initial guesses and joined at the end, so
     // that the launch gaps and the converged-and-return launches of one chain are hidden behind the other's work
