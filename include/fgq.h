@@ -182,7 +182,11 @@ int fgq_gausshermite_sweeps(const void* workspace_dev, int* sweeps);
 int fgq_gausslaguerre_host(int64_t n, double alpha, int reduced, double* x, double* w, int64_t* n_out);
 int64_t fgq_gausslaguerre_workspace_bytes(int64_t n);
 /* Device-resident: x_dev/w_dev hold all n entries; the reduced length is available through
- * fgq_gausslaguerre_stats.  Enqueues a fixed sequence of launches; no host synchronisation. */
+ * fgq_gausslaguerre_stats.  Enqueues a fixed sequence of launches; no host synchronisation.  workspace_dev:
+ * fgq_gausslaguerre_workspace_bytes(n) bytes, 32-byte aligned (the error estimates, the list of nodes handed to the
+ * recompute hook, and for n >= 128 the second candidate expansion of the ~0.1 n + 8 sqrt(n) nodes next to the two
+ * hand-over indices).  The asymptotic rule forks onto library-owned side streams and joins them before it
+ * returns to the caller's stream: stream-ordered and graph-capturable like the others. */
 int fgq_gausslaguerre_device(int64_t n, double alpha, double* x_dev, double* w_dev, void* workspace_dev,
                              void* stream);
 /* hand-over indices (1-based; n+1 = never), number of recompute candidates, reduced length. */
