@@ -94,6 +94,7 @@ SIGNATURES = {
     "fgq_debug_codec_stats": (ctypes.c_int, [_i64p, _i64p]),
     "fgq_debug_codec_roundtrip_host": (ctypes.c_int, [_vp, _i64, _vp, _i64p]),
     "fgq_debug_jacobi_skip_angles": (ctypes.c_int, [_i64, ctypes.c_double, ctypes.c_double, _dp, _dp]),
+    "fgq_debug_jacobi_norm_tiles": (ctypes.c_int, [_i64, ctypes.c_double, ctypes.c_double, _vp]),
     "fgq_debug_codec_unpack_host": (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, ctypes.c_int, ctypes.c_int]),
     "fgq_debug_drain_stats": (ctypes.c_int, [_i64p, _i64p, _i64p, ctypes.POINTER(ctypes.c_int)]),
     # multi-GPU, one process

@@ -634,6 +634,41 @@ static double jacobi_tt_host(int64_t n, double a, double b, int64_t i) {
     return K + (1 / (d * d)) * ((0.25 - a * a) * (1.0 / tan(K / 2)) - (0.25 - b * b) * tan(K / 2));
 }
 
+// Norm passes: only nodes with theta < tskip are evaluated (see jacobi_norm_skip_angle), and theta = tt(i) (right
+// half, h = 0) / pi - tt(i) (left half) is monotone in i, small at the outer end of the half.  Bound the node range
+// generously on the initial guesses — angle 2 tskip (Newton moves an interior theta by a 1e-6 fraction at most),
+// never fewer than 4096 nodes — and return the tiles (of JAC_THREADS nodes, counted within the half) that cover it.
+// A half whose inner end could exceed JAC_SKIP_TMAX (it cannot: the split is at pi/2) keeps every tile.
+static void jacobi_norm_tiles(int64_t n, double a, double b, int64_t n_left, int h, int64_t count, double tskip,
+                              int64_t* tile_lo, int64_t* tile_hi) {
+    const double PI = 3.141592653589793;
+    const int64_t ntiles = (count + JAC_THREADS - 1) / JAC_THREADS;
+    *tile_lo = 0;
+    *tile_hi = ntiles;
+    if (count <= 8192 || !(tskip > 0)) return;
+    const double inner = h == 0 ? jacobi_tt_host(n, a, b, n_left) : PI - jacobi_tt_host(n, a, b, n_left - 1);
+    if (!(inner < JAC_SKIP_TMAX - 5e-4)) return;
+    const double bound = 2 * tskip;
+    auto theta_at = [&](int64_t c) {  // initial theta of the c-th node from the outer end of the half
+        return h == 0 ? jacobi_tt_host(n, a, b, n - 1 - c) : PI - jacobi_tt_host(n, a, b, c);
+    };
+    if (!(theta_at(count - 1) >= bound)) return;  // the whole half is below the bound: every tile
+    int64_t lo_c = 0, hi_c = count - 1;           // first c with theta_at(c) >= bound, by bisection
+    while (hi_c - lo_c > 1) {
+        const int64_t mid = lo_c + (hi_c - lo_c) / 2;
+        if (theta_at(mid) >= bound) hi_c = mid; else lo_c = mid;
+    }
+    int64_t keep = hi_c + 1;
+    if (keep < 4096) keep = 4096;
+    if (keep >= count) return;
+    if (h == 0) {
+        *tile_lo = (count - keep) / JAC_THREADS;                // nodes r >= count - keep of the half
+    } else {
+        *tile_hi = (keep + JAC_THREADS - 1) / JAC_THREADS;      // nodes r < keep of the half
+    }
+}
+
+
 }  // namespace fgq
 
 using namespace fgq;
@@ -832,38 +867,8 @@ static int jacobi_asy_device(int64_t n, double a, double b, int64_t lo, int64_t 
     L[0].idx_lo = n_left;         L[0].idx_hi = n - (JAC_NBDY - 1);   // all but the last 9 (:206)
     L[1].first = 0;               L[1].count = n_left;
     L[1].idx_lo = JAC_NBDY;       L[1].idx_hi = n_left;              // all but the first 10 (:228)
-    // Norm passes: only nodes with theta < tskip are evaluated (see jacobi_norm_skip_angle), and theta = tt(i) (right
-    // half) / pi - tt(i) (left half) is monotone in i, small at the outer end of the half.  Bound the node range
-    // generously on the initial guesses — angle 2 tskip (Newton moves an interior theta by a 1e-6 fraction at most),
-    // never fewer than 4096 nodes — and hand the kernels the tiles that cover it.  A half whose inner end could exceed
-    // JAC_SKIP_TMAX (it cannot: the split is at pi/2) keeps every tile.
-    for (int h = 0; h < 2; ++h) {
-        const int64_t count = L[h].count;
-        const int64_t ntiles = (count + JAC_THREADS - 1) / JAC_THREADS;
-        L[h].norm_tile_lo = 0;
-        L[h].norm_tile_hi = ntiles;
-        const double inner = h == 0 ? jacobi_tt_host(n, a, b, n_left) : 3.141592653589793 - jacobi_tt_host(n, a, b, n_left - 1);
-        if (!(inner < JAC_SKIP_TMAX - 5e-4) || !(L[h].tskip > 0) || count <= 8192) continue;
-        const double bound = 2 * L[h].tskip;
-        // number of nodes, counted from the outer end, whose initial theta is below the bound
-        int64_t lo_c = 0, hi_c = count;  // theta(outer end + lo_c) < bound assumed for lo_c = 0; bisect the first c with theta >= bound
-        auto theta_at = [&](int64_t c) {  // c-th node from the outer end
-            return h == 0 ? jacobi_tt_host(n, a, b, n - 1 - c) : 3.141592653589793 - jacobi_tt_host(n, a, b, c);
-        };
-        if (!(theta_at(count - 1) >= bound)) continue;  // the whole half is below the bound: every tile
-        while (hi_c - lo_c > 1) {
-            const int64_t mid = lo_c + (hi_c - lo_c) / 2;
-            if (theta_at(mid) >= bound) hi_c = mid; else lo_c = mid;
-        }
-        int64_t keep = hi_c + 1;
-        if (keep < 4096) keep = 4096;
-        if (keep >= count) continue;
-        if (h == 0) {
-            L[h].norm_tile_lo = (count - keep) / JAC_THREADS;   // nodes r >= count - keep
-        } else {
-            L[h].norm_tile_hi = (keep + JAC_THREADS - 1) / JAC_THREADS;  // nodes r < keep
-        }
-    }
+    for (int h = 0; h < 2; ++h)
+        jacobi_norm_tiles(n, a, b, n_left, h, L[h].count, L[h].tskip, &L[h].norm_tile_lo, &L[h].norm_tile_hi);
     // The two halves are independent chains (their own phase flags, norms, tickets, theta ranges and outputs): the
     // left half's 33 launches go to a second side stream, forked after the initial guesses and joined at the end, so
     // that the launch gaps and the converged-and-return launches of one chain are hidden behind the other's work
@@ -1226,6 +1231,33 @@ extern "C" int fgq_debug_jacobi_skip_angles(int64_t n, double a, double b, doubl
     *t_right = jacobi_norm_skip_angle(hp);
     jacobi_interior_plan(n, b, a, &hp);
     *t_left = jacobi_norm_skip_angle(hp);
+    return FGQ_OK;
+}
+
+// The split index and, per half (right, left), the node range [first, first + count) and the tiles its norm passes
+// walk: out = {n_left, lo_r, hi_r, lo_l, hi_l} (host only; tests check the bound against the initial guesses).
+extern "C" int fgq_debug_jacobi_norm_tiles(int64_t n, double a, double b, int64_t* out) {
+    clear_status();
+    if (n < 101 || !out) return FGQ_EINVAL;
+    const double PIO2 = 3.141592653589793 / 2;
+    int64_t n_left;
+    if (!(jacobi_tt_host(n, a, b, 0) > PIO2)) {
+        n_left = 0;
+    } else if (jacobi_tt_host(n, a, b, n - 1) > PIO2) {
+        n_left = n;
+    } else {
+        int64_t l = 0, r = n - 1;
+        while (r - l > 1) {
+            const int64_t mid = l + (r - l) / 2;
+            if (jacobi_tt_host(n, a, b, mid) > PIO2) l = mid; else r = mid;
+        }
+        n_left = r;
+    }
+    double tr, tl;
+    FGQ_TRY(fgq_debug_jacobi_skip_angles(n, a, b, &tr, &tl));
+    out[0] = n_left;
+    jacobi_norm_tiles(n, a, b, n_left, 0, n - n_left, tr, &out[1], &out[2]);
+    jacobi_norm_tiles(n, a, b, n_left, 1, n_left, tl, &out[3], &out[4]);
     return FGQ_OK;
 }
 

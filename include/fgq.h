@@ -384,6 +384,10 @@ int fgq_debug_codec_roundtrip_host(const double* in, int64_t cnt, double* out, i
  * a quarter of the reference's eps/100 threshold there), for the right half (a, b) and the mirrored left half (b, a);
  * +inf = no skipping.  Host-only; tests check the bound against the oracle's series terms. */
 int fgq_debug_jacobi_skip_angles(int64_t n, double a, double b, double* t_right, double* t_left);
+/* The tiles (128 nodes, counted within a half) the truncation-norm passes of gaussjacobi(n, a, b) walk — those that can
+ * hold a node below the skip angle: out = {n_left (split index), tile_lo, tile_hi of the right half, of the left half}
+ * (host only; tests). */
+int fgq_debug_jacobi_norm_tiles(int64_t n, double a, double b, int64_t* out);
 /* The host half of a coded transfer without a device (tests): codes `in` with the reference encoder and unpacks it
  * through the routine the pipeline's host threads run: left[e] = in[e], right[cnt-1-e] = +-in[e] for e < mirror_cnt.
  * fused != 0 selects the register-to-destination variant (FGQ_CODEC_FUSED=1 in the product; off by default). */

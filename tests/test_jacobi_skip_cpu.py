@@ -54,3 +54,43 @@ def test_skipped_nodes_are_below_the_truncation_threshold(n, a, b):
     # the skip angle scales like 1/n: n * tskip is a constant of the series (~77), i.e. ~25 nodes per end stay
     if n >= 10 ** 6 and np.isfinite(tr.value):
         assert 40 < n * tr.value < 200
+
+
+@pytest.mark.parametrize("n,a,b", [(101, 0.3, -0.7), (9000, 0.3, -0.7), (20000, -0.9, 2.5), (123457, 4.9, 4.9),
+                                    (10 ** 6, 0.3, -0.7), (3 * 10 ** 6 + 1, 0.0, 1.0), (10 ** 7, 0.3, -0.7),
+                                    (10 ** 6, -0.99, -0.99)])
+def test_norm_pass_tiles_hold_every_node_below_the_skip_angle(n, a, b):
+    """The norm passes do not even read the tiles the host rules out (`jacobi_norm_tiles`): every node whose initial
+    theta (gaussjacobi.jl:202-204, the formula of jacobi_init_kernel) is below the skip angle — with a margin of 50 %
+    for the Newton updates, which move an interior theta by a 1e-6 fraction at most — must lie in a tile that is
+    walked; for large rules the walked range is a few dozen tiles out of tens of thousands."""
+    import fgq_b200
+    L = fgq_b200.lib()
+    tr, tl = ctypes.c_double(0), ctypes.c_double(0)
+    assert L.fgq_debug_jacobi_skip_angles(n, a, b, ctypes.byref(tr), ctypes.byref(tl)) == 0
+    out = (ctypes.c_int64 * 5)()
+    assert L.fgq_debug_jacobi_norm_tiles(n, a, b, out) == 0
+    n_left, lo_r, hi_r, lo_l, hi_l = (int(v) for v in out)
+    i = np.arange(n, dtype=np.float64)
+    j = n - i
+    d = 2 * n + a + b + 1
+    K = PI * (2 * j + a - 0.5) / d
+    tt = K + (1 / (d * d)) * ((0.25 - a * a) * (1.0 / np.tan(K / 2)) - (0.25 - b * b) * np.tan(K / 2))
+    assert 0 < n_left < n and tt[n_left - 1] > PI / 2 >= tt[n_left]
+    T = 128
+    # right half: nodes n_left .. n-1, theta = tt; r = index - n_left
+    th = tt[n_left:]
+    need = np.nonzero(th < 1.5 * tr.value)[0] if np.isfinite(tr.value) else np.arange(len(th))
+    if len(need):
+        assert lo_r * T <= need.min() and need.max() < hi_r * T
+    assert 0 <= lo_r < hi_r == (len(th) + T - 1) // T
+    # left half: nodes 0 .. n_left-1, theta = pi - tt; r = index
+    th = PI - tt[:n_left]
+    need = np.nonzero(th < 1.5 * tl.value)[0] if np.isfinite(tl.value) else np.arange(len(th))
+    if len(need):
+        assert lo_l * T <= need.min() and need.max() < hi_l * T
+    assert 0 == lo_l < hi_l <= (len(th) + T - 1) // T
+    if n >= 10 ** 6:
+        assert hi_r - lo_r <= 64 and hi_l - lo_l <= 64   # the bound is not vacuous
+    if n <= 9000:
+        assert lo_r == 0 and hi_l == (n_left + T - 1) // T   # small halves are walked whole
